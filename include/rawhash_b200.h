@@ -1,0 +1,221 @@
+/*
+ * rawhash_b200.h — C-ABI of the B200-native RawHash2 mapping hot path.
+ *
+ * This header is the drop-in boundary.  Everything here is
+ * `extern "C"`, plain pointers and sizes; no torch / CUDA types cross it.
+ *
+ * What it replaces in the reference (paths relative to the RawHash tree):
+ *   - src/rmap.cpp:700   `kt_for(p->n_threads, map_worker_for, in, s->n_sig)`
+ *                        -> rh_gpu_map_batch_raw()
+ *   - src/rmap.cpp:389   map_worker_for (per-read chunk loop, stop rules, PAF fields)
+ *   - src/rsig.c:496-503 raw int16 -> pA conversion + (30,200) outlier drop
+ *                        (moves onto the GPU: the batch call takes raw int16)
+ *   - src/rindex.c:497   ri_idx_get (khash lookup) -> flattened device index
+ *                        built by rh_index_* below
+ *   - src/roptions.c:4-138, src/main.cpp:111-210,363-376
+ *                        option defaults / presets -> rh_params_*
+ *   - src/rmap.cpp:751-772 PAF line formatting -> rh_format_paf()
+ *
+ * All mapping compute runs in CUDA kernels (sm_100a).  There is no CPU
+ * fallback: every rh_gpu_* entry point returns RH_ERR_CUDA when no device
+ * is usable.
+ */
+#ifndef RAWHASH_B200_H
+#define RAWHASH_B200_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- flags (values identical to src/roptions.h:6-41) ------------------- */
+#define RH_I_SIG_TARGET     0x20      /* RI_I_SIG_TARGET  */
+#define RH_M_NO_ADAPTIVE    0x20      /* RI_M_NO_ADAPTIVE */
+#define RH_M_ALL_CHAINS     0x2000    /* RI_M_ALL_CHAINS  */
+
+/* ---- error codes -------------------------------------------------------- */
+#define RH_OK            0
+#define RH_ERR_ARG      -1
+#define RH_ERR_IO       -2
+#define RH_ERR_CUDA     -3
+#define RH_ERR_NOMEM    -4
+#define RH_ERR_FORMAT   -5
+
+/*
+ * Flat mirror of the fields of ri_idxopt_t / ri_mapopt_t (src/roptions.h:50-143)
+ * that the hot path reads.  Same names, same meaning.
+ */
+typedef struct rh_params_s {
+	/* sketch / index (ri_idxopt_t; stored in ri_idx_t, src/rindex.h:29-60) */
+	int32_t w, e, n, q, k, idx_flag, lev_col;
+	float diff, fine_min, fine_max, fine_range;
+	/* event segmentation (--seg-*) */
+	uint32_t window_length1, window_length2;
+	float threshold1, threshold2, peak_height;
+	/* device */
+	uint32_t bp_per_sec, sample_rate, chunk_size;
+	float sample_per_base;
+	/* seeding */
+	float mid_occ_frac;
+	int32_t min_mid_occ, max_mid_occ, mid_occ;
+	/* chaining */
+	uint32_t min_events;
+	int32_t bw, max_target_gap_length, max_query_gap_length, max_chain_iter;
+	int32_t max_num_skips, min_num_anchors, min_chaining_score, min_chaining_score2;
+	float chain_gap_scale, chain_skip_scale;
+	/* primary/secondary + mapq */
+	float mask_level;
+	int32_t mask_len;
+	float pri_ratio;
+	int32_t best_n;
+	float alt_drop;
+	/* decision */
+	float w_bestq, w_bestmq, w_bestmc, w_threshold;
+	uint32_t max_num_chunk;
+	int32_t min_mapq;
+	int64_t map_flag;
+} rh_params_t;
+
+/*
+ * One output record = one PAF line (mirrors ri_map_t, src/rmap.h:12-22, plus
+ * the integer tag fields written at src/rmap.cpp:527-570).  Unmapped reads
+ * get exactly one record with mapped == 0 (src/rmap.cpp:521-556).
+ */
+typedef struct rh_map_rec_s {
+	uint32_t read_idx;       /* index of the read in the batch */
+	uint32_t c_id;
+	uint32_t read_length;
+	uint32_t ref_id;
+	uint32_t read_start_position;
+	uint32_t read_end_position;
+	uint32_t fragment_start_position;
+	uint32_t fragment_length;
+	uint8_t  mapq, rev, mapped, _pad;
+	uint32_t ci;             /* chunks consumed  (ci:i) */
+	uint32_t sl;             /* filtered signal length (sl:i) */
+	int32_t  cm, nc, s1;     /* cm:i nc:i s1:i */
+} rh_map_rec_t;
+
+/* ---- parameters / presets ---------------------------------------------- */
+/* defaults of ri_idxopt_init + ri_mapopt_init (src/roptions.c:4-138) */
+void rh_params_init(rh_params_t *p);
+/* presets of ri_set_opt (src/main.cpp:111-210); returns RH_ERR_ARG on unknown name */
+int  rh_params_preset(rh_params_t *p, const char *preset);
+/* the --r10 macro flag (src/main.cpp:363-376) */
+void rh_params_r10(rh_params_t *p);
+
+/* ---- pore model (load_pore, src/rutils.c:133-178) ----------------------- */
+/* Parses a k-mer model file; returns malloc'ed z-normalised levels (4^k floats) */
+int rh_pore_load(const char *path, int k, int lev_col, float **vals, uint32_t *n_vals);
+void rh_free(void *p);
+
+/* ---- index -------------------------------------------------------------- */
+typedef struct rh_index_s rh_index_t;   /* flattened host-side index */
+
+/* Build from sequences (semantics of ri_idx_gen, src/rindex.c:900-925:
+ * ri_seq_to_sig + ri_sketch on both strands, positions ascending per key). */
+rh_index_t *rh_index_build(const rh_params_t *p, const float *pore_vals, uint32_t n_pore_vals,
+                           uint32_t n_seq, const char *const *names, const char *const *seqs,
+                           const uint32_t *lens, int n_threads);
+/* Build from raw signals for Rawsamble (semantics of ri_idx_siggen, src/rindex.c:927-969).
+ * Event detection runs on the GPU. */
+rh_index_t *rh_index_build_sig(const rh_params_t *p, uint32_t n_reads, const char *const *names,
+                               const int16_t *const *raw, const uint64_t *raw_len,
+                               const double *offset, const double *range, const double *digitisation);
+/* Load a reference-format `.ind` file (reader of src/rindex.c:650-776). */
+rh_index_t *rh_index_load(const char *path, rh_params_t *p_inout);
+void        rh_index_destroy(rh_index_t *idx);
+uint32_t    rh_index_n_seq(const rh_index_t *idx);
+const char *rh_index_seq_name(const rh_index_t *idx, uint32_t i);
+uint32_t    rh_index_seq_len(const rh_index_t *idx, uint32_t i);
+uint64_t    rh_index_n_keys(const rh_index_t *idx);
+uint64_t    rh_index_n_pos(const rh_index_t *idx);
+/* ri_idx_cal_max_occ + ri_mapopt_update (src/rindex.c:1018-1053): sets p->mid_occ */
+void        rh_index_update_mapopt(const rh_index_t *idx, rh_params_t *p);
+/* ri_idx_get (src/rindex.c:497-514): returns pointer to ascending position list */
+const uint64_t *rh_index_get(const rh_index_t *idx, uint32_t hash, int *n);
+
+/* ---- GPU context --------------------------------------------------------- */
+typedef struct rh_gpu_ctx_s rh_gpu_ctx;
+
+/* Uploads the index to device `device` and allocates work arenas.
+ * arena_bytes == 0 picks a default from free device memory. */
+rh_gpu_ctx *rh_gpu_init(const rh_index_t *idx, const rh_params_t *p, int device, size_t arena_bytes);
+void        rh_gpu_destroy(rh_gpu_ctx *ctx);
+const char *rh_gpu_last_error(void);
+
+/*
+ * The drop-in for `kt_for(n_threads, map_worker_for, step, n_sig)` with the
+ * signal payload moved one step earlier (raw int16 + calibration instead of
+ * pA floats).  For each read i in [0,n): raw[i] points to raw_len[i] samples
+ * in HOST memory.  Output: *recs is a malloc'ed array of *n_recs records in
+ * read order (free with rh_free).  Returns RH_OK or an error code.
+ */
+int rh_gpu_map_batch_raw(rh_gpu_ctx *ctx, uint32_t n,
+                         const int16_t *const *raw, const uint64_t *raw_len,
+                         const double *offset, const double *range, const double *digitisation,
+                         const char *const *names,
+                         rh_map_rec_t **recs, uint64_t *n_recs);
+
+/*
+ * Same computation with the raw samples already resident in device memory as
+ * one concatenated int16 buffer (d_raw, device pointer) with per-read start
+ * offsets raw_off[n+1] (host).  Used by bench.py for the HBM-resident number.
+ */
+int rh_gpu_map_batch_dev(rh_gpu_ctx *ctx, uint32_t n,
+                         const void *d_raw, const uint64_t *raw_off,
+                         const double *offset, const double *range, const double *digitisation,
+                         const char *const *names,
+                         rh_map_rec_t **recs, uint64_t *n_recs);
+
+/* Per-stage statistics of the last rh_gpu_map_batch_* call. */
+typedef struct rh_gpu_stats_s {
+	uint64_t n_reads, n_chunks, n_rounds;
+	uint64_t raw_samples_consumed;   /* int16 samples read by the event kernel   */
+	uint64_t n_events, n_seeds, n_anchors, n_chains;
+	uint64_t kernel_launches;        /* launches of our own kernels              */
+	double   ms_total;               /* CUDA-event time of the whole call        */
+	double   ms_event_kernel;        /* signal->seeds kernel(s) only             */
+	double   ms_seed, ms_sort, ms_chain, ms_post;
+	uint64_t event_kernel_launches;
+	uint64_t h2d_bytes, d2h_bytes;
+} rh_gpu_stats_t;
+void rh_gpu_get_stats(const rh_gpu_ctx *ctx, rh_gpu_stats_t *st);
+
+/*
+ * Stage tap (parity tests only): map ONE read through every chunk up to
+ * max_num_chunk WITHOUT the stop rules and copy each stage's device output
+ * back.  Arrays are concatenated over chunks; cnt[c*RH_TAP_NCNT + j] holds
+ * the per-chunk counts.  Capacities are in elements; returns RH_ERR_NOMEM if
+ * a buffer is too small.
+ */
+#define RH_TAP_NCNT 8
+enum { RH_TAP_NSIG = 0, RH_TAP_NEVENTS, RH_TAP_NSEEDS, RH_TAP_NANCHORS, RH_TAP_NU, RH_TAP_NV, RH_TAP_NREGS, RH_TAP_REPLEN };
+#define RH_TAP_REG_NF 14  /* score cnt rid rev qs qe rs re parent subsc n_sub mapq as score0 */
+typedef struct rh_tap_s {
+	uint32_t n_chunks;
+	int32_t  *cnt;      uint64_t cap_chunks;
+	float    *events;   uint64_t cap_events;
+	uint64_t *seeds;    uint64_t cap_seeds;    /* x,y pairs */
+	uint64_t *anchors;  uint64_t cap_anchors;  /* x,y pairs, sorted list fed to chaining */
+	uint64_t *u;        uint64_t cap_u;
+	uint64_t *chain_a;  uint64_t cap_chain_a;  /* x,y pairs, compacted target-sorted anchors */
+	uint64_t *prev_a;   uint64_t cap_prev_a;   /* x,y pairs, backtrack-order copy carried to next chunk */
+	int32_t  *regs;     uint64_t cap_regs;     /* RH_TAP_REG_NF ints per region */
+} rh_tap_t;
+int rh_gpu_tap_read(rh_gpu_ctx *ctx, const int16_t *raw, uint64_t raw_len,
+                    double offset, double range, double digitisation,
+                    const char *name, rh_tap_t *tap);
+
+/* ---- PAF ------------------------------------------------------------------ */
+/* Formats records exactly like src/rmap.cpp:751-772 (mt:f: is printed as 0).
+ * Returns a malloc'ed NUL-terminated string (free with rh_free). */
+char *rh_format_paf(const rh_index_t *idx, const rh_map_rec_t *recs, uint64_t n_recs,
+                    const char *const *names);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RAWHASH_B200_H */

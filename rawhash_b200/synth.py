@@ -1,0 +1,167 @@
+"""Seeded synthetic inputs for tests and bench (SURVEY.md §8d recipe).
+
+No genome or signal files exist on the build/GPU boxes and there is no network, so every
+input is generated: an i.i.d. ACGT genome and nanopore-like raw int16 reads sampled from it
+through a k-mer pore model (level mean per k-mer held for an exponential dwell, Gaussian
+noise, ADC quantisation with digitisation 8192 / range 1400 / offset 10).
+
+The pore model is the ONT table the reference vendors (extern/kmer_models); build() stages a
+copy under data/models/ (git-ignored).  When it is absent a seeded synthetic table of the
+same shape is used and reported as such.
+"""
+from __future__ import annotations
+
+import os
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_ROOT = os.path.dirname(_HERE)
+
+DIGITISATION = 8192.0
+RANGE = 1400.0
+OFFSET = 10.0
+
+
+def model_path(kind: str = "r9.4") -> str | None:
+    """Path of the staged ONT k-mer model, or None."""
+    name = {"r9.4": "r9.4_6mer.model", "r10.4.1": "r10.4.1_9mer.txt"}[kind]
+    for d in (os.path.join(_ROOT, "data", "models"),
+              "/root/reference/extern/kmer_models/legacy/legacy_r9.4_180mv_450bps_6mer" if kind == "r9.4"
+              else "/root/reference/extern/kmer_models/dna_r10.4.1_e8.2_400bps"):
+        for cand in (name, "template_median68pA.model", "9mer_levels_v1.txt"):
+            p = os.path.join(d, cand)
+            if os.path.isfile(p):
+                return p
+    return None
+
+
+def write_synthetic_model(path: str, k: int = 6, seed: int = 7) -> str:
+    """Seeded stand-in for an ONT model file (same columns as the R9.4 table)."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    n = 4 ** k
+    mean = rng.normal(90.0, 12.0, n).clip(55.0, 130.0)
+    stdv = np.full(n, 1.5)
+    with open(path, "w") as f:
+        f.write("kmer\tlevel_mean\tlevel_stdv\n")
+        for i in range(n):
+            kmer = "".join("ACGT"[(i >> (2 * (k - 1 - j))) & 3] for j in range(k))
+            f.write(f"{kmer}\t{mean[i]:.6f}\t{stdv[i]:.6f}\n")
+    return path
+
+
+def load_model_pa(path: str, k: int, r10_mean: float = 90.0, r10_sd: float = 13.0):
+    """Returns (level_mean_pA[4^k], level_stdv_pA[4^k]) indexed by 2-bit packed k-mer (A=0..T=3).
+
+    The R10.4.1 table holds normalised levels without a stdv column; it is de-normalised as
+    90 + 13*level pA with a fixed 2 pA noise."""
+    means = np.zeros(4 ** k, dtype=np.float64)
+    stdv = np.zeros(4 ** k, dtype=np.float64)
+    i = 0
+    with open(path) as f:
+        for line in f:
+            if line.startswith("kmer"):
+                continue
+            t = line.rstrip("\n").split("\t")
+            if len(t) < 2:
+                continue
+            means[i] = float(t[1])
+            stdv[i] = float(t[2]) if len(t) > 2 else -1.0
+            i += 1
+    assert i == 4 ** k, (i, k)
+    if stdv[0] < 0:  # normalised table (R10)
+        means = r10_mean + r10_sd * means
+        stdv[:] = 2.0
+    return means, stdv
+
+
+def make_genome(n_contigs: int, total_len: int, seed: int = 1):
+    """List of (name, uint8 array of 0..3) contigs, i.i.d. uniform."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    per = total_len // n_contigs
+    out = []
+    for c in range(n_contigs):
+        ln = per if c < n_contigs - 1 else total_len - per * (n_contigs - 1)
+        out.append((f"chr{c + 1}", rng.integers(0, 4, ln, dtype=np.uint8)))
+    return out
+
+
+def genome_to_strings(genome):
+    lut = np.frombuffer(b"ACGT", dtype=np.uint8)
+    return [(name, lut[seq].tobytes().decode()) for name, seq in genome]
+
+
+def write_fasta(path: str, genome, width: int = 80):
+    lut = np.frombuffer(b"ACGT", dtype=np.uint8)
+    with open(path, "wb") as f:
+        for name, seq in genome:
+            f.write(b">" + name.encode() + b"\n")
+            s = lut[seq]
+            for i in range(0, len(s), width * 1000):
+                blk = s[i:i + width * 1000]
+                nfull = len(blk) // width
+                if nfull:
+                    a = np.empty((nfull, width + 1), dtype=np.uint8)
+                    a[:, :width] = blk[:nfull * width].reshape(nfull, width)
+                    a[:, width] = 10
+                    f.write(a.tobytes())
+                if len(blk) % width:
+                    f.write(blk[nfull * width:].tobytes() + b"\n")
+
+
+def _kmer_codes(seq: np.ndarray, k: int) -> np.ndarray:
+    """2-bit packed k-mer code at every position (len - k + 1 codes)."""
+    n = len(seq) - k + 1
+    code = np.zeros(n, dtype=np.int64)
+    for j in range(k):
+        code = (code << 2) | seq[j:j + n].astype(np.int64)
+    return code
+
+
+def make_reads(genome, n_reads: int, read_len_bp: int, k: int, means, stdv,
+               sample_rate: float = 4000.0, bp_per_sec: float = 450.0, seed: int = 2,
+               max_samples: int | None = None):
+    """Synthetic raw reads.
+
+    Returns dict with: raw (list of int16 arrays), names, truth (contig idx, start, strand),
+    offset/range/digitisation (float64 arrays)."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    scale = RANGE / DIGITISATION
+    mean_dwell = sample_rate / bp_per_sec
+    raws, names, truth = [], [], []
+    lens = np.array([len(s) for _, s in genome], dtype=np.float64)
+    prob = lens / lens.sum()
+    for r in range(n_reads):
+        ci = int(rng.choice(len(genome), p=prob))
+        seq = genome[ci][1]
+        ln = min(read_len_bp, len(seq))
+        st = int(rng.integers(0, len(seq) - ln + 1))
+        strand = int(rng.integers(0, 2))
+        frag = seq[st:st + ln]
+        if strand:
+            frag = (3 - frag)[::-1]
+        codes = _kmer_codes(frag, k)
+        dwell = np.maximum(1, np.rint(rng.exponential(mean_dwell, len(codes)))).astype(np.int64)
+        if max_samples is not None:
+            cs = np.cumsum(dwell)
+            keep = int(np.searchsorted(cs, max_samples)) + 1
+            codes, dwell = codes[:keep], dwell[:keep]
+        lv = np.repeat(means[codes], dwell)
+        sd = np.repeat(stdv[codes], dwell)
+        pa = lv + rng.standard_normal(len(lv)) * sd
+        raw = np.rint(pa / scale - OFFSET).clip(-32768, 32767).astype(np.int16)
+        raws.append(raw)
+        names.append(f"read_{r:07d}")
+        truth.append((ci, st, strand))
+    n = len(raws)
+    return {
+        "raw": raws, "names": names, "truth": truth,
+        "offset": np.full(n, OFFSET), "range": np.full(n, RANGE), "digitisation": np.full(n, DIGITISATION),
+    }
+
+
+def raw_to_pa(raw: np.ndarray, offset: float, rng_: float, digitisation: float) -> np.ndarray:
+    """Host restatement of the slow5 pA conversion + (30,200) drop (src/rsig.c:488-503);
+    used only to feed the CPU checkers, never the product path."""
+    scale = np.float32(rng_ / digitisation)
+    pa = ((raw.astype(np.float64) + offset) * np.float64(scale)).astype(np.float32)
+    return pa[(pa > np.float32(30.0)) & (pa < np.float32(200.0))]
