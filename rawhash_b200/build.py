@@ -1,0 +1,79 @@
+"""In-tree build of the CUDA library (sm_100a) and staging of input data.
+
+    python -m rawhash_b200.build            # builds rawhash_b200/librawhash_b200.so
+
+nvcc cross-compiles without a GPU; the .so travels to the GPU box with the repo snapshot.
+"""
+from __future__ import annotations
+
+import os
+import shutil
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+CSRC = os.path.join(HERE, "csrc")
+LIB = os.path.join(HERE, "librawhash_b200.so")
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a",
+    "-lineinfo", "-O3", "-std=c++17",
+    "--fmad=false",            # no implicit FMA: every fused op in the kernels is an explicit __fmaf_rn/__fma_rn
+    "-prec-div=true", "-prec-sqrt=true", "-ftz=false",
+    "-Xcompiler", "-fPIC,-ffp-contract=off,-O2",
+    "-shared",
+]
+SOURCES = ["rh_gpu.cu", "rh_host.cpp"]
+HEADERS = ["rh_dev.cuh", "rh_sort.cuh", "rh_kernels.cuh", "rh_host.h", os.path.join(ROOT, "include", "rawhash_b200.h")]
+
+
+def _newer(target, deps):
+    if not os.path.isfile(target):
+        return True
+    t = os.path.getmtime(target)
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build_lib(force: bool = False, verbose: bool = False) -> str:
+    srcs = [os.path.join(CSRC, s) for s in SOURCES]
+    deps = srcs + [h if os.path.isabs(h) else os.path.join(CSRC, h) for h in HEADERS] + [os.path.abspath(__file__)]
+    if not force and not _newer(LIB, deps):
+        return LIB
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + srcs
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        sys.stderr.write(r.stdout + r.stderr)
+        raise RuntimeError("nvcc failed building librawhash_b200.so")
+    if verbose:
+        sys.stderr.write(r.stdout + r.stderr)
+    return LIB
+
+
+def stage_models() -> None:
+    """Copy the ONT k-mer model tables the reference vendors into data/models/ (git-ignored)."""
+    srcs = {
+        "r9.4_6mer.model": "/root/reference/extern/kmer_models/legacy/legacy_r9.4_180mv_450bps_6mer/template_median68pA.model",
+        "r10.4.1_9mer.txt": "/root/reference/extern/kmer_models/dna_r10.4.1_e8.2_400bps/9mer_levels_v1.txt",
+    }
+    dst_dir = os.path.join(ROOT, "data", "models")
+    os.makedirs(dst_dir, exist_ok=True)
+    for name, src in srcs.items():
+        dst = os.path.join(dst_dir, name)
+        if os.path.isfile(src) and not os.path.isfile(dst):
+            shutil.copyfile(src, dst)
+
+
+def build_oracle() -> None:
+    """Build the checkers (oracle/librh_oracle.so and, when the reference tree exists, oracle/_ref)."""
+    r = subprocess.run(["make", "-C", os.path.join(ROOT, "oracle"), "all"], capture_output=True, text=True)
+    if r.returncode != 0:
+        sys.stderr.write(r.stdout + r.stderr)
+        raise RuntimeError("oracle build failed")
+
+
+if __name__ == "__main__":
+    build_lib(force="--force" in sys.argv, verbose="-v" in sys.argv)
+    stage_models()
+    print(LIB)

@@ -1,0 +1,656 @@
+/*
+ * rh_gpu.cu — host driver of the GPU mapping path behind the C-ABI (include/rawhash_b200.h).
+ *
+ * rh_gpu_map_batch_raw() is the drop-in for the reference's
+ *     kt_for(p->n_threads, map_worker_for, in, s->n_sig)          (src/rmap.cpp:700)
+ * The per-read chunk loop of map_worker_for (src/rmap.cpp:415-501) becomes "chunk rounds":
+ * round c processes chunk c of every read that has not stopped yet, all reads in parallel on
+ * the device; reads that satisfy a stop rule (or run out of signal/chunks) emit their final
+ * record in that round and drop out of the active set.
+ *
+ * There is no CPU fallback anywhere in this file: without a CUDA device every entry point
+ * fails with RH_ERR_CUDA.
+ */
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <math.h>
+#include <algorithm>
+#include <numeric>
+#include <string>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "rh_host.h"
+#include "rh_kernels.cuh"
+
+#define CUDA_TRY(call)                                                                                   \
+	do {                                                                                                 \
+		cudaError_t e_ = (call);                                                                         \
+		if (e_ != cudaSuccess) {                                                                         \
+			rh_set_error("%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_));            \
+			return RH_ERR_CUDA;                                                                          \
+		}                                                                                                \
+	} while (0)
+
+namespace {
+
+template <class T> struct dbuf { /* grow-only device buffer */
+	T *p = nullptr; size_t cap = 0;
+	int reserve(size_t n)
+	{
+		if (n <= cap) return RH_OK;
+		if (p) cudaFree(p);
+		p = nullptr; cap = 0;
+		size_t want = n + n / 4 + 64;
+		cudaError_t e = cudaMalloc((void **)&p, want * sizeof(T));
+		if (e != cudaSuccess) { rh_set_error("cudaMalloc(%zu bytes): %s", want * sizeof(T), cudaGetErrorString(e)); return RH_ERR_NOMEM; }
+		cap = want;
+		return RH_OK;
+	}
+	void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+struct timed_span { cudaEvent_t a, b; int kind; };
+
+} // namespace
+
+enum { T_EVENT = 0, T_SEED, T_SORT, T_CHAIN, T_POST, T_LEN, T_NKIND };
+
+struct rh_gpu_ctx_s {
+	int device = 0;
+	rh_params_t P;
+	dev_params_t D;
+	const rh_index_s *idx = nullptr;
+	dev_index_t I;
+	cudaStream_t stream = nullptr;
+	/* index storage */
+	dbuf<uint32_t> d_keys, d_bucket, d_seqlen, d_namerank;
+	dbuf<uint64_t> d_off, d_pos;
+	dbuf<float> d_logf;
+	uint32_t logf_n = 0;
+	std::vector<uint32_t> name_order; /* sorted target names (indices) for Rawsamble */
+	/* per-batch */
+	dbuf<int16_t> d_raw;
+	const int16_t *raw_ptr = nullptr; /* raw buffer of the current call (ours or the caller's) */
+	dbuf<read_state_t> d_rs;
+	dbuf<slot_t> d_slots;
+	dbuf<float> d_z, d_events;
+	dbuf<uint32_t> d_peaks, d_seed_hash, d_seed_pos, d_seed_cnt, d_seed_dst;
+	dbuf<uint64_t> d_seed_src;
+	dbuf<uint8_t> d_arena;
+	dbuf<anchor_t> d_carry[2];
+	dbuf<unsigned long long> d_counters; /* [0] carry_top, [1] rec_top */
+	dbuf<uint32_t> d_err, d_rec_start, d_rec_cnt;
+	dbuf<rh_map_rec_t> d_recs;
+	size_t arena_bytes = 0, carry_elems = 0, sig_budget = 0;
+	std::vector<timed_span> spans;
+	std::vector<cudaEvent_t> ev_pool; size_t ev_used = 0;
+	rh_gpu_stats_t st;
+};
+
+namespace {
+
+cudaEvent_t get_event(rh_gpu_ctx *c)
+{
+	if (c->ev_used == c->ev_pool.size()) { cudaEvent_t e; cudaEventCreate(&e); c->ev_pool.push_back(e); }
+	return c->ev_pool[c->ev_used++];
+}
+struct span_guard {
+	rh_gpu_ctx *c; timed_span s;
+	span_guard(rh_gpu_ctx *c_, int kind) : c(c_) { s.kind = kind; s.a = get_event(c); s.b = get_event(c); cudaEventRecord(s.a, c->stream); }
+	~span_guard() { cudaEventRecord(s.b, c->stream); c->spans.push_back(s); c->st.kernel_launches++; if (s.kind == T_EVENT) c->st.event_kernel_launches++; }
+};
+
+void fill_dev_params(const rh_params_t &P, dev_params_t &D)
+{
+	memset(&D, 0, sizeof(D));
+	D.w = P.w; D.e = P.e; D.q = P.q; D.k = P.k;
+	D.diff = P.diff; D.fine_min = P.fine_min; D.fine_max = P.fine_max; D.fine_range = P.fine_range;
+	D.w1 = P.window_length1; D.w2 = P.window_length2; D.thr1 = P.threshold1; D.thr2 = P.threshold2; D.height = P.peak_height;
+	D.min_events = P.min_events; D.mid_occ = P.mid_occ;
+	D.bw = P.bw; D.max_t = P.max_target_gap_length; D.max_q = P.max_query_gap_length; D.max_iter = P.max_chain_iter;
+	D.max_skip = P.max_num_skips; D.min_cnt = P.min_num_anchors; D.min_sc = P.min_chaining_score; D.min_sc2 = P.min_chaining_score2;
+	/* rmap.cpp:318: evaluated in double, narrowed to float */
+	D.pen_gap = (float)(P.chain_gap_scale * 0.01 * (P.e + P.k - 1));
+	D.pen_skip = (float)(P.chain_skip_scale * 0.01 * (P.e + P.k - 1));
+	D.mask_level = P.mask_level; D.mask_len = P.mask_len; D.pri_ratio = P.pri_ratio; D.best_n = P.best_n;
+	D.min_strand_sc = (int)(P.max_target_gap_length * 0.8); /* rmap.cpp:354 */
+	D.w_bestq = P.w_bestq; D.w_bestmq = P.w_bestmq; D.w_bestmc = P.w_bestmc; D.w_threshold = P.w_threshold;
+	D.min_mapq = P.min_mapq; D.max_num_chunk = P.max_num_chunk; D.chunk_size = P.chunk_size; D.sample_per_base = P.sample_per_base;
+	D.ava = (P.map_flag & RH_M_ALL_CHAINS) ? 1 : 0; D.noadapt = (P.map_flag & RH_M_NO_ADAPTIVE) ? 1 : 0;
+	D.sig_target = (P.idx_flag & RH_I_SIG_TARGET) ? 1 : 0;
+}
+
+template <class T> int upload(dbuf<T> &d, const std::vector<T> &h, cudaStream_t s)
+{
+	int rc = d.reserve(h.size() ? h.size() : 1);
+	if (rc) return rc;
+	if (h.size()) CUDA_TRY(cudaMemcpyAsync(d.p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice, s));
+	return RH_OK;
+}
+
+struct batch_in {
+	uint32_t n;
+	const int16_t *const *raw; const uint64_t *raw_len;   /* host pointers, or null when d_raw given */
+	const void *d_raw; const uint64_t *raw_off;            /* device-resident variant                  */
+	const double *offset, *range, *digitisation;
+	const char *const *names;
+};
+
+int check_params(const rh_params_t &P)
+{
+	if (P.window_length1 > 15 || P.window_length2 > 15) { rh_set_error("segmentation windows > 15 are not supported"); return RH_ERR_ARG; }
+	if (P.e < 1 || P.q < 1 || P.e * P.q > 64) { rh_set_error("bad e/q"); return RH_ERR_ARG; }
+	if (P.w != 0) { rh_set_error("minimizer seeding (w>0) is not implemented on the GPU path yet"); return RH_ERR_ARG; }
+	if (P.n != 0) { rh_set_error("BLEND seeding (n>0) is disabled in the reference and unsupported here"); return RH_ERR_ARG; }
+	return RH_OK;
+}
+
+/* ---- one chunk round over a set of slots ---------------------------------------------------- */
+struct round_io {
+	std::vector<slot_t> slots;         /* host copy */
+	int tap = 0;
+	rh_tap_t *tap_out = nullptr; uint64_t *tap_off = nullptr; /* running offsets: ev, seed, anc, u, ca, reg */
+	uint32_t tap_chunk = 0;
+};
+
+int run_round(rh_gpu_ctx *c, round_io &io, int carry_in_idx)
+{
+	const uint32_t ns = (uint32_t)io.slots.size();
+	if (ns == 0) return RH_OK;
+	cudaStream_t s = c->stream;
+	/* scratch offsets */
+	uint64_t zt = 0, et = 0;
+	for (slot_t &sl : io.slots) {
+		sl.z_off = zt; zt += sl.chunk_len;
+		sl.e_cap = (uint32_t)((uint64_t)sl.chunk_len * 2 / 3 + 8);
+		sl.e_off = et; et += sl.e_cap;
+	}
+	int rc;
+	if ((rc = c->d_z.reserve(zt))) return rc;
+	if ((rc = c->d_events.reserve(et)) || (rc = c->d_peaks.reserve(et)) || (rc = c->d_seed_hash.reserve(et)) || (rc = c->d_seed_pos.reserve(et)) ||
+	    (rc = c->d_seed_cnt.reserve(et)) || (rc = c->d_seed_dst.reserve(et)) || (rc = c->d_seed_src.reserve(et))) return rc;
+	if ((rc = upload(c->d_slots, io.slots, s))) return rc;
+	c->st.h2d_bytes += ns * sizeof(slot_t);
+
+	k1_args_t a1;
+	a1.raw = c->raw_ptr; a1.rs = c->d_rs.p; a1.slots = c->d_slots.p; a1.n_slots = ns;
+	a1.z = c->d_z.p; a1.peaks = c->d_peaks.p; a1.events = c->d_events.p; a1.seed_hash = c->d_seed_hash.p; a1.seed_pos = c->d_seed_pos.p;
+	{
+		span_guard g(c, T_EVENT);
+		k_signal_to_seeds<<<(ns + K1_THREADS - 1) / K1_THREADS, K1_THREADS, 0, s>>>(a1, c->D);
+	}
+	k2_args_t a2;
+	a2.slots = c->d_slots.p; a2.n_slots = ns; a2.rs = c->d_rs.p;
+	a2.seed_hash = c->d_seed_hash.p; a2.seed_pos = c->d_seed_pos.p; a2.seed_cnt = c->d_seed_cnt.p; a2.seed_src = c->d_seed_src.p; a2.seed_dst = c->d_seed_dst.p;
+	a2.arena = c->d_arena.p; a2.carry_in = c->d_carry[carry_in_idx].p; a2.carry_out = c->d_carry[carry_in_idx ^ 1].p;
+	const uint32_t wblocks = (ns * RH_WARP + 255) / 256;
+	{
+		span_guard g(c, T_SEED);
+		k_seed_count<<<wblocks, 256, 0, s>>>(a2, c->I, c->D);
+	}
+	CUDA_TRY(cudaMemcpyAsync(io.slots.data(), c->d_slots.p, ns * sizeof(slot_t), cudaMemcpyDeviceToHost, s));
+	CUDA_TRY(cudaStreamSynchronize(s));
+	c->st.d2h_bytes += ns * sizeof(slot_t);
+
+	/* anchor-arena groups */
+	k3_args_t a3;
+	a3.slots = nullptr; a3.n_slots = 0; a3.rs = c->d_rs.p; a3.arena = c->d_arena.p;
+	a3.carry_out = c->d_carry[carry_in_idx ^ 1].p; a3.carry_top = c->d_counters.p; a3.carry_cap = c->carry_elems;
+	a3.logf_tab = c->d_logf.p; a3.logf_n = c->logf_n;
+	a3.recs = c->d_recs.p; a3.rec_top = c->d_counters.p + 1; a3.rec_cap = c->d_recs.cap;
+	a3.rec_start = c->d_rec_start.p; a3.rec_cnt = c->d_rec_cnt.p; a3.seq_len = c->d_seqlen.p; a3.tap = io.tap; a3.err = c->d_err.p;
+
+	uint32_t g0 = 0;
+	while (g0 < ns) {
+		uint64_t used = 0; uint32_t g1 = g0;
+		while (g1 < ns) {
+			const uint64_t need = slot_region_bytes(io.slots[g1].n_anchors);
+			if (need > c->arena_bytes) { rh_set_error("a single chunk needs %llu bytes of anchor arena (have %zu)", (unsigned long long)need, c->arena_bytes); return RH_ERR_NOMEM; }
+			if (used + need > c->arena_bytes) break;
+			io.slots[g1].a_off = used; used += need; ++g1;
+		}
+		const uint32_t gn = g1 - g0;
+		CUDA_TRY(cudaMemcpyAsync(c->d_slots.p + g0, io.slots.data() + g0, gn * sizeof(slot_t), cudaMemcpyHostToDevice, s));
+		c->st.h2d_bytes += gn * sizeof(slot_t);
+		a2.slots = c->d_slots.p + g0; a2.n_slots = gn;
+		a3.slots = c->d_slots.p + g0; a3.n_slots = gn;
+		const uint32_t gw = (gn * RH_WARP + 255) / 256, gt = (gn + 63) / 64;
+		{ span_guard g(c, T_SEED); k_seed_expand<<<gw, 256, 0, s>>>(a2, c->I, c->D); }
+		{ span_guard g(c, T_SORT); k_anchor_sort<<<gt, 64, 0, s>>>(a3); }
+		if (io.tap) { /* sorted anchor list of the single tapped slot */
+			rh_tap_t *T = io.tap_out; const slot_t &sl = io.slots[0];
+			if (!sl.gated) {
+				if (io.tap_off[2] + sl.n_anchors > T->cap_anchors) return RH_ERR_NOMEM;
+				CUDA_TRY(cudaMemcpyAsync(T->anchors + 2 * io.tap_off[2], c->d_arena.p + sl.a_off, (size_t)sl.n_anchors * 16, cudaMemcpyDeviceToHost, s));
+				CUDA_TRY(cudaStreamSynchronize(s));
+				io.tap_off[2] += sl.n_anchors;
+			}
+		}
+		{ span_guard g(c, T_CHAIN); k_chain_dp<<<gt, 64, 0, s>>>(a3, c->D); }
+		{ span_guard g(c, T_CHAIN); k_chain_backtrack<<<gt, 64, 0, s>>>(a3, c->D); }
+		{ span_guard g(c, T_POST); k_regions<<<gt, 64, 0, s>>>(a3, c->D); }
+		if (io.tap) {
+			CUDA_TRY(cudaMemcpyAsync(io.slots.data(), c->d_slots.p, sizeof(slot_t), cudaMemcpyDeviceToHost, s));
+			CUDA_TRY(cudaStreamSynchronize(s));
+		}
+		g0 = g1;
+	}
+	for (const slot_t &sl : io.slots) {
+		c->st.n_chunks++; c->st.n_events += sl.n_events; c->st.n_seeds += sl.n_seeds; c->st.n_anchors += sl.n_anchors;
+	}
+	return RH_OK;
+}
+
+int collect_spans(rh_gpu_ctx *c)
+{
+	double ms[T_NKIND] = {0};
+	for (const timed_span &sp : c->spans) { float t = 0; if (cudaEventElapsedTime(&t, sp.a, sp.b) == cudaSuccess) ms[sp.kind] += t; }
+	c->st.ms_event_kernel += ms[T_EVENT]; c->st.ms_seed += ms[T_SEED]; c->st.ms_sort += ms[T_SORT];
+	c->st.ms_chain += ms[T_CHAIN]; c->st.ms_post += ms[T_POST] + ms[T_LEN];
+	c->spans.clear(); c->ev_used = 0;
+	return RH_OK;
+}
+
+int check_dev_err(rh_gpu_ctx *c)
+{
+	uint32_t e = 0;
+	CUDA_TRY(cudaMemcpyAsync(&e, c->d_err.p, 4, cudaMemcpyDeviceToHost, c->stream));
+	CUDA_TRY(cudaStreamSynchronize(c->stream));
+	if (e == 0) return RH_OK;
+	const char *what = e == 2 ? "carry arena exhausted" : e == 3 ? "region scratch exhausted" : e == 4 ? "logf argument outside the exact table" : e == 5 ? "record arena exhausted" : "device error";
+	rh_set_error("device reported: %s (code %u)", what, e);
+	return e == 4 ? RH_ERR_ARG : RH_ERR_NOMEM;
+}
+
+/* set up per-read state on the device; raw already resident in c->d_raw */
+int setup_reads(rh_gpu_ctx *c, const batch_in &in, const std::vector<uint64_t> &beg, const std::vector<uint64_t> &len, std::vector<uint32_t> &l_sig)
+{
+	const uint32_t n = in.n;
+	std::vector<read_state_t> rs(n);
+	/* Rawsamble: #target names <= read name, against the sorted target-name list */
+	const bool ava = c->D.ava != 0;
+	for (uint32_t i = 0; i < n; ++i) {
+		read_state_t &r = rs[i];
+		memset(&r, 0, sizeof(r));
+		r.raw_beg = beg[i]; r.raw_end = beg[i] + len[i]; r.cursor = beg[i];
+		r.cal_offset = in.offset[i];
+		r.cal_scale = (double)(float)(in.range[i] / in.digitisation[i]); /* rsig.c:493: float scale */
+		if (ava && in.names) {
+			const char *q = in.names[i];
+			uint32_t lo = 0, hi = (uint32_t)c->name_order.size();
+			while (lo < hi) { uint32_t mid = (lo + hi) / 2; if (strcmp(c->idx->names[c->name_order[mid]].c_str(), q) <= 0) lo = mid + 1; else hi = mid; }
+			r.name_ub = lo;
+		}
+	}
+	int rc;
+	if ((rc = upload(c->d_rs, rs, c->stream))) return rc;
+	c->st.h2d_bytes += n * sizeof(read_state_t);
+	if ((rc = c->d_rec_start.reserve(n)) || (rc = c->d_rec_cnt.reserve(n))) return rc;
+	CUDA_TRY(cudaMemsetAsync(c->d_rec_cnt.p, 0xff, n * 4, c->stream));
+	CUDA_TRY(cudaMemsetAsync(c->d_counters.p, 0, 2 * sizeof(unsigned long long), c->stream));
+	CUDA_TRY(cudaMemsetAsync(c->d_err.p, 0, 4, c->stream));
+	{
+		span_guard g(c, T_LEN);
+		k_filtered_len<<<(n * RH_WARP + 255) / 256, 256, 0, c->stream>>>(c->raw_ptr, c->d_rs.p, n);
+	}
+	CUDA_TRY(cudaMemcpyAsync(rs.data(), c->d_rs.p, n * sizeof(read_state_t), cudaMemcpyDeviceToHost, c->stream));
+	CUDA_TRY(cudaStreamSynchronize(c->stream));
+	c->st.d2h_bytes += n * sizeof(read_state_t);
+	l_sig.resize(n);
+	for (uint32_t i = 0; i < n; ++i) l_sig[i] = rs[i].l_sig;
+	return RH_OK;
+}
+
+int map_resident(rh_gpu_ctx *c, const batch_in &in, const std::vector<uint64_t> &beg, const std::vector<uint64_t> &len, rh_map_rec_t **recs_out, uint64_t *n_recs_out)
+{
+	const uint32_t n = in.n;
+	std::vector<uint32_t> l_sig;
+	int rc = setup_reads(c, in, beg, len, l_sig);
+	if (rc) return rc;
+	const rh_params_t &P = c->P;
+	const bool noadapt = c->D.noadapt != 0;
+	const uint32_t max_chunk = noadapt ? 1u : P.max_num_chunk;
+	const uint64_t rec_cap = (uint64_t)n * (c->D.ava ? 64 : 1) + 1024;
+	if ((rc = c->d_recs.reserve(rec_cap))) return rc;
+
+	std::vector<uint32_t> active;
+	for (uint32_t i = 0; i < n; ++i) if (l_sig[i] > 0) active.push_back(i);
+	std::vector<uint32_t> rec_cnt(n);
+	uint32_t round = 0;
+	while (!active.empty() && round < max_chunk) {
+		/* split the active set into groups whose signal scratch fits the budget */
+		CUDA_TRY(cudaMemsetAsync(c->d_counters.p, 0, sizeof(unsigned long long), c->stream)); /* carry_top of the round's output arena */
+		size_t a0 = 0;
+		while (a0 < active.size()) {
+			round_io io;
+			uint64_t samples = 0; size_t a1 = a0;
+			while (a1 < active.size()) {
+				const uint32_t r = active[a1], qlen = l_sig[r];
+				const uint32_t l_chunk = (P.chunk_size > qlen || noadapt) ? qlen : P.chunk_size;
+				const uint64_t s_qs = (uint64_t)round * l_chunk;
+				const uint32_t len = (uint32_t)std::min<uint64_t>(l_chunk, qlen - s_qs);
+				if (samples + len > c->sig_budget && a1 > a0) break;
+				slot_t sl; memset(&sl, 0, sizeof(sl));
+				sl.read = r; sl.chunk_len = len; sl.c_count = round;
+				io.slots.push_back(sl);
+				samples += len; ++a1;
+			}
+			if ((rc = run_round(c, io, round & 1))) return rc;
+			a0 = a1;
+		}
+		c->st.n_rounds++;
+		CUDA_TRY(cudaMemcpyAsync(rec_cnt.data(), c->d_rec_cnt.p, n * 4, cudaMemcpyDeviceToHost, c->stream));
+		CUDA_TRY(cudaStreamSynchronize(c->stream));
+		c->st.d2h_bytes += n * 4;
+		std::vector<uint32_t> next;
+		for (uint32_t r : active) if (rec_cnt[r] == 0xffffffffu) next.push_back(r);
+		active.swap(next);
+		++round;
+	}
+	if ((rc = check_dev_err(c))) return rc;
+	if (!active.empty()) { rh_set_error("internal: %zu reads still active after the last round", active.size()); return RH_ERR_CUDA; }
+	/* gather records in read order */
+	unsigned long long tops[2];
+	CUDA_TRY(cudaMemcpyAsync(tops, c->d_counters.p, sizeof(tops), cudaMemcpyDeviceToHost, c->stream));
+	std::vector<uint32_t> rec_start(n);
+	CUDA_TRY(cudaMemcpyAsync(rec_start.data(), c->d_rec_start.p, n * 4, cudaMemcpyDeviceToHost, c->stream));
+	CUDA_TRY(cudaStreamSynchronize(c->stream));
+	std::vector<rh_map_rec_t> dev_recs(tops[1]);
+	if (tops[1]) CUDA_TRY(cudaMemcpyAsync(dev_recs.data(), c->d_recs.p, tops[1] * sizeof(rh_map_rec_t), cudaMemcpyDeviceToHost, c->stream));
+	CUDA_TRY(cudaStreamSynchronize(c->stream));
+	c->st.d2h_bytes += tops[1] * sizeof(rh_map_rec_t) + n * 4;
+	uint64_t total = 0;
+	for (uint32_t i = 0; i < n; ++i) total += (l_sig[i] == 0) ? 1 : rec_cnt[i];
+	rh_map_rec_t *out = (rh_map_rec_t *)malloc((total ? total : 1) * sizeof(rh_map_rec_t));
+	uint64_t k = 0;
+	for (uint32_t i = 0; i < n; ++i) {
+		if (l_sig[i] == 0) { /* loop of map_worker_for never runs: one unmapped record, ci = 1 */
+			rh_map_rec_t r; memset(&r, 0, sizeof(r)); r.read_idx = i; r.ci = 1; r.sl = 0;
+			out[k++] = r; continue;
+		}
+		for (uint32_t m = 0; m < rec_cnt[i]; ++m) out[k++] = dev_recs[rec_start[i] + m];
+	}
+	*recs_out = out; *n_recs_out = k;
+	c->st.n_reads += n;
+	return RH_OK;
+}
+
+void begin_call(rh_gpu_ctx *c) { memset(&c->st, 0, sizeof(c->st)); c->spans.clear(); c->ev_used = 0; }
+
+} // namespace
+
+/* ============================================================================================ */
+extern "C" rh_gpu_ctx *rh_gpu_init(const rh_index_t *idx, const rh_params_t *p, int device, size_t arena_bytes)
+{
+	if (!idx || !p) { rh_set_error("rh_gpu_init: null argument"); return NULL; }
+	if (check_params(*p) != RH_OK) return NULL;
+	int ndev = 0;
+	if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0 || device >= ndev) { rh_set_error("no usable CUDA device (count=%d, asked %d)", ndev, device); return NULL; }
+	if (cudaSetDevice(device) != cudaSuccess) { rh_set_error("cudaSetDevice(%d) failed", device); return NULL; }
+	rh_gpu_ctx *c = new rh_gpu_ctx();
+	c->device = device; c->P = *p; c->idx = idx;
+	fill_dev_params(*p, c->D);
+	if (p->mid_occ <= 0) { rh_params_t q = *p; rh_index_update_mapopt(idx, &q); c->P.mid_occ = q.mid_occ; c->D.mid_occ = q.mid_occ; }
+	auto fail = [&](const char *what) -> rh_gpu_ctx * { if (what) rh_set_error("%s", what); rh_gpu_destroy(c); return NULL; };
+	if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) return fail("cudaStreamCreate failed");
+	/* ---- index upload ---- */
+	const size_t nk = idx->keys.size();
+	int bits = 10; while (bits < 26 && ((size_t)1 << bits) < nk) ++bits;
+	std::vector<uint32_t> bucket(((size_t)1 << bits) + 1);
+	{
+		size_t ki = 0;
+		for (size_t b = 0; b <= ((size_t)1 << bits); ++b) {
+			const uint64_t lo = (uint64_t)b << (32 - bits);
+			while (ki < nk && (uint64_t)idx->keys[ki] < lo) ++ki;
+			bucket[b] = (uint32_t)ki;
+		}
+	}
+	std::vector<uint32_t> rank(idx->names.size());
+	c->name_order.resize(idx->names.size());
+	std::iota(c->name_order.begin(), c->name_order.end(), 0u);
+	std::sort(c->name_order.begin(), c->name_order.end(), [&](uint32_t a, uint32_t b) { int s = strcmp(idx->names[a].c_str(), idx->names[b].c_str()); return s ? s < 0 : a < b; });
+	for (uint32_t i = 0; i < c->name_order.size(); ++i) rank[c->name_order[i]] = i;
+	std::vector<float> lt;
+	c->logf_n = 1u << 20;
+	lt.resize(c->logf_n);
+	for (uint32_t i = 0; i < c->logf_n; ++i) lt[i] = logf((float)i); /* host libm: identical to the reference's calls */
+	if (upload(c->d_keys, idx->keys, c->stream) || upload(c->d_off, idx->off, c->stream) || upload(c->d_pos, idx->pos, c->stream) ||
+	    upload(c->d_bucket, bucket, c->stream) || upload(c->d_seqlen, idx->lens, c->stream) || upload(c->d_namerank, rank, c->stream) ||
+	    upload(c->d_logf, lt, c->stream)) return fail(NULL);
+	c->I.keys = c->d_keys.p; c->I.off = c->d_off.p; c->I.pos = c->d_pos.p; c->I.bucket = c->d_bucket.p; c->I.bucket_bits = bits;
+	c->I.n_keys = nk; c->I.seq_len = c->d_seqlen.p; c->I.name_rank = c->d_namerank.p; c->I.n_seq = (uint32_t)idx->names.size();
+	if (c->d_counters.reserve(2) || c->d_err.reserve(1)) return fail(NULL);
+	if (cudaStreamSynchronize(c->stream) != cudaSuccess) return fail("index upload failed");
+	/* ---- work arenas ---- */
+	size_t free_b = 0, total_b = 0;
+	cudaMemGetInfo(&free_b, &total_b);
+	if (arena_bytes == 0) arena_bytes = free_b / 2;
+	if (arena_bytes > free_b * 7 / 10) arena_bytes = free_b * 7 / 10;
+	c->arena_bytes = arena_bytes;
+	c->carry_elems = arena_bytes / 8 / sizeof(anchor_t);
+	c->sig_budget = std::max<size_t>(arena_bytes / 16 / 28, (size_t)1 << 20); /* ~28 B of scratch per sample */
+	if (c->d_arena.reserve(arena_bytes) || c->d_carry[0].reserve(c->carry_elems) || c->d_carry[1].reserve(c->carry_elems)) return fail(NULL);
+	c->arena_bytes = c->d_arena.cap; c->carry_elems = std::min(c->d_carry[0].cap, c->d_carry[1].cap);
+	return c;
+}
+
+extern "C" void rh_gpu_destroy(rh_gpu_ctx *c)
+{
+	if (!c) return;
+	cudaSetDevice(c->device);
+	c->d_keys.release(); c->d_bucket.release(); c->d_seqlen.release(); c->d_namerank.release(); c->d_off.release(); c->d_pos.release(); c->d_logf.release();
+	c->d_raw.release(); c->d_rs.release(); c->d_slots.release(); c->d_z.release(); c->d_events.release(); c->d_peaks.release();
+	c->d_seed_hash.release(); c->d_seed_pos.release(); c->d_seed_cnt.release(); c->d_seed_dst.release(); c->d_seed_src.release();
+	c->d_arena.release(); c->d_carry[0].release(); c->d_carry[1].release(); c->d_counters.release(); c->d_err.release();
+	c->d_rec_start.release(); c->d_rec_cnt.release(); c->d_recs.release();
+	for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
+	if (c->stream) cudaStreamDestroy(c->stream);
+	delete c;
+}
+
+extern "C" void rh_gpu_get_stats(const rh_gpu_ctx *c, rh_gpu_stats_t *st) { *st = c->st; }
+
+static int upload_raw(rh_gpu_ctx *c, uint32_t n, const int16_t *const *raw, const uint64_t *raw_len, std::vector<uint64_t> &beg, std::vector<uint64_t> &len)
+{
+	beg.assign(n, 0); len.assign(n, 0);
+	uint64_t tot = 0;
+	for (uint32_t i = 0; i < n; ++i) { beg[i] = tot; len[i] = raw_len[i]; tot += (raw_len[i] + 7) & ~7ULL; } /* 16-byte aligned starts */
+	int rc = c->d_raw.reserve(tot + 8);
+	if (rc) return rc;
+	for (uint32_t i = 0; i < n; ++i)
+		if (raw_len[i]) { CUDA_TRY(cudaMemcpyAsync(c->d_raw.p + beg[i], raw[i], raw_len[i] * 2, cudaMemcpyHostToDevice, c->stream)); c->st.h2d_bytes += raw_len[i] * 2; }
+	c->raw_ptr = c->d_raw.p;
+	return RH_OK;
+}
+
+extern "C" int rh_gpu_map_batch_raw(rh_gpu_ctx *c, uint32_t n, const int16_t *const *raw, const uint64_t *raw_len,
+                                    const double *offset, const double *range, const double *digitisation,
+                                    const char *const *names, rh_map_rec_t **recs, uint64_t *n_recs)
+{
+	if (!c || !recs || !n_recs || (n && (!raw || !raw_len || !offset || !range || !digitisation))) { rh_set_error("rh_gpu_map_batch_raw: null argument"); return RH_ERR_ARG; }
+	if (c->D.ava && n && !names) { rh_set_error("read names are required in all-vs-all mode"); return RH_ERR_ARG; }
+	CUDA_TRY(cudaSetDevice(c->device));
+	begin_call(c);
+	cudaEvent_t t0 = get_event(c), t1 = get_event(c);
+	c->ev_used = 0; /* t0/t1 stay reserved at the front of the pool */
+	c->ev_used = 2;
+	cudaEventRecord(t0, c->stream);
+	std::vector<uint64_t> beg, len;
+	int rc = upload_raw(c, n, raw, raw_len, beg, len);
+	batch_in in{n, raw, raw_len, nullptr, nullptr, offset, range, digitisation, names};
+	if (rc == RH_OK) rc = map_resident(c, in, beg, len, recs, n_recs);
+	cudaEventRecord(t1, c->stream);
+	cudaEventSynchronize(t1);
+	float ms = 0; cudaEventElapsedTime(&ms, t0, t1); c->st.ms_total = ms;
+	collect_spans(c);
+	return rc;
+}
+
+extern "C" int rh_gpu_map_batch_dev(rh_gpu_ctx *c, uint32_t n, const void *d_raw, const uint64_t *raw_off,
+                                    const double *offset, const double *range, const double *digitisation,
+                                    const char *const *names, rh_map_rec_t **recs, uint64_t *n_recs)
+{
+	if (!c || !recs || !n_recs || (n && (!d_raw || !raw_off || !offset || !range || !digitisation))) { rh_set_error("rh_gpu_map_batch_dev: null argument"); return RH_ERR_ARG; }
+	if (((uintptr_t)d_raw & 15) != 0) { rh_set_error("device raw buffer must be 16-byte aligned"); return RH_ERR_ARG; }
+	if (c->D.ava && n && !names) { rh_set_error("read names are required in all-vs-all mode"); return RH_ERR_ARG; }
+	CUDA_TRY(cudaSetDevice(c->device));
+	begin_call(c);
+	cudaEvent_t t0 = get_event(c), t1 = get_event(c);
+	cudaEventRecord(t0, c->stream);
+	std::vector<uint64_t> beg(n), len(n);
+	for (uint32_t i = 0; i < n; ++i) { beg[i] = raw_off[i]; len[i] = raw_off[i + 1] - raw_off[i]; }
+	c->raw_ptr = (const int16_t *)d_raw;
+	batch_in in{n, nullptr, nullptr, d_raw, raw_off, offset, range, digitisation, names};
+	int rc = map_resident(c, in, beg, len, recs, n_recs);
+	cudaEventRecord(t1, c->stream);
+	cudaEventSynchronize(t1);
+	float ms = 0; cudaEventElapsedTime(&ms, t0, t1); c->st.ms_total = ms;
+	collect_spans(c);
+	return rc;
+}
+
+/* Stage tap: one read, every chunk, no stop rules (parity tests). */
+extern "C" int rh_gpu_tap_read(rh_gpu_ctx *c, const int16_t *raw, uint64_t raw_len, double offset, double range, double digitisation,
+                               const char *name, rh_tap_t *tap)
+{
+	if (!c || !raw || !tap) { rh_set_error("rh_gpu_tap_read: null argument"); return RH_ERR_ARG; }
+	CUDA_TRY(cudaSetDevice(c->device));
+	begin_call(c);
+	std::vector<uint64_t> beg, len;
+	const int16_t *rp[1] = {raw}; const uint64_t rl[1] = {raw_len};
+	const char *nm[1] = {name ? name : ""};
+	int rc = upload_raw(c, 1, rp, rl, beg, len);
+	if (rc) return rc;
+	batch_in in{1, rp, rl, nullptr, nullptr, &offset, &range, &digitisation, nm};
+	std::vector<uint32_t> l_sig;
+	if ((rc = setup_reads(c, in, beg, len, l_sig))) return rc;
+	if ((rc = c->d_recs.reserve(1024))) return rc;
+	const rh_params_t &P = c->P;
+	const bool noadapt = c->D.noadapt != 0;
+	const uint32_t qlen = l_sig[0];
+	const uint32_t l_chunk = (P.chunk_size > qlen || noadapt) ? qlen : P.chunk_size;
+	const uint32_t max_chunk = noadapt ? 1u : P.max_num_chunk;
+	uint64_t toff[6] = {0, 0, 0, 0, 0, 0}; /* ev, seed, anc, u, chain, reg */
+	uint32_t cc = 0;
+	cudaStream_t s = c->stream;
+	for (uint64_t s_qs = 0; s_qs < qlen && cc < max_chunk; s_qs += l_chunk, ++cc) {
+		if (cc >= tap->cap_chunks) return RH_ERR_NOMEM;
+		CUDA_TRY(cudaMemsetAsync(c->d_counters.p, 0, sizeof(unsigned long long), s));
+		round_io io; io.tap = 1; io.tap_out = tap; io.tap_off = toff; io.tap_chunk = cc;
+		slot_t sl; memset(&sl, 0, sizeof(sl));
+		sl.read = 0; sl.chunk_len = (uint32_t)std::min<uint64_t>(l_chunk, qlen - s_qs); sl.c_count = cc;
+		io.slots.push_back(sl);
+		if ((rc = run_round(c, io, cc & 1))) return rc;
+		const slot_t &r = io.slots[0];
+		int32_t *cnt = tap->cnt + (size_t)cc * RH_TAP_NCNT;
+		memset(cnt, 0, sizeof(int32_t) * RH_TAP_NCNT);
+		cnt[RH_TAP_NSIG] = r.n_sig; cnt[RH_TAP_NEVENTS] = r.n_events;
+		if (toff[0] + r.n_events > tap->cap_events) return RH_ERR_NOMEM;
+		if (r.n_events) CUDA_TRY(cudaMemcpyAsync(tap->events + toff[0], c->d_events.p + r.e_off, r.n_events * 4, cudaMemcpyDeviceToHost, s));
+		toff[0] += r.n_events;
+		if (r.gated) { CUDA_TRY(cudaStreamSynchronize(s)); continue; }
+		cnt[RH_TAP_NSEEDS] = r.n_seeds; cnt[RH_TAP_NANCHORS] = r.n_anchors; cnt[RH_TAP_NU] = r.n_u; cnt[RH_TAP_NV] = r.n_v;
+		cnt[RH_TAP_NREGS] = r.n_regs; cnt[RH_TAP_REPLEN] = r.rep_len;
+		if (toff[1] + r.n_seeds > tap->cap_seeds || toff[3] + r.n_u > tap->cap_u || toff[4] + r.n_v > tap->cap_chain_a || toff[4] + r.n_v > tap->cap_prev_a ||
+		    toff[5] + r.n_regs > tap->cap_regs) return RH_ERR_NOMEM;
+		std::vector<uint32_t> sh(r.n_seeds), sp(r.n_seeds);
+		if (r.n_seeds) {
+			CUDA_TRY(cudaMemcpyAsync(sh.data(), c->d_seed_hash.p + r.e_off, r.n_seeds * 4, cudaMemcpyDeviceToHost, s));
+			CUDA_TRY(cudaMemcpyAsync(sp.data(), c->d_seed_pos.p + r.e_off, r.n_seeds * 4, cudaMemcpyDeviceToHost, s));
+		}
+		std::vector<dev_reg_t> regs(r.n_regs);
+		read_state_t rs;
+		CUDA_TRY(cudaMemcpyAsync(&rs, c->d_rs.p, sizeof(rs), cudaMemcpyDeviceToHost, s));
+		if (r.n_anchors) {
+			const uint64_t n = r.n_anchors;
+			const uint8_t *base = c->d_arena.p + r.a_off;
+			if (r.n_u) CUDA_TRY(cudaMemcpyAsync(tap->u + toff[3], base + 80 * n, r.n_u * 8, cudaMemcpyDeviceToHost, s));   /* slot_mem: U  */
+			if (r.n_v) CUDA_TRY(cudaMemcpyAsync(tap->chain_a + 2 * toff[4], base, (size_t)r.n_v * 16, cudaMemcpyDeviceToHost, s)); /* A */
+			if (r.n_regs) CUDA_TRY(cudaMemcpyAsync(regs.data(), base + 96 * n, r.n_regs * sizeof(dev_reg_t), cudaMemcpyDeviceToHost, s));
+		}
+		CUDA_TRY(cudaStreamSynchronize(s));
+		if (r.n_v) CUDA_TRY(cudaMemcpy(tap->prev_a + 2 * toff[4], c->d_carry[(cc & 1) ^ 1].p + rs.prev_off, (size_t)r.n_v * 16, cudaMemcpyDeviceToHost));
+		const uint64_t span = (uint64_t)(P.k + P.e - 1);
+		for (uint32_t i = 0; i < r.n_seeds; ++i) { tap->seeds[2 * (toff[1] + i)] = (uint64_t)sh[i] << 6 | span; tap->seeds[2 * (toff[1] + i) + 1] = (uint64_t)sp[i] << 1; }
+		for (uint32_t i = 0; i < r.n_regs; ++i) {
+			const dev_reg_t &g = regs[i];
+			int32_t *f = tap->regs + (toff[5] + i) * RH_TAP_REG_NF;
+			f[0] = g.score; f[1] = g.cnt; f[2] = g.rid; f[3] = (int32_t)g.rev; f[4] = g.qs; f[5] = g.qe; f[6] = g.rs; f[7] = g.re;
+			f[8] = g.parent; f[9] = g.subsc; f[10] = g.n_sub; f[11] = (int32_t)g.mapq; f[12] = g.as; f[13] = g.score0;
+		}
+		toff[1] += r.n_seeds; toff[3] += r.n_u; toff[4] += r.n_v; toff[5] += r.n_regs;
+	}
+	tap->n_chunks = cc;
+	rc = check_dev_err(c);
+	collect_spans(c);
+	return rc;
+}
+
+/* Rawsamble index (ri_idx_siggen / worker_sig_pipeline, src/rindex.c:239-309,927-969): whole-read
+ * event detection with fresh sums on the GPU (the same k_signal_to_seeds phases A-C), sketching of
+ * the target side on the host like the sequence index. */
+extern "C" rh_index_t *rh_index_build_sig(const rh_params_t *p, uint32_t n_reads, const char *const *names,
+                                           const int16_t *const *raw, const uint64_t *raw_len,
+                                           const double *offset, const double *range, const double *digitisation)
+{
+	if (!p || (n_reads && (!names || !raw || !raw_len))) { rh_set_error("rh_index_build_sig: null argument"); return NULL; }
+	rh_index_s empty;
+	rh_params_t q = *p; q.w = 0; q.mid_occ = 1; /* event detection only; w/mid_occ are irrelevant to it */
+	q.map_flag |= RH_M_NO_ADAPTIVE;
+	rh_gpu_ctx *c = rh_gpu_init(&empty, &q, 0, (size_t)256 << 20);
+	if (!c) return NULL;
+	rh_index_s *idx = new rh_index_s();
+	idx->flag = p->idx_flag; idx->w = p->w; idx->e = p->e; idx->n = p->n; idx->q = p->q; idx->k = p->k;
+	idx->diff = p->diff; idx->fine_min = p->fine_min; idx->fine_max = p->fine_max; idx->fine_range = p->fine_range;
+	std::vector<rh_seed_t> all;
+	int rc = RH_OK;
+	const uint32_t B = 2048;
+	for (uint32_t b0 = 0; b0 < n_reads && rc == RH_OK; b0 += B) {
+		const uint32_t bn = std::min(B, n_reads - b0);
+		begin_call(c);
+		std::vector<uint64_t> beg, len;
+		rc = upload_raw(c, bn, raw + b0, raw_len + b0, beg, len);
+		if (rc) break;
+		batch_in in{bn, raw + b0, raw_len + b0, nullptr, nullptr, offset + b0, range + b0, digitisation + b0, names + b0};
+		std::vector<uint32_t> l_sig;
+		if ((rc = setup_reads(c, in, beg, len, l_sig))) break;
+		round_io io;
+		for (uint32_t i = 0; i < bn; ++i) {
+			if (l_sig[i] == 0) continue;
+			slot_t sl; memset(&sl, 0, sizeof(sl)); sl.read = i; sl.chunk_len = l_sig[i];
+			io.slots.push_back(sl);
+		}
+		/* events only: run phases A-D, then read the events back */
+		const uint32_t ns = (uint32_t)io.slots.size();
+		std::vector<float> ev; std::vector<uint32_t> ev_off(ns), ev_n(ns);
+		if (ns) {
+			uint64_t zt = 0, et = 0;
+			for (slot_t &sl : io.slots) { sl.z_off = zt; zt += sl.chunk_len; sl.e_cap = (uint32_t)((uint64_t)sl.chunk_len * 2 / 3 + 8); sl.e_off = et; et += sl.e_cap; }
+			if ((rc = c->d_z.reserve(zt)) || (rc = c->d_events.reserve(et)) || (rc = c->d_peaks.reserve(et)) || (rc = c->d_seed_hash.reserve(et)) ||
+			    (rc = c->d_seed_pos.reserve(et)) || (rc = upload(c->d_slots, io.slots, c->stream))) break;
+			k1_args_t a1;
+			a1.raw = c->raw_ptr; a1.rs = c->d_rs.p; a1.slots = c->d_slots.p; a1.n_slots = ns;
+			a1.z = c->d_z.p; a1.peaks = c->d_peaks.p; a1.events = c->d_events.p; a1.seed_hash = c->d_seed_hash.p; a1.seed_pos = c->d_seed_pos.p;
+			dev_params_t D = c->D; D.min_events = 0xffffffffu; /* skip phase D */
+			k_signal_to_seeds<<<(ns + K1_THREADS - 1) / K1_THREADS, K1_THREADS, 0, c->stream>>>(a1, D);
+			if (cudaMemcpyAsync(io.slots.data(), c->d_slots.p, ns * sizeof(slot_t), cudaMemcpyDeviceToHost, c->stream) != cudaSuccess) { rc = RH_ERR_CUDA; break; }
+			ev.resize(et);
+			if (cudaMemcpyAsync(ev.data(), c->d_events.p, et * 4, cudaMemcpyDeviceToHost, c->stream) != cudaSuccess) { rc = RH_ERR_CUDA; break; }
+			if (cudaStreamSynchronize(c->stream) != cudaSuccess) { rh_set_error("event kernel failed: %s", cudaGetErrorString(cudaGetLastError())); rc = RH_ERR_CUDA; break; }
+		}
+		size_t si = 0;
+		for (uint32_t i = 0; i < bn; ++i) {
+			idx->names.emplace_back(names[b0 + i]); idx->lens.push_back(l_sig[i]);
+			if (l_sig[i] == 0) continue;
+			const slot_t &sl = io.slots[si++];
+			if (sl.n_events) rh_host_sketch(*p, ev.data() + sl.e_off, sl.n_events, b0 + i, 0, all);
+		}
+	}
+	rh_gpu_destroy(c);
+	if (rc != RH_OK) { delete idx; return NULL; }
+	rh_index_from_seeds(idx, all, 8);
+	return idx;
+}

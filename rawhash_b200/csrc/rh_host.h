@@ -1,0 +1,31 @@
+/* rh_host.h — host-side structures shared by rh_host.cpp and rh_gpu.cu (product code). */
+#ifndef RH_HOST_H
+#define RH_HOST_H
+
+#include <stdint.h>
+#include <string>
+#include <vector>
+#include "../../include/rawhash_b200.h"
+
+/* Flattened index: key -> ascending position list (the mapping ri_idx_get returns,
+ * reference src/rindex.c:497-514), stored as sorted keys + CSR offsets so it can be copied
+ * to HBM verbatim. */
+struct rh_index_s {
+	std::vector<uint32_t> keys;   /* distinct 32-bit seed hashes, ascending            */
+	std::vector<uint64_t> off;    /* keys.size()+1 offsets into pos                    */
+	std::vector<uint64_t> pos;    /* id<<32 | pos<<1 | strand, ascending within a key  */
+	std::vector<std::string> names;
+	std::vector<uint32_t> lens;   /* sequence length, or l_sig for a signal index      */
+	int32_t flag = 0;
+	int32_t w = 0, e = 0, n = 0, q = 0, k = 0;
+	float diff = 0, fine_min = 0, fine_max = 0, fine_range = 0;
+};
+
+struct rh_seed_t { uint64_t x, y; };
+
+/* sketch of one event array on the host (index build side; the read side runs on the GPU) */
+void rh_host_sketch(const rh_params_t &P, const float *ev, uint32_t len, uint32_t id, int strand, std::vector<rh_seed_t> &out);
+void rh_index_from_seeds(rh_index_s *idx, std::vector<rh_seed_t> &seeds, int n_threads);
+void rh_set_error(const char *fmt, ...);
+
+#endif

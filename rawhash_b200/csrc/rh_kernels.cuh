@@ -1,0 +1,841 @@
+/*
+ * rh_kernels.cuh — the CUDA kernels of the mapping hot path (sm_100a).
+ *
+ * Stage map (reference function each kernel takes over, paths relative to the RawHash tree):
+ *   k_filtered_len      src/rsig.c:496-503        raw int16 -> pA, count samples with 30<pA<200
+ *   k_signal_to_seeds   src/revent.c:221-316 + src/rsketch.c:143-204   (the fused metric kernel)
+ *   k_seed_count        src/rseed.c:60-154 + src/rindex.c:497-514      lookup, occ filter, rep_len
+ *   k_seed_expand       src/rmap.cpp:74-116       anchors from position lists + previous chunk's
+ *   k_anchor_sort       src/ksort.h:101-151       exact klib radix sort (tie order matters)
+ *   k_chain_dp          src/lchain.c:385-505      chaining DP
+ *   k_chain_backtrack   src/lchain.c:95-281       backtrack + compaction
+ *   k_regions           src/hit.c:100-150,195-263,338-367,502-539 + src/rmap.cpp:423-586
+ *
+ * Work decomposition: a "slot" is one (read, chunk) pair of the current chunk round.
+ */
+#ifndef RH_KERNELS_CUH
+#define RH_KERNELS_CUH
+
+#include "rh_dev.cuh"
+#include "rh_sort.cuh"
+
+#define RH_WARP 32
+
+/* per-read state carried across chunk rounds (reference: locals of map_worker_for + ri_reg1_t) */
+struct read_state_t {
+	uint64_t raw_beg, raw_end;     /* sample range of this read in the concatenated raw buffer */
+	uint64_t cursor;               /* next raw sample to consume (absolute index)              */
+	double cal_offset, cal_scale;  /* slow5 offset; (double)(float)(range/digitisation)        */
+	double sum, sum2;              /* running Σx, Σx² of normalize_signal                      */
+	uint32_t n_sum;                /* running sample count                                     */
+	uint32_t l_sig;                /* total samples surviving the pA filter (qlen)             */
+	uint32_t ev_offset;            /* reg->offset: events consumed by earlier chunks           */
+	uint32_t prev_n;               /* carried chain anchors                                    */
+	uint64_t prev_off;             /* their offset in the carry arena of the previous round    */
+	uint32_t name_ub;              /* Rawsamble: #target names <= this read's name             */
+	uint32_t done;
+};
+
+/* per-slot bookkeeping for one chunk round */
+struct slot_t {
+	uint32_t read;                 /* read index in the batch                                  */
+	uint32_t chunk_len;            /* filtered samples this chunk must consume                 */
+	uint32_t c_count;              /* chunk number                                             */
+	uint32_t n_sig, n_peaks, n_events, n_seeds;
+	uint32_t gated;                /* n_events < min_events                                    */
+	uint64_t z_off;                /* offsets into the signal scratch arenas                   */
+	uint64_t e_off;
+	uint32_t e_cap;
+	uint32_t n_new;                /* anchors from seed hits                                   */
+	uint32_t n_anchors;            /* n_new + prev_n                                           */
+	int32_t  rep_len;
+	uint64_t a_off;                /* byte offset of this slot's region in the anchor arena    */
+	uint32_t n_u, n_v, n_regs;
+	uint32_t err;
+};
+
+/* layout of a slot's region in the anchor arena (n = n_anchors) */
+#define RH_SLOT_BYTES_PER_ANCHOR 144
+__host__ __device__ inline uint64_t slot_region_bytes(uint64_t n) { return ((n * RH_SLOT_BYTES_PER_ANCHOR + 1024 + 255) / 256) * 256; }
+struct slot_mem_t {
+	anchor_t *A, *B, *Z, *W;
+	int32_t *f, *p, *v, *t;
+	uint64_t *U, *U2;
+	dev_reg_t *regs;
+	uint32_t reg_cap;
+};
+__device__ __forceinline__ slot_mem_t slot_mem(uint8_t *arena, uint64_t a_off, uint64_t n)
+{
+	slot_mem_t m; uint8_t *b = arena + a_off;
+	m.A = (anchor_t *)b; b += 16 * n;
+	m.B = (anchor_t *)b; b += 16 * n;
+	m.Z = (anchor_t *)b; b += 16 * n;
+	m.W = (anchor_t *)b; b += 16 * n;
+	m.f = (int32_t *)b; b += 4 * n;
+	m.p = (int32_t *)b; b += 4 * n;
+	m.v = (int32_t *)b; b += 4 * n;
+	m.t = (int32_t *)b; b += 4 * n;
+	m.U = (uint64_t *)b; b += 8 * n;
+	m.U2 = (uint64_t *)b; b += 8 * n;
+	m.regs = (dev_reg_t *)b; /* 48n + 1024 bytes left */
+	m.reg_cap = (uint32_t)((48 * n + 1024) / sizeof(dev_reg_t));
+	return m;
+}
+
+/* =============================================================================================
+ * K0  filtered length of every read: one warp per read, 16-byte vector loads.
+ * Pure streaming (2 B/sample, ~6 instr/sample): the one HBM-bound kernel of the path.
+ * ===========================================================================================*/
+__global__ void __launch_bounds__(256) k_filtered_len(const int16_t *__restrict__ raw, read_state_t *__restrict__ rs, uint32_t n_reads)
+{
+	const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) / RH_WARP, lane = threadIdx.x % RH_WARP;
+	if (warp >= n_reads) return;
+	const uint64_t beg = rs[warp].raw_beg, end = rs[warp].raw_end;
+	const double off = rs[warp].cal_offset, sc = rs[warp].cal_scale;
+	uint32_t kept = 0;
+	/* head: up to the first 16-byte boundary */
+	uint64_t a0 = (beg + 7) & ~7ULL; if (a0 > end) a0 = end;
+	for (uint64_t i = beg + lane; i < a0; i += RH_WARP) kept += pa_keep(raw_to_pa(raw[i], off, sc));
+	const uint64_t nvec = (end - a0) / 8;
+	const int4 *v = (const int4 *)(raw + a0);
+	for (uint64_t j = lane; j < nvec; j += RH_WARP) {
+		const int4 q = __ldg(v + j);
+		const int w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+		for (int t = 0; t < 4; ++t) {
+			kept += pa_keep(raw_to_pa((int)(short)(w[t] & 0xffff), off, sc));
+			kept += pa_keep(raw_to_pa((int)(short)(w[t] >> 16), off, sc));
+		}
+	}
+	for (uint64_t i = a0 + nvec * 8 + lane; i < end; i += RH_WARP) kept += pa_keep(raw_to_pa(raw[i], off, sc));
+#pragma unroll
+	for (int o = 16; o > 0; o >>= 1) kept += __shfl_xor_sync(0xffffffffu, kept, o);
+	if (lane == 0) rs[warp].l_sig = kept;
+}
+
+/* =============================================================================================
+ * K1  fused signal -> events -> seeds.
+ *
+ * One CTA owns K1_THREADS slots.  Phases, separated by __syncthreads():
+ *   A  (thread = slot)   stream raw, pA filter, Σx / Σx² in double until chunk_len samples kept
+ *   B  (thread = slot)   re-stream the same raw window: z-normalise, |z|<3 filter, float prefix
+ *                        sums kept in a 32-deep shared-memory ring, both t-statistics and the
+ *                        two coupled peak detectors evaluated on the fly -> peak positions
+ *   C  (thread = segment, all slots of the CTA pooled)   IQR-filtered mean of every segment
+ *   D  (thread = slot)   diff filter, quantise, pack e events, hash -> (hash, first event pos)
+ *
+ * The sequential float recurrences (prefix sums, peak detectors, diff filter) make a chunk
+ * inherently serial; parallelism comes from running 32 chunks per warp, one
+ * per lane, with identical control flow.
+ * ===========================================================================================*/
+#define K1_THREADS 128
+#define K1_RING 32
+
+struct k1_args_t {
+	const int16_t *raw;
+	read_state_t *rs;
+	slot_t *slots;
+	uint32_t n_slots;
+	float *z;              /* [z_off .. +chunk_len)            */
+	uint32_t *peaks;       /* [e_off .. +e_cap)                */
+	float *events;         /* [e_off .. +e_cap)                */
+	uint32_t *seed_hash;   /* [e_off .. +e_cap)                */
+	uint32_t *seed_pos;    /* [e_off .. +e_cap)                */
+};
+
+struct peak_det_t { uint32_t masked_to; int peak_pos; float peak_val; int valid; };
+
+__device__ __forceinline__ float window_tstat(const float *ps, const float *pq, uint32_t i, uint32_t w, float fw)
+{ /* comp_tstat body, reference src/revent.c:49-69, contractions as in the compiled object */
+	const float a = ps[(i & (K1_RING - 1)) * K1_THREADS], aq = pq[(i & (K1_RING - 1)) * K1_THREADS];
+	const float b = ps[((i + w) & (K1_RING - 1)) * K1_THREADS], bq = pq[((i + w) & (K1_RING - 1)) * K1_THREADS];
+	float s1 = a, q1 = aq;
+	if (i > w) {
+		s1 = __fsub_rn(a, ps[((i - w) & (K1_RING - 1)) * K1_THREADS]);
+		q1 = __fsub_rn(aq, pq[((i - w) & (K1_RING - 1)) * K1_THREADS]);
+	}
+	const float s2 = __fsub_rn(b, a), q2 = __fsub_rn(bq, aq);
+	const float m1 = __fdiv_rn(s1, fw), m2 = __fdiv_rn(s2, fw);
+	float acc = __fmaf_rn(-m1, m1, __fdiv_rn(q1, fw));
+	acc = __fadd_rn(acc, __fdiv_rn(q2, fw));
+	acc = __fmaf_rn(-m2, m2, acc);
+	const float var = fmaxf(__fdiv_rn(acc, fw), FLT_MIN);
+	return __fdiv_rn(fabsf(__fsub_rn(m2, m1)), __fsqrt_rn(var));
+}
+
+/* one step of gen_peaks for detector k (reference src/revent.c:100-146) */
+__device__ __forceinline__ void detector_step(peak_det_t &D, peak_det_t *other /* next detector or null */, uint32_t i, float cur,
+                                              float thr, uint32_t win, uint32_t win0, float height, uint32_t *peaks, uint32_t &n_peaks)
+{
+	if (D.masked_to >= i) return;
+	if (D.peak_pos == -1) {
+		if (cur < D.peak_val) D.peak_val = cur;
+		else if (__fsub_rn(cur, D.peak_val) > height) { D.peak_val = cur; D.peak_pos = (int)i; }
+	} else {
+		if (cur > D.peak_val) { D.peak_val = cur; D.peak_pos = (int)i; }
+		if (other && D.peak_val > thr) {
+			other->masked_to = D.peak_pos + win0;
+			other->peak_pos = -1; other->peak_val = FLT_MAX; other->valid = 0;
+		}
+		if (__fsub_rn(D.peak_val, cur) > height && D.peak_val > thr) D.valid = 1;
+		if (D.valid && (i - D.peak_pos) > win / 2) {
+			peaks[n_peaks++] = (uint32_t)D.peak_pos;
+			D.peak_pos = -1; D.peak_val = cur; D.valid = 0;
+		}
+	}
+}
+
+__global__ void __launch_bounds__(K1_THREADS) k_signal_to_seeds(k1_args_t A, dev_params_t P)
+{
+	__shared__ float s_ps[K1_RING * K1_THREADS];
+	__shared__ float s_pq[K1_RING * K1_THREADS];
+	__shared__ uint32_t s_npk[K1_THREADS + 1];
+
+	const uint32_t tid = threadIdx.x;
+	const uint32_t slot_id = blockIdx.x * K1_THREADS + tid;
+	const bool live = slot_id < A.n_slots;
+	slot_t *S = live ? &A.slots[slot_id] : nullptr;
+	const int16_t *raw = A.raw;
+
+	uint32_t n_sig = 0, n_peaks = 0;
+	if (live) {
+		read_state_t *R = &A.rs[S->read];
+		const double off = R->cal_offset, scale = R->cal_scale;
+		const uint64_t cur0 = R->cursor, rend = R->raw_end;
+		const uint32_t want = S->chunk_len;
+		/* ---- phase A: sums over the chunk (normalize_signal first loop, revent.c:233-236) ---- */
+		double sum = R->sum, sum2 = R->sum2;
+		uint32_t got = 0; uint64_t c = cur0;
+		while (c < rend && got < want) {
+			const float pa = raw_to_pa(raw[c], off, scale);
+			++c;
+			if (!pa_keep(pa)) continue;
+			sum = __dadd_rn(sum, (double)pa);
+			sum2 = __dadd_rn(sum2, (double)__fmul_rn(pa, pa));
+			++got;
+		}
+		const uint64_t cur1 = c;
+		const uint32_t n_tot = R->n_sum + got;
+		R->sum = sum; R->sum2 = sum2; R->n_sum = n_tot; R->cursor = cur1;
+		const double mean = __ddiv_rn(sum, (double)n_tot);
+		const double sd = __dsqrt_rn(__fma_rn(-mean, mean, __ddiv_rn(sum2, (double)n_tot)));
+
+		/* ---- phase B: z, prefix rings, t-stats, peak detectors, streaming ---- */
+		float *ps = s_ps + tid, *pq = s_pq + tid;
+		float *zout = A.z + S->z_off;
+		uint32_t *peaks = A.peaks + S->e_off;
+		const uint32_t w1 = P.w1, w2 = P.w2, W = w1 > w2 ? w1 : w2;
+		const float fw1 = (float)w1, fw2 = (float)w2;
+		peak_det_t d1 = {0u, -1, FLT_MAX, 0}, d2 = {0u, -1, FLT_MAX, 0};
+		float run_s = 0.0f, run_q = 0.0f;
+		ps[0] = 0.0f; pq[0] = 0.0f;
+		uint32_t n = 0;
+		for (c = cur0; c < cur1; ++c) {
+			const float pa = raw_to_pa(raw[c], off, scale);
+			if (!pa_keep(pa)) continue;
+			const float zv = __double2float_rn(__ddiv_rn(__dsub_rn((double)pa, mean), sd));
+			if (!(zv < 3.0f && zv > -3.0f)) continue;
+			zout[n] = zv;
+			run_s = __fadd_rn(run_s, zv);
+			run_q = __fmaf_rn(zv, zv, run_q);
+			++n;
+			ps[(n & (K1_RING - 1)) * K1_THREADS] = run_s;
+			pq[(n & (K1_RING - 1)) * K1_THREADS] = run_q;
+			if (n >= W) {
+				const uint32_t i = n - W;
+				const float t1 = (w1 >= 2 && i >= w1) ? window_tstat(ps, pq, i, w1, fw1) : 0.0f;
+				const float t2 = (w2 >= 2 && i >= w2) ? window_tstat(ps, pq, i, w2, fw2) : 0.0f;
+				detector_step(d1, &d2, i, t1, P.thr1, w1, w1, P.height, peaks, n_peaks);
+				detector_step(d2, nullptr, i, t2, P.thr2, w2, w1, P.height, peaks, n_peaks);
+			}
+		}
+		/* tail: positions whose right window runs past the end have t = 0 (revent.c:70-71) */
+		for (uint32_t i = (n >= W ? n - W + 1 : 0); i < n; ++i) {
+			const float t1 = (w1 >= 2 && i >= w1 && i + w1 <= n) ? window_tstat(ps, pq, i, w1, fw1) : 0.0f;
+			const float t2 = (w2 >= 2 && i >= w2 && i + w2 <= n) ? window_tstat(ps, pq, i, w2, fw2) : 0.0f;
+			detector_step(d1, &d2, i, t1, P.thr1, w1, w1, P.height, peaks, n_peaks);
+			detector_step(d2, nullptr, i, t2, P.thr2, w2, w1, P.height, peaks, n_peaks);
+		}
+		n_sig = n;
+		S->n_sig = n_sig; S->n_peaks = n_peaks;
+	}
+	s_npk[tid] = n_peaks;
+	__syncthreads();
+
+	/* ---- phase C: one thread per segment, all slots of the CTA pooled (gen_events, revent.c:193-219) ---- */
+	if (tid == 0) { /* exclusive scan of 128 counts; tiny */
+		uint32_t acc = 0;
+		for (int i = 0; i < K1_THREADS; ++i) { uint32_t v = s_npk[i]; s_npk[i] = acc; acc += v; }
+		s_npk[K1_THREADS] = acc;
+	}
+	__syncthreads();
+	{
+		const uint32_t total = s_npk[K1_THREADS];
+		for (uint32_t g = tid; g < total; g += K1_THREADS) {
+			int lo = 0, hi = K1_THREADS - 1; /* owner slot: last s with s_npk[s] <= g */
+			while (lo < hi) { int mid = (lo + hi + 1) >> 1; if (s_npk[mid] <= g) lo = mid; else hi = mid - 1; }
+			const slot_t *T = &A.slots[blockIdx.x * K1_THREADS + lo];
+			const uint32_t j = g - s_npk[lo];
+			const uint32_t *pk = A.peaks + T->e_off;
+			float *zz = A.z + T->z_off;
+			const uint32_t p = pk[j], start = j ? pk[j - 1] : 0u;
+			const uint32_t len = p > start ? p - start : 0u; /* the reference assumes increasing peaks */
+			float ev = 0.0f;
+			if (len) {
+				float *seg = zz + start;
+				for (uint32_t a = 1; a < len; ++a) { /* in-place ascending sort (qsort in the reference; order of equals is immaterial) */
+					const float cur = seg[a];
+					uint32_t b = a;
+					while (b > 0 && seg[b - 1] > cur) { seg[b] = seg[b - 1]; --b; }
+					seg[b] = cur;
+				}
+				const float q1 = seg[len / 4], q3 = seg[3 * len / 4], iqr = __fsub_rn(q3, q1);
+				const float lob = __fsub_rn(q1, iqr), hib = __fadd_rn(q3, iqr);
+				float sum = 0.0f; uint32_t cnt = 0;
+				for (uint32_t a = 0; a < len; ++a) { const float v = seg[a]; if (v >= lob && v <= hib) { sum = __fadd_rn(sum, v); ++cnt; } }
+				ev = cnt ? __fdiv_rn(sum, (float)cnt) : 0.0f;
+			}
+			A.events[T->e_off + j] = ev;
+		}
+	}
+	__syncthreads();
+
+	/* ---- phase D: diff filter + quantise + pack + hash (ri_sketch_reg, rsketch.c:143-204) ---- */
+	if (live) {
+		const uint32_t n_events = n_peaks; /* every emitted peak is in (0, n_sig) */
+		uint32_t n_seeds = 0;
+		const bool gated = n_events < P.min_events;
+		if (!gated) {
+			const float *ev = A.events + S->e_off;
+			uint32_t *sh = A.seed_hash + S->e_off, *sp = A.seed_pos + S->e_off;
+			const int e = P.e, q = P.q;
+			const uint64_t mev = (q * e >= 64) ? ~0ULL : ((1ULL << (q * e)) - 1), mq = (1ULL << q) - 1;
+			uint64_t packed = 0; float last = 0.0f; uint32_t kept = 0;
+			for (uint32_t i = 0; i < n_events; ++i) {
+				const float v = ev[i];
+				if (i && fabsf(__fsub_rn(v, last)) < P.diff) continue;
+				last = v;
+				packed = ((packed << q) | (quantize_event(v, P.fine_min, P.fine_max, P.fine_range, 1u << q) & mq)) & mev;
+				sp[kept] = i; /* position of the kept event; seed j starts at kept event j */
+				++kept;
+				if (kept >= (uint32_t)e) sh[n_seeds++] = (uint32_t)seed_mix(packed);
+			}
+		}
+		S->n_events = n_events; S->n_seeds = n_seeds; S->gated = gated ? 1u : 0u;
+	}
+}
+
+/* =============================================================================================
+ * K2a  seed lookup + occurrence filter + repeat length.  One warp per slot; lanes stride over
+ * the slot's seeds.  Index lookup = bucket table on the hash's top bits, then a short scan of
+ * the sorted key array.  Per seed we keep (count, position offset); count 0 = absent/filtered.
+ * ===========================================================================================*/
+struct k2_args_t {
+	slot_t *slots; uint32_t n_slots;
+	read_state_t *rs;
+	const uint32_t *seed_hash; const uint32_t *seed_pos;
+	uint32_t *seed_cnt;      /* [e_off..] kept hits of the seed (after filters)          */
+	uint64_t *seed_src;      /* [e_off..] offset of the seed's position list in idx.pos   */
+	uint32_t *seed_dst;      /* [e_off..] exclusive prefix of seed_cnt inside the slot    */
+	uint8_t *arena;          /* anchor arena                                              */
+	const anchor_t *carry_in; anchor_t *carry_out;
+};
+
+__device__ __forceinline__ bool index_find(const dev_index_t &I, uint32_t h, uint64_t *src, uint32_t *n)
+{
+	const uint32_t b = I.bucket_bits >= 32 ? h : (h >> (32 - I.bucket_bits));
+	uint32_t lo = I.bucket[b], hi = I.bucket[b + 1];
+	while (lo < hi) { /* buckets hold ~1 key on average */
+		const uint32_t mid = (lo + hi) >> 1;
+		const uint32_t kv = I.keys[mid];
+		if (kv == h) { const uint64_t o = I.off[mid]; *src = o; *n = (uint32_t)(I.off[mid + 1] - o); return true; }
+		if (kv < h) lo = mid + 1; else hi = mid;
+	}
+	return false;
+}
+
+__global__ void __launch_bounds__(256) k_seed_count(k2_args_t A, dev_index_t I, dev_params_t P)
+{
+	const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) / RH_WARP, lane = threadIdx.x % RH_WARP;
+	if (warp >= A.n_slots) return;
+	slot_t *S = &A.slots[warp];
+	const read_state_t *R = &A.rs[S->read];
+	if (S->gated) { if (lane == 0) { S->n_new = 0; S->rep_len = 0; S->n_anchors = R->prev_n; } return; }
+	const uint32_t ns = S->n_seeds;
+	const uint32_t *sh = A.seed_hash + S->e_off, *sp = A.seed_pos + S->e_off;
+	uint32_t *scnt = A.seed_cnt + S->e_off, *sdst = A.seed_dst + S->e_off;
+	uint64_t *ssrc = A.seed_src + S->e_off;
+	const uint32_t span = (uint32_t)(P.k + P.e - 1);
+	uint32_t running = 0;
+	int rep_st = 0, rep_en = 0, rep_len = 0;
+	for (uint32_t base = 0; base < ns; base += RH_WARP) {
+		const uint32_t i = base + lane;
+		uint32_t n = 0, flt = 0; uint64_t src = 0;
+		if (i < ns) {
+			const uint32_t h = sh[i];
+			if (index_find(I, h, &src, &n)) {
+				if ((int)n > P.mid_occ) flt = 1;
+				else if (P.ava) { /* Rawsamble self/duplicate filter, rmap.cpp:86: keep iff qname < target name */
+					uint32_t keep = 0;
+					for (uint32_t k = 0; k < n; ++k) keep += I.name_rank[(uint32_t)(I.pos[src + k] >> 32)] >= R->name_ub;
+					/* the count is what expands; the list is re-filtered at expansion */
+					n = keep | 0x80000000u; /* mark: needs per-hit filtering */
+				}
+			}
+		}
+		/* repeat length (rseed.c:134-151) is a sequential merge over filtered seeds in read order */
+		const uint32_t fmask = __ballot_sync(0xffffffffu, flt);
+		if (fmask) {
+			uint32_t m = fmask;
+			while (m) {
+				const int b = __ffs(m) - 1; m &= m - 1;
+				const uint32_t qp = __shfl_sync(0xffffffffu, (i < ns) ? sp[i] : 0u, b);
+				const int st = (int)qp + 1, en = st + (int)span + 1;
+				if (st > rep_en) { rep_len += rep_en - rep_st; rep_st = st; rep_en = en; } else rep_en = en;
+			}
+		}
+		const uint32_t cnt = flt ? 0u : (n & 0x7fffffffu);
+		uint32_t incl = cnt;
+#pragma unroll
+		for (int o = 1; o < RH_WARP; o <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+		if (i < ns) { scnt[i] = flt ? 0u : n; ssrc[i] = src; sdst[i] = running + incl - cnt; }
+		running += __shfl_sync(0xffffffffu, incl, RH_WARP - 1);
+	}
+	rep_len += rep_en - rep_st;
+	if (lane == 0) { S->n_new = running; S->rep_len = rep_len; S->n_anchors = running + R->prev_n; }
+}
+
+/* K2b  anchors (rmap.cpp:74-116): for each kept seed, lanes cover its position list (coalesced
+ * reads of idx.pos, coalesced 16-byte anchor writes); then the previous chunk's chain anchors. */
+__global__ void __launch_bounds__(256) k_seed_expand(k2_args_t A, dev_index_t I, dev_params_t P)
+{
+	const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) / RH_WARP, lane = threadIdx.x % RH_WARP;
+	if (warp >= A.n_slots) return;
+	slot_t *S = &A.slots[warp];
+	read_state_t *R = &A.rs[S->read];
+	const uint32_t n_tot = S->n_anchors;
+	if (n_tot == 0) return;
+	anchor_t *out = (anchor_t *)(A.arena + S->a_off);
+	const uint32_t n_new = S->n_new;
+	if (!S->gated) {
+		const uint32_t ns = S->n_seeds;
+		const uint32_t *sh = A.seed_hash + S->e_off, *sp = A.seed_pos + S->e_off;
+		const uint32_t *scnt = A.seed_cnt + S->e_off, *sdst = A.seed_dst + S->e_off;
+		const uint64_t *ssrc = A.seed_src + S->e_off;
+		const uint64_t span = (uint64_t)(P.k + P.e - 1);
+		const uint32_t ev_off = R->ev_offset;
+		for (uint32_t i = 0; i < ns; ++i) {
+			const uint32_t craw = scnt[i];
+			if (craw == 0) continue;
+			const bool per_hit = craw & 0x80000000u;
+			const uint32_t h = sh[i];
+			const bool tandem = (i > 0 && sh[i - 1] == h) || (i + 1 < ns && sh[i + 1] == h); /* rseed.c:80-81 */
+			const uint64_t y = span << 32 | (uint64_t)(uint32_t)(sp[i] + ev_off) | (tandem ? (1ULL << 38) : 0ULL);
+			const uint64_t *src = I.pos + ssrc[i];
+			anchor_t *dst = out + sdst[i];
+			if (!per_hit) {
+				for (uint32_t k = lane; k < craw; k += RH_WARP) {
+					const uint64_t hv = src[k];
+					anchor_t a;
+					a.x = (hv & 0x7fffffff80000000ULL) | (uint64_t)((uint32_t)(hv >> 1) & 0x7fffffffu) | ((hv & 1) << 63);
+					a.y = y;
+					dst[k] = a;
+				}
+			} else { /* Rawsamble: list length is the unfiltered count; compact kept hits in order */
+				uint32_t full; uint64_t dummy;
+				index_find(I, h, &dummy, &full);
+				uint32_t w = 0;
+				for (uint32_t base = 0; base < full; base += RH_WARP) {
+					const uint32_t k = base + lane;
+					uint64_t hv = 0; bool keep = false;
+					if (k < full) { hv = src[k]; keep = I.name_rank[(uint32_t)(hv >> 32)] >= R->name_ub; }
+					const uint32_t km = __ballot_sync(0xffffffffu, keep);
+					if (keep) {
+						anchor_t a;
+						a.x = (hv & 0x7fffffff80000000ULL) | (uint64_t)((uint32_t)(hv >> 1) & 0x7fffffffu) | ((hv & 1) << 63);
+						a.y = y;
+						dst[w + __popc(km & ((1u << lane) - 1))] = a;
+					}
+					w += __popc(km);
+				}
+			}
+		}
+	}
+	/* previous chunk's chain anchors go last (rmap.cpp:111-116) */
+	const uint32_t pn = R->prev_n;
+	const anchor_t *pv = A.carry_in + R->prev_off;
+	for (uint32_t k = lane; k < pn; k += RH_WARP) out[n_new + k] = pv[k];
+}
+
+/* =============================================================================================
+ * K3..K6: one thread per slot (v1).  Every step below is order-dependent inside a chunk;
+ * throughput comes from the number of chunks in flight.
+ * ===========================================================================================*/
+struct k3_args_t {
+	slot_t *slots; uint32_t n_slots;
+	read_state_t *rs;
+	uint8_t *arena;
+	anchor_t *carry_out; unsigned long long *carry_top; uint64_t carry_cap;
+	const float *logf_tab; uint32_t logf_n;
+	rh_map_rec_t *recs; unsigned long long *rec_top; uint64_t rec_cap;
+	uint32_t *rec_start, *rec_cnt;   /* per read */
+	const uint32_t *seq_len;
+	int tap;                         /* tap mode: never stop early */
+	uint32_t *err;
+};
+
+__global__ void __launch_bounds__(64) k_anchor_sort(k3_args_t A)
+{
+	const uint32_t id = blockIdx.x * blockDim.x + threadIdx.x;
+	if (id >= A.n_slots) return;
+	slot_t *S = &A.slots[id];
+	if (S->gated || S->n_anchors == 0) return;
+	slot_mem_t M = slot_mem(A.arena, S->a_off, S->n_anchors);
+	seq_klib_sort(M.A, S->n_anchors, key_of_anchor_x(), (sort_seg_t *)M.B);
+}
+
+/* mg_lchain_dp main loop, reference src/lchain.c:439-505 */
+__global__ void __launch_bounds__(64) k_chain_dp(k3_args_t A, dev_params_t P)
+{
+	const uint32_t id = blockIdx.x * blockDim.x + threadIdx.x;
+	if (id >= A.n_slots) return;
+	slot_t *S = &A.slots[id];
+	if (S->gated || S->n_anchors == 0) return;
+	const int32_t n = (int32_t)S->n_anchors;
+	slot_mem_t M = slot_mem(A.arena, S->a_off, S->n_anchors);
+	const anchor_t *a = M.A;
+	int32_t *f = M.f, *p = M.p, *v = M.v, *t = M.t;
+	int32_t max_t = P.max_t, max_q = P.max_q;
+	const int32_t bw = P.bw;
+	if (max_t < bw) max_t = bw;
+	if (max_q < bw) max_q = bw;
+	for (int32_t i = 0; i < n; ++i) t[i] = 0;
+	int32_t st = 0, band_best = -1;
+	for (int32_t i = 0; i < n; ++i) {
+		const uint64_t ix = a[i].x, iy = a[i].y;
+		int32_t best = (int32_t)((iy >> 32) & 63), best_j = -1, skipped = 0, j;
+		while (st < i && ((ix >> 32) != (a[st].x >> 32) || ix > a[st].x + (uint64_t)max_t)) ++st;
+		if (i - st > P.max_iter) st = i - P.max_iter;
+		for (j = i - 1; j >= st; --j) {
+			int32_t sc = pair_score(ix, iy, a[j].x, a[j].y, max_t, max_q, bw, P.pen_gap, P.pen_skip);
+			if (sc == INT32_MIN) continue;
+			sc += f[j];
+			if (sc > best) { best = sc; best_j = j; if (skipped > 0) --skipped; }
+			else if (t[j] == i) { if (++skipped > P.max_skip) break; }
+			if (p[j] >= 0) t[p[j]] = i;
+		}
+		const int32_t end_j = j;
+		if (band_best < 0 || ix - a[band_best].x > (uint64_t)(int64_t)max_t) {
+			int32_t mx = INT32_MIN; band_best = -1;
+			for (j = i - 1; j >= st; --j) if (mx < f[j]) { mx = f[j]; band_best = j; }
+		}
+		if (band_best >= 0 && band_best < end_j) {
+			const int32_t sc = pair_score(ix, iy, a[band_best].x, a[band_best].y, max_t, max_q, bw, P.pen_gap, P.pen_skip);
+			if (sc != INT32_MIN && best < sc + f[band_best]) { best = sc + f[band_best]; best_j = band_best; }
+		}
+		f[i] = best; p[i] = best_j;
+		v[i] = (best_j >= 0 && v[best_j] > best) ? v[best_j] : best;
+		if (band_best < 0 || (ix - a[band_best].x <= (uint64_t)(int64_t)max_t && f[band_best] < f[i])) band_best = i;
+	}
+}
+
+/* mg_chain_backtrack + compact_a, reference src/lchain.c:95-281 */
+__global__ void __launch_bounds__(64) k_chain_backtrack(k3_args_t A, dev_params_t P)
+{
+	const uint32_t id = blockIdx.x * blockDim.x + threadIdx.x;
+	if (id >= A.n_slots) return;
+	slot_t *S = &A.slots[id];
+	read_state_t *R = &A.rs[S->read];
+	S->n_u = 0; S->n_v = 0;
+	if (S->gated) { /* chunk skipped by the min_events gate: carried anchors stay for the next chunk */
+		const uint32_t pn = R->prev_n;
+		if (pn) {
+			const unsigned long long o = atomicAdd(A.carry_top, (unsigned long long)pn);
+			if (o + pn > A.carry_cap) { atomicExch(A.err, 2u); R->prev_n = 0; return; }
+			const anchor_t *src = (const anchor_t *)(A.arena + S->a_off);
+			for (uint32_t k = 0; k < pn; ++k) A.carry_out[o + k] = src[k];
+			R->prev_off = o;
+		}
+		return;
+	}
+	R->prev_n = 0; /* consumed by collect_seed_hits */
+	const int32_t n = (int32_t)S->n_anchors;
+	if (n == 0) return;
+	slot_mem_t M = slot_mem(A.arena, S->a_off, S->n_anchors);
+	anchor_t *a = M.A, *b = M.B, *z = M.Z, *w = M.W;
+	int32_t *f = M.f, *p = M.p, *v = M.v, *t = M.t;
+	uint64_t *u = M.U, *u2 = M.U2;
+	const int32_t min_sc = P.min_sc, min_cnt = P.min_cnt, max_drop = P.bw;
+	uint32_t n_z = 0;
+	for (int32_t i = 0; i < n; ++i) if (f[i] >= min_sc) { z[n_z].x = (uint64_t)(int64_t)f[i]; z[n_z].y = (uint64_t)i; ++n_z; }
+	if (n_z == 0) return;
+	seq_klib_sort(z, n_z, key_of_anchor_x(), (sort_seg_t *)b);
+	for (int32_t i = 0; i < n; ++i) t[i] = 0;
+	uint32_t n_u = 0, n_v = 0;
+	for (int64_t k = (int64_t)n_z - 1; k >= 0; --k) {
+		const int32_t i0 = (int32_t)z[k].y, zs = (int32_t)z[k].x;
+		if (t[i0] != 0) continue;
+		int32_t end_i = -1, max_i = i0, c = i0, max_s = 0; /* mg_chain_bk_end, lchain.c:47-75 */
+		do {
+			t[c] = 2;
+			end_i = c = p[c];
+			const int32_t s = c < 0 ? zs : zs - f[c];
+			if (s > max_s) { max_s = s; max_i = c; }
+			else if (max_s - s > max_drop) break;
+		} while (c >= 0 && t[c] == 0);
+		for (c = i0; c >= 0 && c != end_i; c = p[c]) t[c] = 0;
+		const uint32_t n_v0 = n_v;
+		for (c = i0; c != max_i; c = p[c]) { v[n_v++] = c; t[c] = 1; }
+		const int32_t sc = c < 0 ? zs : zs - f[c];
+		if (sc >= min_sc && n_v > n_v0 && (int32_t)(n_v - n_v0) >= min_cnt) u[n_u++] = (uint64_t)sc << 32 | (n_v - n_v0);
+		else n_v = n_v0;
+	}
+	if (n_u == 0) return;
+	/* compact: chain anchors in forward order; that order is also next chunk's prev_anchors */
+	const unsigned long long co = atomicAdd(A.carry_top, (unsigned long long)n_v);
+	const bool carry_ok = co + n_v <= A.carry_cap;
+	if (!carry_ok) atomicExch(A.err, 2u);
+	uint32_t k = 0;
+	for (uint32_t ci = 0; ci < n_u; ++ci) {
+		const uint32_t ni = (uint32_t)u[ci], k0 = k;
+		for (uint32_t j = 0; j < ni; ++j) {
+			const anchor_t x = a[v[k0 + (ni - j - 1)]];
+			b[k] = x;
+			if (carry_ok) A.carry_out[co + k] = x;
+			++k;
+		}
+	}
+	if (carry_ok) { R->prev_off = co; R->prev_n = n_v; }
+	k = 0;
+	for (uint32_t ci = 0; ci < n_u; ++ci) { w[ci].x = b[k].x; w[ci].y = (uint64_t)k << 32 | ci; k += (uint32_t)u[ci]; }
+	seq_klib_sort(w, n_u, key_of_anchor_x(), (sort_seg_t *)z);
+	k = 0;
+	for (uint32_t ci = 0; ci < n_u; ++ci) {
+		const uint32_t j = (uint32_t)w[ci].y, cnt = (uint32_t)u[j];
+		u2[ci] = u[j];
+		const anchor_t *src = b + (w[ci].y >> 32);
+		for (uint32_t q = 0; q < cnt; ++q) a[k + q] = src[q];
+		k += cnt;
+	}
+	for (uint32_t ci = 0; ci < n_u; ++ci) u[ci] = u2[ci];
+	S->n_u = n_u; S->n_v = n_v;
+}
+
+/* regions + primary/secondary + MAPQ + the per-chunk stop rules and final record
+ * (hit.c:100-150,195-263,338-367,502-539; rmap.cpp:423-586) */
+__device__ __forceinline__ float logf_exact(const k3_args_t &A, int32_t x, uint32_t *flag)
+{ /* glibc logf of an integer argument, tabulated on the host so MAPQ is bit-identical */
+	if (x >= 0 && (uint32_t)x < A.logf_n) return A.logf_tab[x];
+	*flag = 1;
+	return logf((float)x);
+}
+
+__global__ void __launch_bounds__(64) k_regions(k3_args_t A, dev_params_t P)
+{
+	const uint32_t id = blockIdx.x * blockDim.x + threadIdx.x;
+	if (id >= A.n_slots) return;
+	slot_t *S = &A.slots[id];
+	read_state_t *R = &A.rs[S->read];
+	uint32_t n_regs = 0;
+	dev_reg_t *r = nullptr;
+	uint32_t inexact = 0;
+	if (!S->gated && S->n_anchors > 0 && S->n_u > 0) {
+		slot_mem_t M = slot_mem(A.arena, S->a_off, S->n_anchors);
+		const anchor_t *a = M.A;
+		const uint64_t *u = M.U;
+		anchor_t *z = M.Z;
+		r = M.regs;
+		const uint32_t n_u = S->n_u;
+		if (n_u > M.reg_cap) { atomicExch(A.err, 3u); S->n_regs = 0; return; }
+		const uint32_t hash = wang32(wang32(R->ev_offset + S->n_events) + wang32(11u)); /* rmap.cpp:346-348 */
+		uint32_t k = 0;
+		for (uint32_t i = 0; i < n_u; ++i) {
+			const uint32_t h = (uint32_t)mix64((mix64(a[k].x) + mix64(a[k].y)) ^ hash);
+			z[i].x = u[i] ^ h; z[i].y = (uint64_t)k << 32 | (uint32_t)u[i];
+			k += (uint32_t)u[i];
+		}
+		seq_klib_sort(z, n_u, key_of_anchor_x(), (sort_seg_t *)M.B);
+		for (uint32_t i = 0; i < n_u; ++i) { /* descending score */
+			const anchor_t zz = z[n_u - 1 - i];
+			dev_reg_t g;
+			g.id = (int32_t)i; g.parent = -1; g.subsc = 0; g.n_sub = 0; g.mapq = 0;
+			g.score = g.score0 = (int32_t)(zz.x >> 32); g.hash = (uint32_t)zz.x;
+			g.cnt = (int32_t)zz.y; g.as = (int32_t)(zz.y >> 32);
+			const anchor_t fa = a[g.as], la = a[g.as + g.cnt - 1];
+			g.rev = (uint32_t)(fa.x >> 63); g.rid = (int32_t)(fa.x << 1 >> 33);
+			g.rs = (int32_t)fa.x; g.re = (int32_t)la.x + 1; g.qs = (int32_t)fa.y; g.qe = (int32_t)la.y + 1;
+			r[i] = g;
+		}
+		n_regs = n_u;
+		/* mm_set_parent (hit.c:195-263); w[] and cov[] live in the slot's scratch */
+		int *wl = (int *)M.p; uint64_t *cov = M.U2;
+		wl[0] = 0; r[0].parent = 0;
+		int kk = 1;
+		for (int i = 1; i < (int)n_regs; ++i) {
+			dev_reg_t *ri = &r[i];
+			const int si = ri->qs, ei = ri->qe;
+			int n_cov = 0, uncov = 0, j;
+			for (j = 0; j < kk; ++j) {
+				const dev_reg_t *rp = &r[wl[j]];
+				int sj = rp->qs, ej = rp->qe;
+				if (ej <= si || sj >= ei) continue;
+				if (sj < si) sj = si;
+				if (ej > ei) ej = ei;
+				cov[n_cov++] = (uint64_t)sj << 32 | (uint32_t)ej;
+			}
+			j = kk;
+			if (n_cov > 0) {
+				int x = si;
+				seq_klib_sort(cov, (uint32_t)n_cov, key_of_u64(), (sort_seg_t *)M.B);
+				for (int c = 0; c < n_cov; ++c) {
+					if ((int)(cov[c] >> 32) > x) uncov += (int)(cov[c] >> 32) - x;
+					x = (int32_t)cov[c] > x ? (int32_t)cov[c] : x;
+				}
+				if (ei > x) uncov += ei - x;
+				for (j = 0; j < kk; ++j) {
+					dev_reg_t *rp = &r[wl[j]];
+					const int sj = rp->qs, ej = rp->qe;
+					if (ej <= si || sj >= ei) continue;
+					const int mn = ej - sj < ei - si ? ej - sj : ei - si;
+					const int mx = ej - sj > ei - si ? ej - sj : ei - si;
+					const int ol = si < sj ? (ei < sj ? 0 : ei < ej ? ei - sj : ej - sj) : (ej < si ? 0 : ej < ei ? ej - si : ei - si);
+					if (__fsub_rn(__fdiv_rn((float)ol, (float)mn), __fdiv_rn((float)uncov, (float)mx)) > P.mask_level && uncov <= P.mask_len) {
+						ri->parent = rp->parent;
+						rp->subsc = rp->subsc > ri->score ? rp->subsc : ri->score;
+						if (ri->cnt >= rp->cnt) ++rp->n_sub;
+						break;
+					}
+				}
+			}
+			if (j == kk) { wl[kk++] = i; ri->parent = i; ri->n_sub = 0; }
+		}
+		/* mm_select_sub + mm_sync_regs (hit.c:338-367, 312-336) */
+		if (!P.ava && P.pri_ratio > 0.0f) {
+			int kept = 0, n2 = 0;
+			const int nn = (int)n_regs;
+			for (int i = 0; i < nn; ++i) {
+				const int pp = r[i].parent;
+				bool keep = false;
+				if (pp == i) keep = true;
+				else if ((float)r[i].score >= __fmul_rn((float)r[pp].score, P.pri_ratio) && n2 < P.best_n) {
+					if (!(r[i].qs == r[pp].qs && r[i].qe == r[pp].qe && r[i].rid == r[pp].rid && r[i].rs == r[pp].rs && r[i].re == r[pp].re)) { keep = true; ++n2; }
+				} else if (n2 < P.best_n && r[i].score > P.min_strand_sc && r[i].rev != r[pp].rev) { keep = true; ++n2; }
+				if (keep) r[kept++] = r[i];
+			}
+			if (kept != nn) {
+				int *tmp = (int *)M.v;
+				int max_id = -1;
+				for (int i = 0; i < kept; ++i) max_id = max_id > r[i].id ? max_id : r[i].id;
+				for (int i = 0; i <= max_id; ++i) tmp[i] = -1;
+				for (int i = 0; i < kept; ++i) if (r[i].id >= 0) tmp[r[i].id] = i;
+				for (int i = 0; i < kept; ++i) {
+					dev_reg_t *g = &r[i];
+					g->id = i;
+					if (g->parent == -2) g->parent = i;
+					else if (g->parent >= 0 && g->parent <= max_id && tmp[g->parent] >= 0) g->parent = tmp[g->parent];
+					else g->parent = -1;
+				}
+			}
+			n_regs = (uint32_t)kept;
+		}
+		/* mm_set_mapq (hit.c:502-539), float/double sequence of the compiled reference */
+		{
+			long long sum_sc = 0;
+			for (uint32_t i = 0; i < n_regs; ++i) if (r[i].parent == r[i].id) sum_sc += r[i].score;
+			const float uniq = __fdiv_rn((float)sum_sc, (float)(sum_sc + (long long)S->rep_len));
+			for (uint32_t i = 0; i < n_regs; ++i) {
+				dev_reg_t *g = &r[i];
+				const double s1 = g->score > 100 ? 1.0 : __dmul_rn(0.01, (double)g->score);
+				const float pen_s1 = __double2float_rn(__dmul_rn(s1, (double)uniq));
+				float pen_cm = g->cnt > 10 ? 1.0f : __fmul_rn(0.1f, (float)g->cnt);
+				pen_cm = pen_s1 < pen_cm ? pen_s1 : pen_cm;
+				const int subsc = g->subsc > P.min_sc ? g->subsc : P.min_sc;
+				const float x = __fdiv_rn((float)subsc, (float)g->score0);
+				const float lead = __fmul_rn(__fmul_rn(__fmul_rn(pen_cm, 40.0f), __fsub_rn(1.0f, x)), logf_exact(A, g->score, &inexact));
+				int mapq = (int)lead;
+				mapq -= (int)__fmaf_rn(logf_exact(A, g->n_sub + 1, &inexact), 4.343f, .499f);
+				mapq = mapq > 0 ? mapq : 0;
+				g->mapq = mapq < 60 ? mapq : 60;
+			}
+		}
+	}
+	if (inexact) atomicExch(A.err, 4u);
+	S->n_regs = n_regs;
+	if (!S->gated) R->ev_offset += S->n_events;
+	if (A.tap) return;
+
+	/* ---- stop rules after this chunk (rmap.cpp:423-500) ---- */
+	const uint32_t qlen = R->l_sig;
+	const uint32_t l_chunk = (P.chunk_size > qlen || P.noadapt) ? qlen : P.chunk_size;
+	const uint32_t max_chunk = P.noadapt ? 1u : P.max_num_chunk;
+	uint32_t c_count = S->c_count;
+	unsigned long long rec_base = 0; uint32_t n_maps = 0;
+	auto push_map = [&](uint32_t cid) {
+		/* records are appended with a bump allocator; one thread writes one read's block contiguously */
+		if (n_maps == 0) rec_base = atomicAdd(A.rec_top, (unsigned long long)(P.ava ? (n_regs ? n_regs : 1u) : 1u));
+		if (rec_base + n_maps < A.rec_cap) A.recs[rec_base + n_maps].c_id = cid;
+		++n_maps;
+	};
+	bool stop = false;
+	if (n_regs == 1 && (int)r[0].mapq >= P.min_mapq) { push_map(0); stop = true; }
+	if (!stop) {
+		float meanC = 0.0f, meanQ = 0.0f;
+		for (uint32_t i = 0; i < n_regs; ++i) { meanC = __fadd_rn(meanC, (float)r[i].score); meanQ = __fadd_rn(meanQ, (float)r[i].mapq); }
+		if (n_regs > 0) { meanC = __fdiv_rn(meanC, (float)n_regs); meanQ = __fdiv_rn(meanQ, (float)n_regs); }
+		const uint32_t n_chains = (P.ava || n_regs < 1) ? n_regs : 1u;
+		for (uint32_t ic = 0; ic < n_chains; ++ic) {
+			float weighted = 0.0f;
+			const float bestQ = (float)r[ic].mapq, bestC = (float)r[ic].score;
+			if (!P.ava) {
+				float r_q = bestQ > 0 ? __fdiv_rn(bestQ, 30.0f) : 0.0f; if (r_q > 1) r_q = 1.0f;
+				float r_mq = bestQ > 0 ? __fsub_rn(1.0f, __fdiv_rn(meanQ, bestQ)) : 0.0f; if (r_mq < 0) r_mq = 0.0f;
+				float r_mc = bestC > 0 ? __fsub_rn(1.0f, __fdiv_rn(meanC, bestC)) : 0.0f; if (r_mc < 0) r_mc = 0.0f;
+				weighted = __fmaf_rn(r_mc, P.w_bestmc, __fmaf_rn(r_q, P.w_bestq, __fmul_rn(P.w_bestmq, r_mq)));
+			}
+			if (weighted >= P.w_threshold || (P.ava && r[ic].score >= P.min_sc2)) push_map(ic);
+		}
+		if (n_maps > 0) stop = true;
+	}
+	bool exhausted = false;
+	if (!stop) { /* loop increment: s_qs += l_chunk, ++c_count; continue while s_qs < qlen && c_count < max_chunk */
+		const uint64_t s_qs_next = (uint64_t)(c_count + 1) * l_chunk;
+		++c_count;
+		if (!(s_qs_next < qlen && c_count < max_chunk)) { exhausted = true; if (c_count > 0) --c_count; /* rmap.cpp:507 */ }
+	}
+	if (!stop && !exhausted) return; /* next round continues this read */
+
+	/* ---- final record(s) (rmap.cpp:507-586) ---- */
+	R->done = 1;
+	const uint32_t offset = R->ev_offset;
+	const float scale = offset == 0 ? 0.0f : (P.sample_per_base == 0.0f ? 0.0f :
+		__fdiv_rn(__fdiv_rn(__fmul_rn((float)(c_count + 1), (float)l_chunk), (float)offset), P.sample_per_base));
+	if (n_maps == 0 && n_regs > 0 && (int)r[0].mapq > P.min_mapq) push_map(0);
+	rh_map_rec_t base; memset(&base, 0, sizeof(base));
+	base.read_idx = S->read; base.ci = c_count + 1; base.sl = qlen;
+	if (n_maps == 0) {
+		rec_base = atomicAdd(A.rec_top, 1ULL);
+		base.read_length = P.sig_target ? offset : (uint32_t)__fmul_rn(scale, (float)offset);
+		if (n_regs >= 1) { base.cm = r[0].cnt; base.nc = (int32_t)n_regs; base.s1 = r[0].score; }
+		if (rec_base < A.rec_cap) A.recs[rec_base] = base; else atomicExch(A.err, 5u);
+		A.rec_start[S->read] = (uint32_t)rec_base; A.rec_cnt[S->read] = 1;
+		return;
+	}
+	if (rec_base + n_maps > A.rec_cap) { atomicExch(A.err, 5u); A.rec_cnt[S->read] = 0; return; }
+	for (uint32_t m = 0; m < n_maps; ++m) {
+		const uint32_t cid = A.recs[rec_base + m].c_id;
+		const dev_reg_t g = r[cid];
+		rh_map_rec_t o = base;
+		o.c_id = cid; o.cm = g.cnt; o.nc = (int32_t)n_regs; o.s1 = g.score;
+		o.read_length = P.sig_target ? offset : (uint32_t)__fmul_rn(scale, (float)g.qe);
+		o.ref_id = (uint32_t)g.rid;
+		o.read_start_position = P.sig_target ? (uint32_t)g.qs : (uint32_t)__fmul_rn(scale, (float)g.qs);
+		o.read_end_position = P.sig_target ? (uint32_t)g.qe : (uint32_t)__fmul_rn(scale, (float)g.qe);
+		o.fragment_start_position = g.rev ? (uint32_t)(A.seq_len[g.rid] + 1 - g.re) : (uint32_t)g.rs;
+		o.fragment_length = (uint32_t)(g.re - g.rs + 1);
+		o.mapq = (uint8_t)g.mapq; o.rev = g.rev ? 1 : 0; o.mapped = 1;
+		A.recs[rec_base + m] = o;
+	}
+	A.rec_start[S->read] = (uint32_t)rec_base; A.rec_cnt[S->read] = n_maps;
+}
+
+#endif
