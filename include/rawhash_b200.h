@@ -145,6 +145,8 @@ typedef struct rh_gpu_ctx_s rh_gpu_ctx;
 rh_gpu_ctx *rh_gpu_init(const rh_index_t *idx, const rh_params_t *p, int device, size_t arena_bytes);
 void        rh_gpu_destroy(rh_gpu_ctx *ctx);
 const char *rh_gpu_last_error(void);
+/* Launch on the caller's CUDA stream (a cudaStream_t passed as void*; NULL = the context's own). */
+void        rh_gpu_set_stream(rh_gpu_ctx *ctx, void *cuda_stream);
 
 /*
  * The drop-in for `kt_for(n_threads, map_worker_for, step, n_sig)` with the

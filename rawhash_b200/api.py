@@ -138,6 +138,7 @@ def _load():
         "rh_gpu_init": (vp, [vp, PP, i32, C.c_size_t]),
         "rh_gpu_destroy": (None, [vp]),
         "rh_gpu_last_error": (cp, []),
+        "rh_gpu_set_stream": (None, [vp, vp]),
         "rh_gpu_map_batch_raw": (i32, [vp, u32, vp, vp, vp, vp, vp, vp, C.POINTER(vp), C.POINTER(u64)]),
         "rh_gpu_map_batch_dev": (i32, [vp, u32, vp, vp, vp, vp, vp, vp, C.POINTER(vp), C.POINTER(u64)]),
         "rh_gpu_get_stats": (None, [vp, C.POINTER(GpuStats)]),
@@ -318,6 +319,9 @@ class Mapper:
         rc = _lib.rh_gpu_map_batch_dev(self.h, n, C.c_void_p(d_raw_ptr), raw_off.ctypes.data, off.ctypes.data, rg.ctypes.data, dg.ctypes.data, nm,
                                        C.byref(recs_p), C.byref(n_recs))
         return self._take(rc, recs_p, n_recs)
+
+    def set_stream(self, cuda_stream: int | None):
+        _lib.rh_gpu_set_stream(self.h, C.c_void_p(cuda_stream or 0))
 
     def stats(self) -> dict:
         st = GpuStats()

@@ -64,7 +64,7 @@ struct rh_gpu_ctx_s {
 	dev_params_t D;
 	const rh_index_s *idx = nullptr;
 	dev_index_t I;
-	cudaStream_t stream = nullptr;
+	cudaStream_t stream = nullptr, own_stream = nullptr;
 	/* index storage */
 	dbuf<uint32_t> d_keys, d_bucket, d_seqlen, d_namerank;
 	dbuf<uint64_t> d_off, d_pos;
@@ -239,6 +239,7 @@ int run_round(rh_gpu_ctx *c, round_io &io, int carry_in_idx)
 		g0 = g1;
 	}
 	for (const slot_t &sl : io.slots) {
+		c->st.raw_samples_consumed += sl.raw_used; c->st.n_chains += sl.n_u;
 		c->st.n_chunks++; c->st.n_events += sl.n_events; c->st.n_seeds += sl.n_seeds; c->st.n_anchors += sl.n_anchors;
 	}
 	return RH_OK;
@@ -395,7 +396,8 @@ extern "C" rh_gpu_ctx *rh_gpu_init(const rh_index_t *idx, const rh_params_t *p, 
 	fill_dev_params(*p, c->D);
 	if (p->mid_occ <= 0) { rh_params_t q = *p; rh_index_update_mapopt(idx, &q); c->P.mid_occ = q.mid_occ; c->D.mid_occ = q.mid_occ; }
 	auto fail = [&](const char *what) -> rh_gpu_ctx * { if (what) rh_set_error("%s", what); rh_gpu_destroy(c); return NULL; };
-	if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) return fail("cudaStreamCreate failed");
+	if (cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) != cudaSuccess) return fail("cudaStreamCreate failed");
+	c->stream = c->own_stream;
 	/* ---- index upload ---- */
 	const size_t nk = idx->keys.size();
 	int bits = 10; while (bits < 26 && ((size_t)1 << bits) < nk) ++bits;
@@ -447,9 +449,11 @@ extern "C" void rh_gpu_destroy(rh_gpu_ctx *c)
 	c->d_arena.release(); c->d_carry[0].release(); c->d_carry[1].release(); c->d_counters.release(); c->d_err.release();
 	c->d_rec_start.release(); c->d_rec_cnt.release(); c->d_recs.release();
 	for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
-	if (c->stream) cudaStreamDestroy(c->stream);
+	if (c->own_stream) cudaStreamDestroy(c->own_stream);
 	delete c;
 }
+
+extern "C" void rh_gpu_set_stream(rh_gpu_ctx *c, void *cuda_stream) { if (c) c->stream = cuda_stream ? (cudaStream_t)cuda_stream : c->own_stream; }
 
 extern "C" void rh_gpu_get_stats(const rh_gpu_ctx *c, rh_gpu_stats_t *st) { *st = c->st; }
 

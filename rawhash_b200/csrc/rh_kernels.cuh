@@ -51,7 +51,7 @@ struct slot_t {
 	int32_t  rep_len;
 	uint64_t a_off;                /* byte offset of this slot's region in the anchor arena    */
 	uint32_t n_u, n_v, n_regs;
-	uint32_t err;
+	uint32_t raw_used;             /* raw samples streamed by the event kernel for this chunk  */
 };
 
 /* layout of a slot's region in the anchor arena (n = n_anchors) */
@@ -217,6 +217,7 @@ __global__ void __launch_bounds__(K1_THREADS) k_signal_to_seeds(k1_args_t A, dev
 		const uint64_t cur1 = c;
 		const uint32_t n_tot = R->n_sum + got;
 		R->sum = sum; R->sum2 = sum2; R->n_sum = n_tot; R->cursor = cur1;
+		S->raw_used = (uint32_t)(cur1 - cur0);
 		const double mean = __ddiv_rn(sum, (double)n_tot);
 		const double sd = __dsqrt_rn(__fma_rn(-mean, mean, __ddiv_rn(sum2, (double)n_tot)));
 

@@ -165,3 +165,52 @@ def raw_to_pa(raw: np.ndarray, offset: float, rng_: float, digitisation: float) 
     scale = np.float32(rng_ / digitisation)
     pa = ((raw.astype(np.float64) + offset) * np.float64(scale)).astype(np.float32)
     return pa[(pa > np.float32(30.0)) & (pa < np.float32(200.0))]
+
+
+def make_reads_torch(genome, n_reads: int, read_len_bp: int, k: int, means, stdv, device="cuda",
+                     sample_rate: float = 4000.0, bp_per_sec: float = 450.0, seed: int = 2, batch: int = 4000):
+    """Same recipe as make_reads, generated on the GPU with torch (bench-sized inputs: 10^5 reads).
+
+    Returns (raw int16 tensor on `device`, reads concatenated back to back; raw_off uint64 numpy
+    [n+1]; lens uint64 numpy [n]; truth list).  Read i is raw[raw_off[i] : raw_off[i+1]]."""
+    import torch
+    gen = torch.Generator(device=device)
+    gen.manual_seed(seed)
+    G = torch.from_numpy(np.concatenate([s for _, s in genome])).to(device)
+    clen = np.array([len(s) for _, s in genome], dtype=np.int64)
+    cstart = np.concatenate([[0], np.cumsum(clen)[:-1]])
+    M = torch.from_numpy(np.asarray(means, dtype=np.float32)).to(device)
+    SD = torch.from_numpy(np.asarray(stdv, dtype=np.float32)).to(device)
+    scale = RANGE / DIGITISATION
+    mean_dwell = sample_rate / bp_per_sec
+    rng = np.random.Generator(np.random.PCG64(seed))
+    chunks, lens_all, truth = [], [], []
+    for b0 in range(0, n_reads, batch):
+        B = min(batch, n_reads - b0)
+        ci = rng.choice(len(genome), size=B, p=clen / clen.sum())
+        L = int(min(read_len_bp, clen.min()))
+        st = (rng.random(B) * (clen[ci] - L + 1)).astype(np.int64)
+        strand = rng.integers(0, 2, B)
+        truth += list(zip(ci.tolist(), st.tolist(), strand.tolist()))
+        base = torch.from_numpy(cstart[ci] + st).to(device)[:, None]
+        j = torch.arange(L, device=device)[None, :]
+        sd_t = torch.from_numpy(strand).to(device)[:, None]
+        pos = torch.where(sd_t == 1, base + (L - 1 - j), base + j)
+        bases = G[pos].to(torch.int64)
+        bases = torch.where(sd_t == 1, 3 - bases, bases)
+        nk = L - k + 1
+        code = torch.zeros((B, nk), dtype=torch.int64, device=device)
+        for t in range(k):
+            code = (code << 2) | bases[:, t:t + nk]
+        dwell = torch.empty((B, nk), device=device, dtype=torch.float32).exponential_(1.0 / mean_dwell, generator=gen)
+        dwell = torch.clamp(torch.round(dwell), min=1).to(torch.int64)
+        n_per = dwell.sum(dim=1)
+        flat_code = torch.repeat_interleave(code.flatten(), dwell.flatten())
+        pa = M[flat_code] + torch.randn(flat_code.shape, device=device, generator=gen) * SD[flat_code]
+        raw = torch.clamp(torch.round(pa / scale - OFFSET), -32768, 32767).to(torch.int16)
+        chunks.append((raw, n_per.cpu().numpy()))
+        lens_all.append(n_per.cpu().numpy())
+    lens = np.concatenate(lens_all).astype(np.uint64)
+    raw_off = np.concatenate([[0], np.cumsum(lens)]).astype(np.uint64)
+    out = torch.cat([c for c, _ in chunks] + [torch.zeros(8, dtype=torch.int16, device=device)])
+    return out, raw_off, lens, truth
