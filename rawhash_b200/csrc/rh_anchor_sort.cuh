@@ -1,0 +1,269 @@
+/*
+ * rh_anchor_sort.cuh — anchor sort (reference src/rmap.cpp:121: radix_sort_128x on anchor.x).
+ *
+ * The reference's klib radix sort is unstable and its tie order is observable,
+ * but any two correct sorts agree on every element whose key is unique.  So:
+ *
+ *   k_sort_block     one CTA per chunk: stable LSD byte-radix sort of (x, source index) pairs,
+ *                    skipping byte positions on which all keys of the chunk agree; then a scan
+ *                    for adjacent equal keys.  Chunks without ties (the large majority) are
+ *                    finished here: A[j] = B[idx[j]].
+ *   k_sort_ties      one warp per chunk WITH ties: replays klib's in-place MSD pass exactly, but
+ *                    only along the sub-arrays that contain a tie group — for those it needs the
+ *                    true element order the reference would have at that recursion level, which
+ *                    it tracks as a permutation of source indices.  Histogram/permute are
+ *                    warp-parallel; the displacement-cycle walk itself is order dependent and is
+ *                    done by lane 0 on a byte array.  The result patches the index order inside
+ *                    the tie-containing terminal buckets, then A[j] = B[idx[j]].
+ *
+ * Slot region usage (slot_mem): B = anchors as expanded (input), A = sorted output,
+ * Z/W = (x, idx) ping-pong, f = ord, p = ord scratch, v = dst, t = tied flags (n bytes) +
+ * level bytes (n bytes), U/U2 = segment work lists.
+ */
+#ifndef RH_ANCHOR_SORT_CUH
+#define RH_ANCHOR_SORT_CUH
+
+#include "rh_kernels.cuh"
+
+#define SORT_THREADS 256
+#define SORT_WARPS (SORT_THREADS / 32)
+
+struct sort_args_t {
+	slot_t *slots; uint32_t n_slots;
+	uint8_t *arena;
+};
+
+__device__ __forceinline__ uint32_t lanemask_lt() { uint32_t m; asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m)); return m; }
+
+__global__ void __launch_bounds__(SORT_THREADS) k_sort_block(sort_args_t A)
+{
+	__shared__ uint32_t s_hist[256];
+	__shared__ uint32_t s_base[256];
+	__shared__ uint32_t s_wcnt[SORT_WARPS][256];
+	__shared__ unsigned long long s_diff;
+	__shared__ uint32_t s_ties;
+
+	slot_t *S = &A.slots[blockIdx.x];
+	const uint32_t n = S->n_anchors;
+	if (S->gated || n == 0) return;
+	slot_mem_t M = slot_mem(A.arena, S->a_off, n);
+	const anchor_t *in = M.B;
+	anchor_t *cur = M.Z, *nxt = M.W;
+	const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+	if (tid == 0) { s_diff = 0ULL; s_ties = 0; }
+	__syncthreads();
+	/* (x, idx) pairs + which key bits differ anywhere in the chunk */
+	const uint64_t x0 = in[0].x;
+	unsigned long long diff = 0;
+	for (uint32_t i = tid; i < n; i += SORT_THREADS) {
+		const uint64_t x = in[i].x;
+		diff |= x ^ x0;
+		anchor_t pr; pr.x = x; pr.y = i;
+		cur[i] = pr;
+	}
+#pragma unroll
+	for (int o = 16; o > 0; o >>= 1) diff |= __shfl_xor_sync(0xffffffffu, diff, o);
+	if (lane == 0 && diff) atomicOr(&s_diff, diff);
+	__syncthreads();
+	const unsigned long long dmask = s_diff;
+
+	for (uint32_t shift = 0; shift < 64; shift += 8) {
+		if (((dmask >> shift) & 255ULL) == 0) continue; /* every key has the same byte here */
+		s_hist[tid] = 0;
+		__syncthreads();
+		for (uint32_t i = tid; i < n; i += SORT_THREADS) atomicAdd(&s_hist[(cur[i].x >> shift) & 255], 1u);
+		__syncthreads();
+		{ /* exclusive scan of 256 counters: warp scans + warp totals */
+			const uint32_t v = s_hist[tid];
+			uint32_t incl = v;
+#pragma unroll
+			for (int o = 1; o < 32; o <<= 1) { const uint32_t u = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += u; }
+			if (lane == 31) s_wcnt[0][warp] = incl;
+			__syncthreads();
+			uint32_t woff = 0;
+			for (uint32_t w = 0; w < warp; ++w) woff += s_wcnt[0][w];
+			s_base[tid] = woff + incl - v;
+		}
+		__syncthreads();
+		/* stable scatter, one tile of SORT_THREADS elements at a time */
+		for (uint32_t t0 = 0; t0 < n; t0 += SORT_THREADS) {
+			for (uint32_t k = tid; k < SORT_WARPS * 256; k += SORT_THREADS) (&s_wcnt[0][0])[k] = 0;
+			__syncthreads();
+			const uint32_t i = t0 + tid;
+			const bool ok = i < n;
+			anchor_t e; e.x = 0; e.y = 0;
+			uint32_t d = 0, peers = 0;
+			if (ok) { e = cur[i]; d = (uint32_t)(e.x >> shift) & 255; }
+			const uint32_t act = __ballot_sync(0xffffffffu, ok);
+			if (ok) {
+				peers = __match_any_sync(act, d);
+				if ((peers & lanemask_lt()) == 0) s_wcnt[warp][d] = __popc(peers);
+			}
+			__syncthreads();
+			{ /* thread d: prefix over warps for digit d, advance the bucket base */
+				uint32_t run = s_base[tid];
+#pragma unroll
+				for (int w = 0; w < SORT_WARPS; ++w) { const uint32_t c = s_wcnt[w][tid]; s_wcnt[w][tid] = run; run += c; }
+				s_base[tid] = run;
+			}
+			__syncthreads();
+			if (ok) nxt[s_wcnt[warp][d] + __popc(peers & lanemask_lt())] = e;
+			__syncthreads();
+		}
+		anchor_t *tmp = cur; cur = nxt; nxt = tmp;
+	}
+	/* sorted pairs must end in Z for the tie kernel */
+	if (cur != M.Z) {
+		for (uint32_t i = tid; i < n; i += SORT_THREADS) M.Z[i] = cur[i];
+		__syncthreads();
+		cur = M.Z;
+	}
+	/* tie detection on the sorted keys; flags are per SOURCE index */
+	uint8_t *tied = (uint8_t *)M.t;
+	for (uint32_t i = tid; i < n; i += SORT_THREADS) tied[i] = 0;
+	__syncthreads();
+	uint32_t my_ties = 0;
+	for (uint32_t i = tid; i + 1 < n; i += SORT_THREADS) {
+		const anchor_t a = cur[i], b = cur[i + 1];
+		if (a.x == b.x) { tied[(uint32_t)a.y] = 1; tied[(uint32_t)b.y] = 1; ++my_ties; }
+	}
+	if (my_ties) atomicAdd(&s_ties, my_ties);
+	__syncthreads();
+	const uint32_t ties = s_ties;
+	if (tid == 0) S->n_ties = ties;
+	if (ties == 0 || n <= 64) { /* <=64: klib uses a stable insertion sort -> same as the stable order */
+		anchor_t *out = M.A;
+		for (uint32_t i = tid; i < n; i += SORT_THREADS) out[i] = in[(uint32_t)cur[i].y];
+		if (tid == 0) S->n_ties = 0;
+	}
+}
+
+/* exact replay along tie-containing sub-arrays; one warp per slot */
+__global__ void __launch_bounds__(128) k_sort_ties(sort_args_t A)
+{
+	__shared__ uint32_t s_cnt[4][256];
+	__shared__ uint32_t s_head[4][256];
+	__shared__ uint32_t s_flag[4][256];
+
+	const uint32_t wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	const uint32_t slot_id = blockIdx.x * 4 + wib;
+	if (slot_id >= A.n_slots) return;
+	slot_t *S = &A.slots[slot_id];
+	const uint32_t n = S->n_anchors;
+	if (S->gated || n == 0 || S->n_ties == 0) return;
+	slot_mem_t M = slot_mem(A.arena, S->a_off, n);
+	const anchor_t *in = M.B;
+	anchor_t *srt = M.Z;
+	uint32_t *ord = (uint32_t *)M.f, *ord2 = (uint32_t *)M.p, *dst = (uint32_t *)M.v;
+	const uint8_t *tied = (const uint8_t *)M.t;
+	uint8_t *bytes = (uint8_t *)M.t + n;
+	uint2 *wl_cur = (uint2 *)M.U, *wl_nxt = (uint2 *)M.U2;
+	uint32_t *cnt = s_cnt[wib], *head = s_head[wib], *flag = s_flag[wib];
+	const uint32_t FULL = 0xffffffffu;
+
+	for (uint32_t i = lane; i < n; i += 32) ord[i] = i;
+	uint32_t n_cur = 1, n_nxt = 0;
+	if (lane == 0) wl_cur[0] = make_uint2(0u, n);
+	__syncwarp();
+
+	for (int shift = 56; shift >= 0 && n_cur > 0; shift -= 8) {
+		n_nxt = 0;
+		for (uint32_t s = 0; s < n_cur; ++s) {
+			const uint2 seg = wl_cur[s];
+			const uint32_t beg = seg.x, len = seg.y;
+			for (uint32_t b = lane; b < 256; b += 32) { cnt[b] = 0; flag[b] = 0; }
+			__syncwarp();
+			for (uint32_t i = lane; i < len; i += 32) {
+				const uint32_t o = ord[beg + i];
+				const uint32_t b = (uint32_t)(in[o].x >> shift) & 255;
+				bytes[beg + i] = (uint8_t)b;
+				atomicAdd(&cnt[b], 1u);
+				if (tied[o]) flag[b] = 1;
+			}
+			__syncwarp();
+			const uint32_t b0 = bytes[beg];
+			if (cnt[b0] == len) { /* nothing moves at this level */
+				if (shift > 0) { if (lane == 0) wl_nxt[n_nxt] = seg; ++n_nxt; }
+				else { for (uint32_t i = lane; i < len; i += 32) srt[beg + i].y = ord[beg + i]; }
+				__syncwarp();
+				continue;
+			}
+			/* bucket starts */
+			uint32_t run = 0;
+			for (uint32_t b = lane; b < 256; b += 32) {
+				const uint32_t v = cnt[b];
+				uint32_t incl = v;
+#pragma unroll
+				for (int o = 1; o < 32; o <<= 1) { const uint32_t u = __shfl_up_sync(FULL, incl, o); if (lane >= o) incl += u; }
+				head[b] = run + incl - v;
+				run += __shfl_sync(FULL, incl, 31);
+			}
+			__syncwarp();
+			/* the displacement-cycle walk (ksort.h:126-138), on bytes: dst[i] = slot element i lands in */
+			if (lane == 0) {
+				uint32_t region_end = 0;
+				for (uint32_t k = 0; k < 256; ++k) {
+					region_end += cnt[k];
+					uint32_t hk = head[k];
+					while (hk != region_end) {
+						uint32_t e = hk; /* element in hand = original occupant of slot e */
+						uint32_t d = bytes[beg + e];
+						while (d != k) {
+							const uint32_t hd = head[d];
+							dst[beg + e] = hd;
+							head[d] = hd + 1;
+							e = hd;
+							d = bytes[beg + e];
+						}
+						dst[beg + e] = hk;
+						++hk;
+					}
+					head[k] = hk;
+				}
+			}
+			__syncwarp();
+			for (uint32_t i = lane; i < len; i += 32) ord2[beg + dst[beg + i]] = ord[beg + i];
+			__syncwarp();
+			for (uint32_t i = lane; i < len; i += 32) ord[beg + i] = ord2[beg + i];
+			__syncwarp();
+			/* children that contain a tie group */
+			uint32_t acc = 0;
+			for (uint32_t bb = 0; bb < 256; bb += 32) {
+				const uint32_t b = bb + lane;
+				const uint32_t c = cnt[b];
+				uint32_t incl = c;
+#pragma unroll
+				for (int o = 1; o < 32; o <<= 1) { const uint32_t u = __shfl_up_sync(FULL, incl, o); if (lane >= o) incl += u; }
+				const uint32_t start = beg + acc + incl - c;
+				acc += __shfl_sync(FULL, incl, 31);
+				const bool has = flag[b] && c > 1;
+				const bool recurse = has && shift > 0 && c > 64;
+				const uint32_t rm = __ballot_sync(FULL, recurse);
+				if (recurse) wl_nxt[n_nxt + __popc(rm & lanemask_lt())] = make_uint2(start, c);
+				n_nxt += __popc(rm);
+				if (has && !recurse) {
+					if (shift > 0) { /* <=64 elements: klib finishes with a stable insertion sort on the full key */
+						for (uint32_t i = 1; i < c; ++i) {
+							const uint32_t o = ord[start + i];
+							const uint64_t ko = in[o].x;
+							uint32_t j = i;
+							while (j > 0 && ko < in[ord[start + j - 1]].x) { ord[start + j] = ord[start + j - 1]; --j; }
+							ord[start + j] = o;
+						}
+					}
+					for (uint32_t i = 0; i < c; ++i) srt[start + i].y = ord[start + i];
+				}
+			}
+			__syncwarp();
+		}
+		uint2 *t = wl_cur; wl_cur = wl_nxt; wl_nxt = t;
+		n_cur = n_nxt;
+		__syncwarp();
+	}
+	__syncwarp();
+	anchor_t *out = M.A;
+	for (uint32_t i = lane; i < n; i += 32) out[i] = in[(uint32_t)srt[i].y];
+}
+
+#endif

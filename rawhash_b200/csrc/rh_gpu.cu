@@ -24,6 +24,7 @@
 
 #include "rh_host.h"
 #include "rh_kernels.cuh"
+#include "rh_anchor_sort.cuh"
 
 #define CUDA_TRY(call)                                                                                   \
 	do {                                                                                                 \
@@ -219,7 +220,9 @@ int run_round(rh_gpu_ctx *c, round_io &io, int carry_in_idx)
 		a3.slots = c->d_slots.p + g0; a3.n_slots = gn;
 		const uint32_t gw = (gn * RH_WARP + 255) / 256, gt = (gn + 63) / 64;
 		{ span_guard g(c, T_SEED); k_seed_expand<<<gw, 256, 0, s>>>(a2, c->I, c->D); }
-		{ span_guard g(c, T_SORT); k_anchor_sort<<<gt, 64, 0, s>>>(a3); }
+		sort_args_t as; as.slots = a3.slots; as.n_slots = gn; as.arena = c->d_arena.p;
+		{ span_guard g(c, T_SORT); k_sort_block<<<gn, SORT_THREADS, 0, s>>>(as); }
+		{ span_guard g(c, T_SORT); k_sort_ties<<<(gn + 3) / 4, 128, 0, s>>>(as); }
 		if (io.tap) { /* sorted anchor list of the single tapped slot */
 			rh_tap_t *T = io.tap_out; const slot_t &sl = io.slots[0];
 			if (!sl.gated) {
@@ -229,7 +232,7 @@ int run_round(rh_gpu_ctx *c, round_io &io, int carry_in_idx)
 				io.tap_off[2] += sl.n_anchors;
 			}
 		}
-		{ span_guard g(c, T_CHAIN); k_chain_dp<<<gt, 64, 0, s>>>(a3, c->D); }
+		{ span_guard g(c, T_CHAIN); k_chain_dp<<<gn, DP_THREADS, 0, s>>>(a3, c->D); }
 		{ span_guard g(c, T_CHAIN); k_chain_backtrack<<<gt, 64, 0, s>>>(a3, c->D); }
 		{ span_guard g(c, T_POST); k_regions<<<gt, 64, 0, s>>>(a3, c->D); }
 		if (io.tap) {

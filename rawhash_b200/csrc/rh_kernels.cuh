@@ -52,6 +52,8 @@ struct slot_t {
 	uint64_t a_off;                /* byte offset of this slot's region in the anchor arena    */
 	uint32_t n_u, n_v, n_regs;
 	uint32_t raw_used;             /* raw samples streamed by the event kernel for this chunk  */
+	uint32_t n_ties;               /* adjacent equal keys found by the anchor sort              */
+	uint32_t n_seg;                /* independent DP segments                                   */
 };
 
 /* layout of a slot's region in the anchor arena (n = n_anchors) */
@@ -416,7 +418,7 @@ __global__ void __launch_bounds__(256) k_seed_expand(k2_args_t A, dev_index_t I,
 	read_state_t *R = &A.rs[S->read];
 	const uint32_t n_tot = S->n_anchors;
 	if (n_tot == 0) return;
-	anchor_t *out = (anchor_t *)(A.arena + S->a_off);
+	anchor_t *out = (anchor_t *)(A.arena + S->a_off) + n_tot; /* slot_mem::B: unsorted input of the anchor sort */
 	const uint32_t n_new = S->n_new;
 	if (!S->gated) {
 		const uint32_t ns = S->n_seeds;
@@ -485,58 +487,72 @@ struct k3_args_t {
 	uint32_t *err;
 };
 
-__global__ void __launch_bounds__(64) k_anchor_sort(k3_args_t A)
+/* mg_lchain_dp main loop, reference src/lchain.c:439-505.
+ *
+ * The recurrence only looks back over anchors of the same strand/target within max_dist_t, and
+ * both pieces of loop-carried state (`st`, `max_ii`) re-derive themselves from scratch whenever
+ * the previous anchor is on another target or more than max_dist_t behind.  So the sorted anchor
+ * array falls apart into independent DP segments at every such gap: one CTA per chunk marks the
+ * gaps, then its threads take segments round-robin.  (Random hits are sparse in target space, so
+ * a chunk has thousands of short segments and a few long ones around true loci.) */
+#define DP_THREADS 128
+__global__ void __launch_bounds__(DP_THREADS) k_chain_dp(k3_args_t A, dev_params_t P)
 {
-	const uint32_t id = blockIdx.x * blockDim.x + threadIdx.x;
-	if (id >= A.n_slots) return;
-	slot_t *S = &A.slots[id];
-	if (S->gated || S->n_anchors == 0) return;
-	slot_mem_t M = slot_mem(A.arena, S->a_off, S->n_anchors);
-	seq_klib_sort(M.A, S->n_anchors, key_of_anchor_x(), (sort_seg_t *)M.B);
-}
-
-/* mg_lchain_dp main loop, reference src/lchain.c:439-505 */
-__global__ void __launch_bounds__(64) k_chain_dp(k3_args_t A, dev_params_t P)
-{
-	const uint32_t id = blockIdx.x * blockDim.x + threadIdx.x;
-	if (id >= A.n_slots) return;
-	slot_t *S = &A.slots[id];
+	__shared__ uint32_t s_nseg;
+	slot_t *S = &A.slots[blockIdx.x];
 	if (S->gated || S->n_anchors == 0) return;
 	const int32_t n = (int32_t)S->n_anchors;
 	slot_mem_t M = slot_mem(A.arena, S->a_off, S->n_anchors);
 	const anchor_t *a = M.A;
 	int32_t *f = M.f, *p = M.p, *v = M.v, *t = M.t;
+	uint32_t *starts = (uint32_t *)M.U;
+	uint8_t *is_start = (uint8_t *)M.U2;
 	int32_t max_t = P.max_t, max_q = P.max_q;
 	const int32_t bw = P.bw;
 	if (max_t < bw) max_t = bw;
 	if (max_q < bw) max_q = bw;
-	for (int32_t i = 0; i < n; ++i) t[i] = 0;
-	int32_t st = 0, band_best = -1;
-	for (int32_t i = 0; i < n; ++i) {
-		const uint64_t ix = a[i].x, iy = a[i].y;
-		int32_t best = (int32_t)((iy >> 32) & 63), best_j = -1, skipped = 0, j;
-		while (st < i && ((ix >> 32) != (a[st].x >> 32) || ix > a[st].x + (uint64_t)max_t)) ++st;
-		if (i - st > P.max_iter) st = i - P.max_iter;
-		for (j = i - 1; j >= st; --j) {
-			int32_t sc = pair_score(ix, iy, a[j].x, a[j].y, max_t, max_q, bw, P.pen_gap, P.pen_skip);
-			if (sc == INT32_MIN) continue;
-			sc += f[j];
-			if (sc > best) { best = sc; best_j = j; if (skipped > 0) --skipped; }
-			else if (t[j] == i) { if (++skipped > P.max_skip) break; }
-			if (p[j] >= 0) t[p[j]] = i;
+	const uint32_t tid = threadIdx.x;
+	if (tid == 0) s_nseg = 0;
+	__syncthreads();
+	for (int32_t i = tid; i < n; i += DP_THREADS) {
+		t[i] = 0;
+		bool st = true;
+		if (i > 0) { const uint64_t x = a[i].x, px = a[i - 1].x; st = (x >> 32) != (px >> 32) || x > px + (uint64_t)max_t; }
+		is_start[i] = st ? 1 : 0;
+		if (st) starts[atomicAdd(&s_nseg, 1u)] = (uint32_t)i;
+	}
+	__syncthreads();
+	const uint32_t n_seg = s_nseg;
+	if (tid == 0) S->n_seg = n_seg;
+	for (uint32_t sg = tid; sg < n_seg; sg += DP_THREADS) {
+		const int32_t i0 = (int32_t)starts[sg];
+		int32_t st = i0, band_best = -1;
+		for (int32_t i = i0; i < n && (i == i0 || !is_start[i]); ++i) {
+			const uint64_t ix = a[i].x, iy = a[i].y;
+			int32_t best = (int32_t)((iy >> 32) & 63), best_j = -1, skipped = 0, j;
+			while (st < i && ((ix >> 32) != (a[st].x >> 32) || ix > a[st].x + (uint64_t)max_t)) ++st;
+			if (i - st > P.max_iter) st = i - P.max_iter;
+			for (j = i - 1; j >= st; --j) {
+				int32_t sc = pair_score(ix, iy, a[j].x, a[j].y, max_t, max_q, bw, P.pen_gap, P.pen_skip);
+				if (sc == INT32_MIN) continue;
+				sc += f[j];
+				if (sc > best) { best = sc; best_j = j; if (skipped > 0) --skipped; }
+				else if (t[j] == i) { if (++skipped > P.max_skip) break; }
+				if (p[j] >= 0) t[p[j]] = i;
+			}
+			const int32_t end_j = j;
+			if (band_best < 0 || ix - a[band_best].x > (uint64_t)(int64_t)max_t) {
+				int32_t mx = INT32_MIN; band_best = -1;
+				for (j = i - 1; j >= st; --j) if (mx < f[j]) { mx = f[j]; band_best = j; }
+			}
+			if (band_best >= 0 && band_best < end_j) {
+				const int32_t sc = pair_score(ix, iy, a[band_best].x, a[band_best].y, max_t, max_q, bw, P.pen_gap, P.pen_skip);
+				if (sc != INT32_MIN && best < sc + f[band_best]) { best = sc + f[band_best]; best_j = band_best; }
+			}
+			f[i] = best; p[i] = best_j;
+			v[i] = (best_j >= 0 && v[best_j] > best) ? v[best_j] : best;
+			if (band_best < 0 || (ix - a[band_best].x <= (uint64_t)(int64_t)max_t && f[band_best] < f[i])) band_best = i;
 		}
-		const int32_t end_j = j;
-		if (band_best < 0 || ix - a[band_best].x > (uint64_t)(int64_t)max_t) {
-			int32_t mx = INT32_MIN; band_best = -1;
-			for (j = i - 1; j >= st; --j) if (mx < f[j]) { mx = f[j]; band_best = j; }
-		}
-		if (band_best >= 0 && band_best < end_j) {
-			const int32_t sc = pair_score(ix, iy, a[band_best].x, a[band_best].y, max_t, max_q, bw, P.pen_gap, P.pen_skip);
-			if (sc != INT32_MIN && best < sc + f[band_best]) { best = sc + f[band_best]; best_j = band_best; }
-		}
-		f[i] = best; p[i] = best_j;
-		v[i] = (best_j >= 0 && v[best_j] > best) ? v[best_j] : best;
-		if (band_best < 0 || (ix - a[band_best].x <= (uint64_t)(int64_t)max_t && f[band_best] < f[i])) band_best = i;
 	}
 }
 
@@ -553,7 +569,7 @@ __global__ void __launch_bounds__(64) k_chain_backtrack(k3_args_t A, dev_params_
 		if (pn) {
 			const unsigned long long o = atomicAdd(A.carry_top, (unsigned long long)pn);
 			if (o + pn > A.carry_cap) { atomicExch(A.err, 2u); R->prev_n = 0; return; }
-			const anchor_t *src = (const anchor_t *)(A.arena + S->a_off);
+			const anchor_t *src = (const anchor_t *)(A.arena + S->a_off) + pn; /* slot_mem::B (n_anchors == prev_n here) */
 			for (uint32_t k = 0; k < pn; ++k) A.carry_out[o + k] = src[k];
 			R->prev_off = o;
 		}

@@ -43,12 +43,23 @@ __device__ void seq_klib_sort(T *a, uint32_t n, KeyF key, sort_seg_t *stack)
 {
 	if (n <= 64) { seq_insertion_sort(a, n, key); return; }
 	uint32_t cnt[256], head[256];
+	/* byte positions on which every key agrees are identity passes for every sub-array */
+	uint64_t diff = 0;
+	{
+		const uint64_t k0 = key(a[0]);
+#pragma unroll 1
+		for (uint32_t i = 1; i < n; ++i) diff |= key(a[i]) ^ k0;
+	}
 	int sp = 0;
 	stack[sp++] = sort_seg_t{0u, n, 56u};
 	while (sp > 0) {
 		const sort_seg_t s = stack[--sp];
 		T *seg = a + s.beg;
 		const uint32_t len = s.len, shift = s.shift;
+		if (((diff >> shift) & 255ULL) == 0) {
+			if (shift > 0) stack[sp++] = sort_seg_t{s.beg, len, shift > 8 ? shift - 8 : 0};
+			continue;
+		}
 #pragma unroll 1
 		for (int b = 0; b < 256; ++b) cnt[b] = 0;
 #pragma unroll 1
