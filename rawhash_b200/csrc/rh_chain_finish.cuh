@@ -1,0 +1,467 @@
+/*
+ * rh_chain_finish.cuh — everything after the chaining DP, one WARP per chunk:
+ *
+ *   mg_chain_backtrack + compact_a          reference src/lchain.c:95-281
+ *   mm_gen_regs / mm_set_parent / mm_select_sub / mm_sync_regs / mm_set_mapq
+ *                                           reference src/hit.c:100-150,195-263,312-367,502-539
+ *   stop rules + final record of map_worker_for   reference src/rmap.cpp:423-586
+ *
+ * The O(n) passes (candidate collection, mark reset, gathers, histograms, permutes) and the
+ * O(n_u * n_primary) overlap tests of mm_set_parent run on all 32 lanes; only the steps whose
+ * result depends on visiting order (the klib sort's displacement walk, the backtrack itself,
+ * the parent assignment order) are executed by lane 0.
+ */
+#ifndef RH_CHAIN_FINISH_CUH
+#define RH_CHAIN_FINISH_CUH
+
+#include "rh_kernels.cuh"
+#include "rh_anchor_sort.cuh"
+
+#define FIN_WARPS 4
+
+struct fin_scratch_t { uint8_t *bytes; uint32_t *dst; uint2 *wl0, *wl1; };
+__device__ __forceinline__ fin_scratch_t fin_scratch(const slot_mem_t &M, uint64_t n)
+{
+	fin_scratch_t s; uint8_t *b = (uint8_t *)M.regs;
+	s.bytes = b; b += (n + 15) & ~15ULL;
+	s.dst = (uint32_t *)b; b += 4 * n;
+	s.wl0 = (uint2 *)(((uintptr_t)b + 7) & ~(uintptr_t)7); b = (uint8_t *)s.wl0 + 8 * (n / 64 + 2);
+	s.wl1 = (uint2 *)b;
+	return s;
+}
+
+/* Exact klib radix sort (see rh_sort.cuh for the algorithm) of (x = key, y = payload) pairs,
+ * cooperative over one warp.  Every lane must call it. */
+__device__ void warp_klib_sort_pairs(anchor_t *a, uint32_t n, anchor_t *tmp, const fin_scratch_t &X, uint32_t *cnt, uint32_t *head, uint32_t lane)
+{
+	const uint32_t FULL = 0xffffffffu;
+	if (n <= 64) {
+		if (lane == 0) seq_insertion_sort(a, n, key_of_anchor_x());
+		__syncwarp();
+		return;
+	}
+	unsigned long long diff = 0;
+	const uint64_t k0 = a[0].x;
+	for (uint32_t i = lane; i < n; i += 32) diff |= a[i].x ^ k0;
+#pragma unroll
+	for (int o = 16; o > 0; o >>= 1) diff |= __shfl_xor_sync(FULL, diff, o);
+	uint2 *wl_cur = X.wl0, *wl_nxt = X.wl1;
+	uint32_t n_cur = 1, n_nxt = 0;
+	if (lane == 0) wl_cur[0] = make_uint2(0u, n);
+	__syncwarp();
+	for (int shift = 56; shift >= 0 && n_cur > 0; shift -= 8) {
+		if (((diff >> shift) & 255ULL) == 0) continue; /* identity level for every sub-array */
+		n_nxt = 0;
+		for (uint32_t s = 0; s < n_cur; ++s) {
+			const uint2 seg = wl_cur[s];
+			const uint32_t beg = seg.x, len = seg.y;
+			for (uint32_t b = lane; b < 256; b += 32) cnt[b] = 0;
+			__syncwarp();
+			for (uint32_t i = lane; i < len; i += 32) {
+				const uint32_t b = (uint32_t)(a[beg + i].x >> shift) & 255;
+				X.bytes[beg + i] = (uint8_t)b;
+				atomicAdd(&cnt[b], 1u);
+			}
+			__syncwarp();
+			if (cnt[X.bytes[beg]] == len) {
+				if (shift > 0) { if (lane == 0) wl_nxt[n_nxt] = seg; ++n_nxt; }
+				__syncwarp();
+				continue;
+			}
+			uint32_t run = 0;
+			for (uint32_t b = lane; b < 256; b += 32) {
+				const uint32_t v = cnt[b];
+				uint32_t incl = v;
+#pragma unroll
+				for (int o = 1; o < 32; o <<= 1) { const uint32_t u = __shfl_up_sync(FULL, incl, o); if (lane >= o) incl += u; }
+				head[b] = run + incl - v;
+				run += __shfl_sync(FULL, incl, 31);
+			}
+			__syncwarp();
+			if (lane == 0) { /* displacement-cycle walk on the byte array */
+				uint32_t region_end = 0;
+				for (uint32_t k = 0; k < 256; ++k) {
+					region_end += cnt[k];
+					uint32_t hk = head[k];
+					while (hk != region_end) {
+						uint32_t e = hk, d = X.bytes[beg + e];
+						while (d != k) {
+							const uint32_t hd = head[d];
+							X.dst[beg + e] = hd; head[d] = hd + 1;
+							e = hd; d = X.bytes[beg + e];
+						}
+						X.dst[beg + e] = hk;
+						++hk;
+					}
+					head[k] = hk;
+				}
+			}
+			__syncwarp();
+			for (uint32_t i = lane; i < len; i += 32) tmp[beg + X.dst[beg + i]] = a[beg + i];
+			__syncwarp();
+			for (uint32_t i = lane; i < len; i += 32) a[beg + i] = tmp[beg + i];
+			__syncwarp();
+			if (shift > 0) {
+				uint32_t acc = 0;
+				for (uint32_t bb = 0; bb < 256; bb += 32) {
+					const uint32_t c = cnt[bb + lane];
+					uint32_t incl = c;
+#pragma unroll
+					for (int o = 1; o < 32; o <<= 1) { const uint32_t u = __shfl_up_sync(FULL, incl, o); if (lane >= o) incl += u; }
+					const uint32_t start = beg + acc + incl - c;
+					acc += __shfl_sync(FULL, incl, 31);
+					const bool recurse = c > 64;
+					const uint32_t rm = __ballot_sync(FULL, recurse);
+					if (recurse) wl_nxt[n_nxt + __popc(rm & lanemask_lt())] = make_uint2(start, c);
+					n_nxt += __popc(rm);
+					if (!recurse && c > 1) seq_insertion_sort(a + start, c, key_of_anchor_x());
+				}
+				__syncwarp();
+			}
+		}
+		uint2 *t = wl_cur; wl_cur = wl_nxt; wl_nxt = t;
+		n_cur = n_nxt;
+		__syncwarp();
+	}
+	__syncwarp();
+}
+
+__device__ __forceinline__ float logf_tab(const k3_args_t &A, int32_t x, uint32_t *flag)
+{ /* glibc logf of an integer argument, tabulated on the host so MAPQ is bit-identical */
+	if (x >= 0 && (uint32_t)x < A.logf_n) return A.logf_tab[x];
+	*flag = 1;
+	return logf((float)x);
+}
+
+__global__ void __launch_bounds__(FIN_WARPS * 32) k_chain_finish(k3_args_t A, dev_params_t P)
+{
+	__shared__ uint32_t s_cnt[FIN_WARPS][256];
+	__shared__ uint32_t s_head[FIN_WARPS][256];
+	const uint32_t FULL = 0xffffffffu;
+	const uint32_t wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	const uint32_t slot_id = blockIdx.x * FIN_WARPS + wib;
+	if (slot_id >= A.n_slots) return;
+	slot_t *S = &A.slots[slot_id];
+	read_state_t *R = &A.rs[S->read];
+	uint32_t *cnt = s_cnt[wib], *head = s_head[wib];
+
+	uint32_t n_u = 0, n_v = 0, n_regs = 0;
+	dev_reg_t *r = nullptr;
+	uint32_t inexact = 0;
+	const int32_t n = (int32_t)S->n_anchors;
+
+	if (S->gated) { /* chunk skipped by the min_events gate: carried anchors stay for the next chunk */
+		const uint32_t pn = R->prev_n;
+		if (pn) {
+			unsigned long long o = 0;
+			if (lane == 0) o = atomicAdd(A.carry_top, (unsigned long long)pn);
+			o = __shfl_sync(FULL, o, 0);
+			if (o + pn > A.carry_cap) { if (lane == 0) { atomicExch(A.err, 2u); R->prev_n = 0; } }
+			else {
+				const anchor_t *src = (const anchor_t *)(A.arena + S->a_off) + pn; /* slot_mem::B */
+				for (uint32_t k = lane; k < pn; k += 32) A.carry_out[o + k] = src[k];
+				if (lane == 0) R->prev_off = o;
+			}
+		}
+	} else {
+		if (lane == 0) R->prev_n = 0; /* consumed by collect_seed_hits */
+		if (n > 0) {
+			slot_mem_t M = slot_mem(A.arena, S->a_off, S->n_anchors);
+			const fin_scratch_t X = fin_scratch(M, S->n_anchors);
+			anchor_t *a = M.A, *b = M.B, *z = M.Z, *w = M.W;
+			int32_t *f = M.f, *p = M.p, *v = M.v, *t = M.t;
+			uint64_t *u = M.U, *u2 = M.U2;
+			const int32_t min_sc = P.min_sc, min_cnt = P.min_cnt, max_drop = P.bw;
+			/* ---- candidates z = {(f[i], i) : f[i] >= min_sc}, in index order ---- */
+			uint32_t n_z = 0;
+			for (int32_t i0 = 0; i0 < n; i0 += 32) {
+				const int32_t i = i0 + (int32_t)lane;
+				int32_t fi = 0; bool ok = false;
+				if (i < n) { fi = f[i]; ok = fi >= min_sc; t[i] = 0; }
+				const uint32_t m = __ballot_sync(FULL, ok);
+				if (ok) { anchor_t e; e.x = (uint64_t)(int64_t)fi; e.y = (uint64_t)i; z[n_z + __popc(m & lanemask_lt())] = e; }
+				n_z += __popc(m);
+			}
+			__syncwarp();
+			if (n_z > 0) {
+				warp_klib_sort_pairs(z, n_z, w, X, cnt, head, lane);
+				/* ---- backtrack, best score first (order dependent: lane 0) ---- */
+				if (lane == 0) {
+					for (int64_t k = (int64_t)n_z - 1; k >= 0; --k) {
+						const int32_t i0 = (int32_t)z[k].y, zs = (int32_t)z[k].x;
+						if (t[i0] != 0) continue;
+						int32_t end_i = -1, max_i = i0, c = i0, max_s = 0; /* mg_chain_bk_end */
+						do {
+							t[c] = 2;
+							end_i = c = p[c];
+							const int32_t s = c < 0 ? zs : zs - f[c];
+							if (s > max_s) { max_s = s; max_i = c; }
+							else if (max_s - s > max_drop) break;
+						} while (c >= 0 && t[c] == 0);
+						for (c = i0; c >= 0 && c != end_i; c = p[c]) t[c] = 0;
+						const uint32_t n_v0 = n_v;
+						for (c = i0; c != max_i; c = p[c]) { v[n_v++] = c; t[c] = 1; }
+						const int32_t sc = c < 0 ? zs : zs - f[c];
+						if (sc >= min_sc && n_v > n_v0 && (int32_t)(n_v - n_v0) >= min_cnt) u[n_u++] = (uint64_t)sc << 32 | (n_v - n_v0);
+						else n_v = n_v0;
+					}
+				}
+				n_u = __shfl_sync(FULL, n_u, 0); n_v = __shfl_sync(FULL, n_v, 0);
+				__syncwarp();
+			}
+			if (n_u > 0) {
+				/* ---- compact_a: forward-order gather (= next chunk's prev_anchors), then chains by target ---- */
+				unsigned long long co = 0;
+				if (lane == 0) co = atomicAdd(A.carry_top, (unsigned long long)n_v);
+				co = __shfl_sync(FULL, co, 0);
+				const bool carry_ok = co + n_v <= A.carry_cap;
+				if (!carry_ok && lane == 0) atomicExch(A.err, 2u);
+				uint32_t k = 0;
+				for (uint32_t ci = 0; ci < n_u; ++ci) {
+					const uint32_t ni = (uint32_t)u[ci];
+					for (uint32_t j = lane; j < ni; j += 32) {
+						const anchor_t x = a[v[k + (ni - j - 1)]];
+						b[k + j] = x;
+						if (carry_ok) A.carry_out[co + k + j] = x;
+					}
+					if (lane == 0) { w[ci].x = 0; w[ci].y = (uint64_t)k << 32 | ci; }
+					k += ni;
+				}
+				__syncwarp();
+				for (uint32_t ci = lane; ci < n_u; ci += 32) w[ci].x = b[w[ci].y >> 32].x;
+				if (lane == 0 && carry_ok) { R->prev_off = co; R->prev_n = n_v; }
+				__syncwarp();
+				warp_klib_sort_pairs(w, n_u, z, X, cnt, head, lane);
+				k = 0;
+				for (uint32_t ci = 0; ci < n_u; ++ci) {
+					const uint32_t j = (uint32_t)w[ci].y, c = (uint32_t)u[j];
+					const anchor_t *src = b + (w[ci].y >> 32);
+					for (uint32_t q = lane; q < c; q += 32) a[k + q] = src[q];
+					if (lane == 0) u2[ci] = u[j];
+					k += c;
+				}
+				__syncwarp();
+				for (uint32_t ci = lane; ci < n_u; ci += 32) u[ci] = u2[ci];
+				__syncwarp();
+
+				/* ---- mm_gen_regs ---- */
+				if (n_u > M.reg_cap / 2) { if (lane == 0) atomicExch(A.err, 3u); n_u = 0; }
+			}
+			if (n_u > 0) {
+				r = M.regs + M.reg_cap / 2; /* upper half: the lower half is sort scratch (fin_scratch) */
+				const uint32_t hash = wang32(wang32(R->ev_offset + S->n_events) + wang32(11u)); /* rmap.cpp:346-348 */
+				if (lane == 0) {
+					uint32_t k = 0;
+					for (uint32_t i = 0; i < n_u; ++i) {
+						const uint32_t h = (uint32_t)mix64((mix64(a[k].x) + mix64(a[k].y)) ^ hash);
+						z[i].x = u[i] ^ h; z[i].y = (uint64_t)k << 32 | (uint32_t)u[i];
+						k += (uint32_t)u[i];
+					}
+				}
+				__syncwarp();
+				warp_klib_sort_pairs(z, n_u, w, X, cnt, head, lane);
+				for (uint32_t i = lane; i < n_u; i += 32) { /* descending score */
+					const anchor_t zz = z[n_u - 1 - i];
+					dev_reg_t g;
+					g.id = (int32_t)i; g.parent = -1; g.subsc = 0; g.n_sub = 0; g.mapq = 0;
+					g.score = g.score0 = (int32_t)(zz.x >> 32); g.hash = (uint32_t)zz.x;
+					g.cnt = (int32_t)zz.y; g.as = (int32_t)(zz.y >> 32);
+					const anchor_t fa = a[g.as], la = a[g.as + g.cnt - 1];
+					g.rev = (uint32_t)(fa.x >> 63); g.rid = (int32_t)(fa.x << 1 >> 33);
+					g.rs = (int32_t)fa.x; g.re = (int32_t)la.x + 1; g.qs = (int32_t)fa.y; g.qe = (int32_t)la.y + 1;
+					r[i] = g;
+				}
+				n_regs = n_u;
+				__syncwarp();
+				/* ---- mm_set_parent: regions in score order; overlap tests against primaries on all lanes ---- */
+				int *wl = (int *)M.p; uint64_t *cov = M.U2;
+				if (lane == 0) { wl[0] = 0; r[0].parent = 0; }
+				__syncwarp();
+				int kk = 1;
+				for (int i = 1; i < (int)n_regs; ++i) {
+					const int si = r[i].qs, ei = r[i].qe;
+					/* pass 1: clipped overlaps with primaries -> cov[] */
+					int n_cov = 0;
+					for (int j0 = 0; j0 < kk; j0 += 32) {
+						const int j = j0 + (int)lane;
+						bool ov = false; int sj = 0, ej = 0;
+						if (j < kk) { const dev_reg_t *rp = &r[wl[j]]; sj = rp->qs; ej = rp->qe; ov = !(ej <= si || sj >= ei); }
+						const uint32_t m = __ballot_sync(FULL, ov);
+						if (ov) { if (sj < si) sj = si; if (ej > ei) ej = ei; cov[n_cov + __popc(m & lanemask_lt())] = (uint64_t)sj << 32 | (uint32_t)ej; }
+						n_cov += __popc(m);
+					}
+					__syncwarp();
+					int hit = -1, uncov = 0;
+					if (n_cov > 0) {
+						if (lane == 0) { /* union length of the overlaps (sorted by start; ties are identical values) */
+							int x = si;
+							seq_klib_sort(cov, (uint32_t)n_cov, key_of_u64(), (sort_seg_t *)M.B);
+							for (int c = 0; c < n_cov; ++c) {
+								if ((int)(cov[c] >> 32) > x) uncov += (int)(cov[c] >> 32) - x;
+								x = (int32_t)cov[c] > x ? (int32_t)cov[c] : x;
+							}
+							if (ei > x) uncov += ei - x;
+						}
+						uncov = __shfl_sync(FULL, uncov, 0);
+						/* pass 2: first primary (in order) that masks region i */
+						for (int j0 = 0; j0 < kk && hit < 0; j0 += 32) {
+							const int j = j0 + (int)lane;
+							bool sec = false;
+							if (j < kk) {
+								const dev_reg_t *rp = &r[wl[j]];
+								const int sj = rp->qs, ej = rp->qe;
+								if (!(ej <= si || sj >= ei)) {
+									const int mn = ej - sj < ei - si ? ej - sj : ei - si;
+									const int mx = ej - sj > ei - si ? ej - sj : ei - si;
+									const int ol = si < sj ? (ei < sj ? 0 : ei < ej ? ei - sj : ej - sj) : (ej < si ? 0 : ej < ei ? ej - si : ei - si);
+									sec = __fsub_rn(__fdiv_rn((float)ol, (float)mn), __fdiv_rn((float)uncov, (float)mx)) > P.mask_level && uncov <= P.mask_len;
+								}
+							}
+							const uint32_t m = __ballot_sync(FULL, sec);
+							if (m) hit = j0 + __ffs(m) - 1;
+						}
+					}
+					if (lane == 0) {
+						dev_reg_t *ri = &r[i];
+						if (hit >= 0) {
+							dev_reg_t *rp = &r[wl[hit]];
+							ri->parent = rp->parent;
+							rp->subsc = rp->subsc > ri->score ? rp->subsc : ri->score;
+							if (ri->cnt >= rp->cnt) ++rp->n_sub;
+						} else { wl[kk] = i; ri->parent = i; ri->n_sub = 0; }
+					}
+					if (hit < 0) ++kk;
+					__syncwarp();
+				}
+				/* ---- mm_select_sub + mm_sync_regs, mm_set_mapq (small; lane 0) ---- */
+				if (lane == 0) {
+					if (!P.ava && P.pri_ratio > 0.0f) {
+						int kept = 0, n2 = 0;
+						const int nn = (int)n_regs;
+						for (int i = 0; i < nn; ++i) {
+							const int pp = r[i].parent;
+							bool keep = false;
+							if (pp == i) keep = true;
+							else if ((float)r[i].score >= __fmul_rn((float)r[pp].score, P.pri_ratio) && n2 < P.best_n) {
+								if (!(r[i].qs == r[pp].qs && r[i].qe == r[pp].qe && r[i].rid == r[pp].rid && r[i].rs == r[pp].rs && r[i].re == r[pp].re)) { keep = true; ++n2; }
+							} else if (n2 < P.best_n && r[i].score > P.min_strand_sc && r[i].rev != r[pp].rev) { keep = true; ++n2; }
+							if (keep) { if (kept != i) r[kept] = r[i]; ++kept; }
+						}
+						if (kept != nn) {
+							int *tmp = (int *)M.v;
+							int max_id = -1;
+							for (int i = 0; i < kept; ++i) max_id = max_id > r[i].id ? max_id : r[i].id;
+							for (int i = 0; i <= max_id; ++i) tmp[i] = -1;
+							for (int i = 0; i < kept; ++i) if (r[i].id >= 0) tmp[r[i].id] = i;
+							for (int i = 0; i < kept; ++i) {
+								dev_reg_t *g = &r[i];
+								g->id = i;
+								if (g->parent == -2) g->parent = i;
+								else if (g->parent >= 0 && g->parent <= max_id && tmp[g->parent] >= 0) g->parent = tmp[g->parent];
+								else g->parent = -1;
+							}
+						}
+						n_regs = (uint32_t)kept;
+					}
+					long long sum_sc = 0;
+					for (uint32_t i = 0; i < n_regs; ++i) if (r[i].parent == r[i].id) sum_sc += r[i].score;
+					const float uniq = __fdiv_rn((float)sum_sc, (float)(sum_sc + (long long)S->rep_len));
+					for (uint32_t i = 0; i < n_regs; ++i) { /* hit.c:519-538 as compiled */
+						dev_reg_t *g = &r[i];
+						const double s1 = g->score > 100 ? 1.0 : __dmul_rn(0.01, (double)g->score);
+						const float pen_s1 = __double2float_rn(__dmul_rn(s1, (double)uniq));
+						float pen_cm = g->cnt > 10 ? 1.0f : __fmul_rn(0.1f, (float)g->cnt);
+						pen_cm = pen_s1 < pen_cm ? pen_s1 : pen_cm;
+						const int subsc = g->subsc > P.min_sc ? g->subsc : P.min_sc;
+						const float x = __fdiv_rn((float)subsc, (float)g->score0);
+						const float lead = __fmul_rn(__fmul_rn(__fmul_rn(pen_cm, 40.0f), __fsub_rn(1.0f, x)), logf_tab(A, g->score, &inexact));
+						int mapq = (int)lead;
+						mapq -= (int)__fmaf_rn(logf_tab(A, g->n_sub + 1, &inexact), 4.343f, .499f);
+						mapq = mapq > 0 ? mapq : 0;
+						g->mapq = mapq < 60 ? mapq : 60;
+					}
+				}
+				n_regs = __shfl_sync(FULL, n_regs, 0);
+			}
+		}
+	}
+	if (lane != 0) return;
+	if (inexact) atomicExch(A.err, 4u);
+	S->n_u = n_u; S->n_v = n_v; S->n_regs = n_regs;
+	if (!S->gated) R->ev_offset += S->n_events;
+	if (A.tap) return;
+
+	/* ---- stop rules after this chunk (rmap.cpp:423-500) ---- */
+	const uint32_t qlen = R->l_sig;
+	const uint32_t l_chunk = (P.chunk_size > qlen || P.noadapt) ? qlen : P.chunk_size;
+	const uint32_t max_chunk = P.noadapt ? 1u : P.max_num_chunk;
+	uint32_t c_count = S->c_count;
+	unsigned long long rec_base = 0; uint32_t n_maps = 0;
+	auto push_map = [&](uint32_t cid) {
+		if (n_maps == 0) rec_base = atomicAdd(A.rec_top, (unsigned long long)(P.ava ? (n_regs ? n_regs : 1u) : 1u));
+		if (rec_base + n_maps < A.rec_cap) A.recs[rec_base + n_maps].c_id = cid;
+		++n_maps;
+	};
+	bool stop = false;
+	if (n_regs == 1 && (int)r[0].mapq >= P.min_mapq) { push_map(0); stop = true; }
+	if (!stop) {
+		float meanC = 0.0f, meanQ = 0.0f;
+		for (uint32_t i = 0; i < n_regs; ++i) { meanC = __fadd_rn(meanC, (float)r[i].score); meanQ = __fadd_rn(meanQ, (float)r[i].mapq); }
+		if (n_regs > 0) { meanC = __fdiv_rn(meanC, (float)n_regs); meanQ = __fdiv_rn(meanQ, (float)n_regs); }
+		const uint32_t n_chains = (P.ava || n_regs < 1) ? n_regs : 1u;
+		for (uint32_t ic = 0; ic < n_chains; ++ic) {
+			float weighted = 0.0f;
+			const float bestQ = (float)r[ic].mapq, bestC = (float)r[ic].score;
+			if (!P.ava) {
+				float r_q = bestQ > 0 ? __fdiv_rn(bestQ, 30.0f) : 0.0f; if (r_q > 1) r_q = 1.0f;
+				float r_mq = bestQ > 0 ? __fsub_rn(1.0f, __fdiv_rn(meanQ, bestQ)) : 0.0f; if (r_mq < 0) r_mq = 0.0f;
+				float r_mc = bestC > 0 ? __fsub_rn(1.0f, __fdiv_rn(meanC, bestC)) : 0.0f; if (r_mc < 0) r_mc = 0.0f;
+				weighted = __fmaf_rn(r_mc, P.w_bestmc, __fmaf_rn(r_q, P.w_bestq, __fmul_rn(P.w_bestmq, r_mq)));
+			}
+			if (weighted >= P.w_threshold || (P.ava && r[ic].score >= P.min_sc2)) push_map(ic);
+		}
+		if (n_maps > 0) stop = true;
+	}
+	bool exhausted = false;
+	if (!stop) {
+		const uint64_t s_qs_next = (uint64_t)(c_count + 1) * l_chunk;
+		++c_count;
+		if (!(s_qs_next < qlen && c_count < max_chunk)) { exhausted = true; if (c_count > 0) --c_count; /* rmap.cpp:507 */ }
+	}
+	if (!stop && !exhausted) return;
+
+	/* ---- final record(s) (rmap.cpp:507-586) ---- */
+	R->done = 1;
+	const uint32_t offset = R->ev_offset;
+	const float scale = offset == 0 ? 0.0f : (P.sample_per_base == 0.0f ? 0.0f :
+		__fdiv_rn(__fdiv_rn(__fmul_rn((float)(c_count + 1), (float)l_chunk), (float)offset), P.sample_per_base));
+	if (n_maps == 0 && n_regs > 0 && (int)r[0].mapq > P.min_mapq) push_map(0);
+	rh_map_rec_t base; memset(&base, 0, sizeof(base));
+	base.read_idx = S->read; base.ci = c_count + 1; base.sl = qlen;
+	if (n_maps == 0) {
+		rec_base = atomicAdd(A.rec_top, 1ULL);
+		base.read_length = P.sig_target ? offset : (uint32_t)__fmul_rn(scale, (float)offset);
+		if (n_regs >= 1) { base.cm = r[0].cnt; base.nc = (int32_t)n_regs; base.s1 = r[0].score; }
+		if (rec_base < A.rec_cap) A.recs[rec_base] = base; else atomicExch(A.err, 5u);
+		A.rec_start[S->read] = (uint32_t)rec_base; A.rec_cnt[S->read] = 1;
+		return;
+	}
+	if (rec_base + n_maps > A.rec_cap) { atomicExch(A.err, 5u); A.rec_cnt[S->read] = 0; return; }
+	for (uint32_t m = 0; m < n_maps; ++m) {
+		const uint32_t cid = A.recs[rec_base + m].c_id;
+		const dev_reg_t g = r[cid];
+		rh_map_rec_t o = base;
+		o.c_id = cid; o.cm = g.cnt; o.nc = (int32_t)n_regs; o.s1 = g.score;
+		o.read_length = P.sig_target ? offset : (uint32_t)__fmul_rn(scale, (float)g.qe);
+		o.ref_id = (uint32_t)g.rid;
+		o.read_start_position = P.sig_target ? (uint32_t)g.qs : (uint32_t)__fmul_rn(scale, (float)g.qs);
+		o.read_end_position = P.sig_target ? (uint32_t)g.qe : (uint32_t)__fmul_rn(scale, (float)g.qe);
+		o.fragment_start_position = g.rev ? (uint32_t)(A.seq_len[g.rid] + 1 - g.re) : (uint32_t)g.rs;
+		o.fragment_length = (uint32_t)(g.re - g.rs + 1);
+		o.mapq = (uint8_t)g.mapq; o.rev = g.rev ? 1 : 0; o.mapped = 1;
+		A.recs[rec_base + m] = o;
+	}
+	A.rec_start[S->read] = (uint32_t)rec_base; A.rec_cnt[S->read] = n_maps;
+}
+
+#endif

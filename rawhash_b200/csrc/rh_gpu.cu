@@ -25,6 +25,7 @@
 #include "rh_host.h"
 #include "rh_kernels.cuh"
 #include "rh_anchor_sort.cuh"
+#include "rh_chain_finish.cuh"
 
 #define CUDA_TRY(call)                                                                                   \
 	do {                                                                                                 \
@@ -218,7 +219,7 @@ int run_round(rh_gpu_ctx *c, round_io &io, int carry_in_idx)
 		c->st.h2d_bytes += gn * sizeof(slot_t);
 		a2.slots = c->d_slots.p + g0; a2.n_slots = gn;
 		a3.slots = c->d_slots.p + g0; a3.n_slots = gn;
-		const uint32_t gw = (gn * RH_WARP + 255) / 256, gt = (gn + 63) / 64;
+		const uint32_t gw = (gn * RH_WARP + 255) / 256;
 		{ span_guard g(c, T_SEED); k_seed_expand<<<gw, 256, 0, s>>>(a2, c->I, c->D); }
 		sort_args_t as; as.slots = a3.slots; as.n_slots = gn; as.arena = c->d_arena.p;
 		{ span_guard g(c, T_SORT); k_sort_block<<<gn, SORT_THREADS, 0, s>>>(as); }
@@ -233,8 +234,7 @@ int run_round(rh_gpu_ctx *c, round_io &io, int carry_in_idx)
 			}
 		}
 		{ span_guard g(c, T_CHAIN); k_chain_dp<<<gn, DP_THREADS, 0, s>>>(a3, c->D); }
-		{ span_guard g(c, T_CHAIN); k_chain_backtrack<<<gt, 64, 0, s>>>(a3, c->D); }
-		{ span_guard g(c, T_POST); k_regions<<<gt, 64, 0, s>>>(a3, c->D); }
+		{ span_guard g(c, T_POST); k_chain_finish<<<(gn + FIN_WARPS - 1) / FIN_WARPS, FIN_WARPS * 32, 0, s>>>(a3, c->D); }
 		if (io.tap) {
 			CUDA_TRY(cudaMemcpyAsync(io.slots.data(), c->d_slots.p, sizeof(slot_t), cudaMemcpyDeviceToHost, s));
 			CUDA_TRY(cudaStreamSynchronize(s));
@@ -576,7 +576,8 @@ extern "C" int rh_gpu_tap_read(rh_gpu_ctx *c, const int16_t *raw, uint64_t raw_l
 			const uint8_t *base = c->d_arena.p + r.a_off;
 			if (r.n_u) CUDA_TRY(cudaMemcpyAsync(tap->u + toff[3], base + 80 * n, r.n_u * 8, cudaMemcpyDeviceToHost, s));   /* slot_mem: U  */
 			if (r.n_v) CUDA_TRY(cudaMemcpyAsync(tap->chain_a + 2 * toff[4], base, (size_t)r.n_v * 16, cudaMemcpyDeviceToHost, s)); /* A */
-			if (r.n_regs) CUDA_TRY(cudaMemcpyAsync(regs.data(), base + 96 * n, r.n_regs * sizeof(dev_reg_t), cudaMemcpyDeviceToHost, s));
+			const uint64_t reg_cap = (48 * n + 1024) / sizeof(dev_reg_t); /* slot_mem::regs, upper half (k_chain_finish) */
+			if (r.n_regs) CUDA_TRY(cudaMemcpyAsync(regs.data(), base + 96 * n + (reg_cap / 2) * sizeof(dev_reg_t), r.n_regs * sizeof(dev_reg_t), cudaMemcpyDeviceToHost, s));
 		}
 		CUDA_TRY(cudaStreamSynchronize(s));
 		if (r.n_v) CUDA_TRY(cudaMemcpy(tap->prev_a + 2 * toff[4], c->d_carry[(cc & 1) ^ 1].p + rs.prev_off, (size_t)r.n_v * 16, cudaMemcpyDeviceToHost));

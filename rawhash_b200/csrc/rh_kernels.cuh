@@ -6,10 +6,10 @@
  *   k_signal_to_seeds   src/revent.c:221-316 + src/rsketch.c:143-204   (the fused metric kernel)
  *   k_seed_count        src/rseed.c:60-154 + src/rindex.c:497-514      lookup, occ filter, rep_len
  *   k_seed_expand       src/rmap.cpp:74-116       anchors from position lists + previous chunk's
- *   k_anchor_sort       src/ksort.h:101-151       exact klib radix sort (tie order matters)
+ *   k_sort_block/_ties  src/ksort.h:101-151       anchor sort with klib's exact tie order (rh_anchor_sort.cuh)
  *   k_chain_dp          src/lchain.c:385-505      chaining DP
- *   k_chain_backtrack   src/lchain.c:95-281       backtrack + compaction
- *   k_regions           src/hit.c:100-150,195-263,338-367,502-539 + src/rmap.cpp:423-586
+ *   k_chain_finish      src/lchain.c:95-281, src/hit.c:100-150,195-263,338-367,502-539,
+ *                       src/rmap.cpp:423-586      backtrack, regions, MAPQ, stop rules (rh_chain_finish.cuh)
  *
  * Work decomposition: a "slot" is one (read, chunk) pair of the current chunk round.
  */
@@ -470,10 +470,6 @@ __global__ void __launch_bounds__(256) k_seed_expand(k2_args_t A, dev_index_t I,
 	for (uint32_t k = lane; k < pn; k += RH_WARP) out[n_new + k] = pv[k];
 }
 
-/* =============================================================================================
- * K3..K6: one thread per slot (v1).  Every step below is order-dependent inside a chunk;
- * throughput comes from the number of chunks in flight.
- * ===========================================================================================*/
 struct k3_args_t {
 	slot_t *slots; uint32_t n_slots;
 	read_state_t *rs;
@@ -554,305 +550,6 @@ __global__ void __launch_bounds__(DP_THREADS) k_chain_dp(k3_args_t A, dev_params
 			if (band_best < 0 || (ix - a[band_best].x <= (uint64_t)(int64_t)max_t && f[band_best] < f[i])) band_best = i;
 		}
 	}
-}
-
-/* mg_chain_backtrack + compact_a, reference src/lchain.c:95-281 */
-__global__ void __launch_bounds__(64) k_chain_backtrack(k3_args_t A, dev_params_t P)
-{
-	const uint32_t id = blockIdx.x * blockDim.x + threadIdx.x;
-	if (id >= A.n_slots) return;
-	slot_t *S = &A.slots[id];
-	read_state_t *R = &A.rs[S->read];
-	S->n_u = 0; S->n_v = 0;
-	if (S->gated) { /* chunk skipped by the min_events gate: carried anchors stay for the next chunk */
-		const uint32_t pn = R->prev_n;
-		if (pn) {
-			const unsigned long long o = atomicAdd(A.carry_top, (unsigned long long)pn);
-			if (o + pn > A.carry_cap) { atomicExch(A.err, 2u); R->prev_n = 0; return; }
-			const anchor_t *src = (const anchor_t *)(A.arena + S->a_off) + pn; /* slot_mem::B (n_anchors == prev_n here) */
-			for (uint32_t k = 0; k < pn; ++k) A.carry_out[o + k] = src[k];
-			R->prev_off = o;
-		}
-		return;
-	}
-	R->prev_n = 0; /* consumed by collect_seed_hits */
-	const int32_t n = (int32_t)S->n_anchors;
-	if (n == 0) return;
-	slot_mem_t M = slot_mem(A.arena, S->a_off, S->n_anchors);
-	anchor_t *a = M.A, *b = M.B, *z = M.Z, *w = M.W;
-	int32_t *f = M.f, *p = M.p, *v = M.v, *t = M.t;
-	uint64_t *u = M.U, *u2 = M.U2;
-	const int32_t min_sc = P.min_sc, min_cnt = P.min_cnt, max_drop = P.bw;
-	uint32_t n_z = 0;
-	for (int32_t i = 0; i < n; ++i) if (f[i] >= min_sc) { z[n_z].x = (uint64_t)(int64_t)f[i]; z[n_z].y = (uint64_t)i; ++n_z; }
-	if (n_z == 0) return;
-	seq_klib_sort(z, n_z, key_of_anchor_x(), (sort_seg_t *)b);
-	for (int32_t i = 0; i < n; ++i) t[i] = 0;
-	uint32_t n_u = 0, n_v = 0;
-	for (int64_t k = (int64_t)n_z - 1; k >= 0; --k) {
-		const int32_t i0 = (int32_t)z[k].y, zs = (int32_t)z[k].x;
-		if (t[i0] != 0) continue;
-		int32_t end_i = -1, max_i = i0, c = i0, max_s = 0; /* mg_chain_bk_end, lchain.c:47-75 */
-		do {
-			t[c] = 2;
-			end_i = c = p[c];
-			const int32_t s = c < 0 ? zs : zs - f[c];
-			if (s > max_s) { max_s = s; max_i = c; }
-			else if (max_s - s > max_drop) break;
-		} while (c >= 0 && t[c] == 0);
-		for (c = i0; c >= 0 && c != end_i; c = p[c]) t[c] = 0;
-		const uint32_t n_v0 = n_v;
-		for (c = i0; c != max_i; c = p[c]) { v[n_v++] = c; t[c] = 1; }
-		const int32_t sc = c < 0 ? zs : zs - f[c];
-		if (sc >= min_sc && n_v > n_v0 && (int32_t)(n_v - n_v0) >= min_cnt) u[n_u++] = (uint64_t)sc << 32 | (n_v - n_v0);
-		else n_v = n_v0;
-	}
-	if (n_u == 0) return;
-	/* compact: chain anchors in forward order; that order is also next chunk's prev_anchors */
-	const unsigned long long co = atomicAdd(A.carry_top, (unsigned long long)n_v);
-	const bool carry_ok = co + n_v <= A.carry_cap;
-	if (!carry_ok) atomicExch(A.err, 2u);
-	uint32_t k = 0;
-	for (uint32_t ci = 0; ci < n_u; ++ci) {
-		const uint32_t ni = (uint32_t)u[ci], k0 = k;
-		for (uint32_t j = 0; j < ni; ++j) {
-			const anchor_t x = a[v[k0 + (ni - j - 1)]];
-			b[k] = x;
-			if (carry_ok) A.carry_out[co + k] = x;
-			++k;
-		}
-	}
-	if (carry_ok) { R->prev_off = co; R->prev_n = n_v; }
-	k = 0;
-	for (uint32_t ci = 0; ci < n_u; ++ci) { w[ci].x = b[k].x; w[ci].y = (uint64_t)k << 32 | ci; k += (uint32_t)u[ci]; }
-	seq_klib_sort(w, n_u, key_of_anchor_x(), (sort_seg_t *)z);
-	k = 0;
-	for (uint32_t ci = 0; ci < n_u; ++ci) {
-		const uint32_t j = (uint32_t)w[ci].y, cnt = (uint32_t)u[j];
-		u2[ci] = u[j];
-		const anchor_t *src = b + (w[ci].y >> 32);
-		for (uint32_t q = 0; q < cnt; ++q) a[k + q] = src[q];
-		k += cnt;
-	}
-	for (uint32_t ci = 0; ci < n_u; ++ci) u[ci] = u2[ci];
-	S->n_u = n_u; S->n_v = n_v;
-}
-
-/* regions + primary/secondary + MAPQ + the per-chunk stop rules and final record
- * (hit.c:100-150,195-263,338-367,502-539; rmap.cpp:423-586) */
-__device__ __forceinline__ float logf_exact(const k3_args_t &A, int32_t x, uint32_t *flag)
-{ /* glibc logf of an integer argument, tabulated on the host so MAPQ is bit-identical */
-	if (x >= 0 && (uint32_t)x < A.logf_n) return A.logf_tab[x];
-	*flag = 1;
-	return logf((float)x);
-}
-
-__global__ void __launch_bounds__(64) k_regions(k3_args_t A, dev_params_t P)
-{
-	const uint32_t id = blockIdx.x * blockDim.x + threadIdx.x;
-	if (id >= A.n_slots) return;
-	slot_t *S = &A.slots[id];
-	read_state_t *R = &A.rs[S->read];
-	uint32_t n_regs = 0;
-	dev_reg_t *r = nullptr;
-	uint32_t inexact = 0;
-	if (!S->gated && S->n_anchors > 0 && S->n_u > 0) {
-		slot_mem_t M = slot_mem(A.arena, S->a_off, S->n_anchors);
-		const anchor_t *a = M.A;
-		const uint64_t *u = M.U;
-		anchor_t *z = M.Z;
-		r = M.regs;
-		const uint32_t n_u = S->n_u;
-		if (n_u > M.reg_cap) { atomicExch(A.err, 3u); S->n_regs = 0; return; }
-		const uint32_t hash = wang32(wang32(R->ev_offset + S->n_events) + wang32(11u)); /* rmap.cpp:346-348 */
-		uint32_t k = 0;
-		for (uint32_t i = 0; i < n_u; ++i) {
-			const uint32_t h = (uint32_t)mix64((mix64(a[k].x) + mix64(a[k].y)) ^ hash);
-			z[i].x = u[i] ^ h; z[i].y = (uint64_t)k << 32 | (uint32_t)u[i];
-			k += (uint32_t)u[i];
-		}
-		seq_klib_sort(z, n_u, key_of_anchor_x(), (sort_seg_t *)M.B);
-		for (uint32_t i = 0; i < n_u; ++i) { /* descending score */
-			const anchor_t zz = z[n_u - 1 - i];
-			dev_reg_t g;
-			g.id = (int32_t)i; g.parent = -1; g.subsc = 0; g.n_sub = 0; g.mapq = 0;
-			g.score = g.score0 = (int32_t)(zz.x >> 32); g.hash = (uint32_t)zz.x;
-			g.cnt = (int32_t)zz.y; g.as = (int32_t)(zz.y >> 32);
-			const anchor_t fa = a[g.as], la = a[g.as + g.cnt - 1];
-			g.rev = (uint32_t)(fa.x >> 63); g.rid = (int32_t)(fa.x << 1 >> 33);
-			g.rs = (int32_t)fa.x; g.re = (int32_t)la.x + 1; g.qs = (int32_t)fa.y; g.qe = (int32_t)la.y + 1;
-			r[i] = g;
-		}
-		n_regs = n_u;
-		/* mm_set_parent (hit.c:195-263); w[] and cov[] live in the slot's scratch */
-		int *wl = (int *)M.p; uint64_t *cov = M.U2;
-		wl[0] = 0; r[0].parent = 0;
-		int kk = 1;
-		for (int i = 1; i < (int)n_regs; ++i) {
-			dev_reg_t *ri = &r[i];
-			const int si = ri->qs, ei = ri->qe;
-			int n_cov = 0, uncov = 0, j;
-			for (j = 0; j < kk; ++j) {
-				const dev_reg_t *rp = &r[wl[j]];
-				int sj = rp->qs, ej = rp->qe;
-				if (ej <= si || sj >= ei) continue;
-				if (sj < si) sj = si;
-				if (ej > ei) ej = ei;
-				cov[n_cov++] = (uint64_t)sj << 32 | (uint32_t)ej;
-			}
-			j = kk;
-			if (n_cov > 0) {
-				int x = si;
-				seq_klib_sort(cov, (uint32_t)n_cov, key_of_u64(), (sort_seg_t *)M.B);
-				for (int c = 0; c < n_cov; ++c) {
-					if ((int)(cov[c] >> 32) > x) uncov += (int)(cov[c] >> 32) - x;
-					x = (int32_t)cov[c] > x ? (int32_t)cov[c] : x;
-				}
-				if (ei > x) uncov += ei - x;
-				for (j = 0; j < kk; ++j) {
-					dev_reg_t *rp = &r[wl[j]];
-					const int sj = rp->qs, ej = rp->qe;
-					if (ej <= si || sj >= ei) continue;
-					const int mn = ej - sj < ei - si ? ej - sj : ei - si;
-					const int mx = ej - sj > ei - si ? ej - sj : ei - si;
-					const int ol = si < sj ? (ei < sj ? 0 : ei < ej ? ei - sj : ej - sj) : (ej < si ? 0 : ej < ei ? ej - si : ei - si);
-					if (__fsub_rn(__fdiv_rn((float)ol, (float)mn), __fdiv_rn((float)uncov, (float)mx)) > P.mask_level && uncov <= P.mask_len) {
-						ri->parent = rp->parent;
-						rp->subsc = rp->subsc > ri->score ? rp->subsc : ri->score;
-						if (ri->cnt >= rp->cnt) ++rp->n_sub;
-						break;
-					}
-				}
-			}
-			if (j == kk) { wl[kk++] = i; ri->parent = i; ri->n_sub = 0; }
-		}
-		/* mm_select_sub + mm_sync_regs (hit.c:338-367, 312-336) */
-		if (!P.ava && P.pri_ratio > 0.0f) {
-			int kept = 0, n2 = 0;
-			const int nn = (int)n_regs;
-			for (int i = 0; i < nn; ++i) {
-				const int pp = r[i].parent;
-				bool keep = false;
-				if (pp == i) keep = true;
-				else if ((float)r[i].score >= __fmul_rn((float)r[pp].score, P.pri_ratio) && n2 < P.best_n) {
-					if (!(r[i].qs == r[pp].qs && r[i].qe == r[pp].qe && r[i].rid == r[pp].rid && r[i].rs == r[pp].rs && r[i].re == r[pp].re)) { keep = true; ++n2; }
-				} else if (n2 < P.best_n && r[i].score > P.min_strand_sc && r[i].rev != r[pp].rev) { keep = true; ++n2; }
-				if (keep) r[kept++] = r[i];
-			}
-			if (kept != nn) {
-				int *tmp = (int *)M.v;
-				int max_id = -1;
-				for (int i = 0; i < kept; ++i) max_id = max_id > r[i].id ? max_id : r[i].id;
-				for (int i = 0; i <= max_id; ++i) tmp[i] = -1;
-				for (int i = 0; i < kept; ++i) if (r[i].id >= 0) tmp[r[i].id] = i;
-				for (int i = 0; i < kept; ++i) {
-					dev_reg_t *g = &r[i];
-					g->id = i;
-					if (g->parent == -2) g->parent = i;
-					else if (g->parent >= 0 && g->parent <= max_id && tmp[g->parent] >= 0) g->parent = tmp[g->parent];
-					else g->parent = -1;
-				}
-			}
-			n_regs = (uint32_t)kept;
-		}
-		/* mm_set_mapq (hit.c:502-539), float/double sequence of the compiled reference */
-		{
-			long long sum_sc = 0;
-			for (uint32_t i = 0; i < n_regs; ++i) if (r[i].parent == r[i].id) sum_sc += r[i].score;
-			const float uniq = __fdiv_rn((float)sum_sc, (float)(sum_sc + (long long)S->rep_len));
-			for (uint32_t i = 0; i < n_regs; ++i) {
-				dev_reg_t *g = &r[i];
-				const double s1 = g->score > 100 ? 1.0 : __dmul_rn(0.01, (double)g->score);
-				const float pen_s1 = __double2float_rn(__dmul_rn(s1, (double)uniq));
-				float pen_cm = g->cnt > 10 ? 1.0f : __fmul_rn(0.1f, (float)g->cnt);
-				pen_cm = pen_s1 < pen_cm ? pen_s1 : pen_cm;
-				const int subsc = g->subsc > P.min_sc ? g->subsc : P.min_sc;
-				const float x = __fdiv_rn((float)subsc, (float)g->score0);
-				const float lead = __fmul_rn(__fmul_rn(__fmul_rn(pen_cm, 40.0f), __fsub_rn(1.0f, x)), logf_exact(A, g->score, &inexact));
-				int mapq = (int)lead;
-				mapq -= (int)__fmaf_rn(logf_exact(A, g->n_sub + 1, &inexact), 4.343f, .499f);
-				mapq = mapq > 0 ? mapq : 0;
-				g->mapq = mapq < 60 ? mapq : 60;
-			}
-		}
-	}
-	if (inexact) atomicExch(A.err, 4u);
-	S->n_regs = n_regs;
-	if (!S->gated) R->ev_offset += S->n_events;
-	if (A.tap) return;
-
-	/* ---- stop rules after this chunk (rmap.cpp:423-500) ---- */
-	const uint32_t qlen = R->l_sig;
-	const uint32_t l_chunk = (P.chunk_size > qlen || P.noadapt) ? qlen : P.chunk_size;
-	const uint32_t max_chunk = P.noadapt ? 1u : P.max_num_chunk;
-	uint32_t c_count = S->c_count;
-	unsigned long long rec_base = 0; uint32_t n_maps = 0;
-	auto push_map = [&](uint32_t cid) {
-		/* records are appended with a bump allocator; one thread writes one read's block contiguously */
-		if (n_maps == 0) rec_base = atomicAdd(A.rec_top, (unsigned long long)(P.ava ? (n_regs ? n_regs : 1u) : 1u));
-		if (rec_base + n_maps < A.rec_cap) A.recs[rec_base + n_maps].c_id = cid;
-		++n_maps;
-	};
-	bool stop = false;
-	if (n_regs == 1 && (int)r[0].mapq >= P.min_mapq) { push_map(0); stop = true; }
-	if (!stop) {
-		float meanC = 0.0f, meanQ = 0.0f;
-		for (uint32_t i = 0; i < n_regs; ++i) { meanC = __fadd_rn(meanC, (float)r[i].score); meanQ = __fadd_rn(meanQ, (float)r[i].mapq); }
-		if (n_regs > 0) { meanC = __fdiv_rn(meanC, (float)n_regs); meanQ = __fdiv_rn(meanQ, (float)n_regs); }
-		const uint32_t n_chains = (P.ava || n_regs < 1) ? n_regs : 1u;
-		for (uint32_t ic = 0; ic < n_chains; ++ic) {
-			float weighted = 0.0f;
-			const float bestQ = (float)r[ic].mapq, bestC = (float)r[ic].score;
-			if (!P.ava) {
-				float r_q = bestQ > 0 ? __fdiv_rn(bestQ, 30.0f) : 0.0f; if (r_q > 1) r_q = 1.0f;
-				float r_mq = bestQ > 0 ? __fsub_rn(1.0f, __fdiv_rn(meanQ, bestQ)) : 0.0f; if (r_mq < 0) r_mq = 0.0f;
-				float r_mc = bestC > 0 ? __fsub_rn(1.0f, __fdiv_rn(meanC, bestC)) : 0.0f; if (r_mc < 0) r_mc = 0.0f;
-				weighted = __fmaf_rn(r_mc, P.w_bestmc, __fmaf_rn(r_q, P.w_bestq, __fmul_rn(P.w_bestmq, r_mq)));
-			}
-			if (weighted >= P.w_threshold || (P.ava && r[ic].score >= P.min_sc2)) push_map(ic);
-		}
-		if (n_maps > 0) stop = true;
-	}
-	bool exhausted = false;
-	if (!stop) { /* loop increment: s_qs += l_chunk, ++c_count; continue while s_qs < qlen && c_count < max_chunk */
-		const uint64_t s_qs_next = (uint64_t)(c_count + 1) * l_chunk;
-		++c_count;
-		if (!(s_qs_next < qlen && c_count < max_chunk)) { exhausted = true; if (c_count > 0) --c_count; /* rmap.cpp:507 */ }
-	}
-	if (!stop && !exhausted) return; /* next round continues this read */
-
-	/* ---- final record(s) (rmap.cpp:507-586) ---- */
-	R->done = 1;
-	const uint32_t offset = R->ev_offset;
-	const float scale = offset == 0 ? 0.0f : (P.sample_per_base == 0.0f ? 0.0f :
-		__fdiv_rn(__fdiv_rn(__fmul_rn((float)(c_count + 1), (float)l_chunk), (float)offset), P.sample_per_base));
-	if (n_maps == 0 && n_regs > 0 && (int)r[0].mapq > P.min_mapq) push_map(0);
-	rh_map_rec_t base; memset(&base, 0, sizeof(base));
-	base.read_idx = S->read; base.ci = c_count + 1; base.sl = qlen;
-	if (n_maps == 0) {
-		rec_base = atomicAdd(A.rec_top, 1ULL);
-		base.read_length = P.sig_target ? offset : (uint32_t)__fmul_rn(scale, (float)offset);
-		if (n_regs >= 1) { base.cm = r[0].cnt; base.nc = (int32_t)n_regs; base.s1 = r[0].score; }
-		if (rec_base < A.rec_cap) A.recs[rec_base] = base; else atomicExch(A.err, 5u);
-		A.rec_start[S->read] = (uint32_t)rec_base; A.rec_cnt[S->read] = 1;
-		return;
-	}
-	if (rec_base + n_maps > A.rec_cap) { atomicExch(A.err, 5u); A.rec_cnt[S->read] = 0; return; }
-	for (uint32_t m = 0; m < n_maps; ++m) {
-		const uint32_t cid = A.recs[rec_base + m].c_id;
-		const dev_reg_t g = r[cid];
-		rh_map_rec_t o = base;
-		o.c_id = cid; o.cm = g.cnt; o.nc = (int32_t)n_regs; o.s1 = g.score;
-		o.read_length = P.sig_target ? offset : (uint32_t)__fmul_rn(scale, (float)g.qe);
-		o.ref_id = (uint32_t)g.rid;
-		o.read_start_position = P.sig_target ? (uint32_t)g.qs : (uint32_t)__fmul_rn(scale, (float)g.qs);
-		o.read_end_position = P.sig_target ? (uint32_t)g.qe : (uint32_t)__fmul_rn(scale, (float)g.qe);
-		o.fragment_start_position = g.rev ? (uint32_t)(A.seq_len[g.rid] + 1 - g.re) : (uint32_t)g.rs;
-		o.fragment_length = (uint32_t)(g.re - g.rs + 1);
-		o.mapq = (uint8_t)g.mapq; o.rev = g.rev ? 1 : 0; o.mapped = 1;
-		A.recs[rec_base + m] = o;
-	}
-	A.rec_start[S->read] = (uint32_t)rec_base; A.rec_cnt[S->read] = n_maps;
 }
 
 #endif

@@ -16,8 +16,11 @@ def _setup(world, preset="sensitive", r10=False, **over):
     idx = api.Index.build(P, pore, names, seqs, 8)
     idx.update_mapopt(P)
     orc = OracleLib().open(preset, r10, world.model)
+    if "sample_rate" in over:
+        orc.set_sampling(over["sample_rate"], over["bp_per_sec"])
     orc.build_index(world.fasta, "", 4)
-    assert orc.mapopt_update() == P.mid_occ
+    if "mid_occ" not in over:
+        assert orc.mapopt_update() == P.mid_occ
     return api, P, idx, orc
 
 
@@ -48,3 +51,92 @@ def test_paf_matches_oracle(built):
     st = m.stats()
     assert st["kernel_launches"] > 0 and st["n_reads"] == len(w.names)
     m.close()
+
+
+def _check_paf(world, preset="sensitive", r10=False, extra_raw=None, arena=2 << 30, **over):
+    from rawhash_b200 import synth
+    from _bind import strip_mt
+    api, P, idx, orc = _setup(world, preset, r10, **over)
+    raws = list(world.reads["raw"]); names = list(world.names)
+    if extra_raw:
+        for k, r in enumerate(extra_raw):
+            raws.append(r); names.append(f"extra_{k:03d}")
+    n = len(raws)
+    cal = (np.full(n, synth.OFFSET), np.full(n, synth.RANGE), np.full(n, synth.DIGITISATION))
+    m = api.Mapper(idx, P, 0, arena)
+    recs = m.map_batch(raws, *cal, names)
+    got = strip_mt(idx.format_paf(recs, names)).splitlines()
+    exp, _ = orc.map_paf([synth.raw_to_pa(r, synth.OFFSET, synth.RANGE, synth.DIGITISATION) for r in raws], names, 4)
+    exp = strip_mt(exp).splitlines()
+    m.close()
+    assert len(got) == len(exp)
+    bad = [(g, e) for g, e in zip(got, exp) if g != e]
+    assert not bad, f"{len(bad)} of {len(exp)} PAF lines differ, first: {bad[0]}"
+    return recs
+
+
+def _repeat_genome(unit=3000, copies=40, flank=100_000, seed=9):
+    """Tandem repeats: reads from them produce many anchors with identical target position
+    (equal sort keys), exercising klib's tie order."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    u = rng.integers(0, 4, unit, dtype=np.uint8)
+    left = rng.integers(0, 4, flank, dtype=np.uint8); right = rng.integers(0, 4, flank, dtype=np.uint8)
+    # a short internal tandem duplication inside the unit makes reads repeat their own hashes
+    u[1000:1400] = u[600:1000]
+    return [("rep1", np.concatenate([left] + [u] * copies + [right])), ("chr2", rng.integers(0, 4, 150_000, dtype=np.uint8))]
+
+
+def test_tie_order_on_repeats(built):
+    """Equal anchor keys and equal chain scores: tap every stage on reads from a tandem-repeat locus."""
+    from rawhash_b200 import synth
+    w = World(n_contigs=2, genome_len=200_000, n_reads=2, read_bp=1000, seed=3)
+    w.genome = _repeat_genome()
+    w.fasta = "/tmp/rh_world_repeat.fa"
+    synth.write_fasta(w.fasta, w.genome)
+    # reads sampled inside the repeat array
+    import numpy as _np
+    w.reads = synth.make_reads([("rep1", w.genome[0][1][100_000:220_000])], 10, 4000, w.k, w.means, w.stdv, seed=11)
+    w.names = w.reads["names"]
+    api, P, idx, orc = _setup(w, mid_occ=2000)
+    orc.set_mid_occ(2000)
+    m = api.Mapper(idx, P, 0, 2 << 30)
+    n_ties = 0
+    for i in range(len(w.names)):
+        got = m.tap_read(w.reads["raw"][i], synth.OFFSET, synth.RANGE, synth.DIGITISATION, w.names[i])
+        exp = orc.tap_read(w.pa(i), w.names[i])
+        assert tap_equal(got, exp) == [], f"read {i}"
+        for c in exp:
+            x = c["anchors"][:, 0]
+            n_ties += int((x[1:] == x[:-1]).sum())
+    m.close()
+    assert n_ties > 0, "test world produced no equal keys"
+
+
+@pytest.mark.parametrize("preset", ["sensitive", "fast", "viral"])
+def test_presets_paf(built, preset):
+    w = World(n_contigs=4, genome_len=2_000_000 if preset != "viral" else 60_000, n_reads=150, read_bp=4000, seed=4)
+    _check_paf(w, preset)
+
+
+def test_unmappable_and_edge_reads(built):
+    """Reads from another genome (all 10 chunks, carried anchors, unmapped output), empty reads,
+    reads shorter than a chunk, reads whose samples are all outside (30,200) pA."""
+    from rawhash_b200 import synth
+    w = World(n_contigs=2, genome_len=800_000, n_reads=40, read_bp=6000, seed=6)
+    other = synth.make_genome(1, 300_000, seed=77)
+    alien = synth.make_reads(other, 40, 6000, w.k, w.means, w.stdv, seed=78)["raw"]
+    extra = alien + [np.zeros(0, np.int16), np.full(5000, 2000, np.int16), w.reads["raw"][0][:1500], w.reads["raw"][1][:300],
+                     w.reads["raw"][2][:4003]]
+    recs = _check_paf(w, "sensitive", extra_raw=extra)
+    assert (recs["mapped"] == 0).sum() > 0 and recs["ci"].max() == 10
+
+
+def test_r10_paf(built):
+    w = World(n_contigs=2, genome_len=600_000, n_reads=60, read_bp=3000, seed=8, kind="r10.4.1", sample_rate=5000.0, bp_per_sec=400.0)
+    _check_paf(w, "sensitive", r10=True, sample_rate=5000, bp_per_sec=400)
+
+
+def test_small_arena_groups(built):
+    """A tiny anchor arena forces the chunk round to run in several groups; results must not change."""
+    w = World(n_contigs=3, genome_len=1_000_000, n_reads=120, read_bp=5000, seed=2)
+    _check_paf(w, "sensitive", arena=48 << 20)
