@@ -192,7 +192,8 @@ def main():
     names = [f"read_{rank}_{i:07d}" for i in range(R)]
 
     free_b, _ = torch.cuda.mem_get_info()
-    mapper = api.Mapper(idx, P, local_rank, int(free_b * 0.55))
+    arena = int(float(os.environ["RH_ARENA_GB"]) * (1 << 30)) if "RH_ARENA_GB" in os.environ else int(free_b * 0.55)
+    mapper = api.Mapper(idx, P, local_rank, arena)
     stream = torch.cuda.Stream(device=dev)          # the library launches on this stream; torch events time it
     torch.cuda.set_stream(stream)
     mapper.set_stream(stream.cuda_stream)

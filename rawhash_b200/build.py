@@ -25,7 +25,7 @@ NVCC_FLAGS = [
     "-shared",
 ]
 SOURCES = ["rh_gpu.cu", "rh_host.cpp"]
-HEADERS = ["rh_dev.cuh", "rh_sort.cuh", "rh_kernels.cuh", "rh_host.h", os.path.join(ROOT, "include", "rawhash_b200.h")]
+HEADERS = sorted(f for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))) + [os.path.join(ROOT, "include", "rawhash_b200.h")]
 
 
 def _newer(target, deps):

@@ -133,17 +133,171 @@ __device__ __forceinline__ float logf_tab(const k3_args_t &A, int32_t x, uint32_
 	return logf((float)x);
 }
 
-__global__ void __launch_bounds__(FIN_WARPS * 32) k_chain_finish(k3_args_t A, dev_params_t P)
+
+#define FIN_BITS 8192             /* query (event) coordinates covered by the shared-memory bitset */
+#define FIN_PCAP 64               /* primaries cached in shared memory                              */
+struct prim_cache_t { int qs[FIN_PCAP], qe[FIN_PCAP], idx[FIN_PCAP], subsc[FIN_PCAP], nsub[FIN_PCAP], cnt[FIN_PCAP]; };
+
+/* mm_set_parent (hit.c:195-263), general form: overlaps clipped and sorted, as the reference does. */
+__device__ void set_parent_general(dev_reg_t *r, uint32_t n_regs, const dev_params_t &P, const slot_mem_t &M, uint32_t lane)
+{
+	const uint32_t FULL = 0xffffffffu;
+	int *wl = (int *)M.p; uint64_t *cov = M.U2;
+	if (lane == 0) { wl[0] = 0; r[0].parent = 0; }
+	__syncwarp();
+	int kk = 1;
+	for (int i = 1; i < (int)n_regs; ++i) {
+		const int si = r[i].qs, ei = r[i].qe;
+		int n_cov = 0;
+		for (int j0 = 0; j0 < kk; j0 += 32) {
+			const int j = j0 + (int)lane;
+			bool ov = false; int sj = 0, ej = 0;
+			if (j < kk) { const dev_reg_t *rp = &r[wl[j]]; sj = rp->qs; ej = rp->qe; ov = !(ej <= si || sj >= ei); }
+			const uint32_t m = __ballot_sync(FULL, ov);
+			if (ov) { if (sj < si) sj = si; if (ej > ei) ej = ei; cov[n_cov + __popc(m & lanemask_lt())] = (uint64_t)sj << 32 | (uint32_t)ej; }
+			n_cov += __popc(m);
+		}
+		__syncwarp();
+		int hit = -1, uncov = 0;
+		if (n_cov > 0) {
+			if (lane == 0) {
+				int x = si;
+				seq_klib_sort(cov, (uint32_t)n_cov, key_of_u64(), (sort_seg_t *)M.B);
+				for (int c = 0; c < n_cov; ++c) {
+					if ((int)(cov[c] >> 32) > x) uncov += (int)(cov[c] >> 32) - x;
+					x = (int32_t)cov[c] > x ? (int32_t)cov[c] : x;
+				}
+				if (ei > x) uncov += ei - x;
+			}
+			uncov = __shfl_sync(FULL, uncov, 0);
+			for (int j0 = 0; j0 < kk && hit < 0; j0 += 32) {
+				const int j = j0 + (int)lane;
+				bool sec = false;
+				if (j < kk) {
+					const dev_reg_t *rp = &r[wl[j]];
+					const int sj = rp->qs, ej = rp->qe;
+					if (!(ej <= si || sj >= ei)) {
+						const int mn = ej - sj < ei - si ? ej - sj : ei - si;
+						const int mx = ej - sj > ei - si ? ej - sj : ei - si;
+						const int ol = si < sj ? (ei < sj ? 0 : ei < ej ? ei - sj : ej - sj) : (ej < si ? 0 : ej < ei ? ej - si : ei - si);
+						sec = __fsub_rn(__fdiv_rn((float)ol, (float)mn), __fdiv_rn((float)uncov, (float)mx)) > P.mask_level && uncov <= P.mask_len;
+					}
+				}
+				const uint32_t m = __ballot_sync(FULL, sec);
+				if (m) hit = j0 + __ffs(m) - 1;
+			}
+		}
+		if (lane == 0) {
+			dev_reg_t *ri = &r[i];
+			if (hit >= 0) {
+				dev_reg_t *rp = &r[wl[hit]];
+				ri->parent = rp->parent;
+				rp->subsc = rp->subsc > ri->score ? rp->subsc : ri->score;
+				if (ri->cnt >= rp->cnt) ++rp->n_sub;
+			} else { wl[kk] = i; ri->parent = i; ri->n_sub = 0; }
+		}
+		if (hit < 0) ++kk;
+		__syncwarp();
+	}
+}
+
+/* Same function for the common case (query coordinates < FIN_BITS, few primaries): the union of
+ * the primaries' query intervals is a bitset in shared memory, so the uncovered length of region
+ * i is a popcount, and the primaries' fields live in shared memory instead of behind two
+ * dependent global loads.  The uncovered length equals the reference's sorted-interval sweep
+ * because all coordinates are integers. */
+__device__ bool set_parent_bitset(dev_reg_t *r, uint32_t n_regs, const dev_params_t &P, uint32_t *bits, prim_cache_t *pc, uint32_t lane)
+{
+	const uint32_t FULL = 0xffffffffu;
+	for (uint32_t w = lane; w < FIN_BITS / 32; w += 32) bits[w] = 0;
+	__syncwarp();
+	int kk = 0;
+	for (uint32_t i0 = 0; i0 < n_regs; i0 += 32) { /* 32 regions' fields are fetched at once */
+		const uint32_t ii = i0 + lane;
+		int my_qs = 0, my_qe = 0, my_score = 0, my_cnt = 0;
+		if (ii < n_regs) { const dev_reg_t g = r[ii]; my_qs = g.qs; my_qe = g.qe; my_score = g.score; my_cnt = g.cnt; }
+		const uint32_t nb = min(32u, n_regs - i0);
+		for (uint32_t b = 0; b < nb; ++b) {
+			const int i = (int)(i0 + b);
+			const int si = __shfl_sync(FULL, my_qs, b), ei = __shfl_sync(FULL, my_qe, b);
+			const int sci = __shfl_sync(FULL, my_score, b), cni = __shfl_sync(FULL, my_cnt, b);
+			/* covered positions of [si, ei) */
+			int covered = 0;
+			if (kk > 0 && ei > si) {
+				const int w0 = si >> 5, w1 = (ei - 1) >> 5;
+				for (int w = w0 + (int)lane; w <= w1; w += 32) {
+					uint32_t m = bits[w];
+					if (w == w0) m &= 0xffffffffu << (si & 31);
+					if (w == w1) m &= 0xffffffffu >> (31 - ((ei - 1) & 31));
+					covered += __popc(m);
+				}
+#pragma unroll
+				for (int o = 16; o > 0; o >>= 1) covered += __shfl_xor_sync(FULL, covered, o);
+			}
+			int hit = -1;
+			if (covered > 0) {
+				const int uncov = (ei - si) - covered;
+				for (int j0 = 0; j0 < kk && hit < 0; j0 += 32) {
+					const int j = j0 + (int)lane;
+					bool sec = false;
+					if (j < kk) {
+						int sj, ej;
+						sj = pc->qs[j]; ej = pc->qe[j];
+						if (!(ej <= si || sj >= ei)) {
+							const int mn = ej - sj < ei - si ? ej - sj : ei - si;
+							const int mx = ej - sj > ei - si ? ej - sj : ei - si;
+							const int ol = si < sj ? (ei < sj ? 0 : ei < ej ? ei - sj : ej - sj) : (ej < si ? 0 : ej < ei ? ej - si : ei - si);
+							sec = __fsub_rn(__fdiv_rn((float)ol, (float)mn), __fdiv_rn((float)uncov, (float)mx)) > P.mask_level && uncov <= P.mask_len;
+						}
+					}
+					const uint32_t m = __ballot_sync(FULL, sec);
+					if (m) hit = j0 + __ffs(m) - 1;
+				}
+			}
+			if (hit >= 0) {
+				if (lane == 0) {
+					r[i].parent = pc->idx[hit]; /* a primary's parent is itself */
+					pc->subsc[hit] = pc->subsc[hit] > sci ? pc->subsc[hit] : sci;
+					if (cni >= pc->cnt[hit]) ++pc->nsub[hit];
+				}
+			} else {
+				if (lane == 0) { pc->qs[kk] = si; pc->qe[kk] = ei; pc->idx[kk] = i; pc->subsc[kk] = 0; pc->nsub[kk] = 0; pc->cnt[kk] = cni; r[i].parent = i; }
+				if (ei > si) {
+					const int w0 = si >> 5, w1 = (ei - 1) >> 5;
+					for (int w = w0 + (int)lane; w <= w1; w += 32) {
+						uint32_t m = 0xffffffffu;
+						if (w == w0) m &= 0xffffffffu << (si & 31);
+						if (w == w1) m &= 0xffffffffu >> (31 - ((ei - 1) & 31));
+						bits[w] |= m;
+					}
+				}
+				++kk;
+			}
+			__syncwarp();
+			if (kk >= FIN_PCAP) return false; /* primary cache full: caller redoes the chunk with the general form */
+		}
+	}
+	__syncwarp();
+	/* write the primaries' accumulated fields back */
+	for (int j = (int)lane; j < kk; j += 32) { dev_reg_t *g = &r[pc->idx[j]]; g->subsc = pc->subsc[j]; g->n_sub = pc->nsub[j]; }
+	__syncwarp();
+	return true;
+}
+
+__global__ void __launch_bounds__(FIN_WARPS * 32, 8) k_chain_finish(k3_args_t A, dev_params_t P)
 {
 	__shared__ uint32_t s_cnt[FIN_WARPS][256];
 	__shared__ uint32_t s_head[FIN_WARPS][256];
+	__shared__ uint32_t s_bits[FIN_WARPS][FIN_BITS / 32];
+	__shared__ prim_cache_t s_pc[FIN_WARPS];
 	const uint32_t FULL = 0xffffffffu;
 	const uint32_t wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
 	const uint32_t slot_id = blockIdx.x * FIN_WARPS + wib;
 	if (slot_id >= A.n_slots) return;
 	slot_t *S = &A.slots[slot_id];
 	read_state_t *R = &A.rs[S->read];
-	uint32_t *cnt = s_cnt[wib], *head = s_head[wib];
+	uint32_t *cnt = s_cnt[wib], *head = s_head[wib], *bits = s_bits[wib];
+	prim_cache_t *pc = &s_pc[wib];
 
 	uint32_t n_u = 0, n_v = 0, n_regs = 0;
 	dev_reg_t *r = nullptr;
@@ -185,26 +339,36 @@ __global__ void __launch_bounds__(FIN_WARPS * 32) k_chain_finish(k3_args_t A, de
 			__syncwarp();
 			if (n_z > 0) {
 				warp_klib_sort_pairs(z, n_z, w, X, cnt, head, lane);
-				/* ---- backtrack, best score first (order dependent: lane 0) ---- */
-				if (lane == 0) {
-					for (int64_t k = (int64_t)n_z - 1; k >= 0; --k) {
-						const int32_t i0 = (int32_t)z[k].y, zs = (int32_t)z[k].x;
-						if (t[i0] != 0) continue;
-						int32_t end_i = -1, max_i = i0, c = i0, max_s = 0; /* mg_chain_bk_end */
-						do {
-							t[c] = 2;
-							end_i = c = p[c];
-							const int32_t s = c < 0 ? zs : zs - f[c];
-							if (s > max_s) { max_s = s; max_i = c; }
-							else if (max_s - s > max_drop) break;
-						} while (c >= 0 && t[c] == 0);
-						for (c = i0; c >= 0 && c != end_i; c = p[c]) t[c] = 0;
-						const uint32_t n_v0 = n_v;
-						for (c = i0; c != max_i; c = p[c]) { v[n_v++] = c; t[c] = 1; }
-						const int32_t sc = c < 0 ? zs : zs - f[c];
-						if (sc >= min_sc && n_v > n_v0 && (int32_t)(n_v - n_v0) >= min_cnt) u[n_u++] = (uint64_t)sc << 32 | (n_v - n_v0);
-						else n_v = n_v0;
+				/* ---- backtrack, best score first.  Visiting order matters, so lane 0 walks the chains;
+				 *      the test that skips candidates already swallowed by an earlier chain (the vast
+				 *      majority) is prefetched 32 candidates at a time.  t[] only ever goes 0 -> nonzero
+				 *      for good, so a nonzero prefetch is final and a zero one is re-read by lane 0. ---- */
+				for (int64_t kb = (int64_t)n_z - 1; kb >= 0; kb -= 32) {
+					const int64_t kq = kb - (int64_t)lane;
+					int32_t ci0 = 0, czs = 0; bool open = false;
+					if (kq >= 0) { const anchor_t e = z[kq]; ci0 = (int32_t)e.y; czs = (int32_t)e.x; open = t[ci0] == 0; }
+					uint32_t cand = __ballot_sync(FULL, open);
+					while (cand) {
+						const int bsel = __ffs(cand) - 1; cand &= cand - 1;
+						const int32_t i0 = __shfl_sync(FULL, ci0, bsel), zs = __shfl_sync(FULL, czs, bsel);
+						if (lane == 0 && t[i0] == 0) {
+							int32_t end_i = -1, max_i = i0, c = i0, max_s = 0; /* mg_chain_bk_end */
+							do {
+								t[c] = 2;
+								end_i = c = p[c];
+								const int32_t s = c < 0 ? zs : zs - f[c];
+								if (s > max_s) { max_s = s; max_i = c; }
+								else if (max_s - s > max_drop) break;
+							} while (c >= 0 && t[c] == 0);
+							for (c = i0; c >= 0 && c != end_i; c = p[c]) t[c] = 0;
+							const uint32_t n_v0 = n_v;
+							for (c = i0; c != max_i; c = p[c]) { v[n_v++] = c; t[c] = 1; }
+							const int32_t sc = c < 0 ? zs : zs - f[c];
+							if (sc >= min_sc && n_v > n_v0 && (int32_t)(n_v - n_v0) >= min_cnt) u[n_u++] = (uint64_t)sc << 32 | (n_v - n_v0);
+							else n_v = n_v0;
+						}
 					}
+					__syncwarp();
 				}
 				n_u = __shfl_sync(FULL, n_u, 0); n_v = __shfl_sync(FULL, n_v, 0);
 				__syncwarp();
@@ -216,29 +380,58 @@ __global__ void __launch_bounds__(FIN_WARPS * 32) k_chain_finish(k3_args_t A, de
 				co = __shfl_sync(FULL, co, 0);
 				const bool carry_ok = co + n_v <= A.carry_cap;
 				if (!carry_ok && lane == 0) atomicExch(A.err, 2u);
-				uint32_t k = 0;
-				for (uint32_t ci = 0; ci < n_u; ++ci) {
-					const uint32_t ni = (uint32_t)u[ci];
-					for (uint32_t j = lane; j < ni; j += 32) {
-						const anchor_t x = a[v[k + (ni - j - 1)]];
-						b[k + j] = x;
-						if (carry_ok) A.carry_out[co + k + j] = x;
+				/* chain start offsets in backtrack order: exclusive scan of the chain sizes */
+				uint32_t *koff = (uint32_t *)t; /* t[] is free once the backtrack is over */
+				{
+					uint32_t run = 0;
+					for (uint32_t c0 = 0; c0 < n_u; c0 += 32) {
+						const uint32_t ci = c0 + lane;
+						const uint32_t ni = ci < n_u ? (uint32_t)u[ci] : 0u;
+						uint32_t incl = ni;
+#pragma unroll
+						for (int o = 1; o < 32; o <<= 1) { const uint32_t q = __shfl_up_sync(FULL, incl, o); if (lane >= o) incl += q; }
+						if (ci < n_u) koff[ci] = run + incl - ni;
+						run += __shfl_sync(FULL, incl, 31);
 					}
-					if (lane == 0) { w[ci].x = 0; w[ci].y = (uint64_t)k << 32 | ci; }
-					k += ni;
 				}
 				__syncwarp();
-				for (uint32_t ci = lane; ci < n_u; ci += 32) w[ci].x = b[w[ci].y >> 32].x;
+				for (uint32_t ci = lane; ci < n_u; ci += 32) { /* one lane per chain: chains are a few anchors long */
+					const uint32_t ni = (uint32_t)u[ci], k0 = koff[ci];
+					for (uint32_t j = 0; j < ni; ++j) {
+						const anchor_t x = a[v[k0 + (ni - j - 1)]];
+						b[k0 + j] = x;
+						if (carry_ok) A.carry_out[co + k0 + j] = x;
+						if (j == 0) { anchor_t e; e.x = x.x; e.y = (uint64_t)k0 << 32 | ci; w[ci] = e; }
+					}
+				}
 				if (lane == 0 && carry_ok) { R->prev_off = co; R->prev_n = n_v; }
 				__syncwarp();
 				warp_klib_sort_pairs(w, n_u, z, X, cnt, head, lane);
-				k = 0;
-				for (uint32_t ci = 0; ci < n_u; ++ci) {
-					const uint32_t j = (uint32_t)w[ci].y, c = (uint32_t)u[j];
+				/* output offsets in target order, then copy chains and pre-compute the region keys (mm_gen_regs) */
+				uint32_t *kout = (uint32_t *)v; /* the backtrack order list is no longer needed */
+				{
+					uint32_t run = 0;
+					for (uint32_t c0 = 0; c0 < n_u; c0 += 32) {
+						const uint32_t ci = c0 + lane;
+						const uint32_t ni = ci < n_u ? (uint32_t)u[(uint32_t)w[ci].y] : 0u;
+						uint32_t incl = ni;
+#pragma unroll
+						for (int o = 1; o < 32; o <<= 1) { const uint32_t q = __shfl_up_sync(FULL, incl, o); if (lane >= o) incl += q; }
+						if (ci < n_u) kout[ci] = run + incl - ni;
+						run += __shfl_sync(FULL, incl, 31);
+					}
+				}
+				__syncwarp();
+				const uint32_t rhash = wang32(wang32(R->ev_offset + S->n_events) + wang32(11u)); /* rmap.cpp:346-348 */
+				for (uint32_t ci = lane; ci < n_u; ci += 32) {
+					const uint32_t j = (uint32_t)w[ci].y, c = (uint32_t)u[j], k0 = kout[ci];
 					const anchor_t *src = b + (w[ci].y >> 32);
-					for (uint32_t q = lane; q < c; q += 32) a[k + q] = src[q];
-					if (lane == 0) u2[ci] = u[j];
-					k += c;
+					for (uint32_t q = 0; q < c; ++q) a[k0 + q] = src[q];
+					u2[ci] = u[j];
+					const anchor_t fa = src[0];
+					const uint32_t h = (uint32_t)mix64((mix64(fa.x) + mix64(fa.y)) ^ rhash); /* hit.c:120 */
+					anchor_t e; e.x = u[j] ^ h; e.y = (uint64_t)k0 << 32 | c;
+					z[ci] = e;
 				}
 				__syncwarp();
 				for (uint32_t ci = lane; ci < n_u; ci += 32) u[ci] = u2[ci];
@@ -249,16 +442,6 @@ __global__ void __launch_bounds__(FIN_WARPS * 32) k_chain_finish(k3_args_t A, de
 			}
 			if (n_u > 0) {
 				r = M.regs + M.reg_cap / 2; /* upper half: the lower half is sort scratch (fin_scratch) */
-				const uint32_t hash = wang32(wang32(R->ev_offset + S->n_events) + wang32(11u)); /* rmap.cpp:346-348 */
-				if (lane == 0) {
-					uint32_t k = 0;
-					for (uint32_t i = 0; i < n_u; ++i) {
-						const uint32_t h = (uint32_t)mix64((mix64(a[k].x) + mix64(a[k].y)) ^ hash);
-						z[i].x = u[i] ^ h; z[i].y = (uint64_t)k << 32 | (uint32_t)u[i];
-						k += (uint32_t)u[i];
-					}
-				}
-				__syncwarp();
 				warp_klib_sort_pairs(z, n_u, w, X, cnt, head, lane);
 				for (uint32_t i = lane; i < n_u; i += 32) { /* descending score */
 					const anchor_t zz = z[n_u - 1 - i];
@@ -273,69 +456,33 @@ __global__ void __launch_bounds__(FIN_WARPS * 32) k_chain_finish(k3_args_t A, de
 				}
 				n_regs = n_u;
 				__syncwarp();
-				/* ---- mm_set_parent: regions in score order; overlap tests against primaries on all lanes ---- */
-				int *wl = (int *)M.p; uint64_t *cov = M.U2;
-				if (lane == 0) { wl[0] = 0; r[0].parent = 0; }
+				/* ---- mm_set_parent: regions in score order ---- */
+				int maxq = 0;
+				for (uint32_t i = lane; i < n_regs; i += 32) maxq = max(maxq, r[i].qe);
+#pragma unroll
+				for (int o = 16; o > 0; o >>= 1) maxq = max(maxq, __shfl_xor_sync(FULL, maxq, o));
+				bool done_sp = false;
+				if (maxq <= FIN_BITS) done_sp = set_parent_bitset(r, n_regs, P, bits, pc, lane);
+				if (!done_sp) set_parent_general(r, n_regs, P, M, lane);
 				__syncwarp();
-				int kk = 1;
-				for (int i = 1; i < (int)n_regs; ++i) {
-					const int si = r[i].qs, ei = r[i].qe;
-					/* pass 1: clipped overlaps with primaries -> cov[] */
-					int n_cov = 0;
-					for (int j0 = 0; j0 < kk; j0 += 32) {
-						const int j = j0 + (int)lane;
-						bool ov = false; int sj = 0, ej = 0;
-						if (j < kk) { const dev_reg_t *rp = &r[wl[j]]; sj = rp->qs; ej = rp->qe; ov = !(ej <= si || sj >= ei); }
-						const uint32_t m = __ballot_sync(FULL, ov);
-						if (ov) { if (sj < si) sj = si; if (ej > ei) ej = ei; cov[n_cov + __popc(m & lanemask_lt())] = (uint64_t)sj << 32 | (uint32_t)ej; }
-						n_cov += __popc(m);
-					}
-					__syncwarp();
-					int hit = -1, uncov = 0;
-					if (n_cov > 0) {
-						if (lane == 0) { /* union length of the overlaps (sorted by start; ties are identical values) */
-							int x = si;
-							seq_klib_sort(cov, (uint32_t)n_cov, key_of_u64(), (sort_seg_t *)M.B);
-							for (int c = 0; c < n_cov; ++c) {
-								if ((int)(cov[c] >> 32) > x) uncov += (int)(cov[c] >> 32) - x;
-								x = (int32_t)cov[c] > x ? (int32_t)cov[c] : x;
-							}
-							if (ei > x) uncov += ei - x;
-						}
-						uncov = __shfl_sync(FULL, uncov, 0);
-						/* pass 2: first primary (in order) that masks region i */
-						for (int j0 = 0; j0 < kk && hit < 0; j0 += 32) {
-							const int j = j0 + (int)lane;
-							bool sec = false;
-							if (j < kk) {
-								const dev_reg_t *rp = &r[wl[j]];
-								const int sj = rp->qs, ej = rp->qe;
-								if (!(ej <= si || sj >= ei)) {
-									const int mn = ej - sj < ei - si ? ej - sj : ei - si;
-									const int mx = ej - sj > ei - si ? ej - sj : ei - si;
-									const int ol = si < sj ? (ei < sj ? 0 : ei < ej ? ei - sj : ej - sj) : (ej < si ? 0 : ej < ei ? ej - si : ei - si);
-									sec = __fsub_rn(__fdiv_rn((float)ol, (float)mn), __fdiv_rn((float)uncov, (float)mx)) > P.mask_level && uncov <= P.mask_len;
-								}
-							}
-							const uint32_t m = __ballot_sync(FULL, sec);
-							if (m) hit = j0 + __ffs(m) - 1;
-						}
-					}
-					if (lane == 0) {
-						dev_reg_t *ri = &r[i];
-						if (hit >= 0) {
-							dev_reg_t *rp = &r[wl[hit]];
-							ri->parent = rp->parent;
-							rp->subsc = rp->subsc > ri->score ? rp->subsc : ri->score;
-							if (ri->cnt >= rp->cnt) ++rp->n_sub;
-						} else { wl[kk] = i; ri->parent = i; ri->n_sub = 0; }
-					}
-					if (hit < 0) ++kk;
-					__syncwarp();
-				}
 				/* ---- mm_select_sub + mm_sync_regs, mm_set_mapq (small; lane 0) ---- */
+				if (!P.ava && P.pri_ratio > 0.0f && P.best_n == 0) {
+					/* mm_select_sub with best_n = 0 keeps exactly the primaries (hit.c:350-364); mm_sync_regs then
+					 * renumbers them, and a primary's parent is itself: an order-preserving compaction. */
+					uint32_t kept = 0;
+					for (uint32_t i0 = 0; i0 < n_regs; i0 += 32) {
+						const uint32_t i = i0 + lane;
+						dev_reg_t g; bool keep = false;
+						if (i < n_regs) { g = r[i]; keep = g.parent == (int32_t)i; }
+						const uint32_t m = __ballot_sync(FULL, keep);
+						if (keep) { const uint32_t d = kept + __popc(m & lanemask_lt()); g.id = (int32_t)d; g.parent = (int32_t)d; r[d] = g; }
+						kept += __popc(m);
+						__syncwarp();
+					}
+					n_regs = kept;
+				}
 				if (lane == 0) {
-					if (!P.ava && P.pri_ratio > 0.0f) {
+					if (!P.ava && P.pri_ratio > 0.0f && P.best_n != 0) {
 						int kept = 0, n2 = 0;
 						const int nn = (int)n_regs;
 						for (int i = 0; i < nn; ++i) {
