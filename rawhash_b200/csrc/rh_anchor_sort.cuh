@@ -31,15 +31,65 @@
 struct sort_args_t {
 	slot_t *slots; uint32_t n_slots;
 	uint8_t *arena;
+	uint32_t *tie_list;      /* slots (indices into `slots`) whose chunk has equal keys */
+	uint32_t *tie_count;
 };
 
 __device__ __forceinline__ uint32_t lanemask_lt() { uint32_t m; asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m)); return m; }
 
+/* One stable counting-sort pass of (key, idx) arrays on digit (key >> shift) & 255.
+ * s_base[] must hold the exclusive bucket starts on entry. */
+template <class KeyT>
+__device__ __forceinline__ void sort_scatter_pass(const KeyT *__restrict__ kin, const uint32_t *__restrict__ iin, KeyT *__restrict__ kout, uint32_t *__restrict__ iout,
+                                                  uint32_t n, uint32_t shift, uint32_t *s_base, uint32_t (*s_wcnt)[256])
+{
+	const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	for (uint32_t t0 = 0; t0 < n; t0 += SORT_THREADS) {
+		for (uint32_t k = tid; k < SORT_WARPS * 256; k += SORT_THREADS) (&s_wcnt[0][0])[k] = 0;
+		__syncthreads();
+		const uint32_t i = t0 + tid;
+		const bool ok = i < n;
+		KeyT key = 0; uint32_t ix = 0, d = 0, peers = 0;
+		if (ok) { key = kin[i]; ix = iin[i]; d = (uint32_t)(key >> shift) & 255; }
+		const uint32_t act = __ballot_sync(0xffffffffu, ok);
+		if (ok) {
+			peers = __match_any_sync(act, d);
+			if ((peers & lanemask_lt()) == 0) s_wcnt[warp][d] = __popc(peers);
+		}
+		__syncthreads();
+		{ /* thread d: prefix over warps for digit d, advance the bucket base */
+			uint32_t run = s_base[tid];
+#pragma unroll
+			for (int w = 0; w < SORT_WARPS; ++w) { const uint32_t c = s_wcnt[w][tid]; s_wcnt[w][tid] = run; run += c; }
+			s_base[tid] = run;
+		}
+		__syncthreads();
+		if (ok) { const uint32_t dst = s_wcnt[warp][d] + __popc(peers & lanemask_lt()); kout[dst] = key; iout[dst] = ix; }
+		__syncthreads();
+	}
+}
+
+/* exclusive scan of 256 counters held one per thread -> s_base */
+__device__ __forceinline__ void sort_scan256(uint32_t v, uint32_t *s_base, uint32_t *s_tmp)
+{
+	const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	uint32_t incl = v;
+#pragma unroll
+	for (int o = 1; o < 32; o <<= 1) { const uint32_t u = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += u; }
+	if (lane == 31) s_tmp[warp] = incl;
+	__syncthreads();
+	uint32_t woff = 0;
+	for (uint32_t w = 0; w < warp; ++w) woff += s_tmp[w];
+	s_base[tid] = woff + incl - v;
+	__syncthreads();
+}
+
 __global__ void __launch_bounds__(SORT_THREADS) k_sort_block(sort_args_t A)
 {
-	__shared__ uint32_t s_hist[256];
+	__shared__ uint32_t s_hist[8][256];
 	__shared__ uint32_t s_base[256];
 	__shared__ uint32_t s_wcnt[SORT_WARPS][256];
+	__shared__ uint32_t s_tmp[SORT_WARPS];
 	__shared__ unsigned long long s_diff;
 	__shared__ uint32_t s_ties;
 
@@ -48,94 +98,88 @@ __global__ void __launch_bounds__(SORT_THREADS) k_sort_block(sort_args_t A)
 	if (S->gated || n == 0) return;
 	slot_mem_t M = slot_mem(A.arena, S->a_off, n);
 	const anchor_t *in = M.B;
-	anchor_t *cur = M.Z, *nxt = M.W;
-	const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	const uint32_t tid = threadIdx.x, lane = tid & 31;
+	uint32_t *sidx = (uint32_t *)M.U; /* final sorted order (source indices) */
 
 	if (tid == 0) { s_diff = 0ULL; s_ties = 0; }
+	for (uint32_t k = tid; k < 8 * 256; k += SORT_THREADS) (&s_hist[0][0])[k] = 0;
 	__syncthreads();
-	/* (x, idx) pairs + which key bits differ anywhere in the chunk */
+	/* which key bits differ anywhere in the chunk */
 	const uint64_t x0 = in[0].x;
 	unsigned long long diff = 0;
-	for (uint32_t i = tid; i < n; i += SORT_THREADS) {
-		const uint64_t x = in[i].x;
-		diff |= x ^ x0;
-		anchor_t pr; pr.x = x; pr.y = i;
-		cur[i] = pr;
-	}
+	for (uint32_t i = tid; i < n; i += SORT_THREADS) diff |= in[i].x ^ x0;
 #pragma unroll
 	for (int o = 16; o > 0; o >>= 1) diff |= __shfl_xor_sync(0xffffffffu, diff, o);
 	if (lane == 0 && diff) atomicOr(&s_diff, diff);
 	__syncthreads();
 	const unsigned long long dmask = s_diff;
+	/* anchor.x = strand<<63 | rid<<32 | pos (31 bits): pack the varying low bits of each field into one word.
+	 * Order and equality are preserved because the dropped high bits are identical across the chunk. */
+	const uint32_t posbits = 32 - __clz((uint32_t)(dmask & 0x7fffffffULL));
+	const uint32_t ridbits = 32 - __clz((uint32_t)((dmask >> 32) & 0x7fffffffULL));
+	const uint32_t sbit = (uint32_t)(dmask >> 63);
+	const uint32_t kbits = posbits + ridbits + sbit;
+	uint32_t ties_found = 0;
 
-	for (uint32_t shift = 0; shift < 64; shift += 8) {
-		if (((dmask >> shift) & 255ULL) == 0) continue; /* every key has the same byte here */
-		s_hist[tid] = 0;
-		__syncthreads();
-		for (uint32_t i = tid; i < n; i += SORT_THREADS) atomicAdd(&s_hist[(cur[i].x >> shift) & 255], 1u);
-		__syncthreads();
-		{ /* exclusive scan of 256 counters: warp scans + warp totals */
-			const uint32_t v = s_hist[tid];
-			uint32_t incl = v;
-#pragma unroll
-			for (int o = 1; o < 32; o <<= 1) { const uint32_t u = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += u; }
-			if (lane == 31) s_wcnt[0][warp] = incl;
-			__syncthreads();
-			uint32_t woff = 0;
-			for (uint32_t w = 0; w < warp; ++w) woff += s_wcnt[0][w];
-			s_base[tid] = woff + incl - v;
+	if (kbits <= 32) {
+		uint32_t *k0 = (uint32_t *)M.Z, *i0 = k0 + n, *k1 = i0 + n, *i1 = k1 + n;
+		const uint32_t npass = (kbits + 7) / 8;
+		const uint32_t pmask = posbits ? (0xffffffffu >> (32 - posbits)) : 0u, rmask = ridbits ? (0xffffffffu >> (32 - ridbits)) : 0u;
+		for (uint32_t i = tid; i < n; i += SORT_THREADS) {
+			const uint64_t x = in[i].x;
+			const uint32_t key = ((uint32_t)x & pmask) | ((((uint32_t)(x >> 32)) & rmask) << posbits) | (sbit ? ((uint32_t)(x >> 63) << (posbits + ridbits)) : 0u);
+			k0[i] = key; i0[i] = i;
+			for (uint32_t p = 0; p < npass; ++p) atomicAdd(&s_hist[p][(key >> (8 * p)) & 255], 1u);
 		}
 		__syncthreads();
-		/* stable scatter, one tile of SORT_THREADS elements at a time */
-		for (uint32_t t0 = 0; t0 < n; t0 += SORT_THREADS) {
-			for (uint32_t k = tid; k < SORT_WARPS * 256; k += SORT_THREADS) (&s_wcnt[0][0])[k] = 0;
-			__syncthreads();
-			const uint32_t i = t0 + tid;
-			const bool ok = i < n;
-			anchor_t e; e.x = 0; e.y = 0;
-			uint32_t d = 0, peers = 0;
-			if (ok) { e = cur[i]; d = (uint32_t)(e.x >> shift) & 255; }
-			const uint32_t act = __ballot_sync(0xffffffffu, ok);
-			if (ok) {
-				peers = __match_any_sync(act, d);
-				if ((peers & lanemask_lt()) == 0) s_wcnt[warp][d] = __popc(peers);
-			}
-			__syncthreads();
-			{ /* thread d: prefix over warps for digit d, advance the bucket base */
-				uint32_t run = s_base[tid];
-#pragma unroll
-				for (int w = 0; w < SORT_WARPS; ++w) { const uint32_t c = s_wcnt[w][tid]; s_wcnt[w][tid] = run; run += c; }
-				s_base[tid] = run;
-			}
-			__syncthreads();
-			if (ok) nxt[s_wcnt[warp][d] + __popc(peers & lanemask_lt())] = e;
-			__syncthreads();
+		uint32_t *kc = k0, *ic = i0, *kn = k1, *inx = i1;
+		for (uint32_t p = 0; p < npass; ++p) {
+			sort_scan256(s_hist[p][tid], s_base, s_tmp);
+			sort_scatter_pass<uint32_t>(kc, ic, kn, inx, n, 8 * p, s_base, s_wcnt);
+			uint32_t *t1 = kc; kc = kn; kn = t1; t1 = ic; ic = inx; inx = t1;
 		}
-		anchor_t *tmp = cur; cur = nxt; nxt = tmp;
-	}
-	/* sorted pairs must end in Z for the tie kernel */
-	if (cur != M.Z) {
-		for (uint32_t i = tid; i < n; i += SORT_THREADS) M.Z[i] = cur[i];
+		uint32_t my = 0;
+		uint8_t *tied = (uint8_t *)M.t;
+		for (uint32_t i = tid; i < n; i += SORT_THREADS) { tied[i] = 0; sidx[i] = ic[i]; }
 		__syncthreads();
-		cur = M.Z;
+		for (uint32_t i = tid; i + 1 < n; i += SORT_THREADS)
+			if (kc[i] == kc[i + 1]) { tied[ic[i]] = 1; tied[ic[i + 1]] = 1; ++my; }
+		if (my) atomicAdd(&s_ties, my);
+	} else {
+		/* wide keys: same passes on 64-bit keys, skipping bytes on which all keys agree */
+		uint64_t *k0 = (uint64_t *)M.Z, *k1 = (uint64_t *)M.W;
+		uint32_t *i0 = (uint32_t *)M.f, *i1 = (uint32_t *)M.p;
+		for (uint32_t i = tid; i < n; i += SORT_THREADS) {
+			const uint64_t x = in[i].x;
+			k0[i] = x; i0[i] = i;
+#pragma unroll
+			for (uint32_t p = 0; p < 8; ++p) atomicAdd(&s_hist[p][(uint32_t)(x >> (8 * p)) & 255], 1u);
+		}
+		__syncthreads();
+		uint64_t *kc = k0, *kn = k1; uint32_t *ic = i0, *inx = i1;
+		for (uint32_t p = 0; p < 8; ++p) {
+			if (((dmask >> (8 * p)) & 255ULL) == 0) continue;
+			sort_scan256(s_hist[p][tid], s_base, s_tmp);
+			sort_scatter_pass<uint64_t>(kc, ic, kn, inx, n, 8 * p, s_base, s_wcnt);
+			uint64_t *t1 = kc; kc = kn; kn = t1; uint32_t *t2 = ic; ic = inx; inx = t2;
+		}
+		uint32_t my = 0;
+		uint8_t *tied = (uint8_t *)M.t;
+		for (uint32_t i = tid; i < n; i += SORT_THREADS) { tied[i] = 0; sidx[i] = ic[i]; }
+		__syncthreads();
+		for (uint32_t i = tid; i + 1 < n; i += SORT_THREADS)
+			if (kc[i] == kc[i + 1]) { tied[ic[i]] = 1; tied[ic[i + 1]] = 1; ++my; }
+		if (my) atomicAdd(&s_ties, my);
 	}
-	/* tie detection on the sorted keys; flags are per SOURCE index */
-	uint8_t *tied = (uint8_t *)M.t;
-	for (uint32_t i = tid; i < n; i += SORT_THREADS) tied[i] = 0;
 	__syncthreads();
-	uint32_t my_ties = 0;
-	for (uint32_t i = tid; i + 1 < n; i += SORT_THREADS) {
-		const anchor_t a = cur[i], b = cur[i + 1];
-		if (a.x == b.x) { tied[(uint32_t)a.y] = 1; tied[(uint32_t)b.y] = 1; ++my_ties; }
-	}
-	if (my_ties) atomicAdd(&s_ties, my_ties);
-	__syncthreads();
-	const uint32_t ties = s_ties;
-	if (tid == 0) S->n_ties = ties;
-	if (ties == 0 || n <= 64) { /* <=64: klib uses a stable insertion sort -> same as the stable order */
+	ties_found = s_ties;
+	if (ties_found == 0 || n <= 64) { /* <=64: klib uses a stable insertion sort -> same as the stable order */
 		anchor_t *out = M.A;
-		for (uint32_t i = tid; i < n; i += SORT_THREADS) out[i] = in[(uint32_t)cur[i].y];
+		for (uint32_t i = tid; i < n; i += SORT_THREADS) out[i] = in[sidx[i]];
 		if (tid == 0) S->n_ties = 0;
+	} else if (tid == 0) {
+		S->n_ties = ties_found;
+		A.tie_list[atomicAdd(A.tie_count, 1u)] = blockIdx.x;
 	}
 }
 
@@ -147,18 +191,17 @@ __global__ void __launch_bounds__(128) k_sort_ties(sort_args_t A)
 	__shared__ uint32_t s_flag[4][256];
 
 	const uint32_t wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
-	const uint32_t slot_id = blockIdx.x * 4 + wib;
-	if (slot_id >= A.n_slots) return;
-	slot_t *S = &A.slots[slot_id];
+	const uint32_t li = blockIdx.x * 4 + wib;
+	if (li >= *A.tie_count) return;
+	slot_t *S = &A.slots[A.tie_list[li]];
 	const uint32_t n = S->n_anchors;
-	if (S->gated || n == 0 || S->n_ties == 0) return;
 	slot_mem_t M = slot_mem(A.arena, S->a_off, n);
 	const anchor_t *in = M.B;
-	anchor_t *srt = M.Z;
+	uint32_t *sidx = (uint32_t *)M.U;
 	uint32_t *ord = (uint32_t *)M.f, *ord2 = (uint32_t *)M.p, *dst = (uint32_t *)M.v;
 	const uint8_t *tied = (const uint8_t *)M.t;
 	uint8_t *bytes = (uint8_t *)M.t + n;
-	uint2 *wl_cur = (uint2 *)M.U, *wl_nxt = (uint2 *)M.U2;
+	uint2 *wl_cur = (uint2 *)M.regs, *wl_nxt = wl_cur + (n / 64 + 2);
 	uint32_t *cnt = s_cnt[wib], *head = s_head[wib], *flag = s_flag[wib];
 	const uint32_t FULL = 0xffffffffu;
 
@@ -185,7 +228,7 @@ __global__ void __launch_bounds__(128) k_sort_ties(sort_args_t A)
 			const uint32_t b0 = bytes[beg];
 			if (cnt[b0] == len) { /* nothing moves at this level */
 				if (shift > 0) { if (lane == 0) wl_nxt[n_nxt] = seg; ++n_nxt; }
-				else { for (uint32_t i = lane; i < len; i += 32) srt[beg + i].y = ord[beg + i]; }
+				else { for (uint32_t i = lane; i < len; i += 32) sidx[beg + i] = ord[beg + i]; }
 				__syncwarp();
 				continue;
 			}
@@ -252,7 +295,7 @@ __global__ void __launch_bounds__(128) k_sort_ties(sort_args_t A)
 							ord[start + j] = o;
 						}
 					}
-					for (uint32_t i = 0; i < c; ++i) srt[start + i].y = ord[start + i];
+					for (uint32_t i = 0; i < c; ++i) sidx[start + i] = ord[start + i];
 				}
 			}
 			__syncwarp();
@@ -263,7 +306,7 @@ __global__ void __launch_bounds__(128) k_sort_ties(sort_args_t A)
 	}
 	__syncwarp();
 	anchor_t *out = M.A;
-	for (uint32_t i = lane; i < n; i += 32) out[i] = in[(uint32_t)srt[i].y];
+	for (uint32_t i = lane; i < n; i += 32) out[i] = in[sidx[i]];
 }
 
 #endif

@@ -84,7 +84,7 @@ struct rh_gpu_ctx_s {
 	dbuf<uint8_t> d_arena;
 	dbuf<anchor_t> d_carry[2];
 	dbuf<unsigned long long> d_counters; /* [0] carry_top, [1] rec_top */
-	dbuf<uint32_t> d_err, d_rec_start, d_rec_cnt;
+	dbuf<uint32_t> d_err, d_rec_start, d_rec_cnt, d_tie_list, d_tie_count;
 	dbuf<rh_map_rec_t> d_recs;
 	size_t arena_bytes = 0, carry_elems = 0, sig_budget = 0;
 	std::vector<timed_span> spans;
@@ -221,7 +221,9 @@ int run_round(rh_gpu_ctx *c, round_io &io, int carry_in_idx)
 		a3.slots = c->d_slots.p + g0; a3.n_slots = gn;
 		const uint32_t gw = (gn * RH_WARP + 255) / 256;
 		{ span_guard g(c, T_SEED); k_seed_expand<<<gw, 256, 0, s>>>(a2, c->I, c->D); }
-		sort_args_t as; as.slots = a3.slots; as.n_slots = gn; as.arena = c->d_arena.p;
+		if ((rc = c->d_tie_list.reserve(gn)) || (rc = c->d_tie_count.reserve(1))) return rc;
+		CUDA_TRY(cudaMemsetAsync(c->d_tie_count.p, 0, 4, s));
+		sort_args_t as; as.slots = a3.slots; as.n_slots = gn; as.arena = c->d_arena.p; as.tie_list = c->d_tie_list.p; as.tie_count = c->d_tie_count.p;
 		{ span_guard g(c, T_SORT); k_sort_block<<<gn, SORT_THREADS, 0, s>>>(as); }
 		{ span_guard g(c, T_SORT); k_sort_ties<<<(gn + 3) / 4, 128, 0, s>>>(as); }
 		if (io.tap) { /* sorted anchor list of the single tapped slot */
@@ -450,7 +452,7 @@ extern "C" void rh_gpu_destroy(rh_gpu_ctx *c)
 	c->d_raw.release(); c->d_rs.release(); c->d_slots.release(); c->d_z.release(); c->d_events.release(); c->d_peaks.release();
 	c->d_seed_hash.release(); c->d_seed_pos.release(); c->d_seed_cnt.release(); c->d_seed_dst.release(); c->d_seed_src.release();
 	c->d_arena.release(); c->d_carry[0].release(); c->d_carry[1].release(); c->d_counters.release(); c->d_err.release();
-	c->d_rec_start.release(); c->d_rec_cnt.release(); c->d_recs.release();
+	c->d_rec_start.release(); c->d_rec_cnt.release(); c->d_recs.release(); c->d_tie_list.release(); c->d_tie_count.release();
 	for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
 	if (c->own_stream) cudaStreamDestroy(c->own_stream);
 	delete c;

@@ -140,3 +140,24 @@ def test_small_arena_groups(built):
     """A tiny anchor arena forces the chunk round to run in several groups; results must not change."""
     w = World(n_contigs=3, genome_len=1_000_000, n_reads=120, read_bp=5000, seed=2)
     _check_paf(w, "sensitive", arena=48 << 20)
+
+
+def test_wide_sort_keys(built):
+    """>32 varying key bits (many targets x long target): the 64-bit sort path + tie replay."""
+    from rawhash_b200 import synth
+    w = World(n_contigs=1, genome_len=300_000, n_reads=30, read_bp=3000, seed=12)
+    rng = np.random.Generator(np.random.PCG64(99))
+    small = [(f"s{i:05d}", rng.integers(0, 4, 120, dtype=np.uint8)) for i in range(40_000)]
+    w.genome = [w.genome[0]] + small
+    w.fasta = "/tmp/rh_world_wide.fa"
+    synth.write_fasta(w.fasta, w.genome)
+    api, P, idx, orc = _setup(w)
+    m = api.Mapper(idx, P, 0, 2 << 30)
+    for i in range(6):
+        got = m.tap_read(w.reads["raw"][i], synth.OFFSET, synth.RANGE, synth.DIGITISATION, w.names[i])
+        exp = orc.tap_read(w.pa(i), w.names[i])
+        assert tap_equal(got, exp) == [], f"read {i}"
+        x = exp[0]["anchors"][:, 0]
+        assert len(x) and int(x.max() ^ x.min()).bit_length() > 32
+    m.close()
+    _check_paf(w, "sensitive")
