@@ -283,7 +283,7 @@ def main():
                     "h2d_bytes_per_step": h2d // args.steps, "d2h_bytes_per_step": d2h // args.steps, "records_equal_to_resident_run": same},
             "gpu_launches": int(cnt["kernel_launches"]),
             "clocks": clocks,
-            "roofline": {"kernel": "k_signal_to_seeds", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "roofline": {"kernel": "event stage: k_sig_norm+k_sig_tstat+k_sig_peaks+k_sig_events+k_sig_sketch (5 back-to-back launches per chunk round, timed as one span)", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak if peak else None, "traffic": None, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": alg_bytes / ev_launches, "avg_launch_ms": ev_ms / ev_launches,
                          "note": "bit-exact event detection is instruction-issue bound (~250 instr per 2-byte sample), see DESIGN.md"},

@@ -33,9 +33,32 @@ struct sort_args_t {
 	uint8_t *arena;
 	uint32_t *tie_list;      /* slots (indices into `slots`) whose chunk has equal keys */
 	uint32_t *tie_count;
+	unsigned long long *prof;
 };
 
 __device__ __forceinline__ uint32_t lanemask_lt() { uint32_t m; asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m)); return m; }
+
+/* Stable sort of a bucket of c <= 64 (key, payload) items held two per lane (item L and item 32+L):
+ * returns each item's rank.  Equivalent to klib's stable insertion sort of a small bucket
+ * (ksort.h:105-115), but the 64 x 64 comparisons run out of registers via shuffles instead of a
+ * chain of dependent global loads.  All lanes must call. */
+__device__ __forceinline__ void warp_rank64(uint64_t k0, uint64_t k1, uint32_t c, uint32_t lane, uint32_t *r0, uint32_t *r1)
+{
+	const uint32_t FULL = 0xffffffffu;
+	uint32_t a0 = 0, a1 = 0;
+	const uint32_t c0 = c < 32 ? c : 32;
+	for (uint32_t j = 0; j < c0; ++j) { /* items 0..31 */
+		const uint64_t kj = __shfl_sync(FULL, k0, j);
+		a0 += (kj < k0) || (kj == k0 && j < lane);
+		a1 += (kj <= k1); /* every item of the first half precedes item 32+lane */
+	}
+	for (uint32_t j = 32; j < c; ++j) { /* items 32..c-1 */
+		const uint64_t kj = __shfl_sync(FULL, k1, j - 32);
+		a0 += (kj < k0);
+		a1 += (kj < k1) || (kj == k1 && (j - 32) < lane);
+	}
+	*r0 = a0; *r1 = a1;
+}
 
 /* One stable counting-sort pass of (key, idx) arrays on digit (key >> shift) & 255.
  * s_base[] must hold the exclusive bucket starts on entry. */
@@ -184,14 +207,16 @@ __global__ void __launch_bounds__(SORT_THREADS) k_sort_block(sort_args_t A)
 }
 
 /* exact replay along tie-containing sub-arrays; one warp per slot */
-__global__ void __launch_bounds__(128) k_sort_ties(sort_args_t A)
+/* One warp (= one CTA) per tie-containing chunk.  The byte array the walk chases lives in dynamic
+ * shared memory when the chunk fits (smem_cap bytes), else in the slot's global scratch. */
+__global__ void __launch_bounds__(32) k_sort_ties(sort_args_t A, uint32_t smem_cap)
 {
-	__shared__ uint32_t s_cnt[4][256];
-	__shared__ uint32_t s_head[4][256];
-	__shared__ uint32_t s_flag[4][256];
+	extern __shared__ __align__(16) uint8_t s_dyn[];
+	uint32_t *cnt = (uint32_t *)s_dyn, *head = cnt + 256, *flag = head + 256;
+	uint8_t *s_bytes = s_dyn + 3 * 256 * 4;
 
-	const uint32_t wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
-	const uint32_t li = blockIdx.x * 4 + wib;
+	const uint32_t lane = threadIdx.x & 31;
+	const uint32_t li = blockIdx.x;
 	if (li >= *A.tie_count) return;
 	slot_t *S = &A.slots[A.tie_list[li]];
 	const uint32_t n = S->n_anchors;
@@ -200,11 +225,11 @@ __global__ void __launch_bounds__(128) k_sort_ties(sort_args_t A)
 	uint32_t *sidx = (uint32_t *)M.U;
 	uint32_t *ord = (uint32_t *)M.f, *ord2 = (uint32_t *)M.p, *dst = (uint32_t *)M.v;
 	const uint8_t *tied = (const uint8_t *)M.t;
-	uint8_t *bytes = (uint8_t *)M.t + n;
+	uint8_t *bytes = n <= smem_cap ? s_bytes : (uint8_t *)M.t + n;
 	uint2 *wl_cur = (uint2 *)M.regs, *wl_nxt = wl_cur + (n / 64 + 2);
-	uint32_t *cnt = s_cnt[wib], *head = s_head[wib], *flag = s_flag[wib];
 	const uint32_t FULL = 0xffffffffu;
 
+	RH_PROF_BEGIN(A.prof);
 	for (uint32_t i = lane; i < n; i += 32) ord[i] = i;
 	uint32_t n_cur = 1, n_nxt = 0;
 	if (lane == 0) wl_cur[0] = make_uint2(0u, n);
@@ -225,6 +250,7 @@ __global__ void __launch_bounds__(128) k_sort_ties(sort_args_t A)
 				if (tied[o]) flag[b] = 1;
 			}
 			__syncwarp();
+			RH_PROF_MARK(A.prof, 16, lane == 0);
 			const uint32_t b0 = bytes[beg];
 			if (cnt[b0] == len) { /* nothing moves at this level */
 				if (shift > 0) { if (lane == 0) wl_nxt[n_nxt] = seg; ++n_nxt; }
@@ -243,6 +269,7 @@ __global__ void __launch_bounds__(128) k_sort_ties(sort_args_t A)
 				run += __shfl_sync(FULL, incl, 31);
 			}
 			__syncwarp();
+			RH_PROF_MARK(A.prof, 17, lane == 0);
 			/* the displacement-cycle walk (ksort.h:126-138), on bytes: dst[i] = slot element i lands in */
 			if (lane == 0) {
 				uint32_t region_end = 0;
@@ -266,10 +293,12 @@ __global__ void __launch_bounds__(128) k_sort_ties(sort_args_t A)
 				}
 			}
 			__syncwarp();
+			RH_PROF_MARK(A.prof, 18, lane == 0);
 			for (uint32_t i = lane; i < len; i += 32) ord2[beg + dst[beg + i]] = ord[beg + i];
 			__syncwarp();
 			for (uint32_t i = lane; i < len; i += 32) ord[beg + i] = ord2[beg + i];
 			__syncwarp();
+			RH_PROF_MARK(A.prof, 19, lane == 0);
 			/* children that contain a tie group */
 			uint32_t acc = 0;
 			for (uint32_t bb = 0; bb < 256; bb += 32) {
@@ -285,21 +314,27 @@ __global__ void __launch_bounds__(128) k_sort_ties(sort_args_t A)
 				const uint32_t rm = __ballot_sync(FULL, recurse);
 				if (recurse) wl_nxt[n_nxt + __popc(rm & lanemask_lt())] = make_uint2(start, c);
 				n_nxt += __popc(rm);
-				if (has && !recurse) {
+				/* terminal buckets, one at a time on the whole warp */
+				uint32_t tm = __ballot_sync(FULL, has && !recurse);
+				while (tm) {
+					const int src = __ffs(tm) - 1; tm &= tm - 1;
+					const uint32_t ts = __shfl_sync(FULL, start, src), tc = __shfl_sync(FULL, c, src);
 					if (shift > 0) { /* <=64 elements: klib finishes with a stable insertion sort on the full key */
-						for (uint32_t i = 1; i < c; ++i) {
-							const uint32_t o = ord[start + i];
-							const uint64_t ko = in[o].x;
-							uint32_t j = i;
-							while (j > 0 && ko < in[ord[start + j - 1]].x) { ord[start + j] = ord[start + j - 1]; --j; }
-							ord[start + j] = o;
-						}
+						uint32_t o0 = 0, o1 = 0; uint64_t k0 = 0, k1 = 0;
+						if (lane < tc) { o0 = ord[ts + lane]; k0 = in[o0].x; }
+						if (32 + lane < tc) { o1 = ord[ts + 32 + lane]; k1 = in[o1].x; }
+						uint32_t r0, r1;
+						warp_rank64(k0, k1, tc, lane, &r0, &r1);
+						if (lane < tc) sidx[ts + r0] = o0;
+						if (32 + lane < tc) sidx[ts + r1] = o1;
+					} else { /* last byte: the bucket keeps the order the walk left it in */
+						for (uint32_t i = lane; i < tc; i += 32) sidx[ts + i] = ord[ts + i];
 					}
-					for (uint32_t i = 0; i < c; ++i) sidx[start + i] = ord[start + i];
 				}
 			}
 			__syncwarp();
 		}
+		RH_PROF_MARK(A.prof, 20, lane == 0);
 		uint2 *t = wl_cur; wl_cur = wl_nxt; wl_nxt = t;
 		n_cur = n_nxt;
 		__syncwarp();
@@ -307,6 +342,7 @@ __global__ void __launch_bounds__(128) k_sort_ties(sort_args_t A)
 	__syncwarp();
 	anchor_t *out = M.A;
 	for (uint32_t i = lane; i < n; i += 32) out[i] = in[sidx[i]];
+	RH_PROF_MARK(A.prof, 21, lane == 0);
 }
 
 #endif

@@ -36,7 +36,14 @@ __device__ void warp_klib_sort_pairs(anchor_t *a, uint32_t n, anchor_t *tmp, con
 {
 	const uint32_t FULL = 0xffffffffu;
 	if (n <= 64) {
-		if (lane == 0) seq_insertion_sort(a, n, key_of_anchor_x());
+		anchor_t e0, e1; e0.x = e0.y = e1.x = e1.y = 0;
+		if (lane < n) e0 = a[lane];
+		if (32 + lane < n) e1 = a[32 + lane];
+		uint32_t r0, r1;
+		warp_rank64(e0.x, e1.x, n, lane, &r0, &r1);
+		__syncwarp();
+		if (lane < n) a[r0] = e0;
+		if (32 + lane < n) a[32 * 0 + r1] = e1;
 		__syncwarp();
 		return;
 	}
@@ -114,7 +121,19 @@ __device__ void warp_klib_sort_pairs(anchor_t *a, uint32_t n, anchor_t *tmp, con
 					const uint32_t rm = __ballot_sync(FULL, recurse);
 					if (recurse) wl_nxt[n_nxt + __popc(rm & lanemask_lt())] = make_uint2(start, c);
 					n_nxt += __popc(rm);
-					if (!recurse && c > 1) seq_insertion_sort(a + start, c, key_of_anchor_x());
+					uint32_t tm = __ballot_sync(FULL, !recurse && c > 1); /* small buckets: stable sort, one bucket per pass */
+					while (tm) {
+						const int src = __ffs(tm) - 1; tm &= tm - 1;
+						const uint32_t ts = __shfl_sync(FULL, start, src), tc = __shfl_sync(FULL, c, src);
+						anchor_t e0, e1; e0.x = e0.y = e1.x = e1.y = 0;
+						if (lane < tc) e0 = a[ts + lane];
+						if (32 + lane < tc) e1 = a[ts + 32 + lane];
+						uint32_t r0, r1;
+						warp_rank64(e0.x, e1.x, tc, lane, &r0, &r1);
+						__syncwarp();
+						if (lane < tc) a[ts + r0] = e0;
+						if (32 + lane < tc) a[ts + r1] = e1;
+					}
 				}
 				__syncwarp();
 			}
@@ -326,6 +345,7 @@ __global__ void __launch_bounds__(FIN_WARPS * 32, 8) k_chain_finish(k3_args_t A,
 			int32_t *f = M.f, *p = M.p, *v = M.v, *t = M.t;
 			uint64_t *u = M.U, *u2 = M.U2;
 			const int32_t min_sc = P.min_sc, min_cnt = P.min_cnt, max_drop = P.bw;
+			RH_PROF_BEGIN(A.prof);
 			/* ---- candidates z = {(f[i], i) : f[i] >= min_sc}, in index order ---- */
 			uint32_t n_z = 0;
 			for (int32_t i0 = 0; i0 < n; i0 += 32) {
@@ -338,7 +358,9 @@ __global__ void __launch_bounds__(FIN_WARPS * 32, 8) k_chain_finish(k3_args_t A,
 			}
 			__syncwarp();
 			if (n_z > 0) {
+				RH_PROF_MARK(A.prof, 32, lane == 0);
 				warp_klib_sort_pairs(z, n_z, w, X, cnt, head, lane);
+				RH_PROF_MARK(A.prof, 33, lane == 0);
 				/* ---- backtrack, best score first.  Visiting order matters, so lane 0 walks the chains;
 				 *      the test that skips candidates already swallowed by an earlier chain (the vast
 				 *      majority) is prefetched 32 candidates at a time.  t[] only ever goes 0 -> nonzero
@@ -370,6 +392,7 @@ __global__ void __launch_bounds__(FIN_WARPS * 32, 8) k_chain_finish(k3_args_t A,
 					}
 					__syncwarp();
 				}
+				RH_PROF_MARK(A.prof, 34, lane == 0);
 				n_u = __shfl_sync(FULL, n_u, 0); n_v = __shfl_sync(FULL, n_v, 0);
 				__syncwarp();
 			}
@@ -406,7 +429,9 @@ __global__ void __launch_bounds__(FIN_WARPS * 32, 8) k_chain_finish(k3_args_t A,
 				}
 				if (lane == 0 && carry_ok) { R->prev_off = co; R->prev_n = n_v; }
 				__syncwarp();
+				RH_PROF_MARK(A.prof, 35, lane == 0);
 				warp_klib_sort_pairs(w, n_u, z, X, cnt, head, lane);
+				RH_PROF_MARK(A.prof, 36, lane == 0);
 				/* output offsets in target order, then copy chains and pre-compute the region keys (mm_gen_regs) */
 				uint32_t *kout = (uint32_t *)v; /* the backtrack order list is no longer needed */
 				{
@@ -442,7 +467,9 @@ __global__ void __launch_bounds__(FIN_WARPS * 32, 8) k_chain_finish(k3_args_t A,
 			}
 			if (n_u > 0) {
 				r = M.regs + M.reg_cap / 2; /* upper half: the lower half is sort scratch (fin_scratch) */
+				RH_PROF_MARK(A.prof, 37, lane == 0);
 				warp_klib_sort_pairs(z, n_u, w, X, cnt, head, lane);
+				RH_PROF_MARK(A.prof, 38, lane == 0);
 				for (uint32_t i = lane; i < n_u; i += 32) { /* descending score */
 					const anchor_t zz = z[n_u - 1 - i];
 					dev_reg_t g;
@@ -461,10 +488,12 @@ __global__ void __launch_bounds__(FIN_WARPS * 32, 8) k_chain_finish(k3_args_t A,
 				for (uint32_t i = lane; i < n_regs; i += 32) maxq = max(maxq, r[i].qe);
 #pragma unroll
 				for (int o = 16; o > 0; o >>= 1) maxq = max(maxq, __shfl_xor_sync(FULL, maxq, o));
+				RH_PROF_MARK(A.prof, 39, lane == 0);
 				bool done_sp = false;
 				if (maxq <= FIN_BITS) done_sp = set_parent_bitset(r, n_regs, P, bits, pc, lane);
 				if (!done_sp) set_parent_general(r, n_regs, P, M, lane);
 				__syncwarp();
+				RH_PROF_MARK(A.prof, 40, lane == 0);
 				/* ---- mm_select_sub + mm_sync_regs, mm_set_mapq (small; lane 0) ---- */
 				if (!P.ava && P.pri_ratio > 0.0f && P.best_n == 0) {
 					/* mm_select_sub with best_n = 0 keeps exactly the primaries (hit.c:350-364); mm_sync_regs then
@@ -529,6 +558,7 @@ __global__ void __launch_bounds__(FIN_WARPS * 32, 8) k_chain_finish(k3_args_t A,
 					}
 				}
 				n_regs = __shfl_sync(FULL, n_regs, 0);
+				RH_PROF_MARK(A.prof, 41, lane == 0);
 			}
 		}
 	}

@@ -125,4 +125,9 @@ __device__ __forceinline__ int32_t pair_score(uint64_t ix, uint64_t iy, uint64_t
 	return sc;
 }
 
+
+/* optional phase timing (RH_PROF=1 at run time): cycles summed over calling warps/threads */
+#define RH_PROF_BEGIN(P) long long prof_t_ = (P) ? clock64() : 0
+#define RH_PROF_MARK(P, idx, leader) do { if ((P) && (leader)) { const long long n_ = clock64(); atomicAdd(&(P)[idx], (unsigned long long)(n_ - prof_t_)); prof_t_ = n_; } } while (0)
+
 #endif

@@ -24,6 +24,7 @@
 
 #include "rh_host.h"
 #include "rh_kernels.cuh"
+#include "rh_signal.cuh"
 #include "rh_anchor_sort.cuh"
 #include "rh_chain_finish.cuh"
 
@@ -58,6 +59,7 @@ struct timed_span { cudaEvent_t a, b; int kind; };
 
 } // namespace
 
+#define TIES_SMEM_CAP (160u * 1024u)
 enum { T_EVENT = 0, T_SEED, T_SORT, T_CHAIN, T_POST, T_LEN, T_NKIND };
 
 struct rh_gpu_ctx_s {
@@ -78,13 +80,14 @@ struct rh_gpu_ctx_s {
 	const int16_t *raw_ptr = nullptr; /* raw buffer of the current call (ours or the caller's) */
 	dbuf<read_state_t> d_rs;
 	dbuf<slot_t> d_slots;
-	dbuf<float> d_z, d_events;
+	dbuf<float> d_z, d_events, d_ps, d_pq, d_t1, d_t2;
 	dbuf<uint32_t> d_peaks, d_seed_hash, d_seed_pos, d_seed_cnt, d_seed_dst;
 	dbuf<uint64_t> d_seed_src;
 	dbuf<uint8_t> d_arena;
 	dbuf<anchor_t> d_carry[2];
 	dbuf<unsigned long long> d_counters; /* [0] carry_top, [1] rec_top */
 	dbuf<uint32_t> d_err, d_rec_start, d_rec_cnt, d_tie_list, d_tie_count;
+	dbuf<unsigned long long> d_prof; bool prof_on = false;
 	dbuf<rh_map_rec_t> d_recs;
 	size_t arena_bytes = 0, carry_elems = 0, sig_budget = 0;
 	std::vector<timed_span> spans;
@@ -100,9 +103,9 @@ cudaEvent_t get_event(rh_gpu_ctx *c)
 	return c->ev_pool[c->ev_used++];
 }
 struct span_guard {
-	rh_gpu_ctx *c; timed_span s;
-	span_guard(rh_gpu_ctx *c_, int kind) : c(c_) { s.kind = kind; s.a = get_event(c); s.b = get_event(c); cudaEventRecord(s.a, c->stream); }
-	~span_guard() { cudaEventRecord(s.b, c->stream); c->spans.push_back(s); c->st.kernel_launches++; if (s.kind == T_EVENT) c->st.event_kernel_launches++; }
+	rh_gpu_ctx *c; timed_span s; int n_launch;
+	span_guard(rh_gpu_ctx *c_, int kind, int n_launch_ = 1) : c(c_), n_launch(n_launch_) { s.kind = kind; s.a = get_event(c); s.b = get_event(c); cudaEventRecord(s.a, c->stream); }
+	~span_guard() { cudaEventRecord(s.b, c->stream); c->spans.push_back(s); c->st.kernel_launches += n_launch; if (s.kind == T_EVENT) c->st.event_kernel_launches++; }
 };
 
 void fill_dev_params(const rh_params_t &P, dev_params_t &D)
@@ -177,12 +180,19 @@ int run_round(rh_gpu_ctx *c, round_io &io, int carry_in_idx)
 	if ((rc = upload(c->d_slots, io.slots, s))) return rc;
 	c->st.h2d_bytes += ns * sizeof(slot_t);
 
-	k1_args_t a1;
+	if ((rc = c->d_ps.reserve(zt + ns)) || (rc = c->d_pq.reserve(zt + ns)) || (rc = c->d_t1.reserve(zt + ns)) || (rc = c->d_t2.reserve(zt + ns))) return rc;
+	sig_args_t a1;
 	a1.raw = c->raw_ptr; a1.rs = c->d_rs.p; a1.slots = c->d_slots.p; a1.n_slots = ns;
-	a1.z = c->d_z.p; a1.peaks = c->d_peaks.p; a1.events = c->d_events.p; a1.seed_hash = c->d_seed_hash.p; a1.seed_pos = c->d_seed_pos.p;
-	{
-		span_guard g(c, T_EVENT);
-		k_signal_to_seeds<<<(ns + K1_THREADS - 1) / K1_THREADS, K1_THREADS, 0, s>>>(a1, c->D);
+	a1.z = c->d_z.p; a1.ps = c->d_ps.p; a1.pq = c->d_pq.p; a1.t1 = c->d_t1.p; a1.t2 = c->d_t2.p;
+	a1.peaks = c->d_peaks.p; a1.events = c->d_events.p; a1.seed_hash = c->d_seed_hash.p; a1.seed_pos = c->d_seed_pos.p;
+	a1.prof = c->prof_on ? c->d_prof.p : nullptr;
+	{ /* the event stage: five launches back to back, timed as one span */
+		span_guard g(c, T_EVENT, 5);
+		k_sig_norm<<<(ns * 32 + 127) / 128, 128, 0, s>>>(a1);
+		k_sig_tstat<<<ns, 256, 0, s>>>(a1, c->D);
+		k_sig_peaks<<<(ns + 127) / 128, 128, 0, s>>>(a1, c->D);
+		k_sig_events<<<ns, EV_THREADS, 0, s>>>(a1);
+		k_sig_sketch<<<(ns + 127) / 128, 128, 0, s>>>(a1, c->D);
 	}
 	k2_args_t a2;
 	a2.slots = c->d_slots.p; a2.n_slots = ns; a2.rs = c->d_rs.p;
@@ -203,7 +213,7 @@ int run_round(rh_gpu_ctx *c, round_io &io, int carry_in_idx)
 	a3.carry_out = c->d_carry[carry_in_idx ^ 1].p; a3.carry_top = c->d_counters.p; a3.carry_cap = c->carry_elems;
 	a3.logf_tab = c->d_logf.p; a3.logf_n = c->logf_n;
 	a3.recs = c->d_recs.p; a3.rec_top = c->d_counters.p + 1; a3.rec_cap = c->d_recs.cap;
-	a3.rec_start = c->d_rec_start.p; a3.rec_cnt = c->d_rec_cnt.p; a3.seq_len = c->d_seqlen.p; a3.tap = io.tap; a3.err = c->d_err.p;
+	a3.rec_start = c->d_rec_start.p; a3.rec_cnt = c->d_rec_cnt.p; a3.seq_len = c->d_seqlen.p; a3.tap = io.tap; a3.err = c->d_err.p; a3.prof = c->prof_on ? c->d_prof.p : nullptr;
 
 	uint32_t g0 = 0;
 	while (g0 < ns) {
@@ -223,9 +233,15 @@ int run_round(rh_gpu_ctx *c, round_io &io, int carry_in_idx)
 		{ span_guard g(c, T_SEED); k_seed_expand<<<gw, 256, 0, s>>>(a2, c->I, c->D); }
 		if ((rc = c->d_tie_list.reserve(gn)) || (rc = c->d_tie_count.reserve(1))) return rc;
 		CUDA_TRY(cudaMemsetAsync(c->d_tie_count.p, 0, 4, s));
-		sort_args_t as; as.slots = a3.slots; as.n_slots = gn; as.arena = c->d_arena.p; as.tie_list = c->d_tie_list.p; as.tie_count = c->d_tie_count.p;
+		sort_args_t as; as.slots = a3.slots; as.n_slots = gn; as.arena = c->d_arena.p; as.tie_list = c->d_tie_list.p; as.tie_count = c->d_tie_count.p; as.prof = c->prof_on ? c->d_prof.p : nullptr;
 		{ span_guard g(c, T_SORT); k_sort_block<<<gn, SORT_THREADS, 0, s>>>(as); }
-		{ span_guard g(c, T_SORT); k_sort_ties<<<(gn + 3) / 4, 128, 0, s>>>(as); }
+		{
+			uint32_t maxn = 0;
+			for (uint32_t q = g0; q < g1; ++q) if (!io.slots[q].gated) maxn = std::max(maxn, io.slots[q].n_anchors);
+			const uint32_t cap = std::min<uint32_t>((maxn + 15) & ~15u, TIES_SMEM_CAP);
+			span_guard g(c, T_SORT);
+			k_sort_ties<<<gn, 32, 3 * 256 * 4 + cap, s>>>(as, cap);
+		}
 		if (io.tap) { /* sorted anchor list of the single tapped slot */
 			rh_tap_t *T = io.tap_out; const slot_t &sl = io.slots[0];
 			if (!sl.gated) {
@@ -252,6 +268,14 @@ int run_round(rh_gpu_ctx *c, round_io &io, int carry_in_idx)
 
 int collect_spans(rh_gpu_ctx *c)
 {
+	if (c->prof_on) {
+		unsigned long long h[64];
+		cudaMemcpy(h, c->d_prof.p, sizeof(h), cudaMemcpyDeviceToHost);
+		cudaMemset(c->d_prof.p, 0, sizeof(h));
+		fprintf(stderr, "[RH_PROF] Mcycles:");
+		for (int i = 0; i < 64; ++i) if (h[i]) fprintf(stderr, " [%d]=%.1f", i, h[i] / 1e6);
+		fprintf(stderr, "  (chunks=%llu)\n", (unsigned long long)c->st.n_chunks);
+	}
 	double ms[T_NKIND] = {0};
 	for (const timed_span &sp : c->spans) { float t = 0; if (cudaEventElapsedTime(&t, sp.a, sp.b) == cudaSuccess) ms[sp.kind] += t; }
 	c->st.ms_event_kernel += ms[T_EVENT]; c->st.ms_seed += ms[T_SEED]; c->st.ms_sort += ms[T_SORT];
@@ -430,6 +454,10 @@ extern "C" rh_gpu_ctx *rh_gpu_init(const rh_index_t *idx, const rh_params_t *p, 
 	c->I.keys = c->d_keys.p; c->I.off = c->d_off.p; c->I.pos = c->d_pos.p; c->I.bucket = c->d_bucket.p; c->I.bucket_bits = bits;
 	c->I.n_keys = nk; c->I.seq_len = c->d_seqlen.p; c->I.name_rank = c->d_namerank.p; c->I.n_seq = (uint32_t)idx->names.size();
 	if (c->d_counters.reserve(2) || c->d_err.reserve(1)) return fail(NULL);
+	c->prof_on = getenv("RH_PROF") != NULL;
+	if (c->d_prof.reserve(64)) return fail(NULL);
+	cudaMemset(c->d_prof.p, 0, 64 * 8);
+	if (cudaFuncSetAttribute(k_sort_ties, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * 256 * 4 + TIES_SMEM_CAP) != cudaSuccess) return fail("cudaFuncSetAttribute(k_sort_ties) failed");
 	if (cudaStreamSynchronize(c->stream) != cudaSuccess) return fail("index upload failed");
 	/* ---- work arenas ---- */
 	size_t free_b = 0, total_b = 0;
@@ -438,7 +466,7 @@ extern "C" rh_gpu_ctx *rh_gpu_init(const rh_index_t *idx, const rh_params_t *p, 
 	if (arena_bytes > free_b * 7 / 10) arena_bytes = free_b * 7 / 10;
 	c->arena_bytes = arena_bytes;
 	c->carry_elems = arena_bytes / 8 / sizeof(anchor_t);
-	c->sig_budget = std::max<size_t>(arena_bytes / 16 / 28, (size_t)1 << 20); /* ~28 B of scratch per sample */
+	c->sig_budget = std::max<size_t>(arena_bytes / 16 / 44, (size_t)1 << 20); /* ~44 B of scratch per sample */
 	if (c->d_arena.reserve(arena_bytes) || c->d_carry[0].reserve(c->carry_elems) || c->d_carry[1].reserve(c->carry_elems)) return fail(NULL);
 	c->arena_bytes = c->d_arena.cap; c->carry_elems = std::min(c->d_carry[0].cap, c->d_carry[1].cap);
 	return c;
@@ -449,6 +477,7 @@ extern "C" void rh_gpu_destroy(rh_gpu_ctx *c)
 	if (!c) return;
 	cudaSetDevice(c->device);
 	c->d_keys.release(); c->d_bucket.release(); c->d_seqlen.release(); c->d_namerank.release(); c->d_off.release(); c->d_pos.release(); c->d_logf.release();
+	c->d_ps.release(); c->d_pq.release(); c->d_t1.release(); c->d_t2.release();
 	c->d_raw.release(); c->d_rs.release(); c->d_slots.release(); c->d_z.release(); c->d_events.release(); c->d_peaks.release();
 	c->d_seed_hash.release(); c->d_seed_pos.release(); c->d_seed_cnt.release(); c->d_seed_dst.release(); c->d_seed_src.release();
 	c->d_arena.release(); c->d_carry[0].release(); c->d_carry[1].release(); c->d_counters.release(); c->d_err.release();
@@ -641,11 +670,15 @@ extern "C" rh_index_t *rh_index_build_sig(const rh_params_t *p, uint32_t n_reads
 			for (slot_t &sl : io.slots) { sl.z_off = zt; zt += sl.chunk_len; sl.e_cap = (uint32_t)((uint64_t)sl.chunk_len * 2 / 3 + 8); sl.e_off = et; et += sl.e_cap; }
 			if ((rc = c->d_z.reserve(zt)) || (rc = c->d_events.reserve(et)) || (rc = c->d_peaks.reserve(et)) || (rc = c->d_seed_hash.reserve(et)) ||
 			    (rc = c->d_seed_pos.reserve(et)) || (rc = upload(c->d_slots, io.slots, c->stream))) break;
-			k1_args_t a1;
+			if ((rc = c->d_ps.reserve(zt + ns)) || (rc = c->d_pq.reserve(zt + ns)) || (rc = c->d_t1.reserve(zt + ns)) || (rc = c->d_t2.reserve(zt + ns))) break;
+			sig_args_t a1; a1.prof = nullptr;
 			a1.raw = c->raw_ptr; a1.rs = c->d_rs.p; a1.slots = c->d_slots.p; a1.n_slots = ns;
-			a1.z = c->d_z.p; a1.peaks = c->d_peaks.p; a1.events = c->d_events.p; a1.seed_hash = c->d_seed_hash.p; a1.seed_pos = c->d_seed_pos.p;
-			dev_params_t D = c->D; D.min_events = 0xffffffffu; /* skip phase D */
-			k_signal_to_seeds<<<(ns + K1_THREADS - 1) / K1_THREADS, K1_THREADS, 0, c->stream>>>(a1, D);
+			a1.z = c->d_z.p; a1.ps = c->d_ps.p; a1.pq = c->d_pq.p; a1.t1 = c->d_t1.p; a1.t2 = c->d_t2.p;
+			a1.peaks = c->d_peaks.p; a1.events = c->d_events.p; a1.seed_hash = c->d_seed_hash.p; a1.seed_pos = c->d_seed_pos.p;
+			k_sig_norm<<<(ns * 32 + 127) / 128, 128, 0, c->stream>>>(a1);
+			k_sig_tstat<<<ns, 256, 0, c->stream>>>(a1, c->D);
+			k_sig_peaks<<<(ns + 127) / 128, 128, 0, c->stream>>>(a1, c->D);
+			k_sig_events<<<ns, EV_THREADS, 0, c->stream>>>(a1);
 			if (cudaMemcpyAsync(io.slots.data(), c->d_slots.p, ns * sizeof(slot_t), cudaMemcpyDeviceToHost, c->stream) != cudaSuccess) { rc = RH_ERR_CUDA; break; }
 			ev.resize(et);
 			if (cudaMemcpyAsync(ev.data(), c->d_events.p, et * 4, cudaMemcpyDeviceToHost, c->stream) != cudaSuccess) { rc = RH_ERR_CUDA; break; }
@@ -656,7 +689,7 @@ extern "C" rh_index_t *rh_index_build_sig(const rh_params_t *p, uint32_t n_reads
 			idx->names.emplace_back(names[b0 + i]); idx->lens.push_back(l_sig[i]);
 			if (l_sig[i] == 0) continue;
 			const slot_t &sl = io.slots[si++];
-			if (sl.n_events) rh_host_sketch(*p, ev.data() + sl.e_off, sl.n_events, b0 + i, 0, all);
+			if (sl.n_peaks) rh_host_sketch(*p, ev.data() + sl.e_off, sl.n_peaks, b0 + i, 0, all);
 		}
 	}
 	rh_gpu_destroy(c);

@@ -3,7 +3,7 @@
  *
  * Stage map (reference function each kernel takes over, paths relative to the RawHash tree):
  *   k_filtered_len      src/rsig.c:496-503        raw int16 -> pA, count samples with 30<pA<200
- *   k_signal_to_seeds   src/revent.c:221-316 + src/rsketch.c:143-204   (the fused metric kernel)
+ *   k_sig_*             src/revent.c:221-316 + src/rsketch.c:143-204   (the event stage, rh_signal.cuh)
  *   k_seed_count        src/rseed.c:60-154 + src/rindex.c:497-514      lookup, occ filter, rep_len
  *   k_seed_expand       src/rmap.cpp:74-116       anchors from position lists + previous chunk's
  *   k_sort_block/_ties  src/ksort.h:101-151       anchor sort with klib's exact tie order (rh_anchor_sort.cuh)
@@ -113,219 +113,6 @@ __global__ void __launch_bounds__(256) k_filtered_len(const int16_t *__restrict_
 #pragma unroll
 	for (int o = 16; o > 0; o >>= 1) kept += __shfl_xor_sync(0xffffffffu, kept, o);
 	if (lane == 0) rs[warp].l_sig = kept;
-}
-
-/* =============================================================================================
- * K1  fused signal -> events -> seeds.
- *
- * One CTA owns K1_THREADS slots.  Phases, separated by __syncthreads():
- *   A  (thread = slot)   stream raw, pA filter, Σx / Σx² in double until chunk_len samples kept
- *   B  (thread = slot)   re-stream the same raw window: z-normalise, |z|<3 filter, float prefix
- *                        sums kept in a 32-deep shared-memory ring, both t-statistics and the
- *                        two coupled peak detectors evaluated on the fly -> peak positions
- *   C  (thread = segment, all slots of the CTA pooled)   IQR-filtered mean of every segment
- *   D  (thread = slot)   diff filter, quantise, pack e events, hash -> (hash, first event pos)
- *
- * The sequential float recurrences (prefix sums, peak detectors, diff filter) make a chunk
- * inherently serial; parallelism comes from running 32 chunks per warp, one
- * per lane, with identical control flow.
- * ===========================================================================================*/
-#define K1_THREADS 128
-#define K1_RING 32
-
-struct k1_args_t {
-	const int16_t *raw;
-	read_state_t *rs;
-	slot_t *slots;
-	uint32_t n_slots;
-	float *z;              /* [z_off .. +chunk_len)            */
-	uint32_t *peaks;       /* [e_off .. +e_cap)                */
-	float *events;         /* [e_off .. +e_cap)                */
-	uint32_t *seed_hash;   /* [e_off .. +e_cap)                */
-	uint32_t *seed_pos;    /* [e_off .. +e_cap)                */
-};
-
-struct peak_det_t { uint32_t masked_to; int peak_pos; float peak_val; int valid; };
-
-__device__ __forceinline__ float window_tstat(const float *ps, const float *pq, uint32_t i, uint32_t w, float fw)
-{ /* comp_tstat body, reference src/revent.c:49-69, contractions as in the compiled object */
-	const float a = ps[(i & (K1_RING - 1)) * K1_THREADS], aq = pq[(i & (K1_RING - 1)) * K1_THREADS];
-	const float b = ps[((i + w) & (K1_RING - 1)) * K1_THREADS], bq = pq[((i + w) & (K1_RING - 1)) * K1_THREADS];
-	float s1 = a, q1 = aq;
-	if (i > w) {
-		s1 = __fsub_rn(a, ps[((i - w) & (K1_RING - 1)) * K1_THREADS]);
-		q1 = __fsub_rn(aq, pq[((i - w) & (K1_RING - 1)) * K1_THREADS]);
-	}
-	const float s2 = __fsub_rn(b, a), q2 = __fsub_rn(bq, aq);
-	const float m1 = __fdiv_rn(s1, fw), m2 = __fdiv_rn(s2, fw);
-	float acc = __fmaf_rn(-m1, m1, __fdiv_rn(q1, fw));
-	acc = __fadd_rn(acc, __fdiv_rn(q2, fw));
-	acc = __fmaf_rn(-m2, m2, acc);
-	const float var = fmaxf(__fdiv_rn(acc, fw), FLT_MIN);
-	return __fdiv_rn(fabsf(__fsub_rn(m2, m1)), __fsqrt_rn(var));
-}
-
-/* one step of gen_peaks for detector k (reference src/revent.c:100-146) */
-__device__ __forceinline__ void detector_step(peak_det_t &D, peak_det_t *other /* next detector or null */, uint32_t i, float cur,
-                                              float thr, uint32_t win, uint32_t win0, float height, uint32_t *peaks, uint32_t &n_peaks)
-{
-	if (D.masked_to >= i) return;
-	if (D.peak_pos == -1) {
-		if (cur < D.peak_val) D.peak_val = cur;
-		else if (__fsub_rn(cur, D.peak_val) > height) { D.peak_val = cur; D.peak_pos = (int)i; }
-	} else {
-		if (cur > D.peak_val) { D.peak_val = cur; D.peak_pos = (int)i; }
-		if (other && D.peak_val > thr) {
-			other->masked_to = D.peak_pos + win0;
-			other->peak_pos = -1; other->peak_val = FLT_MAX; other->valid = 0;
-		}
-		if (__fsub_rn(D.peak_val, cur) > height && D.peak_val > thr) D.valid = 1;
-		if (D.valid && (i - D.peak_pos) > win / 2) {
-			peaks[n_peaks++] = (uint32_t)D.peak_pos;
-			D.peak_pos = -1; D.peak_val = cur; D.valid = 0;
-		}
-	}
-}
-
-__global__ void __launch_bounds__(K1_THREADS) k_signal_to_seeds(k1_args_t A, dev_params_t P)
-{
-	__shared__ float s_ps[K1_RING * K1_THREADS];
-	__shared__ float s_pq[K1_RING * K1_THREADS];
-	__shared__ uint32_t s_npk[K1_THREADS + 1];
-
-	const uint32_t tid = threadIdx.x;
-	const uint32_t slot_id = blockIdx.x * K1_THREADS + tid;
-	const bool live = slot_id < A.n_slots;
-	slot_t *S = live ? &A.slots[slot_id] : nullptr;
-	const int16_t *raw = A.raw;
-
-	uint32_t n_sig = 0, n_peaks = 0;
-	if (live) {
-		read_state_t *R = &A.rs[S->read];
-		const double off = R->cal_offset, scale = R->cal_scale;
-		const uint64_t cur0 = R->cursor, rend = R->raw_end;
-		const uint32_t want = S->chunk_len;
-		/* ---- phase A: sums over the chunk (normalize_signal first loop, revent.c:233-236) ---- */
-		double sum = R->sum, sum2 = R->sum2;
-		uint32_t got = 0; uint64_t c = cur0;
-		while (c < rend && got < want) {
-			const float pa = raw_to_pa(raw[c], off, scale);
-			++c;
-			if (!pa_keep(pa)) continue;
-			sum = __dadd_rn(sum, (double)pa);
-			sum2 = __dadd_rn(sum2, (double)__fmul_rn(pa, pa));
-			++got;
-		}
-		const uint64_t cur1 = c;
-		const uint32_t n_tot = R->n_sum + got;
-		R->sum = sum; R->sum2 = sum2; R->n_sum = n_tot; R->cursor = cur1;
-		S->raw_used = (uint32_t)(cur1 - cur0);
-		const double mean = __ddiv_rn(sum, (double)n_tot);
-		const double sd = __dsqrt_rn(__fma_rn(-mean, mean, __ddiv_rn(sum2, (double)n_tot)));
-
-		/* ---- phase B: z, prefix rings, t-stats, peak detectors, streaming ---- */
-		float *ps = s_ps + tid, *pq = s_pq + tid;
-		float *zout = A.z + S->z_off;
-		uint32_t *peaks = A.peaks + S->e_off;
-		const uint32_t w1 = P.w1, w2 = P.w2, W = w1 > w2 ? w1 : w2;
-		const float fw1 = (float)w1, fw2 = (float)w2;
-		peak_det_t d1 = {0u, -1, FLT_MAX, 0}, d2 = {0u, -1, FLT_MAX, 0};
-		float run_s = 0.0f, run_q = 0.0f;
-		ps[0] = 0.0f; pq[0] = 0.0f;
-		uint32_t n = 0;
-		for (c = cur0; c < cur1; ++c) {
-			const float pa = raw_to_pa(raw[c], off, scale);
-			if (!pa_keep(pa)) continue;
-			const float zv = __double2float_rn(__ddiv_rn(__dsub_rn((double)pa, mean), sd));
-			if (!(zv < 3.0f && zv > -3.0f)) continue;
-			zout[n] = zv;
-			run_s = __fadd_rn(run_s, zv);
-			run_q = __fmaf_rn(zv, zv, run_q);
-			++n;
-			ps[(n & (K1_RING - 1)) * K1_THREADS] = run_s;
-			pq[(n & (K1_RING - 1)) * K1_THREADS] = run_q;
-			if (n >= W) {
-				const uint32_t i = n - W;
-				const float t1 = (w1 >= 2 && i >= w1) ? window_tstat(ps, pq, i, w1, fw1) : 0.0f;
-				const float t2 = (w2 >= 2 && i >= w2) ? window_tstat(ps, pq, i, w2, fw2) : 0.0f;
-				detector_step(d1, &d2, i, t1, P.thr1, w1, w1, P.height, peaks, n_peaks);
-				detector_step(d2, nullptr, i, t2, P.thr2, w2, w1, P.height, peaks, n_peaks);
-			}
-		}
-		/* tail: positions whose right window runs past the end have t = 0 (revent.c:70-71) */
-		for (uint32_t i = (n >= W ? n - W + 1 : 0); i < n; ++i) {
-			const float t1 = (w1 >= 2 && i >= w1 && i + w1 <= n) ? window_tstat(ps, pq, i, w1, fw1) : 0.0f;
-			const float t2 = (w2 >= 2 && i >= w2 && i + w2 <= n) ? window_tstat(ps, pq, i, w2, fw2) : 0.0f;
-			detector_step(d1, &d2, i, t1, P.thr1, w1, w1, P.height, peaks, n_peaks);
-			detector_step(d2, nullptr, i, t2, P.thr2, w2, w1, P.height, peaks, n_peaks);
-		}
-		n_sig = n;
-		S->n_sig = n_sig; S->n_peaks = n_peaks;
-	}
-	s_npk[tid] = n_peaks;
-	__syncthreads();
-
-	/* ---- phase C: one thread per segment, all slots of the CTA pooled (gen_events, revent.c:193-219) ---- */
-	if (tid == 0) { /* exclusive scan of 128 counts; tiny */
-		uint32_t acc = 0;
-		for (int i = 0; i < K1_THREADS; ++i) { uint32_t v = s_npk[i]; s_npk[i] = acc; acc += v; }
-		s_npk[K1_THREADS] = acc;
-	}
-	__syncthreads();
-	{
-		const uint32_t total = s_npk[K1_THREADS];
-		for (uint32_t g = tid; g < total; g += K1_THREADS) {
-			int lo = 0, hi = K1_THREADS - 1; /* owner slot: last s with s_npk[s] <= g */
-			while (lo < hi) { int mid = (lo + hi + 1) >> 1; if (s_npk[mid] <= g) lo = mid; else hi = mid - 1; }
-			const slot_t *T = &A.slots[blockIdx.x * K1_THREADS + lo];
-			const uint32_t j = g - s_npk[lo];
-			const uint32_t *pk = A.peaks + T->e_off;
-			float *zz = A.z + T->z_off;
-			const uint32_t p = pk[j], start = j ? pk[j - 1] : 0u;
-			const uint32_t len = p > start ? p - start : 0u; /* the reference assumes increasing peaks */
-			float ev = 0.0f;
-			if (len) {
-				float *seg = zz + start;
-				for (uint32_t a = 1; a < len; ++a) { /* in-place ascending sort (qsort in the reference; order of equals is immaterial) */
-					const float cur = seg[a];
-					uint32_t b = a;
-					while (b > 0 && seg[b - 1] > cur) { seg[b] = seg[b - 1]; --b; }
-					seg[b] = cur;
-				}
-				const float q1 = seg[len / 4], q3 = seg[3 * len / 4], iqr = __fsub_rn(q3, q1);
-				const float lob = __fsub_rn(q1, iqr), hib = __fadd_rn(q3, iqr);
-				float sum = 0.0f; uint32_t cnt = 0;
-				for (uint32_t a = 0; a < len; ++a) { const float v = seg[a]; if (v >= lob && v <= hib) { sum = __fadd_rn(sum, v); ++cnt; } }
-				ev = cnt ? __fdiv_rn(sum, (float)cnt) : 0.0f;
-			}
-			A.events[T->e_off + j] = ev;
-		}
-	}
-	__syncthreads();
-
-	/* ---- phase D: diff filter + quantise + pack + hash (ri_sketch_reg, rsketch.c:143-204) ---- */
-	if (live) {
-		const uint32_t n_events = n_peaks; /* every emitted peak is in (0, n_sig) */
-		uint32_t n_seeds = 0;
-		const bool gated = n_events < P.min_events;
-		if (!gated) {
-			const float *ev = A.events + S->e_off;
-			uint32_t *sh = A.seed_hash + S->e_off, *sp = A.seed_pos + S->e_off;
-			const int e = P.e, q = P.q;
-			const uint64_t mev = (q * e >= 64) ? ~0ULL : ((1ULL << (q * e)) - 1), mq = (1ULL << q) - 1;
-			uint64_t packed = 0; float last = 0.0f; uint32_t kept = 0;
-			for (uint32_t i = 0; i < n_events; ++i) {
-				const float v = ev[i];
-				if (i && fabsf(__fsub_rn(v, last)) < P.diff) continue;
-				last = v;
-				packed = ((packed << q) | (quantize_event(v, P.fine_min, P.fine_max, P.fine_range, 1u << q) & mq)) & mev;
-				sp[kept] = i; /* position of the kept event; seed j starts at kept event j */
-				++kept;
-				if (kept >= (uint32_t)e) sh[n_seeds++] = (uint32_t)seed_mix(packed);
-			}
-		}
-		S->n_events = n_events; S->n_seeds = n_seeds; S->gated = gated ? 1u : 0u;
-	}
 }
 
 /* =============================================================================================
@@ -481,6 +268,7 @@ struct k3_args_t {
 	const uint32_t *seq_len;
 	int tap;                         /* tap mode: never stop early */
 	uint32_t *err;
+	unsigned long long *prof;
 };
 
 /* mg_lchain_dp main loop, reference src/lchain.c:439-505.
@@ -520,6 +308,7 @@ __global__ void __launch_bounds__(DP_THREADS) k_chain_dp(k3_args_t A, dev_params
 	__syncthreads();
 	const uint32_t n_seg = s_nseg;
 	if (tid == 0) S->n_seg = n_seg;
+	RH_PROF_BEGIN(A.prof);
 	for (uint32_t sg = tid; sg < n_seg; sg += DP_THREADS) {
 		const int32_t i0 = (int32_t)starts[sg];
 		int32_t st = i0, band_best = -1;
@@ -550,6 +339,7 @@ __global__ void __launch_bounds__(DP_THREADS) k_chain_dp(k3_args_t A, dev_params
 			if (band_best < 0 || (ix - a[band_best].x <= (uint64_t)(int64_t)max_t && f[band_best] < f[i])) band_best = i;
 		}
 	}
+	RH_PROF_MARK(A.prof, 8, true);
 }
 
 #endif

@@ -1,0 +1,326 @@
+/*
+ * rh_signal.cuh — the event stage: raw int16 current samples -> events -> seeds.
+ *
+ * Reference functions taken over (paths relative to the RawHash tree):
+ *   src/rsig.c:496-503      int16 -> pA, drop samples outside (30,200) pA
+ *   src/revent.c:221-255    normalize_signal (running Σx, Σx² over the read so far, z, |z|<3 filter)
+ *   src/revent.c:23-36      comp_prefix_prefixsq (sequential float prefix sums)
+ *   src/revent.c:38-74      comp_tstat (two window lengths)
+ *   src/revent.c:91-150     gen_peaks (two coupled detectors)
+ *   src/revent.c:158-219    gen_events / calculate_mean_of_filtered_segment
+ *   src/rsketch.c:143-204   ri_sketch_reg (diff filter, dynamic_quantize, pack, hash64)
+ *
+ * What is parallel and what is not.  Inside one chunk three steps are order dependent and cannot
+ * be re-associated without changing bits: the float prefix sums, the peak state machine and the
+ * diff filter.  Everything else — pA conversion, both filters, Σx/Σx² (exact in
+ * double, hence order free), the t-statistics, the per-segment sort/mean, quantise/hash — is
+ * data parallel.  The stage is therefore five back-to-back launches that alternate between
+ * "all lanes on one chunk" and "one lane per chunk" work shapes, so the serial steps cost one
+ * lane each instead of a whole warp:
+ *
+ *   k_sig_norm    warp / chunk     raw -> pA -> filter -> sums -> z -> filter -> prefix sums
+ *   k_sig_tstat   CTA  / chunk     t-statistics for both windows, one thread per position
+ *   k_sig_peaks   lane / chunk     the two coupled peak detectors
+ *   k_sig_events  CTA  / chunk     one thread per segment: sort, IQR filter, mean
+ *   k_sig_sketch  lane / chunk     diff filter, quantise, pack e events, hash
+ *
+ * Scratch per chunk (float, chunk-major): z[len], ps/pq/t1/t2[len+1]; peaks/events/seeds[e_cap].
+ */
+#ifndef RH_SIGNAL_CUH
+#define RH_SIGNAL_CUH
+
+#include "rh_kernels.cuh"
+
+struct sig_args_t {
+	const int16_t *raw;
+	read_state_t *rs;
+	slot_t *slots;
+	uint32_t n_slots;
+	float *z;              /* [z_off .. +chunk_len)                      */
+	float *ps, *pq;        /* [z_off + slot .. +chunk_len+1)             */
+	float *t1, *t2;        /* [z_off + slot .. +chunk_len+1)             */
+	uint32_t *peaks;       /* [e_off .. +e_cap)                          */
+	float *events;         /* [e_off .. +e_cap)                          */
+	uint32_t *seed_hash;   /* [e_off .. +e_cap)                          */
+	uint32_t *seed_pos;    /* [e_off .. +e_cap)                          */
+	unsigned long long *prof;
+};
+
+/* ------------------------------------------------------------------------------------------- */
+__global__ void __launch_bounds__(128) k_sig_norm(sig_args_t A)
+{
+	const uint32_t FULL = 0xffffffffu;
+	const uint32_t slot_id = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+	if (slot_id >= A.n_slots) return;
+	slot_t *S = &A.slots[slot_id];
+	read_state_t *R = &A.rs[S->read];
+	const int16_t *raw = A.raw;
+	const double off = R->cal_offset, scale = R->cal_scale;
+	const uint64_t cur0 = R->cursor, rend = R->raw_end;
+	const uint32_t want = S->chunk_len;
+	float *xz = A.z + S->z_off;
+	const uint32_t lt = (1u << lane) - 1;
+
+	/* pass 1: pA, outlier drop, compaction; Σx and Σx² are exact in double -> any order */
+	double sum = 0.0, sum2 = 0.0;
+	uint32_t got = 0; uint64_t c = cur0;
+	while (c < rend && got < want) {
+		const uint64_t idx = c + lane;
+		float pa = 0.0f; bool keep = false;
+		if (idx < rend) { pa = raw_to_pa(raw[idx], off, scale); keep = pa_keep(pa); }
+		uint32_t m = __ballot_sync(FULL, keep);
+		const uint32_t nk = __popc(m);
+		if (got + nk >= want) { /* the chunk ends right after its want-th kept sample */
+			const uint32_t need = want - got;
+			keep = keep && (uint32_t)__popc(m & lt) < need;
+			m = __ballot_sync(FULL, keep);
+			if (keep) { xz[got + __popc(m & lt)] = pa; sum += (double)pa; sum2 += (double)__fmul_rn(pa, pa); }
+			c += 32 - __clz(m); /* one past the last consumed sample */
+			got = want;
+			break;
+		}
+		if (keep) { xz[got + __popc(m & lt)] = pa; sum += (double)pa; sum2 += (double)__fmul_rn(pa, pa); }
+		got += nk;
+		c = (c + 32 < rend) ? c + 32 : rend;
+	}
+#pragma unroll
+	for (int o = 16; o > 0; o >>= 1) { sum += __shfl_xor_sync(FULL, sum, o); sum2 += __shfl_xor_sync(FULL, sum2, o); }
+	sum = __dadd_rn(R->sum, sum); sum2 = __dadd_rn(R->sum2, sum2);
+	const uint32_t n_tot = R->n_sum + got;
+	__syncwarp();
+	if (lane == 0) { R->sum = sum; R->sum2 = sum2; R->n_sum = n_tot; R->cursor = c; S->raw_used = (uint32_t)(c - cur0); }
+	const double mean = __ddiv_rn(sum, (double)n_tot);
+	const double sd = __dsqrt_rn(__fma_rn(-mean, mean, __ddiv_rn(sum2, (double)n_tot)));
+
+	/* pass 2: z-normalise, |z| < 3 filter, in-place compaction (writes never pass the reads) */
+	uint32_t n = 0;
+	for (uint32_t t0 = 0; t0 < got; t0 += 32) {
+		const uint32_t i = t0 + lane;
+		float zv = 0.0f; bool keep = false;
+		if (i < got) { zv = __double2float_rn(__ddiv_rn(__dsub_rn((double)xz[i], mean), sd)); keep = zv < 3.0f && zv > -3.0f; }
+		const uint32_t m = __ballot_sync(FULL, keep);
+		if (keep) xz[n + __popc(m & lt)] = zv;
+		n += __popc(m);
+	}
+	__syncwarp();
+
+	/* float prefix sums: strictly sequential recurrences (revent.c:32-35, FMA as compiled).
+	 * Every lane runs the same chain on shuffled values; lane k keeps the k-th partial for a
+	 * coalesced store. */
+	float *ps = A.ps + S->z_off + slot_id, *pq = A.pq + S->z_off + slot_id;
+	float run_s = 0.0f, run_q = 0.0f;
+	if (lane == 0) { ps[0] = 0.0f; pq[0] = 0.0f; }
+	for (uint32_t t0 = 0; t0 < n; t0 += 32) {
+		const float zr = (t0 + lane < n) ? xz[t0 + lane] : 0.0f; /* +0 leaves both chains unchanged */
+		float my_s = 0.0f, my_q = 0.0f;
+#pragma unroll
+		for (int k = 0; k < 32; ++k) {
+			const float v = __shfl_sync(FULL, zr, k);
+			run_s = __fadd_rn(run_s, v);
+			run_q = __fmaf_rn(v, v, run_q);
+			if ((int)lane == k) { my_s = run_s; my_q = run_q; }
+		}
+		if (t0 + lane < n) { ps[t0 + lane + 1] = my_s; pq[t0 + lane + 1] = my_q; }
+	}
+	if (lane == 0) { S->n_sig = n; S->n_peaks = 0; }
+}
+
+/* ------------------------------------------------------------------------------------------- */
+__device__ __forceinline__ float tstat_at(const float *__restrict__ ps, const float *__restrict__ pq, uint32_t i, uint32_t w, float fw)
+{ /* comp_tstat body, revent.c:49-69, contractions as in the compiled reference */
+	const float a = ps[i], aq = pq[i];
+	float s1 = a, q1 = aq;
+	if (i > w) { s1 = __fsub_rn(a, ps[i - w]); q1 = __fsub_rn(aq, pq[i - w]); }
+	const float s2 = __fsub_rn(ps[i + w], a), q2 = __fsub_rn(pq[i + w], aq);
+	const float m1 = __fdiv_rn(s1, fw), m2 = __fdiv_rn(s2, fw);
+	float acc = __fmaf_rn(-m1, m1, __fdiv_rn(q1, fw));
+	acc = __fadd_rn(acc, __fdiv_rn(q2, fw));
+	acc = __fmaf_rn(-m2, m2, acc);
+	const float var = fmaxf(__fdiv_rn(acc, fw), FLT_MIN);
+	return __fdiv_rn(fabsf(__fsub_rn(m2, m1)), __fsqrt_rn(var));
+}
+
+__global__ void __launch_bounds__(256) k_sig_tstat(sig_args_t A, dev_params_t P)
+{
+	const slot_t *S = &A.slots[blockIdx.x];
+	const uint32_t n = S->n_sig;
+	if (n == 0) return;
+	const uint64_t o = S->z_off + blockIdx.x;
+	const float *ps = A.ps + o, *pq = A.pq + o;
+	float *t1 = A.t1 + o, *t2 = A.t2 + o;
+	const uint32_t w1 = P.w1, w2 = P.w2;
+	const float fw1 = (float)w1, fw2 = (float)w2;
+	const bool ok1 = w1 >= 2 && n >= 2 * w1, ok2 = w2 >= 2 && n >= 2 * w2;
+	for (uint32_t i = threadIdx.x; i <= n; i += blockDim.x) {
+		t1[i] = (ok1 && i >= w1 && i + w1 <= n) ? tstat_at(ps, pq, i, w1, fw1) : 0.0f;
+		t2[i] = (ok2 && i >= w2 && i + w2 <= n) ? tstat_at(ps, pq, i, w2, fw2) : 0.0f;
+	}
+}
+
+/* ------------------------------------------------------------------------------------------- */
+struct peak_det_t { uint32_t masked_to; int peak_pos; float peak_val; int valid; };
+
+__device__ __forceinline__ void detector_step(peak_det_t &D, peak_det_t *other /* next detector or null */, uint32_t i, float cur,
+                                              float thr, uint32_t win, uint32_t win0, float height, uint32_t *__restrict__ peaks, uint32_t &n_peaks)
+{ /* one detector at one position, revent.c:100-146 */
+	if (D.masked_to >= i) return;
+	if (D.peak_pos == -1) {
+		if (cur < D.peak_val) D.peak_val = cur;
+		else if (__fsub_rn(cur, D.peak_val) > height) { D.peak_val = cur; D.peak_pos = (int)i; }
+	} else {
+		if (cur > D.peak_val) { D.peak_val = cur; D.peak_pos = (int)i; }
+		if (other && D.peak_val > thr) {
+			other->masked_to = D.peak_pos + win0;
+			other->peak_pos = -1; other->peak_val = FLT_MAX; other->valid = 0;
+		}
+		if (__fsub_rn(D.peak_val, cur) > height && D.peak_val > thr) D.valid = 1;
+		if (D.valid && (i - D.peak_pos) > win / 2) {
+			peaks[n_peaks++] = (uint32_t)D.peak_pos;
+			D.peak_pos = -1; D.peak_val = cur; D.valid = 0;
+		}
+	}
+}
+
+__global__ void __launch_bounds__(128) k_sig_peaks(sig_args_t A, dev_params_t P)
+{
+	const uint32_t slot_id = blockIdx.x * blockDim.x + threadIdx.x;
+	if (slot_id >= A.n_slots) return;
+	slot_t *S = &A.slots[slot_id];
+	const uint32_t n = S->n_sig;
+	const uint64_t o = S->z_off + slot_id;
+	const float *__restrict__ t1 = A.t1 + o, *__restrict__ t2 = A.t2 + o;
+	uint32_t *__restrict__ peaks = A.peaks + S->e_off;
+	peak_det_t d1 = {0u, -1, FLT_MAX, 0}, d2 = {0u, -1, FLT_MAX, 0};
+	uint32_t n_peaks = 0;
+	const uint32_t w1 = P.w1, w2 = P.w2;
+	uint32_t i = 0;
+	for (; i + 4 <= n; i += 4) { /* loads for four positions issued ahead of the state machine */
+		float a[4], b[4];
+#pragma unroll
+		for (int k = 0; k < 4; ++k) { a[k] = t1[i + k]; b[k] = t2[i + k]; }
+#pragma unroll
+		for (int k = 0; k < 4; ++k) {
+			detector_step(d1, &d2, i + k, a[k], P.thr1, w1, w1, P.height, peaks, n_peaks);
+			detector_step(d2, nullptr, i + k, b[k], P.thr2, w2, w1, P.height, peaks, n_peaks);
+		}
+	}
+	for (; i < n; ++i) {
+		detector_step(d1, &d2, i, t1[i], P.thr1, w1, w1, P.height, peaks, n_peaks);
+		detector_step(d2, nullptr, i, t2[i], P.thr2, w2, w1, P.height, peaks, n_peaks);
+	}
+	S->n_peaks = n_peaks;
+}
+
+/* ------------------------------------------------------------------------------------------- */
+#define EV_THREADS 128
+#define EV_SMALL 64                /* segment lengths sorted by one thread in shared memory */
+#define EV_BIG (EV_THREADS * EV_SMALL) /* longest segment the CTA sorts in shared memory */
+
+__device__ __forceinline__ float filtered_mean_sorted(const float *seg, uint32_t len, uint32_t stride)
+{ /* calculate_mean_of_filtered_segment after the sort, revent.c:163-179 (ascending accumulation order) */
+	const float q1 = seg[(len / 4) * stride], q3 = seg[(3 * len / 4) * stride];
+	const float iqr = __fsub_rn(q3, q1), lob = __fsub_rn(q1, iqr), hib = __fadd_rn(q3, iqr);
+	float sum = 0.0f; uint32_t cnt = 0;
+	for (uint32_t a = 0; a < len; ++a) { const float v = seg[a * stride]; if (v >= lob && v <= hib) { sum = __fadd_rn(sum, v); ++cnt; } }
+	return cnt ? __fdiv_rn(sum, (float)cnt) : 0.0f;
+}
+
+__device__ void heapsort_global(float *a, uint32_t n)
+{ /* segments too long for shared memory (whole-read Rawsamble chunks); any correct sort will do */
+	for (uint32_t start = n / 2; start-- > 0;) {
+		uint32_t r = start; const float v = a[r];
+		for (;;) { uint32_t ch = 2 * r + 1; if (ch >= n) break; if (ch + 1 < n && a[ch + 1] > a[ch]) ++ch; if (a[ch] <= v) break; a[r] = a[ch]; r = ch; }
+		a[r] = v;
+	}
+	for (uint32_t end = n; end-- > 1;) {
+		const float v = a[end]; a[end] = a[0];
+		uint32_t r = 0;
+		for (;;) { uint32_t ch = 2 * r + 1; if (ch >= end) break; if (ch + 1 < end && a[ch + 1] > a[ch]) ++ch; if (a[ch] <= v) break; a[r] = a[ch]; r = ch; }
+		a[r] = v;
+	}
+}
+
+__global__ void __launch_bounds__(EV_THREADS) k_sig_events(sig_args_t A)
+{
+	__shared__ float s_buf[EV_BIG];
+	__shared__ uint32_t s_long[256];
+	__shared__ uint32_t s_nlong;
+	slot_t *S = &A.slots[blockIdx.x];
+	const uint32_t n_peaks = S->n_peaks, tid = threadIdx.x;
+	if (n_peaks == 0) return;
+	const uint32_t *pk = A.peaks + S->e_off;
+	float *zz = A.z + S->z_off;
+	float *ev = A.events + S->e_off;
+	if (tid == 0) s_nlong = 0;
+	__syncthreads();
+	/* gen_events (revent.c:193-219): segment j = z[peaks[j-1] .. peaks[j]) */
+	for (uint32_t j = tid; j < n_peaks; j += EV_THREADS) {
+		const uint32_t p = pk[j], start = j ? pk[j - 1] : 0u;
+		const uint32_t len = p > start ? p - start : 0u; /* the reference assumes increasing peaks */
+		if (len == 0) { ev[j] = 0.0f; continue; }
+		if (len > EV_SMALL) { const uint32_t q = atomicAdd(&s_nlong, 1u); if (q < 256) s_long[q] = j; else { heapsort_global(zz + start, len); ev[j] = filtered_mean_sorted(zz + start, len, 1); } continue; }
+		float *seg = s_buf + tid;
+		const float *src = zz + start;
+		for (uint32_t a = 0; a < len; ++a) { /* insertion sort while loading; order of equal values is immaterial */
+			const float cur = src[a];
+			uint32_t b = a;
+			while (b > 0 && seg[(b - 1) * EV_THREADS] > cur) { seg[b * EV_THREADS] = seg[(b - 1) * EV_THREADS]; --b; }
+			seg[b * EV_THREADS] = cur;
+		}
+		ev[j] = filtered_mean_sorted(seg, len, EV_THREADS);
+	}
+	__syncthreads();
+	const uint32_t nl = min(s_nlong, 256u);
+	for (uint32_t q = 0; q < nl; ++q) { /* long segments: the whole CTA sorts one at a time (bitonic, padded with +inf) */
+		const uint32_t j = s_long[q];
+		const uint32_t p = pk[j], start = j ? pk[j - 1] : 0u, len = p - start;
+		if (len > EV_BIG) { if (tid == 0) { heapsort_global(zz + start, len); ev[j] = filtered_mean_sorted(zz + start, len, 1); } __syncthreads(); continue; }
+		uint32_t N = 1; while (N < len) N <<= 1;
+		for (uint32_t i = tid; i < N; i += EV_THREADS) s_buf[i] = i < len ? zz[start + i] : FLT_MAX;
+		__syncthreads();
+		for (uint32_t k = 2; k <= N; k <<= 1)
+			for (uint32_t jj = k >> 1; jj > 0; jj >>= 1) {
+				for (uint32_t i = tid; i < N; i += EV_THREADS) {
+					const uint32_t l = i ^ jj;
+					if (l > i) {
+						const float x = s_buf[i], y = s_buf[l];
+						const bool up = (i & k) == 0;
+						if ((x > y) == up) { s_buf[i] = y; s_buf[l] = x; }
+					}
+				}
+				__syncthreads();
+			}
+		if (tid == 0) ev[j] = filtered_mean_sorted(s_buf, len, 1);
+		__syncthreads();
+	}
+}
+
+/* ------------------------------------------------------------------------------------------- */
+__global__ void __launch_bounds__(128) k_sig_sketch(sig_args_t A, dev_params_t P)
+{ /* ri_sketch_reg, rsketch.c:143-204: diff filter against the last KEPT event, quantise, pack, hash */
+	const uint32_t slot_id = blockIdx.x * blockDim.x + threadIdx.x;
+	if (slot_id >= A.n_slots) return;
+	slot_t *S = &A.slots[slot_id];
+	const uint32_t n_events = S->n_peaks; /* every emitted peak lies in (0, n_sig) */
+	uint32_t n_seeds = 0;
+	const bool gated = n_events < P.min_events;
+	if (!gated) {
+		const float *__restrict__ ev = A.events + S->e_off;
+		uint32_t *__restrict__ sh = A.seed_hash + S->e_off, *__restrict__ sp = A.seed_pos + S->e_off;
+		const int e = P.e, q = P.q;
+		const uint64_t mev = (q * e >= 64) ? ~0ULL : ((1ULL << (q * e)) - 1), mq = (1ULL << q) - 1;
+		uint64_t packed = 0; float last = 0.0f; uint32_t kept = 0;
+		for (uint32_t i = 0; i < n_events; ++i) {
+			const float v = ev[i];
+			if (i && fabsf(__fsub_rn(v, last)) < P.diff) continue;
+			last = v;
+			packed = ((packed << q) | (quantize_event(v, P.fine_min, P.fine_max, P.fine_range, 1u << q) & mq)) & mev;
+			sp[kept] = i; /* position of the kept event; seed j starts at kept event j */
+			++kept;
+			if (kept >= (uint32_t)e) sh[n_seeds++] = (uint32_t)seed_mix(packed);
+		}
+	}
+	S->n_events = n_events; S->n_seeds = n_seeds; S->gated = gated ? 1u : 0u;
+}
+
+#endif
