@@ -224,7 +224,7 @@ def main():
     step_host()
 
     # ---- timed: HBM-resident ----
-    agg = {k: 0.0 for k in ("ms_event_kernel", "ms_seed", "ms_sort", "ms_chain", "ms_post", "ms_total")}
+    agg = {k: 0.0 for k in ("ms_event_kernel", "ms_seed", "ms_sort", "ms_sort_ties", "ms_chain", "ms_post", "ms_total")}
     cnt = {k: 0 for k in ("raw_samples_consumed", "n_seeds", "event_kernel_launches", "kernel_launches", "n_chunks", "n_anchors", "n_rounds")}
     with ClockSampler(local_rank) as clk:
         barrier()

@@ -183,6 +183,7 @@ typedef struct rh_gpu_stats_s {
 	double   ms_seed, ms_sort, ms_chain, ms_post;
 	uint64_t event_kernel_launches;
 	uint64_t h2d_bytes, d2h_bytes;
+	double   ms_sort_ties;           /* part of ms_sort spent replaying klib's tie order */
 } rh_gpu_stats_t;
 void rh_gpu_get_stats(const rh_gpu_ctx *ctx, rh_gpu_stats_t *st);
 

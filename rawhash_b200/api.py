@@ -90,6 +90,7 @@ class GpuStats(C.Structure):
         ("ms_seed", C.c_double), ("ms_sort", C.c_double), ("ms_chain", C.c_double), ("ms_post", C.c_double),
         ("event_kernel_launches", C.c_uint64),
         ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64),
+        ("ms_sort_ties", C.c_double),
     ]
 
     def as_dict(self):

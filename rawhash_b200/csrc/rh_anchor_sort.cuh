@@ -206,143 +206,351 @@ __global__ void __launch_bounds__(SORT_THREADS) k_sort_block(sort_args_t A)
 	}
 }
 
-/* exact replay along tie-containing sub-arrays; one warp per slot */
-/* One warp (= one CTA) per tie-containing chunk.  The byte array the walk chases lives in dynamic
- * shared memory when the chunk fits (smem_cap bytes), else in the slot's global scratch. */
-__global__ void __launch_bounds__(32) k_sort_ties(sort_args_t A, uint32_t smem_cap)
+/* =============================================================================================
+ * k_sort_ties — exact replay of klib's MSD pass along the sub-arrays that hold a tie group.
+ * One CTA (TIE_THREADS) per chunk with ties.
+ *
+ * Per level (byte of x, from bit 56 down; levels on which the whole chunk agrees are skipped):
+ *   - the digit of every element of every pending sub-array goes to shared memory (bytes[]);
+ *   - pending sub-arrays are taken TIE_WALKERS at a time; their 256-bin histograms are built by
+ *     all threads into one table per sub-array, scanned into packed (end<<16 | head) words;
+ *   - a sub-array with ONE occupied bin passes through unchanged; with TWO occupied bins the
+ *     displacement walk has a closed form (below) evaluated by all threads; otherwise lane w of
+ *     warp 0 runs the order-dependent walk for sub-array w — up to 16 independent walks side by
+ *     side, each chasing one shared-memory byte per step;
+ *   - (x, source index) pairs are permuted to the order klib would have in memory, and bins that
+ *     hold a tie group become the next level's sub-arrays (> 64 elements) or are finished by the
+ *     stable rank sort klib's insertion sort is equivalent to (<= 64).
+ *
+ * Two-bin closed form.  Regions R0=[0,c0) and R1=[c0,len); m_1<..<m_J = positions in R0 holding
+ * bin-1 elements, z_1<..<z_J = positions in R1 holding bin-0 elements.  Cycle j drops m_j at the
+ * front of what is left of R1 (c0 for j=1, z_{j-1}+1 after), every bin-1 element up to z_j moves
+ * one slot right, and z_j falls into the hole m_j.  Elements past z_J and bin-0 elements of R0
+ * stay.  (Derived from ksort.h:126-138; checked against the walk in tests.)
+ * ===========================================================================================*/
+#define TIE_THREADS 128
+#define TIE_WARPS (TIE_THREADS / 32)
+#define TIE_WALKERS 16
+#define TIE_CLOSED_MIN 256        /* two-bin sub-arrays at least this long use the closed form */
+
+struct tie_shared_t {
+	uint32_t tab[TIE_WALKERS][256];   /* per walker: (end << 16 | head), relative to the sub-array start */
+	uint32_t tflag[TIE_WALKERS][8];   /* per walker: bins that hold a tied element (bitmask)              */
+	uint32_t wsum[TIE_WARPS];
+	uint32_t seg_beg[TIE_WALKERS], seg_len[TIE_WALKERS], seg_kind[TIE_WALKERS], seg_b0[TIE_WALKERS], seg_b1[TIE_WALKERS], seg_c0[TIE_WALKERS];
+	uint32_t n_nxt, n_term;
+	unsigned long long diff;
+};
+enum { TIE_IDENT = 0, TIE_WALK = 1, TIE_TWO = 2, TIE_BIG = 3 };
+
+/* exclusive rank of `flag` over one tile of TIE_THREADS elements; returns rank within the tile, *total = tile count */
+__device__ __forceinline__ uint32_t tie_tile_rank(bool flag, uint32_t *wsum, uint32_t *total)
+{
+	const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	const uint32_t m = __ballot_sync(0xffffffffu, flag);
+	if (lane == 0) wsum[warp] = __popc(m);
+	__syncthreads();
+	uint32_t base = 0, tot = 0;
+#pragma unroll
+	for (uint32_t w = 0; w < TIE_WARPS; ++w) { const uint32_t c = wsum[w]; if (w < warp) base += c; tot += c; }
+	__syncthreads();
+	*total = tot;
+	return base + __popc(m & lanemask_lt());
+}
+
+#define TIE_FLAG (1ULL << 31)      /* bit 31 of anchor.x is always 0 (31-bit target position): carries "has an equal key" */
+
+__global__ void __launch_bounds__(TIE_THREADS) k_sort_ties(sort_args_t A, uint32_t smem_cap, uint32_t n_lo, uint32_t n_hi)
 {
 	extern __shared__ __align__(16) uint8_t s_dyn[];
-	uint32_t *cnt = (uint32_t *)s_dyn, *head = cnt + 256, *flag = head + 256;
-	uint8_t *s_bytes = s_dyn + 3 * 256 * 4;
+	tie_shared_t &T = *(tie_shared_t *)s_dyn;
+	uint8_t *s_bytes = s_dyn + sizeof(tie_shared_t);
 
-	const uint32_t lane = threadIdx.x & 31;
-	const uint32_t li = blockIdx.x;
-	if (li >= *A.tie_count) return;
-	slot_t *S = &A.slots[A.tie_list[li]];
-	const uint32_t n = S->n_anchors;
-	slot_mem_t M = slot_mem(A.arena, S->a_off, n);
-	const anchor_t *in = M.B;
-	uint32_t *sidx = (uint32_t *)M.U;
-	uint32_t *ord = (uint32_t *)M.f, *ord2 = (uint32_t *)M.p, *dst = (uint32_t *)M.v;
-	const uint8_t *tied = (const uint8_t *)M.t;
-	uint8_t *bytes = n <= smem_cap ? s_bytes : (uint8_t *)M.t + n;
-	uint2 *wl_cur = (uint2 *)M.regs, *wl_nxt = wl_cur + (n / 64 + 2);
+	const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 	const uint32_t FULL = 0xffffffffu;
+	if (blockIdx.x >= *A.tie_count) return;
+	slot_t *S = &A.slots[A.tie_list[blockIdx.x]];
+	const uint32_t n = S->n_anchors;
+	if (n < n_lo || n >= n_hi) return;   /* the launch for the other size class takes this chunk */
+	slot_mem_t M = slot_mem(A.arena, S->a_off, n);
+	const anchor_t *__restrict__ in = M.B;
+	uint32_t *__restrict__ sidx = (uint32_t *)M.U;
+	uint64_t *xk = (uint64_t *)M.Z, *xk2 = (uint64_t *)M.W;             /* x | TIE_FLAG, in klib's current memory order */
+	uint32_t *ord = (uint32_t *)M.f, *ord2 = (uint32_t *)M.p;           /* source index, same order                     */
+	uint32_t *__restrict__ dst = (uint32_t *)M.v;
+	const uint8_t *__restrict__ tied = (const uint8_t *)M.t;
+	uint8_t *bytes = n <= smem_cap ? s_bytes : (uint8_t *)M.t + n;
+	uint32_t *zlist = (uint32_t *)M.U2, *mlist = zlist + n;            /* closed-form scratch      */
+	uint2 *wl_cur = (uint2 *)M.regs, *wl_nxt = wl_cur + (n / 64 + 2);  /* pending sub-arrays (>64) */
+	uint2 *term = (uint2 *)((uint64_t *)M.W + n);                      /* M.W is 16n bytes: upper half holds terminal bins */
 
 	RH_PROF_BEGIN(A.prof);
-	for (uint32_t i = lane; i < n; i += 32) ord[i] = i;
-	uint32_t n_cur = 1, n_nxt = 0;
-	if (lane == 0) wl_cur[0] = make_uint2(0u, n);
-	__syncwarp();
+	if (tid == 0) { T.diff = 0ULL; T.n_nxt = 0; T.n_term = 0; }
+	__syncthreads();
+	{
+		const uint64_t x0 = in[0].x;
+		unsigned long long diff = 0;
+		for (uint32_t i = tid; i < n; i += TIE_THREADS) {
+			const uint64_t x = in[i].x;
+			xk[i] = x | (tied[i] ? TIE_FLAG : 0ULL); ord[i] = i;
+			diff |= x ^ x0;
+		}
+#pragma unroll
+		for (int o = 16; o > 0; o >>= 1) diff |= __shfl_xor_sync(FULL, diff, o);
+		if (lane == 0 && diff) atomicOr(&T.diff, diff);
+	}
+	if (tid == 0) wl_cur[0] = make_uint2(0u, n);
+	__syncthreads();
+	const unsigned long long dmask = T.diff;
+	uint32_t n_cur = 1;
+	RH_PROF_MARK(A.prof, 16, tid == 0);
 
 	for (int shift = 56; shift >= 0 && n_cur > 0; shift -= 8) {
-		n_nxt = 0;
-		for (uint32_t s = 0; s < n_cur; ++s) {
-			const uint2 seg = wl_cur[s];
-			const uint32_t beg = seg.x, len = seg.y;
-			for (uint32_t b = lane; b < 256; b += 32) { cnt[b] = 0; flag[b] = 0; }
-			__syncwarp();
-			for (uint32_t i = lane; i < len; i += 32) {
-				const uint32_t o = ord[beg + i];
-				const uint32_t b = (uint32_t)(in[o].x >> shift) & 255;
-				bytes[beg + i] = (uint8_t)b;
-				atomicAdd(&cnt[b], 1u);
-				if (tied[o]) flag[b] = 1;
-			}
-			__syncwarp();
-			RH_PROF_MARK(A.prof, 16, lane == 0);
-			const uint32_t b0 = bytes[beg];
-			if (cnt[b0] == len) { /* nothing moves at this level */
-				if (shift > 0) { if (lane == 0) wl_nxt[n_nxt] = seg; ++n_nxt; }
-				else { for (uint32_t i = lane; i < len; i += 32) sidx[beg + i] = ord[beg + i]; }
-				__syncwarp();
-				continue;
-			}
-			/* bucket starts */
-			uint32_t run = 0;
-			for (uint32_t b = lane; b < 256; b += 32) {
-				const uint32_t v = cnt[b];
-				uint32_t incl = v;
-#pragma unroll
-				for (int o = 1; o < 32; o <<= 1) { const uint32_t u = __shfl_up_sync(FULL, incl, o); if (lane >= o) incl += u; }
-				head[b] = run + incl - v;
-				run += __shfl_sync(FULL, incl, 31);
-			}
-			__syncwarp();
-			RH_PROF_MARK(A.prof, 17, lane == 0);
-			/* the displacement-cycle walk (ksort.h:126-138), on bytes: dst[i] = slot element i lands in */
-			if (lane == 0) {
-				uint32_t region_end = 0;
-				for (uint32_t k = 0; k < 256; ++k) {
-					region_end += cnt[k];
-					uint32_t hk = head[k];
-					while (hk != region_end) {
-						uint32_t e = hk; /* element in hand = original occupant of slot e */
-						uint32_t d = bytes[beg + e];
-						while (d != k) {
-							const uint32_t hd = head[d];
-							dst[beg + e] = hd;
-							head[d] = hd + 1;
-							e = hd;
-							d = bytes[beg + e];
-						}
-						dst[beg + e] = hk;
-						++hk;
+		if (((dmask >> shift) & 255ULL) == 0) continue; /* every sub-array passes through unchanged */
+		for (uint32_t s0 = 0; s0 < n_cur; s0 += TIE_WALKERS) {
+			const uint32_t nb = min((uint32_t)TIE_WALKERS, n_cur - s0);
+			/* ---- digits, histograms, tie flags ---- */
+			for (uint32_t k = tid; k < nb * 256; k += TIE_THREADS) (&T.tab[0][0])[k] = 0;
+			for (uint32_t k = tid; k < nb * 8; k += TIE_THREADS) (&T.tflag[0][0])[k] = 0;
+			if (tid < nb) { const uint2 seg = wl_cur[s0 + tid]; T.seg_beg[tid] = seg.x; T.seg_len[tid] = seg.y; }
+			__syncthreads();
+			for (uint32_t w = 0; w < nb; ++w) {
+				const uint32_t beg = T.seg_beg[w], len = T.seg_len[w];
+				const uint64_t *__restrict__ xs = xk + beg;
+				for (uint32_t t0 = 0; t0 < len; t0 += TIE_THREADS) {
+					const uint32_t i = t0 + tid;
+					const bool ok = i < len;
+					const uint32_t act = __ballot_sync(FULL, ok);
+					if (ok) {
+						const uint64_t x = xs[i];
+						const uint32_t d = (uint32_t)((x & ~TIE_FLAG) >> shift) & 255u;
+						bytes[beg + i] = (uint8_t)d;
+						const uint32_t peers = __match_any_sync(act, d);
+						if ((peers & lanemask_lt()) == 0) atomicAdd(&T.tab[w][d], (uint32_t)__popc(peers));
+						if (x & TIE_FLAG) atomicOr(&T.tflag[w][d >> 5], 1u << (d & 31));
 					}
-					head[k] = hk;
 				}
 			}
-			__syncwarp();
-			RH_PROF_MARK(A.prof, 18, lane == 0);
-			for (uint32_t i = lane; i < len; i += 32) ord2[beg + dst[beg + i]] = ord[beg + i];
-			__syncwarp();
-			for (uint32_t i = lane; i < len; i += 32) ord[beg + i] = ord2[beg + i];
-			__syncwarp();
-			RH_PROF_MARK(A.prof, 19, lane == 0);
-			/* children that contain a tie group */
-			uint32_t acc = 0;
-			for (uint32_t bb = 0; bb < 256; bb += 32) {
-				const uint32_t b = bb + lane;
-				const uint32_t c = cnt[b];
-				uint32_t incl = c;
+			__syncthreads();
+			/* ---- scan each table into packed (end<<16 | head); classify the sub-array ---- */
+			for (uint32_t w = warp; w < nb; w += TIE_WARPS) {
+				const uint32_t len = T.seg_len[w];
+				uint32_t c[8], tot = 0, nz = 0;
+#pragma unroll
+				for (int q = 0; q < 8; ++q) { c[q] = T.tab[w][lane * 8 + q]; tot += c[q]; nz += c[q] != 0; }
+				uint32_t incl = tot;
 #pragma unroll
 				for (int o = 1; o < 32; o <<= 1) { const uint32_t u = __shfl_up_sync(FULL, incl, o); if (lane >= o) incl += u; }
-				const uint32_t start = beg + acc + incl - c;
-				acc += __shfl_sync(FULL, incl, 31);
-				const bool has = flag[b] && c > 1;
-				const bool recurse = has && shift > 0 && c > 64;
-				const uint32_t rm = __ballot_sync(FULL, recurse);
-				if (recurse) wl_nxt[n_nxt + __popc(rm & lanemask_lt())] = make_uint2(start, c);
-				n_nxt += __popc(rm);
-				/* terminal buckets, one at a time on the whole warp */
-				uint32_t tm = __ballot_sync(FULL, has && !recurse);
-				while (tm) {
-					const int src = __ffs(tm) - 1; tm &= tm - 1;
-					const uint32_t ts = __shfl_sync(FULL, start, src), tc = __shfl_sync(FULL, c, src);
-					if (shift > 0) { /* <=64 elements: klib finishes with a stable insertion sort on the full key */
+				uint32_t nzt = nz;
+#pragma unroll
+				for (int o = 16; o > 0; o >>= 1) nzt += __shfl_xor_sync(FULL, nzt, o);
+				/* first and second occupied bins */
+				uint32_t first = 0xffffffffu, second = 0xffffffffu, first_cnt = 0;
+#pragma unroll
+				for (int q = 7; q >= 0; --q) if (c[q]) { second = first; first = lane * 8 + q; first_cnt = c[q]; }
+				const uint32_t m1 = __ballot_sync(FULL, first != 0xffffffffu);
+				const int l1 = __ffs(m1) - 1;
+				const uint32_t f_first = __shfl_sync(FULL, first, l1), f_second = __shfl_sync(FULL, second, l1);
+				const uint32_t m2 = m1 & ~(1u << l1);
+				const uint32_t g_first = __shfl_sync(FULL, first, m2 ? __ffs(m2) - 1 : 0);
+				const uint32_t b0 = f_first, b1 = f_second != 0xffffffffu ? f_second : g_first;
+				const uint32_t c0 = __shfl_sync(FULL, first_cnt, l1);
+				const uint32_t kind = nzt <= 1 ? TIE_IDENT : ((nzt == 2 && len >= TIE_CLOSED_MIN) ? TIE_TWO : (len > 65535u ? TIE_BIG : TIE_WALK));
+				uint32_t start = incl - tot;
+				if (kind != TIE_BIG) {
+#pragma unroll
+					for (int q = 0; q < 8; ++q) { T.tab[w][lane * 8 + q] = ((start + c[q]) << 16) | start; start += c[q]; }
+				}
+				if (lane == 0) { T.seg_kind[w] = kind; T.seg_b0[w] = b0; T.seg_b1[w] = b1; T.seg_c0[w] = c0; }
+			}
+			__syncthreads();
+			RH_PROF_MARK(A.prof, 17, tid == 0);
+			/* ---- the order-dependent walks: lane w of warp 0 takes sub-array w.  One iteration = one element
+			 *      read (ksort.h:126-138 as a walk over region FIFOs): the element at rp belongs to bin d, goes to
+			 *      the head of region d, and the element found there is read next — unless d is the region being
+			 *      completed (k), whose hole it fills and whose next slot is read.  Branch free so that walkers with
+			 *      different histories stay converged. ---- */
+			if (warp == 0) {
+				const bool walker = lane < nb && T.seg_kind[lane < nb ? lane : 0] == TIE_WALK;
+				uint32_t *tab = T.tab[lane < nb ? lane : 0];
+				const uint8_t *bs = bytes + T.seg_beg[lane < nb ? lane : 0];
+				uint32_t *D = dst + T.seg_beg[lane < nb ? lane : 0];
+				uint32_t k = 0, rp = 0;
+				bool live = walker;
+				if (live) { for (;; ++k) { const uint32_t wk = tab[k]; if ((wk & 0xffffu) != (wk >> 16)) { rp = wk & 0xffffu; break; } } }
+				while (__any_sync(FULL, live)) {
+					if (live) {
+						const uint32_t d = bs[rp];
+						const uint32_t wd = tab[d];
+						const uint32_t h = wd & 0xffffu;
+						const uint32_t home = d == k;
+						D[rp] = h;
+						tab[d] = wd + 1;
+						rp = h + home;
+						if (home && h + 1 == (wd >> 16)) { /* region k complete: next unfinished region */
+							do { ++k; if (k < 256) { const uint32_t wk = tab[k]; rp = wk & 0xffffu; if (rp != (wk >> 16)) break; } } while (k < 256);
+							live = k < 256;
+						}
+					}
+				}
+			}
+			__syncthreads();
+			RH_PROF_MARK(A.prof, 18, tid == 0);
+			/* ---- sub-arrays longer than the packed tables can address: one thread, plain 32-bit tables ---- */
+			for (uint32_t w = 0; w < nb; ++w) {
+				if (T.seg_kind[w] != TIE_BIG) continue;
+				const uint32_t beg = T.seg_beg[w];
+				uint32_t *cnt = T.tab[w];                 /* counts (unscanned)   */
+				uint32_t *head = (uint32_t *)mlist;       /* 256 words of scratch */
+				if (tid == 0) {
+					uint32_t acc = 0;
+					for (uint32_t b = 0; b < 256; ++b) { head[b] = acc; acc += cnt[b]; }
+					uint32_t region_end = 0;
+					for (uint32_t k = 0; k < 256; ++k) {
+						region_end += cnt[k];
+						uint32_t hk = head[k];
+						while (hk != region_end) {
+							uint32_t e = hk, d = bytes[beg + e];
+							while (d != k) { const uint32_t hd = head[d]; dst[beg + e] = hd; head[d] = hd + 1; e = hd; d = bytes[beg + e]; }
+							dst[beg + e] = hk; ++hk;
+						}
+					}
+				}
+				__syncthreads();
+			}
+			/* ---- two occupied bins: closed form, all threads ---- */
+			for (uint32_t w = 0; w < nb; ++w) {
+				if (T.seg_kind[w] != TIE_TWO) continue;
+				const uint32_t beg = T.seg_beg[w], len = T.seg_len[w], b0 = T.seg_b0[w];
+				const uint32_t c0 = T.seg_c0[w]; /* end of region 0 (its start is 0) */
+				uint32_t run = 0;
+				for (uint32_t t0 = c0; t0 < len; t0 += TIE_THREADS) { /* z_j: bin-0 elements inside region 1 */
+					const uint32_t q = t0 + tid;
+					const bool f = q < len && bytes[beg + q] == b0;
+					uint32_t tot; const uint32_t r = tie_tile_rank(f, T.wsum, &tot);
+					if (f) zlist[run + r] = q;
+					run += tot;
+				}
+				const uint32_t J = run;
+				__syncthreads();
+				run = 0;
+				for (uint32_t t0 = 0; t0 < c0; t0 += TIE_THREADS) { /* m_j: bin-1 elements inside region 0 */
+					const uint32_t q = t0 + tid;
+					const bool in_r = q < c0;
+					const bool f = in_r && bytes[beg + q] != b0;
+					uint32_t tot; const uint32_t r = tie_tile_rank(f, T.wsum, &tot);
+					if (f) { const uint32_t j = run + r; mlist[j] = q; dst[beg + q] = j ? zlist[j - 1] + 1 : c0; }
+					else if (in_r) dst[beg + q] = q;
+					run += tot;
+				}
+				__syncthreads();
+				const uint32_t zlast = J ? zlist[J - 1] : 0u;
+				run = 0;
+				for (uint32_t t0 = c0; t0 < len; t0 += TIE_THREADS) {
+					const uint32_t q = t0 + tid;
+					const bool in_r = q < len;
+					const bool f = in_r && bytes[beg + q] == b0;
+					uint32_t tot; const uint32_t r = tie_tile_rank(f, T.wsum, &tot);
+					if (f) dst[beg + q] = mlist[run + r];
+					else if (in_r) dst[beg + q] = (J && q < zlast) ? q + 1 : q;
+					run += tot;
+				}
+				__syncthreads();
+			}
+			RH_PROF_MARK(A.prof, 19, tid == 0);
+			/* ---- move (x, idx) pairs into klib's memory order, into the other buffer pair ---- */
+			for (uint32_t w = 0; w < nb; ++w) {
+				const uint32_t beg = T.seg_beg[w], len = T.seg_len[w];
+				const bool ident = T.seg_kind[w] == TIE_IDENT;
+				const uint64_t *__restrict__ xs = xk + beg; const uint32_t *__restrict__ os = ord + beg; const uint32_t *__restrict__ ds = dst + beg;
+				uint64_t *__restrict__ xd = xk2 + beg; uint32_t *__restrict__ od = ord2 + beg;
+				uint32_t i = tid;
+				for (; i + 3 * TIE_THREADS < len; i += 4 * TIE_THREADS) {
+					uint64_t xv[4]; uint32_t ov[4], jv[4];
+#pragma unroll
+					for (int u = 0; u < 4; ++u) { xv[u] = xs[i + u * TIE_THREADS]; ov[u] = os[i + u * TIE_THREADS]; jv[u] = ident ? i + u * TIE_THREADS : ds[i + u * TIE_THREADS]; }
+#pragma unroll
+					for (int u = 0; u < 4; ++u) { xd[jv[u]] = xv[u]; od[jv[u]] = ov[u]; }
+				}
+				for (; i < len; i += TIE_THREADS) { const uint32_t j = ident ? i : ds[i]; xd[j] = xs[i]; od[j] = os[i]; }
+			}
+			__syncthreads();
+			/* ---- children (their data now lives in xk2/ord2) ---- */
+			for (uint32_t w = 0; w < nb; ++w) {
+				const uint32_t beg = T.seg_beg[w], len = T.seg_len[w], kind = T.seg_kind[w];
+				if (kind == TIE_IDENT) {
+					if (shift > 0) { if (tid == 0) wl_nxt[atomicAdd(&T.n_nxt, 1u)] = make_uint2(beg, len); }
+					else for (uint32_t i = tid; i < len; i += TIE_THREADS) sidx[beg + i] = ord2[beg + i];
+					continue;
+				}
+				for (uint32_t b = tid; b < 256; b += TIE_THREADS) {
+					if (!((T.tflag[w][b >> 5] >> (b & 31)) & 1u)) continue;
+					uint32_t start, end;
+					if (kind == TIE_TWO) { if (b == T.seg_b0[w]) { start = 0; end = T.seg_c0[w]; } else { start = T.seg_c0[w]; end = len; } }
+					else if (kind == TIE_BIG) { start = 0; for (uint32_t q = 0; q < b; ++q) start += T.tab[w][q]; end = start + T.tab[w][b]; }
+					else { start = b ? (T.tab[w][b - 1] >> 16) : 0u; end = T.tab[w][b] >> 16; }
+					const uint32_t c = end - start;
+					if (c < 2) continue;
+					if (shift > 0 && c > 64) wl_nxt[atomicAdd(&T.n_nxt, 1u)] = make_uint2(beg + start, c);
+					else term[atomicAdd(&T.n_term, 1u)] = make_uint2(beg + start, c);
+				}
+			}
+			__syncthreads();
+			/* terminal bins: <= 64 elements finish with klib's stable insertion sort on the full key (a rank
+			 * sort here); on the last byte the bin keeps the order the walk left it in */
+			{
+				const uint32_t nt = T.n_term;
+				for (uint32_t q = warp; q < nt; q += TIE_WARPS) {
+					const uint2 tb = term[q];
+					const uint32_t ts = tb.x, tc = tb.y;
+					if (shift > 0) {
 						uint32_t o0 = 0, o1 = 0; uint64_t k0 = 0, k1 = 0;
-						if (lane < tc) { o0 = ord[ts + lane]; k0 = in[o0].x; }
-						if (32 + lane < tc) { o1 = ord[ts + 32 + lane]; k1 = in[o1].x; }
+						if (lane < tc) { o0 = ord2[ts + lane]; k0 = xk2[ts + lane] & ~TIE_FLAG; }
+						if (32 + lane < tc) { o1 = ord2[ts + 32 + lane]; k1 = xk2[ts + 32 + lane] & ~TIE_FLAG; }
 						uint32_t r0, r1;
 						warp_rank64(k0, k1, tc, lane, &r0, &r1);
 						if (lane < tc) sidx[ts + r0] = o0;
 						if (32 + lane < tc) sidx[ts + r1] = o1;
-					} else { /* last byte: the bucket keeps the order the walk left it in */
-						for (uint32_t i = lane; i < tc; i += 32) sidx[ts + i] = ord[ts + i];
+					} else {
+						for (uint32_t i = lane; i < tc; i += 32) sidx[ts + i] = ord2[ts + i];
 					}
 				}
+				__syncthreads();
+				if (tid == 0) T.n_term = 0;
+				__syncthreads();
 			}
-			__syncwarp();
+			RH_PROF_MARK(A.prof, 20, tid == 0);
 		}
-		RH_PROF_MARK(A.prof, 20, lane == 0);
-		uint2 *t = wl_cur; wl_cur = wl_nxt; wl_nxt = t;
-		n_cur = n_nxt;
-		__syncwarp();
+		/* every pending sub-array of the next level was written to the other buffer pair */
+		{ uint2 *t = wl_cur; wl_cur = wl_nxt; wl_nxt = t; }
+		{ uint64_t *t = xk; xk = xk2; xk2 = t; }
+		{ uint32_t *t = ord; ord = ord2; ord2 = t; }
+		n_cur = T.n_nxt;
+		__syncthreads();
+		if (tid == 0) T.n_nxt = 0;
+		__syncthreads();
 	}
-	__syncwarp();
-	anchor_t *out = M.A;
-	for (uint32_t i = lane; i < n; i += 32) out[i] = in[sidx[i]];
-	RH_PROF_MARK(A.prof, 21, lane == 0);
+	/* sub-arrays that ran out of varying bytes: fully equal keys keep their current order */
+	for (uint32_t s = 0; s < n_cur; ++s) {
+		const uint2 seg = wl_cur[s];
+		for (uint32_t i = tid; i < seg.y; i += TIE_THREADS) sidx[seg.x + i] = ord[seg.x + i];
+	}
+	__syncthreads();
+	anchor_t *__restrict__ out = M.A;
+	{
+		uint32_t i = tid;
+		for (; i + 3 * TIE_THREADS < n; i += 4 * TIE_THREADS) {
+			uint32_t sv[4]; anchor_t av[4];
+#pragma unroll
+			for (int u = 0; u < 4; ++u) sv[u] = sidx[i + u * TIE_THREADS];
+#pragma unroll
+			for (int u = 0; u < 4; ++u) av[u] = in[sv[u]];
+#pragma unroll
+			for (int u = 0; u < 4; ++u) out[i + u * TIE_THREADS] = av[u];
+		}
+		for (; i < n; i += TIE_THREADS) out[i] = in[sidx[i]];
+	}
+	RH_PROF_MARK(A.prof, 21, tid == 0);
 }
 
 #endif

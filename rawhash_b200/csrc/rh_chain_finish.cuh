@@ -463,10 +463,10 @@ __global__ void __launch_bounds__(FIN_WARPS * 32, 8) k_chain_finish(k3_args_t A,
 				__syncwarp();
 
 				/* ---- mm_gen_regs ---- */
-				if (n_u > M.reg_cap / 2) { if (lane == 0) atomicExch(A.err, 3u); n_u = 0; }
+				if (n_u > fin_regs_cap(S->n_anchors)) { if (lane == 0) atomicExch(A.err, 3u); n_u = 0; }
 			}
 			if (n_u > 0) {
-				r = M.regs + M.reg_cap / 2; /* upper half: the lower half is sort scratch (fin_scratch) */
+				r = (dev_reg_t *)((uint8_t *)M.regs + fin_regs_off(S->n_anchors)); /* after the sort scratch (fin_scratch) */
 				RH_PROF_MARK(A.prof, 37, lane == 0);
 				warp_klib_sort_pairs(z, n_u, w, X, cnt, head, lane);
 				RH_PROF_MARK(A.prof, 38, lane == 0);

@@ -44,6 +44,7 @@ struct dev_reg_t {
 	int32_t id, cnt, rid, score, qs, qe, rs, re, parent, subsc, as, n_sub, score0;
 	uint32_t mapq, rev, hash;
 };
+static_assert(sizeof(dev_reg_t) == 64, "fin_regs_cap() assumes 64-byte region records");
 
 /* ---- exact arithmetic helpers: the float/double operations of the reference as compiled
  *      (x86-64 + FMA contraction).  The file is built with --fmad=false so nothing else fuses. */

@@ -59,8 +59,9 @@ struct timed_span { cudaEvent_t a, b; int kind; };
 
 } // namespace
 
-#define TIES_SMEM_CAP (160u * 1024u)
-enum { T_EVENT = 0, T_SEED, T_SORT, T_CHAIN, T_POST, T_LEN, T_NKIND };
+#define TIES_SMEM_CAP (180u * 1024u)   /* digit bytes of the largest chunk kept in shared memory */
+#define TIES_SMALL (24u * 1024u)       /* size class boundary: small chunks run 5 CTAs per SM    */
+enum { T_EVENT = 0, T_SEED, T_SORT, T_CHAIN, T_POST, T_LEN, T_TIES, T_NKIND };
 
 struct rh_gpu_ctx_s {
 	int device = 0;
@@ -238,9 +239,12 @@ int run_round(rh_gpu_ctx *c, round_io &io, int carry_in_idx)
 		{
 			uint32_t maxn = 0;
 			for (uint32_t q = g0; q < g1; ++q) if (!io.slots[q].gated) maxn = std::max(maxn, io.slots[q].n_anchors);
-			const uint32_t cap = std::min<uint32_t>((maxn + 15) & ~15u, TIES_SMEM_CAP);
-			span_guard g(c, T_SORT);
-			k_sort_ties<<<gn, 32, 3 * 256 * 4 + cap, s>>>(as, cap);
+			span_guard g(c, T_TIES, maxn >= TIES_SMALL ? 2 : 1);
+			k_sort_ties<<<gn, TIE_THREADS, sizeof(tie_shared_t) + TIES_SMALL, s>>>(as, TIES_SMALL, 0u, TIES_SMALL);
+			if (maxn >= TIES_SMALL) {
+				const uint32_t cap = std::min<uint32_t>((maxn + 15) & ~15u, TIES_SMEM_CAP);
+				k_sort_ties<<<gn, TIE_THREADS, sizeof(tie_shared_t) + cap, s>>>(as, cap, TIES_SMALL, 0xffffffffu);
+			}
 		}
 		if (io.tap) { /* sorted anchor list of the single tapped slot */
 			rh_tap_t *T = io.tap_out; const slot_t &sl = io.slots[0];
@@ -250,6 +254,17 @@ int run_round(rh_gpu_ctx *c, round_io &io, int carry_in_idx)
 				CUDA_TRY(cudaStreamSynchronize(s));
 				io.tap_off[2] += sl.n_anchors;
 			}
+		}
+		if (c->prof_on) { /* RH_PROF=1: distribution of chunk sizes and tie chunks in this group (debug aid, adds a sync) */
+			std::vector<slot_t> dbg(gn);
+			cudaMemcpyAsync(dbg.data(), c->d_slots.p + g0, gn * sizeof(slot_t), cudaMemcpyDeviceToHost, s);
+			cudaStreamSynchronize(s);
+			std::vector<uint32_t> na, nt;
+			for (const slot_t &q : dbg) { if (q.gated || q.n_anchors == 0) continue; na.push_back(q.n_anchors); if (q.n_ties) nt.push_back(q.n_anchors); }
+			std::sort(na.begin(), na.end()); std::sort(nt.begin(), nt.end());
+			auto pc = [](const std::vector<uint32_t> &v, double f) { return v.empty() ? 0u : v[std::min(v.size() - 1, (size_t)(f * v.size()))]; };
+			fprintf(stderr, "[RH_PROF] group: %u slots, %zu chained (n p50=%u p90=%u p99=%u max=%u), %zu with ties (n p50=%u p90=%u max=%u)\n",
+			        gn, na.size(), pc(na, .5), pc(na, .9), pc(na, .99), pc(na, 1.0), nt.size(), pc(nt, .5), pc(nt, .9), pc(nt, 1.0));
 		}
 		{ span_guard g(c, T_CHAIN); k_chain_dp<<<gn, DP_THREADS, 0, s>>>(a3, c->D); }
 		{ span_guard g(c, T_POST); k_chain_finish<<<(gn + FIN_WARPS - 1) / FIN_WARPS, FIN_WARPS * 32, 0, s>>>(a3, c->D); }
@@ -278,7 +293,7 @@ int collect_spans(rh_gpu_ctx *c)
 	}
 	double ms[T_NKIND] = {0};
 	for (const timed_span &sp : c->spans) { float t = 0; if (cudaEventElapsedTime(&t, sp.a, sp.b) == cudaSuccess) ms[sp.kind] += t; }
-	c->st.ms_event_kernel += ms[T_EVENT]; c->st.ms_seed += ms[T_SEED]; c->st.ms_sort += ms[T_SORT];
+	c->st.ms_event_kernel += ms[T_EVENT]; c->st.ms_seed += ms[T_SEED]; c->st.ms_sort += ms[T_SORT] + ms[T_TIES]; c->st.ms_sort_ties += ms[T_TIES];
 	c->st.ms_chain += ms[T_CHAIN]; c->st.ms_post += ms[T_POST] + ms[T_LEN];
 	c->spans.clear(); c->ev_used = 0;
 	return RH_OK;
@@ -457,7 +472,7 @@ extern "C" rh_gpu_ctx *rh_gpu_init(const rh_index_t *idx, const rh_params_t *p, 
 	c->prof_on = getenv("RH_PROF") != NULL;
 	if (c->d_prof.reserve(64)) return fail(NULL);
 	cudaMemset(c->d_prof.p, 0, 64 * 8);
-	if (cudaFuncSetAttribute(k_sort_ties, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * 256 * 4 + TIES_SMEM_CAP) != cudaSuccess) return fail("cudaFuncSetAttribute(k_sort_ties) failed");
+	if (cudaFuncSetAttribute(k_sort_ties, cudaFuncAttributeMaxDynamicSharedMemorySize, sizeof(tie_shared_t) + TIES_SMEM_CAP) != cudaSuccess) return fail("cudaFuncSetAttribute(k_sort_ties) failed");
 	if (cudaStreamSynchronize(c->stream) != cudaSuccess) return fail("index upload failed");
 	/* ---- work arenas ---- */
 	size_t free_b = 0, total_b = 0;
@@ -607,8 +622,7 @@ extern "C" int rh_gpu_tap_read(rh_gpu_ctx *c, const int16_t *raw, uint64_t raw_l
 			const uint8_t *base = c->d_arena.p + r.a_off;
 			if (r.n_u) CUDA_TRY(cudaMemcpyAsync(tap->u + toff[3], base + 80 * n, r.n_u * 8, cudaMemcpyDeviceToHost, s));   /* slot_mem: U  */
 			if (r.n_v) CUDA_TRY(cudaMemcpyAsync(tap->chain_a + 2 * toff[4], base, (size_t)r.n_v * 16, cudaMemcpyDeviceToHost, s)); /* A */
-			const uint64_t reg_cap = (48 * n + 1024) / sizeof(dev_reg_t); /* slot_mem::regs, upper half (k_chain_finish) */
-			if (r.n_regs) CUDA_TRY(cudaMemcpyAsync(regs.data(), base + 96 * n + (reg_cap / 2) * sizeof(dev_reg_t), r.n_regs * sizeof(dev_reg_t), cudaMemcpyDeviceToHost, s));
+			if (r.n_regs) CUDA_TRY(cudaMemcpyAsync(regs.data(), base + 96 * n + fin_regs_off(n), r.n_regs * sizeof(dev_reg_t), cudaMemcpyDeviceToHost, s));
 		}
 		CUDA_TRY(cudaStreamSynchronize(s));
 		if (r.n_v) CUDA_TRY(cudaMemcpy(tap->prev_a + 2 * toff[4], c->d_carry[(cc & 1) ^ 1].p + rs.prev_off, (size_t)r.n_v * 16, cudaMemcpyDeviceToHost));
