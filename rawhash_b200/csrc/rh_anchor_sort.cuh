@@ -216,7 +216,7 @@ __global__ void __launch_bounds__(SORT_THREADS) k_sort_block(sort_args_t A)
  *     all threads into one table per sub-array, scanned into packed (end<<16 | head) words;
  *   - a sub-array with ONE occupied bin passes through unchanged; with TWO occupied bins the
  *     displacement walk has a closed form (below) evaluated by all threads; otherwise lane w of
- *     warp 0 runs the order-dependent walk for sub-array w — up to 16 independent walks side by
+ *     warp 0 runs the order-dependent walk for sub-array w — up to 8 independent walks side by
  *     side, each chasing one shared-memory byte per step;
  *   - (x, source index) pairs are permuted to the order klib would have in memory, and bins that
  *     hold a tie group become the next level's sub-arrays (> 64 elements) or are finished by the
@@ -230,7 +230,7 @@ __global__ void __launch_bounds__(SORT_THREADS) k_sort_block(sort_args_t A)
  * ===========================================================================================*/
 #define TIE_THREADS 128
 #define TIE_WARPS (TIE_THREADS / 32)
-#define TIE_WALKERS 16
+#define TIE_WALKERS 8
 #define TIE_CLOSED_MIN 256        /* two-bin sub-arrays at least this long use the closed form */
 
 struct tie_shared_t {
@@ -260,41 +260,39 @@ __device__ __forceinline__ uint32_t tie_tile_rank(bool flag, uint32_t *wsum, uin
 
 #define TIE_FLAG (1ULL << 31)      /* bit 31 of anchor.x is always 0 (31-bit target position): carries "has an equal key" */
 
-__global__ void __launch_bounds__(TIE_THREADS) k_sort_ties(sort_args_t A, uint32_t smem_cap, uint32_t n_lo, uint32_t n_hi)
-{
-	extern __shared__ __align__(16) uint8_t s_dyn[];
-	tie_shared_t &T = *(tie_shared_t *)s_dyn;
-	uint8_t *s_bytes = s_dyn + sizeof(tie_shared_t);
+/* global work space of one replay, every array sized for the n elements being sorted */
+struct klib_ws_t {
+	uint64_t *xk, *xk2;      /* keys (| TIE_FLAG in tie mode) in klib's current memory order, ping-pong */
+	uint32_t *ord, *ord2;    /* payload, same order, ping-pong                                          */
+	uint32_t *dst;           /* destination of every element of the level being replayed                */
+	uint32_t *sidx;          /* out: payload of the element at each final position                      */
+	uint32_t *zlist, *mlist; /* closed-form scratch, n words each                                       */
+	uint2 *term;             /* terminal bins of a level, <= n/2 entries (may alias zlist/mlist)         */
+	uint2 *wl0, *wl1;        /* pending sub-arrays (> 64 elements), n/64+2 entries each                 */
+};
 
+/* Exact replay of klib's radix_sort on the n > 64 (key, payload) pairs in W.xk/W.ord, by one CTA of
+ * TIE_THREADS threads.  ALL = false: only bins that hold a TIE_FLAGged element are followed and only
+ * their positions of W.sidx are written (the caller already knows every other position).  ALL = true:
+ * a full sort, every position of W.sidx is written. */
+template <bool ALL>
+__device__ void cta_klib_replay(tie_shared_t &T, uint8_t *bytes, klib_ws_t W, const uint32_t n, unsigned long long *prof)
+{
 	const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 	const uint32_t FULL = 0xffffffffu;
-	if (blockIdx.x >= *A.tie_count) return;
-	slot_t *S = &A.slots[A.tie_list[blockIdx.x]];
-	const uint32_t n = S->n_anchors;
-	if (n < n_lo || n >= n_hi) return;   /* the launch for the other size class takes this chunk */
-	slot_mem_t M = slot_mem(A.arena, S->a_off, n);
-	const anchor_t *__restrict__ in = M.B;
-	uint32_t *__restrict__ sidx = (uint32_t *)M.U;
-	uint64_t *xk = (uint64_t *)M.Z, *xk2 = (uint64_t *)M.W;             /* x | TIE_FLAG, in klib's current memory order */
-	uint32_t *ord = (uint32_t *)M.f, *ord2 = (uint32_t *)M.p;           /* source index, same order                     */
-	uint32_t *__restrict__ dst = (uint32_t *)M.v;
-	const uint8_t *__restrict__ tied = (const uint8_t *)M.t;
-	uint8_t *bytes = n <= smem_cap ? s_bytes : (uint8_t *)M.t + n;
-	uint32_t *zlist = (uint32_t *)M.U2, *mlist = zlist + n;            /* closed-form scratch      */
-	uint2 *wl_cur = (uint2 *)M.regs, *wl_nxt = wl_cur + (n / 64 + 2);  /* pending sub-arrays (>64) */
-	uint2 *term = (uint2 *)((uint64_t *)M.W + n);                      /* M.W is 16n bytes: upper half holds terminal bins */
-
-	RH_PROF_BEGIN(A.prof);
+	uint64_t *xk = W.xk, *xk2 = W.xk2;
+	uint32_t *ord = W.ord, *ord2 = W.ord2;
+	uint32_t *__restrict__ dst = W.dst, *__restrict__ sidx = W.sidx, *zlist = W.zlist, *mlist = W.mlist;
+	uint2 *wl_cur = W.wl0, *wl_nxt = W.wl1, *term = W.term;
+	const uint64_t keymask = ALL ? ~0ULL : ~TIE_FLAG;
+	RH_PROF_BEGIN(prof);
+	__syncthreads();
 	if (tid == 0) { T.diff = 0ULL; T.n_nxt = 0; T.n_term = 0; }
 	__syncthreads();
 	{
-		const uint64_t x0 = in[0].x;
+		const uint64_t x0 = xk[0] & keymask;
 		unsigned long long diff = 0;
-		for (uint32_t i = tid; i < n; i += TIE_THREADS) {
-			const uint64_t x = in[i].x;
-			xk[i] = x | (tied[i] ? TIE_FLAG : 0ULL); ord[i] = i;
-			diff |= x ^ x0;
-		}
+		for (uint32_t i = tid; i < n; i += TIE_THREADS) diff |= (xk[i] & keymask) ^ x0;
 #pragma unroll
 		for (int o = 16; o > 0; o >>= 1) diff |= __shfl_xor_sync(FULL, diff, o);
 		if (lane == 0 && diff) atomicOr(&T.diff, diff);
@@ -303,7 +301,7 @@ __global__ void __launch_bounds__(TIE_THREADS) k_sort_ties(sort_args_t A, uint32
 	__syncthreads();
 	const unsigned long long dmask = T.diff;
 	uint32_t n_cur = 1;
-	RH_PROF_MARK(A.prof, 16, tid == 0);
+	RH_PROF_MARK(prof, 16, tid == 0);
 
 	for (int shift = 56; shift >= 0 && n_cur > 0; shift -= 8) {
 		if (((dmask >> shift) & 255ULL) == 0) continue; /* every sub-array passes through unchanged */
@@ -323,11 +321,11 @@ __global__ void __launch_bounds__(TIE_THREADS) k_sort_ties(sort_args_t A, uint32
 					const uint32_t act = __ballot_sync(FULL, ok);
 					if (ok) {
 						const uint64_t x = xs[i];
-						const uint32_t d = (uint32_t)((x & ~TIE_FLAG) >> shift) & 255u;
+						const uint32_t d = (uint32_t)((x & keymask) >> shift) & 255u;
 						bytes[beg + i] = (uint8_t)d;
 						const uint32_t peers = __match_any_sync(act, d);
 						if ((peers & lanemask_lt()) == 0) atomicAdd(&T.tab[w][d], (uint32_t)__popc(peers));
-						if (x & TIE_FLAG) atomicOr(&T.tflag[w][d >> 5], 1u << (d & 31));
+						if (!ALL && (x & TIE_FLAG)) atomicOr(&T.tflag[w][d >> 5], 1u << (d & 31));
 					}
 				}
 			}
@@ -364,7 +362,7 @@ __global__ void __launch_bounds__(TIE_THREADS) k_sort_ties(sort_args_t A, uint32
 				if (lane == 0) { T.seg_kind[w] = kind; T.seg_b0[w] = b0; T.seg_b1[w] = b1; T.seg_c0[w] = c0; }
 			}
 			__syncthreads();
-			RH_PROF_MARK(A.prof, 17, tid == 0);
+			RH_PROF_MARK(prof, 17, tid == 0);
 			/* ---- the order-dependent walks: lane w of warp 0 takes sub-array w.  One iteration = one element
 			 *      read (ksort.h:126-138 as a walk over region FIFOs): the element at rp belongs to bin d, goes to
 			 *      the head of region d, and the element found there is read next — unless d is the region being
@@ -395,7 +393,7 @@ __global__ void __launch_bounds__(TIE_THREADS) k_sort_ties(sort_args_t A, uint32
 				}
 			}
 			__syncthreads();
-			RH_PROF_MARK(A.prof, 18, tid == 0);
+			RH_PROF_MARK(prof, 18, tid == 0);
 			/* ---- sub-arrays longer than the packed tables can address: one thread, plain 32-bit tables ---- */
 			for (uint32_t w = 0; w < nb; ++w) {
 				if (T.seg_kind[w] != TIE_BIG) continue;
@@ -457,7 +455,7 @@ __global__ void __launch_bounds__(TIE_THREADS) k_sort_ties(sort_args_t A, uint32
 				}
 				__syncthreads();
 			}
-			RH_PROF_MARK(A.prof, 19, tid == 0);
+			RH_PROF_MARK(prof, 19, tid == 0);
 			/* ---- move (x, idx) pairs into klib's memory order, into the other buffer pair ---- */
 			for (uint32_t w = 0; w < nb; ++w) {
 				const uint32_t beg = T.seg_beg[w], len = T.seg_len[w];
@@ -484,12 +482,13 @@ __global__ void __launch_bounds__(TIE_THREADS) k_sort_ties(sort_args_t A, uint32
 					continue;
 				}
 				for (uint32_t b = tid; b < 256; b += TIE_THREADS) {
-					if (!((T.tflag[w][b >> 5] >> (b & 31)) & 1u)) continue;
+					if (!ALL && !((T.tflag[w][b >> 5] >> (b & 31)) & 1u)) continue;
 					uint32_t start, end;
-					if (kind == TIE_TWO) { if (b == T.seg_b0[w]) { start = 0; end = T.seg_c0[w]; } else { start = T.seg_c0[w]; end = len; } }
+					if (kind == TIE_TWO) { if (b == T.seg_b0[w]) { start = 0; end = T.seg_c0[w]; } else if (b == T.seg_b1[w]) { start = T.seg_c0[w]; end = len; } else continue; }
 					else if (kind == TIE_BIG) { start = 0; for (uint32_t q = 0; q < b; ++q) start += T.tab[w][q]; end = start + T.tab[w][b]; }
 					else { start = b ? (T.tab[w][b - 1] >> 16) : 0u; end = T.tab[w][b] >> 16; }
 					const uint32_t c = end - start;
+					if (ALL && c == 1) sidx[beg + start] = ord2[beg + start];
 					if (c < 2) continue;
 					if (shift > 0 && c > 64) wl_nxt[atomicAdd(&T.n_nxt, 1u)] = make_uint2(beg + start, c);
 					else term[atomicAdd(&T.n_term, 1u)] = make_uint2(beg + start, c);
@@ -505,8 +504,8 @@ __global__ void __launch_bounds__(TIE_THREADS) k_sort_ties(sort_args_t A, uint32
 					const uint32_t ts = tb.x, tc = tb.y;
 					if (shift > 0) {
 						uint32_t o0 = 0, o1 = 0; uint64_t k0 = 0, k1 = 0;
-						if (lane < tc) { o0 = ord2[ts + lane]; k0 = xk2[ts + lane] & ~TIE_FLAG; }
-						if (32 + lane < tc) { o1 = ord2[ts + 32 + lane]; k1 = xk2[ts + 32 + lane] & ~TIE_FLAG; }
+						if (lane < tc) { o0 = ord2[ts + lane]; k0 = xk2[ts + lane] & keymask; }
+						if (32 + lane < tc) { o1 = ord2[ts + 32 + lane]; k1 = xk2[ts + 32 + lane] & keymask; }
 						uint32_t r0, r1;
 						warp_rank64(k0, k1, tc, lane, &r0, &r1);
 						if (lane < tc) sidx[ts + r0] = o0;
@@ -519,7 +518,7 @@ __global__ void __launch_bounds__(TIE_THREADS) k_sort_ties(sort_args_t A, uint32
 				if (tid == 0) T.n_term = 0;
 				__syncthreads();
 			}
-			RH_PROF_MARK(A.prof, 20, tid == 0);
+			RH_PROF_MARK(prof, 20, tid == 0);
 		}
 		/* every pending sub-array of the next level was written to the other buffer pair */
 		{ uint2 *t = wl_cur; wl_cur = wl_nxt; wl_nxt = t; }
@@ -536,6 +535,33 @@ __global__ void __launch_bounds__(TIE_THREADS) k_sort_ties(sort_args_t A, uint32
 		for (uint32_t i = tid; i < seg.y; i += TIE_THREADS) sidx[seg.x + i] = ord[seg.x + i];
 	}
 	__syncthreads();
+}
+
+__global__ void __launch_bounds__(TIE_THREADS) k_sort_ties(sort_args_t A, uint32_t smem_cap, uint32_t n_lo, uint32_t n_hi)
+{
+	extern __shared__ __align__(16) uint8_t s_dyn[];
+	tie_shared_t &T = *(tie_shared_t *)s_dyn;
+	uint8_t *s_bytes = s_dyn + sizeof(tie_shared_t);
+	const uint32_t tid = threadIdx.x;
+	if (blockIdx.x >= *A.tie_count) return;
+	slot_t *S = &A.slots[A.tie_list[blockIdx.x]];
+	const uint32_t n = S->n_anchors;
+	if (n < n_lo || n >= n_hi) return;   /* the launch for the other size class takes this chunk */
+	slot_mem_t M = slot_mem(A.arena, S->a_off, n);
+	const anchor_t *__restrict__ in = M.B;
+	const uint8_t *__restrict__ tied = (const uint8_t *)M.t;
+	klib_ws_t W;
+	W.xk = (uint64_t *)M.Z; W.xk2 = (uint64_t *)M.W;
+	W.ord = (uint32_t *)M.f; W.ord2 = (uint32_t *)M.p; W.dst = (uint32_t *)M.v;
+	W.sidx = (uint32_t *)M.U;                       /* stable order from k_sort_block: right wherever keys are unique */
+	W.zlist = (uint32_t *)M.U2; W.mlist = W.zlist + n;
+	W.term = (uint2 *)((uint64_t *)M.W + n);        /* M.W is 16n bytes: the upper half */
+	W.wl0 = (uint2 *)M.regs; W.wl1 = W.wl0 + (n / 64 + 2);
+	uint8_t *bytes = n <= smem_cap ? s_bytes : (uint8_t *)M.t + n;
+	for (uint32_t i = tid; i < n; i += TIE_THREADS) { W.xk[i] = in[i].x | (tied[i] ? TIE_FLAG : 0ULL); W.ord[i] = i; }
+	cta_klib_replay<false>(T, bytes, W, n, A.prof);
+	RH_PROF_BEGIN(A.prof);
+	const uint32_t *__restrict__ sidx = W.sidx;
 	anchor_t *__restrict__ out = M.A;
 	{
 		uint32_t i = tid;

@@ -17,133 +17,9 @@
 #include "rh_kernels.cuh"
 #include "rh_anchor_sort.cuh"
 
-#define FIN_WARPS 4
-
-struct fin_scratch_t { uint8_t *bytes; uint32_t *dst; uint2 *wl0, *wl1; };
-__device__ __forceinline__ fin_scratch_t fin_scratch(const slot_mem_t &M, uint64_t n)
-{
-	fin_scratch_t s; uint8_t *b = (uint8_t *)M.regs;
-	s.bytes = b; b += (n + 15) & ~15ULL;
-	s.dst = (uint32_t *)b; b += 4 * n;
-	s.wl0 = (uint2 *)(((uintptr_t)b + 7) & ~(uintptr_t)7); b = (uint8_t *)s.wl0 + 8 * (n / 64 + 2);
-	s.wl1 = (uint2 *)b;
-	return s;
-}
-
-/* Exact klib radix sort (see rh_sort.cuh for the algorithm) of (x = key, y = payload) pairs,
- * cooperative over one warp.  Every lane must call it. */
-__device__ void warp_klib_sort_pairs(anchor_t *a, uint32_t n, anchor_t *tmp, const fin_scratch_t &X, uint32_t *cnt, uint32_t *head, uint32_t lane)
-{
-	const uint32_t FULL = 0xffffffffu;
-	if (n <= 64) {
-		anchor_t e0, e1; e0.x = e0.y = e1.x = e1.y = 0;
-		if (lane < n) e0 = a[lane];
-		if (32 + lane < n) e1 = a[32 + lane];
-		uint32_t r0, r1;
-		warp_rank64(e0.x, e1.x, n, lane, &r0, &r1);
-		__syncwarp();
-		if (lane < n) a[r0] = e0;
-		if (32 + lane < n) a[32 * 0 + r1] = e1;
-		__syncwarp();
-		return;
-	}
-	unsigned long long diff = 0;
-	const uint64_t k0 = a[0].x;
-	for (uint32_t i = lane; i < n; i += 32) diff |= a[i].x ^ k0;
-#pragma unroll
-	for (int o = 16; o > 0; o >>= 1) diff |= __shfl_xor_sync(FULL, diff, o);
-	uint2 *wl_cur = X.wl0, *wl_nxt = X.wl1;
-	uint32_t n_cur = 1, n_nxt = 0;
-	if (lane == 0) wl_cur[0] = make_uint2(0u, n);
-	__syncwarp();
-	for (int shift = 56; shift >= 0 && n_cur > 0; shift -= 8) {
-		if (((diff >> shift) & 255ULL) == 0) continue; /* identity level for every sub-array */
-		n_nxt = 0;
-		for (uint32_t s = 0; s < n_cur; ++s) {
-			const uint2 seg = wl_cur[s];
-			const uint32_t beg = seg.x, len = seg.y;
-			for (uint32_t b = lane; b < 256; b += 32) cnt[b] = 0;
-			__syncwarp();
-			for (uint32_t i = lane; i < len; i += 32) {
-				const uint32_t b = (uint32_t)(a[beg + i].x >> shift) & 255;
-				X.bytes[beg + i] = (uint8_t)b;
-				atomicAdd(&cnt[b], 1u);
-			}
-			__syncwarp();
-			if (cnt[X.bytes[beg]] == len) {
-				if (shift > 0) { if (lane == 0) wl_nxt[n_nxt] = seg; ++n_nxt; }
-				__syncwarp();
-				continue;
-			}
-			uint32_t run = 0;
-			for (uint32_t b = lane; b < 256; b += 32) {
-				const uint32_t v = cnt[b];
-				uint32_t incl = v;
-#pragma unroll
-				for (int o = 1; o < 32; o <<= 1) { const uint32_t u = __shfl_up_sync(FULL, incl, o); if (lane >= o) incl += u; }
-				head[b] = run + incl - v;
-				run += __shfl_sync(FULL, incl, 31);
-			}
-			__syncwarp();
-			if (lane == 0) { /* displacement-cycle walk on the byte array */
-				uint32_t region_end = 0;
-				for (uint32_t k = 0; k < 256; ++k) {
-					region_end += cnt[k];
-					uint32_t hk = head[k];
-					while (hk != region_end) {
-						uint32_t e = hk, d = X.bytes[beg + e];
-						while (d != k) {
-							const uint32_t hd = head[d];
-							X.dst[beg + e] = hd; head[d] = hd + 1;
-							e = hd; d = X.bytes[beg + e];
-						}
-						X.dst[beg + e] = hk;
-						++hk;
-					}
-					head[k] = hk;
-				}
-			}
-			__syncwarp();
-			for (uint32_t i = lane; i < len; i += 32) tmp[beg + X.dst[beg + i]] = a[beg + i];
-			__syncwarp();
-			for (uint32_t i = lane; i < len; i += 32) a[beg + i] = tmp[beg + i];
-			__syncwarp();
-			if (shift > 0) {
-				uint32_t acc = 0;
-				for (uint32_t bb = 0; bb < 256; bb += 32) {
-					const uint32_t c = cnt[bb + lane];
-					uint32_t incl = c;
-#pragma unroll
-					for (int o = 1; o < 32; o <<= 1) { const uint32_t u = __shfl_up_sync(FULL, incl, o); if (lane >= o) incl += u; }
-					const uint32_t start = beg + acc + incl - c;
-					acc += __shfl_sync(FULL, incl, 31);
-					const bool recurse = c > 64;
-					const uint32_t rm = __ballot_sync(FULL, recurse);
-					if (recurse) wl_nxt[n_nxt + __popc(rm & lanemask_lt())] = make_uint2(start, c);
-					n_nxt += __popc(rm);
-					uint32_t tm = __ballot_sync(FULL, !recurse && c > 1); /* small buckets: stable sort, one bucket per pass */
-					while (tm) {
-						const int src = __ffs(tm) - 1; tm &= tm - 1;
-						const uint32_t ts = __shfl_sync(FULL, start, src), tc = __shfl_sync(FULL, c, src);
-						anchor_t e0, e1; e0.x = e0.y = e1.x = e1.y = 0;
-						if (lane < tc) e0 = a[ts + lane];
-						if (32 + lane < tc) e1 = a[ts + 32 + lane];
-						uint32_t r0, r1;
-						warp_rank64(e0.x, e1.x, tc, lane, &r0, &r1);
-						__syncwarp();
-						if (lane < tc) a[ts + r0] = e0;
-						if (32 + lane < tc) a[ts + r1] = e1;
-					}
-				}
-				__syncwarp();
-			}
-		}
-		uint2 *t = wl_cur; wl_cur = wl_nxt; wl_nxt = t;
-		n_cur = n_nxt;
-		__syncwarp();
-	}
-	__syncwarp();
-}
+#define FIN_THREADS TIE_THREADS
+#define FIN_BYTES_CAP 8192        /* sorts of up to this many elements keep their digit bytes in shared memory */
+#define FIN_SMALL_RUN 8           /* candidate runs up to this long are ordered by selection in registers       */
 
 __device__ __forceinline__ float logf_tab(const k3_args_t &A, int32_t x, uint32_t *flag)
 { /* glibc logf of an integer argument, tabulated on the host so MAPQ is bit-identical */
@@ -154,7 +30,7 @@ __device__ __forceinline__ float logf_tab(const k3_args_t &A, int32_t x, uint32_
 
 
 #define FIN_BITS 8192             /* query (event) coordinates covered by the shared-memory bitset */
-#define FIN_PCAP 64               /* primaries cached in shared memory                              */
+#define FIN_PCAP 256              /* primaries cached in shared memory                              */
 struct prim_cache_t { int qs[FIN_PCAP], qe[FIN_PCAP], idx[FIN_PCAP], subsc[FIN_PCAP], nsub[FIN_PCAP], cnt[FIN_PCAP]; };
 
 /* mm_set_parent (hit.c:195-263), general form: overlaps clipped and sorted, as the reference does. */
@@ -303,264 +179,384 @@ __device__ bool set_parent_bitset(dev_reg_t *r, uint32_t n_regs, const dev_param
 	return true;
 }
 
-__global__ void __launch_bounds__(FIN_WARPS * 32, 8) k_chain_finish(k3_args_t A, dev_params_t P)
+/* inclusive scan of one value per thread over the CTA's current tile; *total = tile sum */
+__device__ __forceinline__ uint32_t fin_tile_scan(uint32_t v, uint32_t *wsum, uint32_t *total)
 {
-	__shared__ uint32_t s_cnt[FIN_WARPS][256];
-	__shared__ uint32_t s_head[FIN_WARPS][256];
-	__shared__ uint32_t s_bits[FIN_WARPS][FIN_BITS / 32];
-	__shared__ prim_cache_t s_pc[FIN_WARPS];
+	const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	uint32_t incl = v;
+#pragma unroll
+	for (int o = 1; o < 32; o <<= 1) { const uint32_t u = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += u; }
+	if (lane == 31) wsum[warp] = incl;
+	__syncthreads();
+	uint32_t base = 0, tot = 0;
+#pragma unroll
+	for (uint32_t w = 0; w < TIE_WARPS; ++w) { const uint32_t c = wsum[w]; if (w < warp) base += c; tot += c; }
+	__syncthreads();
+	*total = tot;
+	return base + incl;
+}
+
+/* exact klib sort of m (key, payload) pairs already placed in W.xk/W.ord; W.sidx[pos] = payload at sorted position pos */
+__device__ __forceinline__ void fin_sort(tie_shared_t &T, uint8_t *s_bytes, uint8_t *g_bytes, const klib_ws_t &W, uint32_t m, unsigned long long *prof)
+{
+	if (m > 64) { cta_klib_replay<true>(T, m <= FIN_BYTES_CAP ? s_bytes : g_bytes, W, m, prof); return; }
+	__syncthreads();
+	if (threadIdx.x < 32 && m > 0) { /* klib: insertion sort (stable) */
+		const uint32_t lane = threadIdx.x;
+		uint64_t k0 = 0, k1 = 0; uint32_t o0 = 0, o1 = 0;
+		if (lane < m) { k0 = W.xk[lane]; o0 = W.ord[lane]; }
+		if (32 + lane < m) { k1 = W.xk[32 + lane]; o1 = W.ord[32 + lane]; }
+		uint32_t r0, r1;
+		warp_rank64(k0, k1, m, lane, &r0, &r1);
+		if (lane < m) W.sidx[r0] = o0;
+		if (32 + lane < m) W.sidx[r1] = o1;
+	}
+	__syncthreads();
+}
+
+/* one backtrack attempt from candidate anchor i0 (mg_chain_backtrack body, lchain.c:162-181 + mg_chain_bk_end);
+ * returns score<<32 | n_anchors of an accepted chain, 0 otherwise */
+__device__ __forceinline__ uint64_t fin_backtrack_one(int32_t i0, const int32_t *__restrict__ f, const int32_t *__restrict__ p, int32_t *t,
+                                                      int32_t min_sc, int32_t min_cnt, int32_t max_drop)
+{
+	if (t[i0] != 0) return 0;
+	const int32_t zs = f[i0];
+	int32_t end_i = -1, max_i = i0, c = i0, max_s = 0;
+	do {
+		t[c] = 2;
+		end_i = c = p[c];
+		const int32_t s = c < 0 ? zs : zs - f[c];
+		if (s > max_s) { max_s = s; max_i = c; }
+		else if (max_s - s > max_drop) break;
+	} while (c >= 0 && t[c] == 0);
+	for (c = i0; c >= 0 && c != end_i; c = p[c]) t[c] = 0;
+	uint32_t cnt = 0;
+	for (c = i0; c != max_i; c = p[c]) { ++cnt; t[c] = 1; }
+	const int32_t sc = c < 0 ? zs : zs - f[c];
+	if (sc >= min_sc && cnt > 0 && (int32_t)cnt >= min_cnt) return (uint64_t)(uint32_t)sc << 32 | cnt;
+	return 0; /* rejected: its anchors stay marked, as in the reference */
+}
+
+struct fin_shared_t {
+	tie_shared_t T;
+	uint8_t bytes[FIN_BYTES_CAP];
+	uint32_t wsum[TIE_WARPS];
+	unsigned long long carry_off;
+};
+
+/* One CTA per chunk.  Phases (all CTA-parallel unless noted):
+ *   1  candidates z = {i : f[i] >= min_sc} in index order, and the runs of candidates that share a DP segment
+ *   2  exact klib sort of z by score (ties are the norm: SURVEY H1b)
+ *   3  backtrack: chains never leave their DP segment, so every run is backtracked by its own thread, visiting
+ *      its candidates in the global sorted order; accepted chains are then numbered in that global order
+ *   4  compact_a (+ the copy carried to the next chunk), exact sort of chains by target, region keys
+ *   5  exact sort of regions, mm_gen_regs
+ * The order-dependent remainder runs in k_chain_decide. */
+__global__ void __launch_bounds__(FIN_THREADS) k_chain_finish(k3_args_t A, dev_params_t P)
+{
+	__shared__ fin_shared_t SH;
 	const uint32_t FULL = 0xffffffffu;
-	const uint32_t wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
-	const uint32_t slot_id = blockIdx.x * FIN_WARPS + wib;
+	const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	const uint32_t slot_id = blockIdx.x;
 	if (slot_id >= A.n_slots) return;
 	slot_t *S = &A.slots[slot_id];
 	read_state_t *R = &A.rs[S->read];
-	uint32_t *cnt = s_cnt[wib], *head = s_head[wib], *bits = s_bits[wib];
-	prim_cache_t *pc = &s_pc[wib];
 
 	uint32_t n_u = 0, n_v = 0, n_regs = 0;
 	dev_reg_t *r = nullptr;
-	uint32_t inexact = 0;
 	const int32_t n = (int32_t)S->n_anchors;
 
 	if (S->gated) { /* chunk skipped by the min_events gate: carried anchors stay for the next chunk */
 		const uint32_t pn = R->prev_n;
 		if (pn) {
-			unsigned long long o = 0;
-			if (lane == 0) o = atomicAdd(A.carry_top, (unsigned long long)pn);
-			o = __shfl_sync(FULL, o, 0);
-			if (o + pn > A.carry_cap) { if (lane == 0) { atomicExch(A.err, 2u); R->prev_n = 0; } }
+			if (tid == 0) SH.carry_off = atomicAdd(A.carry_top, (unsigned long long)pn);
+			__syncthreads();
+			const unsigned long long o = SH.carry_off;
+			if (o + pn > A.carry_cap) { if (tid == 0) { atomicExch(A.err, 2u); R->prev_n = 0; } }
 			else {
 				const anchor_t *src = (const anchor_t *)(A.arena + S->a_off) + pn; /* slot_mem::B */
-				for (uint32_t k = lane; k < pn; k += 32) A.carry_out[o + k] = src[k];
-				if (lane == 0) R->prev_off = o;
+				for (uint32_t k = tid; k < pn; k += FIN_THREADS) A.carry_out[o + k] = src[k];
+				if (tid == 0) R->prev_off = o;
 			}
 		}
 	} else {
-		if (lane == 0) R->prev_n = 0; /* consumed by collect_seed_hits */
+		if (tid == 0) R->prev_n = 0; /* consumed by collect_seed_hits */
 		if (n > 0) {
-			slot_mem_t M = slot_mem(A.arena, S->a_off, S->n_anchors);
-			const fin_scratch_t X = fin_scratch(M, S->n_anchors);
-			anchor_t *a = M.A, *b = M.B, *z = M.Z, *w = M.W;
-			int32_t *f = M.f, *p = M.p, *v = M.v, *t = M.t;
-			uint64_t *u = M.U, *u2 = M.U2;
+			const uint32_t un = (uint32_t)n;
+			slot_mem_t M = slot_mem(A.arena, S->a_off, un);
+			anchor_t *a = M.A, *b = M.B;
+			int32_t *f = M.f, *p = M.p, *t = M.t;
+			uint64_t *u = M.U;
+			const uint8_t *is_start = (const uint8_t *)M.U2;
 			const int32_t min_sc = P.min_sc, min_cnt = P.min_cnt, max_drop = P.bw;
+			klib_ws_t W;
+			W.xk = (uint64_t *)M.Z; W.xk2 = W.xk + un;
+			W.ord = (uint32_t *)M.W; W.ord2 = W.ord + un; W.dst = W.ord2 + un; W.sidx = W.dst + un;
+			W.zlist = (uint32_t *)M.U2; W.mlist = W.zlist + un; W.term = (uint2 *)M.U2;
+			W.wl0 = (uint2 *)M.regs; W.wl1 = W.wl0 + (un / 64 + 2);
+			uint8_t *g_bytes = (uint8_t *)(W.wl1 + (un / 64 + 2));
+			uint32_t *z_idx = (uint32_t *)M.v;
 			RH_PROF_BEGIN(A.prof);
-			/* ---- candidates z = {(f[i], i) : f[i] >= min_sc}, in index order ---- */
-			uint32_t n_z = 0;
-			for (int32_t i0 = 0; i0 < n; i0 += 32) {
-				const int32_t i = i0 + (int32_t)lane;
-				int32_t fi = 0; bool ok = false;
-				if (i < n) { fi = f[i]; ok = fi >= min_sc; t[i] = 0; }
-				const uint32_t m = __ballot_sync(FULL, ok);
-				if (ok) { anchor_t e; e.x = (uint64_t)(int64_t)fi; e.y = (uint64_t)i; z[n_z + __popc(m & lanemask_lt())] = e; }
-				n_z += __popc(m);
+
+			/* ---- 1: candidates in index order; DP segment id of each candidate ---- */
+			uint32_t n_z = 0, n_runs = 0;
+			{
+				uint32_t *zseg = W.dst;
+				uint32_t seg_run = 0;
+				for (uint32_t i0 = 0; i0 < un; i0 += FIN_THREADS) {
+					const uint32_t i = i0 + tid;
+					int32_t fi = 0; bool ok = false; uint32_t st = 0;
+					if (i < un) { fi = f[i]; ok = fi >= min_sc; t[i] = 0; st = is_start[i]; }
+					uint32_t zt, stt;
+					const uint32_t zr = tie_tile_rank(ok, SH.wsum, &zt);
+					const uint32_t sincl = fin_tile_scan(st, SH.wsum, &stt);
+					if (ok) { const uint32_t j = n_z + zr; z_idx[j] = i; zseg[j] = seg_run + sincl; W.xk[j] = (uint64_t)(int64_t)fi; W.ord[j] = j; }
+					n_z += zt; seg_run += stt;
+				}
+				__syncthreads();
+				uint32_t *runs = (uint32_t *)M.U;
+				for (uint32_t j0 = 0; j0 < n_z; j0 += FIN_THREADS) {
+					const uint32_t j = j0 + tid;
+					const bool first = j < n_z && (j == 0 || zseg[j] != zseg[j - 1]);
+					uint32_t tot; const uint32_t rr = tie_tile_rank(first, SH.wsum, &tot);
+					if (first) runs[n_runs + rr] = j;
+					n_runs += tot;
+				}
+				__syncthreads();
 			}
-			__syncwarp();
+			RH_PROF_MARK(A.prof, 32, tid == 0);
 			if (n_z > 0) {
-				RH_PROF_MARK(A.prof, 32, lane == 0);
-				warp_klib_sort_pairs(z, n_z, w, X, cnt, head, lane);
-				RH_PROF_MARK(A.prof, 33, lane == 0);
-				/* ---- backtrack, best score first.  Visiting order matters, so lane 0 walks the chains;
-				 *      the test that skips candidates already swallowed by an earlier chain (the vast
-				 *      majority) is prefetched 32 candidates at a time.  t[] only ever goes 0 -> nonzero
-				 *      for good, so a nonzero prefetch is final and a zero one is re-read by lane 0. ---- */
-				for (int64_t kb = (int64_t)n_z - 1; kb >= 0; kb -= 32) {
-					const int64_t kq = kb - (int64_t)lane;
-					int32_t ci0 = 0, czs = 0; bool open = false;
-					if (kq >= 0) { const anchor_t e = z[kq]; ci0 = (int32_t)e.y; czs = (int32_t)e.x; open = t[ci0] == 0; }
-					uint32_t cand = __ballot_sync(FULL, open);
-					while (cand) {
-						const int bsel = __ffs(cand) - 1; cand &= cand - 1;
-						const int32_t i0 = __shfl_sync(FULL, ci0, bsel), zs = __shfl_sync(FULL, czs, bsel);
-						if (lane == 0 && t[i0] == 0) {
-							int32_t end_i = -1, max_i = i0, c = i0, max_s = 0; /* mg_chain_bk_end */
-							do {
-								t[c] = 2;
-								end_i = c = p[c];
-								const int32_t s = c < 0 ? zs : zs - f[c];
-								if (s > max_s) { max_s = s; max_i = c; }
-								else if (max_s - s > max_drop) break;
-							} while (c >= 0 && t[c] == 0);
-							for (c = i0; c >= 0 && c != end_i; c = p[c]) t[c] = 0;
-							const uint32_t n_v0 = n_v;
-							for (c = i0; c != max_i; c = p[c]) { v[n_v++] = c; t[c] = 1; }
-							const int32_t sc = c < 0 ? zs : zs - f[c];
-							if (sc >= min_sc && n_v > n_v0 && (int32_t)(n_v - n_v0) >= min_cnt) u[n_u++] = (uint64_t)sc << 32 | (n_v - n_v0);
-							else n_v = n_v0;
+				/* ---- 2: z sorted by score exactly as klib leaves it ---- */
+				fin_sort(SH.T, SH.bytes, g_bytes, W, n_z, nullptr);
+				RH_PROF_MARK(A.prof, 33, tid == 0);
+				/* ---- 3: backtrack, best score first inside every run ---- */
+				const uint32_t *__restrict__ sidx = W.sidx;
+				uint32_t *rank_of = W.dst;
+				uint64_t *acc = W.xk2;
+				for (uint32_t pos = tid; pos < n_z; pos += FIN_THREADS) { rank_of[sidx[pos]] = pos; acc[pos] = 0ULL; }
+				__syncthreads();
+				{
+					const uint32_t *runs = (const uint32_t *)M.U;
+					for (uint32_t rr = tid; rr < n_runs; rr += FIN_THREADS) {
+						const uint32_t lo = runs[rr], hi = rr + 1 < n_runs ? runs[rr + 1] : n_z, m = hi - lo;
+						if (m <= FIN_SMALL_RUN) {
+							uint32_t rk[FIN_SMALL_RUN];
+#pragma unroll
+							for (int q = 0; q < FIN_SMALL_RUN; ++q) rk[q] = (uint32_t)q < m ? rank_of[lo + q] : 0xffffffffu;
+							uint32_t prev = 0xffffffffu; /* ranks visited so far are all > the next one */
+							for (uint32_t it = 0; it < m; ++it) {
+								uint32_t best = 0, bq = 0; bool have = false;
+#pragma unroll
+								for (int q = 0; q < FIN_SMALL_RUN; ++q) { const uint32_t v = rk[q]; if (v != 0xffffffffu && v < prev && (!have || v > best)) { best = v; bq = (uint32_t)q; have = true; } }
+								prev = best;
+								const uint64_t res = fin_backtrack_one((int32_t)z_idx[lo + bq], f, p, t, min_sc, min_cnt, max_drop);
+								if (res) acc[best] = res;
+							}
+						} else {
+							for (uint32_t pos = n_z; pos-- > 0;) {
+								const uint32_t j = sidx[pos];
+								if (j < lo || j >= hi) continue;
+								const uint64_t res = fin_backtrack_one((int32_t)z_idx[j], f, p, t, min_sc, min_cnt, max_drop);
+								if (res) acc[pos] = res;
+							}
 						}
 					}
-					__syncwarp();
 				}
-				RH_PROF_MARK(A.prof, 34, lane == 0);
-				n_u = __shfl_sync(FULL, n_u, 0); n_v = __shfl_sync(FULL, n_v, 0);
-				__syncwarp();
+				__syncthreads();
+				RH_PROF_MARK(A.prof, 34, tid == 0);
+				/* chains numbered in discovery order = descending position in sorted z */
+				uint32_t *chain_i0 = (uint32_t *)M.t, *koff = (uint32_t *)M.f;
+				for (uint32_t q0 = 0; q0 < n_z; q0 += FIN_THREADS) {
+					const uint32_t q = q0 + tid;
+					uint64_t av = 0; uint32_t pos = 0;
+					if (q < n_z) { pos = n_z - 1 - q; av = acc[pos]; }
+					uint32_t ct, vt;
+					const uint32_t cr = tie_tile_rank(av != 0, SH.wsum, &ct);
+					const uint32_t vincl = fin_tile_scan((uint32_t)av, SH.wsum, &vt);
+					if (av) { const uint32_t ci = n_u + cr; u[ci] = av; chain_i0[ci] = z_idx[sidx[pos]]; koff[ci] = n_v + vincl - (uint32_t)av; }
+					n_u += ct; n_v += vt;
+				}
+				__syncthreads();
 			}
+			if (n_u > fin_regs_cap(un)) { if (tid == 0) atomicExch(A.err, 3u); n_u = 0; n_v = 0; }
 			if (n_u > 0) {
-				/* ---- compact_a: forward-order gather (= next chunk's prev_anchors), then chains by target ---- */
-				unsigned long long co = 0;
-				if (lane == 0) co = atomicAdd(A.carry_top, (unsigned long long)n_v);
-				co = __shfl_sync(FULL, co, 0);
+				/* ---- 4: compact_a: forward-order gather (= next chunk's prev_anchors), then chains by target ---- */
+				if (tid == 0) SH.carry_off = atomicAdd(A.carry_top, (unsigned long long)n_v);
+				__syncthreads();
+				const unsigned long long co = SH.carry_off;
 				const bool carry_ok = co + n_v <= A.carry_cap;
-				if (!carry_ok && lane == 0) atomicExch(A.err, 2u);
-				/* chain start offsets in backtrack order: exclusive scan of the chain sizes */
-				uint32_t *koff = (uint32_t *)t; /* t[] is free once the backtrack is over */
-				{
-					uint32_t run = 0;
-					for (uint32_t c0 = 0; c0 < n_u; c0 += 32) {
-						const uint32_t ci = c0 + lane;
-						const uint32_t ni = ci < n_u ? (uint32_t)u[ci] : 0u;
-						uint32_t incl = ni;
-#pragma unroll
-						for (int o = 1; o < 32; o <<= 1) { const uint32_t q = __shfl_up_sync(FULL, incl, o); if (lane >= o) incl += q; }
-						if (ci < n_u) koff[ci] = run + incl - ni;
-						run += __shfl_sync(FULL, incl, 31);
-					}
-				}
-				__syncwarp();
-				for (uint32_t ci = lane; ci < n_u; ci += 32) { /* one lane per chain: chains are a few anchors long */
+				if (!carry_ok && tid == 0) atomicExch(A.err, 2u);
+				const uint32_t *chain_i0 = (const uint32_t *)M.t; const uint32_t *koff = (const uint32_t *)M.f;
+				for (uint32_t ci = tid; ci < n_u; ci += FIN_THREADS) { /* one thread per chain: chains are a few anchors long */
 					const uint32_t ni = (uint32_t)u[ci], k0 = koff[ci];
-					for (uint32_t j = 0; j < ni; ++j) {
-						const anchor_t x = a[v[k0 + (ni - j - 1)]];
-						b[k0 + j] = x;
-						if (carry_ok) A.carry_out[co + k0 + j] = x;
-						if (j == 0) { anchor_t e; e.x = x.x; e.y = (uint64_t)k0 << 32 | ci; w[ci] = e; }
+					int32_t c = (int32_t)chain_i0[ci];
+					anchor_t x; x.x = x.y = 0;
+					for (uint32_t q = 0; q < ni; ++q) {
+						x = a[c];
+						const uint32_t j = k0 + (ni - 1 - q);
+						b[j] = x;
+						if (carry_ok) A.carry_out[co + j] = x;
+						c = p[c];
 					}
+					W.xk[ci] = x.x; W.ord[ci] = ci; /* the chain's first anchor */
 				}
-				if (lane == 0 && carry_ok) { R->prev_off = co; R->prev_n = n_v; }
-				__syncwarp();
-				RH_PROF_MARK(A.prof, 35, lane == 0);
-				warp_klib_sort_pairs(w, n_u, z, X, cnt, head, lane);
-				RH_PROF_MARK(A.prof, 36, lane == 0);
+				if (tid == 0 && carry_ok) { R->prev_off = co; R->prev_n = n_v; }
+				__syncthreads();
+				RH_PROF_MARK(A.prof, 35, tid == 0);
+				fin_sort(SH.T, SH.bytes, g_bytes, W, n_u, nullptr);
+				RH_PROF_MARK(A.prof, 36, tid == 0);
 				/* output offsets in target order, then copy chains and pre-compute the region keys (mm_gen_regs) */
-				uint32_t *kout = (uint32_t *)v; /* the backtrack order list is no longer needed */
+				uint32_t *kout = (uint32_t *)M.t;      /* chain_i0 is no longer needed */
+				uint64_t *u2 = (uint64_t *)W.dst;      /* 8 n_u <= 4 n bytes           */
+				uint64_t *keys2 = (uint64_t *)M.v;     /* z_idx is no longer needed; offset 72n is 8-byte aligned for every n */
+				const uint32_t rhash = wang32(wang32(R->ev_offset + S->n_events) + wang32(11u)); /* rmap.cpp:346-348 */
 				{
 					uint32_t run = 0;
-					for (uint32_t c0 = 0; c0 < n_u; c0 += 32) {
-						const uint32_t ci = c0 + lane;
-						const uint32_t ni = ci < n_u ? (uint32_t)u[(uint32_t)w[ci].y] : 0u;
-						uint32_t incl = ni;
-#pragma unroll
-						for (int o = 1; o < 32; o <<= 1) { const uint32_t q = __shfl_up_sync(FULL, incl, o); if (lane >= o) incl += q; }
-						if (ci < n_u) kout[ci] = run + incl - ni;
-						run += __shfl_sync(FULL, incl, 31);
+					for (uint32_t q0 = 0; q0 < n_u; q0 += FIN_THREADS) {
+						const uint32_t pos = q0 + tid;
+						uint32_t ci = 0, c = 0; uint64_t uv = 0;
+						if (pos < n_u) { ci = W.sidx[pos]; uv = u[ci]; c = (uint32_t)uv; }
+						uint32_t tot; const uint32_t incl = fin_tile_scan(c, SH.wsum, &tot);
+						if (pos < n_u) {
+							const uint32_t k0 = run + incl - c;
+							const anchor_t *src = b + koff[ci];
+							for (uint32_t q = 0; q < c; ++q) a[k0 + q] = src[q];
+							const anchor_t fa = src[0];
+							const uint32_t h = (uint32_t)mix64((mix64(fa.x) + mix64(fa.y)) ^ rhash); /* hit.c:120 */
+							const uint64_t key = uv ^ h;
+							kout[pos] = k0; u2[pos] = uv; keys2[pos] = key;
+						}
+						run += tot;
 					}
 				}
-				__syncwarp();
-				const uint32_t rhash = wang32(wang32(R->ev_offset + S->n_events) + wang32(11u)); /* rmap.cpp:346-348 */
-				for (uint32_t ci = lane; ci < n_u; ci += 32) {
-					const uint32_t j = (uint32_t)w[ci].y, c = (uint32_t)u[j], k0 = kout[ci];
-					const anchor_t *src = b + (w[ci].y >> 32);
-					for (uint32_t q = 0; q < c; ++q) a[k0 + q] = src[q];
-					u2[ci] = u[j];
-					const anchor_t fa = src[0];
-					const uint32_t h = (uint32_t)mix64((mix64(fa.x) + mix64(fa.y)) ^ rhash); /* hit.c:120 */
-					anchor_t e; e.x = u[j] ^ h; e.y = (uint64_t)k0 << 32 | c;
-					z[ci] = e;
-				}
-				__syncwarp();
-				for (uint32_t ci = lane; ci < n_u; ci += 32) u[ci] = u2[ci];
-				__syncwarp();
-
-				/* ---- mm_gen_regs ---- */
-				if (n_u > fin_regs_cap(S->n_anchors)) { if (lane == 0) atomicExch(A.err, 3u); n_u = 0; }
-			}
-			if (n_u > 0) {
-				r = (dev_reg_t *)((uint8_t *)M.regs + fin_regs_off(S->n_anchors)); /* after the sort scratch (fin_scratch) */
-				RH_PROF_MARK(A.prof, 37, lane == 0);
-				warp_klib_sort_pairs(z, n_u, w, X, cnt, head, lane);
-				RH_PROF_MARK(A.prof, 38, lane == 0);
-				for (uint32_t i = lane; i < n_u; i += 32) { /* descending score */
-					const anchor_t zz = z[n_u - 1 - i];
+				__syncthreads();
+				for (uint32_t pos = tid; pos < n_u; pos += FIN_THREADS) { u[pos] = u2[pos]; W.xk[pos] = keys2[pos]; W.ord[pos] = pos; }
+				__syncthreads();
+				RH_PROF_MARK(A.prof, 37, tid == 0);
+				/* ---- 5: mm_gen_regs ---- */
+				fin_sort(SH.T, SH.bytes, g_bytes, W, n_u, nullptr);
+				RH_PROF_MARK(A.prof, 38, tid == 0);
+				r = (dev_reg_t *)((uint8_t *)M.regs + fin_regs_off(un)); /* after the sort scratch */
+				for (uint32_t i = tid; i < n_u; i += FIN_THREADS) { /* descending key */
+					const uint32_t pos = W.sidx[n_u - 1 - i];
+					const uint64_t key = keys2[pos];
 					dev_reg_t g;
 					g.id = (int32_t)i; g.parent = -1; g.subsc = 0; g.n_sub = 0; g.mapq = 0;
-					g.score = g.score0 = (int32_t)(zz.x >> 32); g.hash = (uint32_t)zz.x;
-					g.cnt = (int32_t)zz.y; g.as = (int32_t)(zz.y >> 32);
+					g.score = g.score0 = (int32_t)(key >> 32); g.hash = (uint32_t)key;
+					g.cnt = (int32_t)(uint32_t)u[pos]; g.as = (int32_t)kout[pos];
 					const anchor_t fa = a[g.as], la = a[g.as + g.cnt - 1];
 					g.rev = (uint32_t)(fa.x >> 63); g.rid = (int32_t)(fa.x << 1 >> 33);
 					g.rs = (int32_t)fa.x; g.re = (int32_t)la.x + 1; g.qs = (int32_t)fa.y; g.qe = (int32_t)la.y + 1;
 					r[i] = g;
 				}
 				n_regs = n_u;
-				__syncwarp();
-				/* ---- mm_set_parent: regions in score order ---- */
-				int maxq = 0;
-				for (uint32_t i = lane; i < n_regs; i += 32) maxq = max(maxq, r[i].qe);
-#pragma unroll
-				for (int o = 16; o > 0; o >>= 1) maxq = max(maxq, __shfl_xor_sync(FULL, maxq, o));
-				RH_PROF_MARK(A.prof, 39, lane == 0);
-				bool done_sp = false;
-				if (maxq <= FIN_BITS) done_sp = set_parent_bitset(r, n_regs, P, bits, pc, lane);
-				if (!done_sp) set_parent_general(r, n_regs, P, M, lane);
-				__syncwarp();
-				RH_PROF_MARK(A.prof, 40, lane == 0);
-				/* ---- mm_select_sub + mm_sync_regs, mm_set_mapq (small; lane 0) ---- */
-				if (!P.ava && P.pri_ratio > 0.0f && P.best_n == 0) {
-					/* mm_select_sub with best_n = 0 keeps exactly the primaries (hit.c:350-364); mm_sync_regs then
-					 * renumbers them, and a primary's parent is itself: an order-preserving compaction. */
-					uint32_t kept = 0;
-					for (uint32_t i0 = 0; i0 < n_regs; i0 += 32) {
-						const uint32_t i = i0 + lane;
-						dev_reg_t g; bool keep = false;
-						if (i < n_regs) { g = r[i]; keep = g.parent == (int32_t)i; }
-						const uint32_t m = __ballot_sync(FULL, keep);
-						if (keep) { const uint32_t d = kept + __popc(m & lanemask_lt()); g.id = (int32_t)d; g.parent = (int32_t)d; r[d] = g; }
-						kept += __popc(m);
-						__syncwarp();
-					}
-					n_regs = kept;
-				}
-				if (lane == 0) {
-					if (!P.ava && P.pri_ratio > 0.0f && P.best_n != 0) {
-						int kept = 0, n2 = 0;
-						const int nn = (int)n_regs;
-						for (int i = 0; i < nn; ++i) {
-							const int pp = r[i].parent;
-							bool keep = false;
-							if (pp == i) keep = true;
-							else if ((float)r[i].score >= __fmul_rn((float)r[pp].score, P.pri_ratio) && n2 < P.best_n) {
-								if (!(r[i].qs == r[pp].qs && r[i].qe == r[pp].qe && r[i].rid == r[pp].rid && r[i].rs == r[pp].rs && r[i].re == r[pp].re)) { keep = true; ++n2; }
-							} else if (n2 < P.best_n && r[i].score > P.min_strand_sc && r[i].rev != r[pp].rev) { keep = true; ++n2; }
-							if (keep) { if (kept != i) r[kept] = r[i]; ++kept; }
-						}
-						if (kept != nn) {
-							int *tmp = (int *)M.v;
-							int max_id = -1;
-							for (int i = 0; i < kept; ++i) max_id = max_id > r[i].id ? max_id : r[i].id;
-							for (int i = 0; i <= max_id; ++i) tmp[i] = -1;
-							for (int i = 0; i < kept; ++i) if (r[i].id >= 0) tmp[r[i].id] = i;
-							for (int i = 0; i < kept; ++i) {
-								dev_reg_t *g = &r[i];
-								g->id = i;
-								if (g->parent == -2) g->parent = i;
-								else if (g->parent >= 0 && g->parent <= max_id && tmp[g->parent] >= 0) g->parent = tmp[g->parent];
-								else g->parent = -1;
-							}
-						}
-						n_regs = (uint32_t)kept;
-					}
-					long long sum_sc = 0;
-					for (uint32_t i = 0; i < n_regs; ++i) if (r[i].parent == r[i].id) sum_sc += r[i].score;
-					const float uniq = __fdiv_rn((float)sum_sc, (float)(sum_sc + (long long)S->rep_len));
-					for (uint32_t i = 0; i < n_regs; ++i) { /* hit.c:519-538 as compiled */
-						dev_reg_t *g = &r[i];
-						const double s1 = g->score > 100 ? 1.0 : __dmul_rn(0.01, (double)g->score);
-						const float pen_s1 = __double2float_rn(__dmul_rn(s1, (double)uniq));
-						float pen_cm = g->cnt > 10 ? 1.0f : __fmul_rn(0.1f, (float)g->cnt);
-						pen_cm = pen_s1 < pen_cm ? pen_s1 : pen_cm;
-						const int subsc = g->subsc > P.min_sc ? g->subsc : P.min_sc;
-						const float x = __fdiv_rn((float)subsc, (float)g->score0);
-						const float lead = __fmul_rn(__fmul_rn(__fmul_rn(pen_cm, 40.0f), __fsub_rn(1.0f, x)), logf_tab(A, g->score, &inexact));
-						int mapq = (int)lead;
-						mapq -= (int)__fmaf_rn(logf_tab(A, g->n_sub + 1, &inexact), 4.343f, .499f);
-						mapq = mapq > 0 ? mapq : 0;
-						g->mapq = mapq < 60 ? mapq : 60;
-					}
-				}
-				n_regs = __shfl_sync(FULL, n_regs, 0);
-				RH_PROF_MARK(A.prof, 41, lane == 0);
+				__syncthreads();
+				RH_PROF_MARK(A.prof, 39, tid == 0);
 			}
 		}
+	}
+	if (tid == 0) { S->n_u = n_u; S->n_v = n_v; S->n_regs = n_regs; }
+}
+
+/* The order-dependent remainder, one WARP per chunk at full occupancy: mm_set_parent, mm_select_sub,
+ * mm_sync_regs, mm_set_mapq, then the stop rules and the final record of map_worker_for. */
+#define DEC_WARPS 4
+__global__ void __launch_bounds__(DEC_WARPS * 32) k_chain_decide(k3_args_t A, dev_params_t P)
+{
+	__shared__ uint32_t s_bits[DEC_WARPS][FIN_BITS / 32];
+	__shared__ prim_cache_t s_pc[DEC_WARPS];
+	const uint32_t FULL = 0xffffffffu;
+	const uint32_t wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	const uint32_t slot_id = blockIdx.x * DEC_WARPS + wib;
+	if (slot_id >= A.n_slots) return;
+	slot_t *S = &A.slots[slot_id];
+	read_state_t *R = &A.rs[S->read];
+	uint32_t *bits = s_bits[wib];
+	prim_cache_t *pc = &s_pc[wib];
+	const uint32_t n_u = S->n_u, n_v = S->n_v;
+	uint32_t n_regs = S->n_regs;
+	uint32_t inexact = 0;
+	dev_reg_t *r = nullptr;
+	if (n_regs > 0) {
+		slot_mem_t M = slot_mem(A.arena, S->a_off, S->n_anchors);
+		r = (dev_reg_t *)((uint8_t *)M.regs + fin_regs_off(S->n_anchors));
+
+		RH_PROF_BEGIN(A.prof);
+		/* ---- mm_set_parent: regions in score order ---- */
+		int maxq = 0;
+		for (uint32_t i = lane; i < n_regs; i += 32) maxq = max(maxq, r[i].qe);
+#pragma unroll
+		for (int o = 16; o > 0; o >>= 1) maxq = max(maxq, __shfl_xor_sync(FULL, maxq, o));
+		bool done_sp = false;
+		if (maxq <= FIN_BITS) done_sp = set_parent_bitset(r, n_regs, P, bits, pc, lane);
+		if (!done_sp) set_parent_general(r, n_regs, P, M, lane);
+		__syncwarp();
+		RH_PROF_MARK(A.prof, 40, lane == 0);
+		/* ---- mm_select_sub + mm_sync_regs, mm_set_mapq (small; lane 0) ---- */
+		if (!P.ava && P.pri_ratio > 0.0f && P.best_n == 0) {
+			/* mm_select_sub with best_n = 0 keeps exactly the primaries (hit.c:350-364); mm_sync_regs then
+			 * renumbers them, and a primary's parent is itself: an order-preserving compaction. */
+			uint32_t kept = 0;
+			for (uint32_t i0 = 0; i0 < n_regs; i0 += 32) {
+				const uint32_t i = i0 + lane;
+				dev_reg_t g; bool keep = false;
+				if (i < n_regs) { g = r[i]; keep = g.parent == (int32_t)i; }
+				const uint32_t m = __ballot_sync(FULL, keep);
+				if (keep) { const uint32_t d = kept + __popc(m & lanemask_lt()); g.id = (int32_t)d; g.parent = (int32_t)d; r[d] = g; }
+				kept += __popc(m);
+				__syncwarp();
+			}
+			n_regs = kept;
+		}
+		if (lane == 0) {
+			if (!P.ava && P.pri_ratio > 0.0f && P.best_n != 0) {
+				int kept = 0, n2 = 0;
+				const int nn = (int)n_regs;
+				for (int i = 0; i < nn; ++i) {
+					const int pp = r[i].parent;
+					bool keep = false;
+					if (pp == i) keep = true;
+					else if ((float)r[i].score >= __fmul_rn((float)r[pp].score, P.pri_ratio) && n2 < P.best_n) {
+						if (!(r[i].qs == r[pp].qs && r[i].qe == r[pp].qe && r[i].rid == r[pp].rid && r[i].rs == r[pp].rs && r[i].re == r[pp].re)) { keep = true; ++n2; }
+					} else if (n2 < P.best_n && r[i].score > P.min_strand_sc && r[i].rev != r[pp].rev) { keep = true; ++n2; }
+					if (keep) { if (kept != i) r[kept] = r[i]; ++kept; }
+				}
+				if (kept != nn) {
+					int *tmp = (int *)M.v;
+					int max_id = -1;
+					for (int i = 0; i < kept; ++i) max_id = max_id > r[i].id ? max_id : r[i].id;
+					for (int i = 0; i <= max_id; ++i) tmp[i] = -1;
+					for (int i = 0; i < kept; ++i) if (r[i].id >= 0) tmp[r[i].id] = i;
+					for (int i = 0; i < kept; ++i) {
+						dev_reg_t *g = &r[i];
+						g->id = i;
+						if (g->parent == -2) g->parent = i;
+						else if (g->parent >= 0 && g->parent <= max_id && tmp[g->parent] >= 0) g->parent = tmp[g->parent];
+						else g->parent = -1;
+					}
+				}
+				n_regs = (uint32_t)kept;
+			}
+			long long sum_sc = 0;
+			for (uint32_t i = 0; i < n_regs; ++i) if (r[i].parent == r[i].id) sum_sc += r[i].score;
+			const float uniq = __fdiv_rn((float)sum_sc, (float)(sum_sc + (long long)S->rep_len));
+			for (uint32_t i = 0; i < n_regs; ++i) { /* hit.c:519-538 as compiled */
+				dev_reg_t *g = &r[i];
+				const double s1 = g->score > 100 ? 1.0 : __dmul_rn(0.01, (double)g->score);
+				const float pen_s1 = __double2float_rn(__dmul_rn(s1, (double)uniq));
+				float pen_cm = g->cnt > 10 ? 1.0f : __fmul_rn(0.1f, (float)g->cnt);
+				pen_cm = pen_s1 < pen_cm ? pen_s1 : pen_cm;
+				const int subsc = g->subsc > P.min_sc ? g->subsc : P.min_sc;
+				const float x = __fdiv_rn((float)subsc, (float)g->score0);
+				const float lead = __fmul_rn(__fmul_rn(__fmul_rn(pen_cm, 40.0f), __fsub_rn(1.0f, x)), logf_tab(A, g->score, &inexact));
+				int mapq = (int)lead;
+				mapq -= (int)__fmaf_rn(logf_tab(A, g->n_sub + 1, &inexact), 4.343f, .499f);
+				mapq = mapq > 0 ? mapq : 0;
+				g->mapq = mapq < 60 ? mapq : 60;
+			}
+		}
+		n_regs = __shfl_sync(FULL, n_regs, 0);
+		RH_PROF_MARK(A.prof, 41, lane == 0);
 	}
 	if (lane != 0) return;
 	if (inexact) atomicExch(A.err, 4u);

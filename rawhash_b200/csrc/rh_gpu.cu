@@ -151,6 +151,7 @@ int check_params(const rh_params_t &P)
 	if (P.e < 1 || P.q < 1 || P.e * P.q > 64) { rh_set_error("bad e/q"); return RH_ERR_ARG; }
 	if (P.w != 0) { rh_set_error("minimizer seeding (w>0) is not implemented on the GPU path yet"); return RH_ERR_ARG; }
 	if (P.n != 0) { rh_set_error("BLEND seeding (n>0) is disabled in the reference and unsupported here"); return RH_ERR_ARG; }
+	if (P.min_num_anchors < 2) { rh_set_error("min_num_anchors < 2 is not supported (chains are at least two anchors; scratch sizing relies on it)"); return RH_ERR_ARG; }
 	return RH_OK;
 }
 
@@ -267,7 +268,7 @@ int run_round(rh_gpu_ctx *c, round_io &io, int carry_in_idx)
 			        gn, na.size(), pc(na, .5), pc(na, .9), pc(na, .99), pc(na, 1.0), nt.size(), pc(nt, .5), pc(nt, .9), pc(nt, 1.0));
 		}
 		{ span_guard g(c, T_CHAIN); k_chain_dp<<<gn, DP_THREADS, 0, s>>>(a3, c->D); }
-		{ span_guard g(c, T_POST); k_chain_finish<<<(gn + FIN_WARPS - 1) / FIN_WARPS, FIN_WARPS * 32, 0, s>>>(a3, c->D); }
+		{ span_guard g(c, T_POST, 2); k_chain_finish<<<gn, FIN_THREADS, 0, s>>>(a3, c->D); k_chain_decide<<<(gn + DEC_WARPS - 1) / DEC_WARPS, DEC_WARPS * 32, 0, s>>>(a3, c->D); }
 		if (io.tap) {
 			CUDA_TRY(cudaMemcpyAsync(io.slots.data(), c->d_slots.p, sizeof(slot_t), cudaMemcpyDeviceToHost, s));
 			CUDA_TRY(cudaStreamSynchronize(s));
