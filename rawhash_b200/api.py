@@ -140,6 +140,7 @@ def _load():
         "rh_gpu_destroy": (None, [vp]),
         "rh_gpu_last_error": (cp, []),
         "rh_gpu_set_stream": (None, [vp, vp]),
+        "rh_gpu_set_workers": (i32, [vp, i32]),
         "rh_gpu_map_batch_raw": (i32, [vp, u32, vp, vp, vp, vp, vp, vp, C.POINTER(vp), C.POINTER(u64)]),
         "rh_gpu_map_batch_dev": (i32, [vp, u32, vp, vp, vp, vp, vp, vp, C.POINTER(vp), C.POINTER(u64)]),
         "rh_gpu_get_stats": (None, [vp, C.POINTER(GpuStats)]),
@@ -323,6 +324,10 @@ class Mapper:
 
     def set_stream(self, cuda_stream: int | None):
         _lib.rh_gpu_set_stream(self.h, C.c_void_p(cuda_stream or 0))
+
+    def set_workers(self, n: int) -> int:
+        """Concurrent read ranges per batch (own CUDA stream each); returns the count in effect."""
+        return _lib.rh_gpu_set_workers(self.h, int(n))
 
     def stats(self) -> dict:
         st = GpuStats()

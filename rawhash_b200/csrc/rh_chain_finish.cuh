@@ -19,7 +19,6 @@
 
 #define FIN_THREADS TIE_THREADS
 #define FIN_BYTES_CAP 8192        /* sorts of up to this many elements keep their digit bytes in shared memory */
-#define FIN_SMALL_RUN 8           /* candidate runs up to this long are ordered by selection in registers       */
 
 __device__ __forceinline__ float logf_tab(const k3_args_t &A, int32_t x, uint32_t *flag)
 { /* glibc logf of an integer argument, tabulated on the host so MAPQ is bit-identical */
@@ -214,6 +213,107 @@ __device__ __forceinline__ void fin_sort(tie_shared_t &T, uint8_t *s_bytes, uint
 	__syncthreads();
 }
 
+/* One stable counting-sort pass of (key, payload) arrays on digit (key >> shift) & 255 by the whole CTA.
+ * Scratch: tie_shared_t::tab rows 0-5 (free whenever no klib replay is running). */
+template <class KeyT>
+__device__ void fin_radix_pass(tie_shared_t &T, const KeyT *__restrict__ kin, const uint32_t *__restrict__ vin, KeyT *__restrict__ kout, uint32_t *__restrict__ vout,
+                               uint32_t n, uint32_t shift)
+{
+	uint32_t *hist = T.tab[0], *base = T.tab[1];
+	uint32_t (*wcnt)[256] = (uint32_t (*)[256])T.tab[2];
+	const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	const uint32_t FULL = 0xffffffffu;
+	for (uint32_t k = tid; k < 256; k += FIN_THREADS) hist[k] = 0;
+	__syncthreads();
+	for (uint32_t t0 = 0; t0 < n; t0 += FIN_THREADS) {
+		const uint32_t i = t0 + tid;
+		const bool ok = i < n;
+		const uint32_t act = __ballot_sync(FULL, ok);
+		if (ok) {
+			const uint32_t d = (uint32_t)(kin[i] >> shift) & 255u;
+			const uint32_t peers = __match_any_sync(act, d);
+			if ((peers & lanemask_lt()) == 0) atomicAdd(&hist[d], (uint32_t)__popc(peers));
+		}
+	}
+	__syncthreads();
+	if (warp == 0) {
+		uint32_t c[8], tot = 0;
+#pragma unroll
+		for (int q = 0; q < 8; ++q) { c[q] = hist[lane * 8 + q]; tot += c[q]; }
+		uint32_t incl = tot;
+#pragma unroll
+		for (int o = 1; o < 32; o <<= 1) { const uint32_t u = __shfl_up_sync(FULL, incl, o); if (lane >= o) incl += u; }
+		uint32_t start = incl - tot;
+#pragma unroll
+		for (int q = 0; q < 8; ++q) { base[lane * 8 + q] = start; start += c[q]; }
+	}
+	__syncthreads();
+	for (uint32_t t0 = 0; t0 < n; t0 += FIN_THREADS) {
+		for (uint32_t k = tid; k < TIE_WARPS * 256; k += FIN_THREADS) (&wcnt[0][0])[k] = 0;
+		__syncthreads();
+		const uint32_t i = t0 + tid;
+		const bool ok = i < n;
+		KeyT key = 0; uint32_t v = 0, d = 0, peers = 0;
+		const uint32_t act = __ballot_sync(FULL, ok);
+		if (ok) {
+			key = kin[i]; v = vin[i]; d = (uint32_t)(key >> shift) & 255u;
+			peers = __match_any_sync(act, d);
+			if ((peers & lanemask_lt()) == 0) wcnt[warp][d] = __popc(peers);
+		}
+		__syncthreads();
+		for (uint32_t d2 = tid; d2 < 256; d2 += FIN_THREADS) {
+			uint32_t run = base[d2];
+#pragma unroll
+			for (int w = 0; w < TIE_WARPS; ++w) { const uint32_t c = wcnt[w][d2]; wcnt[w][d2] = run; run += c; }
+			base[d2] = run;
+		}
+		__syncthreads();
+		if (ok) { const uint32_t o = wcnt[warp][d] + __popc(peers & lanemask_lt()); kout[o] = key; vout[o] = v; }
+		__syncthreads();
+	}
+}
+
+/* Sort of m (key, payload = position) pairs in W.xk/W.ord whose keys are expected to be unique: every correct
+ * sort then equals klib's, so a parallel LSD radix sort is used; if two equal keys do turn up, klib's exact
+ * order is replayed instead.  W.sidx[pos] = payload at sorted position pos. */
+__device__ void fin_sort_unique(tie_shared_t &T, uint8_t *s_bytes, uint8_t *g_bytes, const klib_ws_t &W, uint32_t m, uint32_t *wsum)
+{
+	if (m <= 64) { fin_sort(T, s_bytes, g_bytes, W, m, nullptr); return; }
+	const uint32_t tid = threadIdx.x, lane = tid & 31;
+	const uint32_t FULL = 0xffffffffu;
+	uint64_t *backup = (uint64_t *)W.zlist; /* 8 m <= 4 n bytes */
+	__syncthreads();
+	if (tid == 0) T.diff = 0ULL;
+	__syncthreads();
+	{
+		const uint64_t x0 = W.xk[0];
+		unsigned long long diff = 0;
+		for (uint32_t i = tid; i < m; i += FIN_THREADS) { const uint64_t x = W.xk[i]; backup[i] = x; diff |= x ^ x0; }
+#pragma unroll
+		for (int o = 16; o > 0; o >>= 1) diff |= __shfl_xor_sync(FULL, diff, o);
+		if (lane == 0 && diff) atomicOr(&T.diff, diff);
+	}
+	__syncthreads();
+	const unsigned long long dmask = T.diff;
+	uint64_t *ka = W.xk, *kb = W.xk2; uint32_t *va = W.ord, *vb = W.ord2;
+	for (uint32_t sh = 0; sh < 64; sh += 8) {
+		if (((dmask >> sh) & 255ULL) == 0) continue;
+		fin_radix_pass<uint64_t>(T, ka, va, kb, vb, m, sh);
+		{ uint64_t *t = ka; ka = kb; kb = t; } { uint32_t *t = va; va = vb; vb = t; }
+	}
+	bool tie = false;
+	for (uint32_t i = tid; i + 1 < m; i += FIN_THREADS) tie |= ka[i] == ka[i + 1];
+	const int any_tie = __syncthreads_or(tie ? 1 : 0);
+	if (!any_tie) {
+		for (uint32_t i = tid; i < m; i += FIN_THREADS) W.sidx[i] = va[i];
+		__syncthreads();
+		return;
+	}
+	for (uint32_t i = tid; i < m; i += FIN_THREADS) { W.xk[i] = backup[i]; W.ord[i] = i; }
+	__syncthreads();
+	fin_sort(T, s_bytes, g_bytes, W, m, nullptr);
+}
+
 /* one backtrack attempt from candidate anchor i0 (mg_chain_backtrack body, lchain.c:162-181 + mg_chain_bk_end);
  * returns score<<32 | n_anchors of an accepted chain, 0 otherwise */
 __device__ __forceinline__ uint64_t fin_backtrack_one(int32_t i0, const int32_t *__restrict__ f, const int32_t *__restrict__ p, int32_t *t,
@@ -252,7 +352,7 @@ struct fin_shared_t {
  *   4  compact_a (+ the copy carried to the next chunk), exact sort of chains by target, region keys
  *   5  exact sort of regions, mm_gen_regs
  * The order-dependent remainder runs in k_chain_decide. */
-__global__ void __launch_bounds__(FIN_THREADS) k_chain_finish(k3_args_t A, dev_params_t P)
+__global__ void __launch_bounds__(FIN_THREADS, 8) k_chain_finish(k3_args_t A, dev_params_t P)
 {
 	__shared__ fin_shared_t SH;
 	const uint32_t FULL = 0xffffffffu;
@@ -314,12 +414,12 @@ __global__ void __launch_bounds__(FIN_THREADS) k_chain_finish(k3_args_t A, dev_p
 					n_z += zt; seg_run += stt;
 				}
 				__syncthreads();
-				uint32_t *runs = (uint32_t *)M.U;
+				uint32_t *runs = (uint32_t *)M.U, *runidx = runs + un; /* M.U is 8n bytes */
 				for (uint32_t j0 = 0; j0 < n_z; j0 += FIN_THREADS) {
 					const uint32_t j = j0 + tid;
 					const bool first = j < n_z && (j == 0 || zseg[j] != zseg[j - 1]);
-					uint32_t tot; const uint32_t rr = tie_tile_rank(first, SH.wsum, &tot);
-					if (first) runs[n_runs + rr] = j;
+					uint32_t tot; const uint32_t incl = fin_tile_scan(first ? 1u : 0u, SH.wsum, &tot);
+					if (j < n_z) { const uint32_t rr = n_runs + incl - 1; runidx[j] = rr; if (first) runs[rr] = j; }
 					n_runs += tot;
 				}
 				__syncthreads();
@@ -329,36 +429,26 @@ __global__ void __launch_bounds__(FIN_THREADS) k_chain_finish(k3_args_t A, dev_p
 				/* ---- 2: z sorted by score exactly as klib leaves it ---- */
 				fin_sort(SH.T, SH.bytes, g_bytes, W, n_z, nullptr);
 				RH_PROF_MARK(A.prof, 33, tid == 0);
-				/* ---- 3: backtrack, best score first inside every run ---- */
+				/* ---- 3: backtrack, best score first inside every run.  Positions of the sorted z are grouped by run
+				 *      (stable radix sort on the run index), so each run walks its own candidates in sorted order ---- */
 				const uint32_t *__restrict__ sidx = W.sidx;
-				uint32_t *rank_of = W.dst;
 				uint64_t *acc = W.xk2;
-				for (uint32_t pos = tid; pos < n_z; pos += FIN_THREADS) { rank_of[sidx[pos]] = pos; acc[pos] = 0ULL; }
+				const uint32_t *runs = (const uint32_t *)M.U, *runidx = runs + un;
+				uint32_t *ka = (uint32_t *)W.xk, *kb = ka + un, *va = W.ord, *vb = W.ord2;
+				for (uint32_t pos = tid; pos < n_z; pos += FIN_THREADS) { ka[pos] = runidx[sidx[pos]]; va[pos] = pos; acc[pos] = 0ULL; }
 				__syncthreads();
+				for (uint32_t sh = 0; sh < 32 && (sh == 0 || ((n_runs - 1) >> sh) != 0); sh += 8) {
+					fin_radix_pass<uint32_t>(SH.T, ka, va, kb, vb, n_z, sh);
+					{ uint32_t *t2 = ka; ka = kb; kb = t2; } { uint32_t *t2 = va; va = vb; vb = t2; }
+				}
 				{
-					const uint32_t *runs = (const uint32_t *)M.U;
+					const uint32_t *__restrict__ grouped = va; /* run rr owns grouped[runs[rr] .. runs[rr+1]) in ascending position */
 					for (uint32_t rr = tid; rr < n_runs; rr += FIN_THREADS) {
-						const uint32_t lo = runs[rr], hi = rr + 1 < n_runs ? runs[rr + 1] : n_z, m = hi - lo;
-						if (m <= FIN_SMALL_RUN) {
-							uint32_t rk[FIN_SMALL_RUN];
-#pragma unroll
-							for (int q = 0; q < FIN_SMALL_RUN; ++q) rk[q] = (uint32_t)q < m ? rank_of[lo + q] : 0xffffffffu;
-							uint32_t prev = 0xffffffffu; /* ranks visited so far are all > the next one */
-							for (uint32_t it = 0; it < m; ++it) {
-								uint32_t best = 0, bq = 0; bool have = false;
-#pragma unroll
-								for (int q = 0; q < FIN_SMALL_RUN; ++q) { const uint32_t v = rk[q]; if (v != 0xffffffffu && v < prev && (!have || v > best)) { best = v; bq = (uint32_t)q; have = true; } }
-								prev = best;
-								const uint64_t res = fin_backtrack_one((int32_t)z_idx[lo + bq], f, p, t, min_sc, min_cnt, max_drop);
-								if (res) acc[best] = res;
-							}
-						} else {
-							for (uint32_t pos = n_z; pos-- > 0;) {
-								const uint32_t j = sidx[pos];
-								if (j < lo || j >= hi) continue;
-								const uint64_t res = fin_backtrack_one((int32_t)z_idx[j], f, p, t, min_sc, min_cnt, max_drop);
-								if (res) acc[pos] = res;
-							}
+						const uint32_t lo = runs[rr], hi = rr + 1 < n_runs ? runs[rr + 1] : n_z;
+						for (uint32_t k = hi; k-- > lo;) {
+							const uint32_t pos = grouped[k];
+							const uint64_t res = fin_backtrack_one((int32_t)z_idx[sidx[pos]], f, p, t, min_sc, min_cnt, max_drop);
+							if (res) acc[pos] = res;
 						}
 					}
 				}
@@ -403,7 +493,7 @@ __global__ void __launch_bounds__(FIN_THREADS) k_chain_finish(k3_args_t A, dev_p
 				if (tid == 0 && carry_ok) { R->prev_off = co; R->prev_n = n_v; }
 				__syncthreads();
 				RH_PROF_MARK(A.prof, 35, tid == 0);
-				fin_sort(SH.T, SH.bytes, g_bytes, W, n_u, nullptr);
+				fin_sort_unique(SH.T, SH.bytes, g_bytes, W, n_u, SH.wsum);
 				RH_PROF_MARK(A.prof, 36, tid == 0);
 				/* output offsets in target order, then copy chains and pre-compute the region keys (mm_gen_regs) */
 				uint32_t *kout = (uint32_t *)M.t;      /* chain_i0 is no longer needed */
@@ -434,7 +524,7 @@ __global__ void __launch_bounds__(FIN_THREADS) k_chain_finish(k3_args_t A, dev_p
 				__syncthreads();
 				RH_PROF_MARK(A.prof, 37, tid == 0);
 				/* ---- 5: mm_gen_regs ---- */
-				fin_sort(SH.T, SH.bytes, g_bytes, W, n_u, nullptr);
+				fin_sort_unique(SH.T, SH.bytes, g_bytes, W, n_u, SH.wsum);
 				RH_PROF_MARK(A.prof, 38, tid == 0);
 				r = (dev_reg_t *)((uint8_t *)M.regs + fin_regs_off(un)); /* after the sort scratch */
 				for (uint32_t i = tid; i < n_u; i += FIN_THREADS) { /* descending key */
@@ -461,7 +551,7 @@ __global__ void __launch_bounds__(FIN_THREADS) k_chain_finish(k3_args_t A, dev_p
 /* The order-dependent remainder, one WARP per chunk at full occupancy: mm_set_parent, mm_select_sub,
  * mm_sync_regs, mm_set_mapq, then the stop rules and the final record of map_worker_for. */
 #define DEC_WARPS 4
-__global__ void __launch_bounds__(DEC_WARPS * 32) k_chain_decide(k3_args_t A, dev_params_t P)
+__global__ void __launch_bounds__(DEC_WARPS * 32, 8) k_chain_decide(k3_args_t A, dev_params_t P)
 {
 	__shared__ uint32_t s_bits[DEC_WARPS][FIN_BITS / 32];
 	__shared__ prim_cache_t s_pc[DEC_WARPS];

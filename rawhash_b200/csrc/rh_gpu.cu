@@ -18,6 +18,7 @@
 #include <algorithm>
 #include <numeric>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include <cuda_runtime.h>
@@ -63,22 +64,23 @@ struct timed_span { cudaEvent_t a, b; int kind; };
 #define TIES_SMALL (24u * 1024u)       /* size class boundary: small chunks run 5 CTAs per SM    */
 enum { T_EVENT = 0, T_SEED, T_SORT, T_CHAIN, T_POST, T_LEN, T_TIES, T_NKIND };
 
-struct rh_gpu_ctx_s {
+/* One worker = one CUDA stream with its own scratch, arenas and per-read state.  A batch is cut into
+ * contiguous read ranges, one per worker; the workers run their chunk rounds concurrently so that the
+ * latency-bound tail of one range (late rounds hold few, slow chunks) overlaps the bulk of the others
+ * and the host->device copy of the raw samples overlaps compute.  Index, log table and raw buffer are shared. */
+struct rh_worker {
 	int device = 0;
 	rh_params_t P;
 	dev_params_t D;
 	const rh_index_s *idx = nullptr;
 	dev_index_t I;
 	cudaStream_t stream = nullptr, own_stream = nullptr;
-	/* index storage */
-	dbuf<uint32_t> d_keys, d_bucket, d_seqlen, d_namerank;
-	dbuf<uint64_t> d_off, d_pos;
-	dbuf<float> d_logf;
-	uint32_t logf_n = 0;
-	std::vector<uint32_t> name_order; /* sorted target names (indices) for Rawsamble */
+	/* shared, owned by the context */
+	dbuf<float> d_logf; uint32_t logf_n = 0;
+	dbuf<uint32_t> d_seqlen;
+	const std::vector<uint32_t> *name_order = nullptr;
+	const int16_t *raw_ptr = nullptr; /* raw buffer of the current call (the context's or the caller's) */
 	/* per-batch */
-	dbuf<int16_t> d_raw;
-	const int16_t *raw_ptr = nullptr; /* raw buffer of the current call (ours or the caller's) */
 	dbuf<read_state_t> d_rs;
 	dbuf<slot_t> d_slots;
 	dbuf<float> d_z, d_events, d_ps, d_pq, d_t1, d_t2;
@@ -90,22 +92,43 @@ struct rh_gpu_ctx_s {
 	dbuf<uint32_t> d_err, d_rec_start, d_rec_cnt, d_tie_list, d_tie_count;
 	dbuf<unsigned long long> d_prof; bool prof_on = false;
 	dbuf<rh_map_rec_t> d_recs;
-	size_t arena_bytes = 0, carry_elems = 0, sig_budget = 0;
+	size_t arena_bytes = 0, sig_budget = 0;
+	unsigned long long carry_known = 0, carry_pending = 0; /* exact top at the last sync + upper bound of what was launched since */
 	std::vector<timed_span> spans;
 	std::vector<cudaEvent_t> ev_pool; size_t ev_used = 0;
+	rh_gpu_stats_t st;
+	char err[512];
+};
+
+struct rh_gpu_ctx_s {
+	int device = 0;
+	rh_params_t P;
+	dev_params_t D;
+	const rh_index_s *idx = nullptr;
+	dev_index_t I;
+	/* index storage */
+	dbuf<uint32_t> d_keys, d_bucket, d_seqlen, d_namerank;
+	dbuf<uint64_t> d_off, d_pos;
+	dbuf<float> d_logf;
+	uint32_t logf_n = 0;
+	std::vector<uint32_t> name_order; /* sorted target names (indices) for Rawsamble */
+	dbuf<int16_t> d_raw;              /* raw samples of the current host-buffer call, shared by the workers */
+	std::vector<rh_worker *> workers;
+	uint32_t n_active = 1;            /* workers used per call */
+	void *user_stream = nullptr;
 	rh_gpu_stats_t st;
 };
 
 namespace {
 
-cudaEvent_t get_event(rh_gpu_ctx *c)
+cudaEvent_t get_event(rh_worker *c)
 {
 	if (c->ev_used == c->ev_pool.size()) { cudaEvent_t e; cudaEventCreate(&e); c->ev_pool.push_back(e); }
 	return c->ev_pool[c->ev_used++];
 }
 struct span_guard {
-	rh_gpu_ctx *c; timed_span s; int n_launch;
-	span_guard(rh_gpu_ctx *c_, int kind, int n_launch_ = 1) : c(c_), n_launch(n_launch_) { s.kind = kind; s.a = get_event(c); s.b = get_event(c); cudaEventRecord(s.a, c->stream); }
+	rh_worker *c; timed_span s; int n_launch;
+	span_guard(rh_worker *c_, int kind, int n_launch_ = 1) : c(c_), n_launch(n_launch_) { s.kind = kind; s.a = get_event(c); s.b = get_event(c); cudaEventRecord(s.a, c->stream); }
 	~span_guard() { cudaEventRecord(s.b, c->stream); c->spans.push_back(s); c->st.kernel_launches += n_launch; if (s.kind == T_EVENT) c->st.event_kernel_launches++; }
 };
 
@@ -163,7 +186,7 @@ struct round_io {
 	uint32_t tap_chunk = 0;
 };
 
-int run_round(rh_gpu_ctx *c, round_io &io, int carry_in_idx)
+int run_round(rh_worker *c, round_io &io, int carry_in_idx)
 {
 	const uint32_t ns = (uint32_t)io.slots.size();
 	if (ns == 0) return RH_OK;
@@ -206,13 +229,16 @@ int run_round(rh_gpu_ctx *c, round_io &io, int carry_in_idx)
 		k_seed_count<<<wblocks, 256, 0, s>>>(a2, c->I, c->D);
 	}
 	CUDA_TRY(cudaMemcpyAsync(io.slots.data(), c->d_slots.p, ns * sizeof(slot_t), cudaMemcpyDeviceToHost, s));
+	CUDA_TRY(cudaMemcpyAsync(&c->carry_known, c->d_counters.p, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
 	CUDA_TRY(cudaStreamSynchronize(s));
-	c->st.d2h_bytes += ns * sizeof(slot_t);
+	c->carry_pending = 0;
+	c->st.d2h_bytes += ns * sizeof(slot_t) + 8;
+	dbuf<anchor_t> &carry_out = c->d_carry[carry_in_idx ^ 1];
 
 	/* anchor-arena groups */
 	k3_args_t a3;
 	a3.slots = nullptr; a3.n_slots = 0; a3.rs = c->d_rs.p; a3.arena = c->d_arena.p;
-	a3.carry_out = c->d_carry[carry_in_idx ^ 1].p; a3.carry_top = c->d_counters.p; a3.carry_cap = c->carry_elems;
+	a3.carry_out = carry_out.p; a3.carry_top = c->d_counters.p; a3.carry_cap = carry_out.cap;
 	a3.logf_tab = c->d_logf.p; a3.logf_n = c->logf_n;
 	a3.recs = c->d_recs.p; a3.rec_top = c->d_counters.p + 1; a3.rec_cap = c->d_recs.cap;
 	a3.rec_start = c->d_rec_start.p; a3.rec_cnt = c->d_rec_cnt.p; a3.seq_len = c->d_seqlen.p; a3.tap = io.tap; a3.err = c->d_err.p; a3.prof = c->prof_on ? c->d_prof.p : nullptr;
@@ -227,6 +253,24 @@ int run_round(rh_gpu_ctx *c, round_io &io, int carry_in_idx)
 			io.slots[g1].a_off = used; used += need; ++g1;
 		}
 		const uint32_t gn = g1 - g0;
+		{ /* the chains of this group carry at most all of its anchors into the next round: make room first */
+			unsigned long long need = 0;
+			for (uint32_t q = g0; q < g1; ++q) need += io.slots[q].n_anchors;
+			if (c->carry_known + c->carry_pending + need > carry_out.cap) {
+				CUDA_TRY(cudaStreamSynchronize(s));
+				CUDA_TRY(cudaMemcpy(&c->carry_known, c->d_counters.p, sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+				c->carry_pending = 0;
+				if (c->carry_known + need > carry_out.cap) {
+					dbuf<anchor_t> bigger;
+					if ((rc = bigger.reserve((size_t)((c->carry_known + need) * 3 / 2)))) return rc;
+					if (c->carry_known) CUDA_TRY(cudaMemcpy(bigger.p, carry_out.p, c->carry_known * sizeof(anchor_t), cudaMemcpyDeviceToDevice));
+					carry_out.release();
+					carry_out = bigger;
+					a2.carry_out = carry_out.p; a3.carry_out = carry_out.p; a3.carry_cap = carry_out.cap;
+				}
+			}
+			c->carry_pending += need;
+		}
 		CUDA_TRY(cudaMemcpyAsync(c->d_slots.p + g0, io.slots.data() + g0, gn * sizeof(slot_t), cudaMemcpyHostToDevice, s));
 		c->st.h2d_bytes += gn * sizeof(slot_t);
 		a2.slots = c->d_slots.p + g0; a2.n_slots = gn;
@@ -282,7 +326,7 @@ int run_round(rh_gpu_ctx *c, round_io &io, int carry_in_idx)
 	return RH_OK;
 }
 
-int collect_spans(rh_gpu_ctx *c)
+int collect_spans(rh_worker *c)
 {
 	if (c->prof_on) {
 		unsigned long long h[64];
@@ -300,19 +344,25 @@ int collect_spans(rh_gpu_ctx *c)
 	return RH_OK;
 }
 
-int check_dev_err(rh_gpu_ctx *c)
+int check_dev_err(rh_worker *c)
 {
 	uint32_t e = 0;
 	CUDA_TRY(cudaMemcpyAsync(&e, c->d_err.p, 4, cudaMemcpyDeviceToHost, c->stream));
 	CUDA_TRY(cudaStreamSynchronize(c->stream));
 	if (e == 0) return RH_OK;
+	if (e == 2) {
+		unsigned long long tops[2] = {0, 0};
+		cudaMemcpy(tops, c->d_counters.p, sizeof(tops), cudaMemcpyDeviceToHost);
+		rh_set_error("device reported: carry arena exhausted (top %llu, capacities %zu / %zu)", tops[0], c->d_carry[0].cap, c->d_carry[1].cap);
+		return RH_ERR_NOMEM;
+	}
 	const char *what = e == 2 ? "carry arena exhausted" : e == 3 ? "region scratch exhausted" : e == 4 ? "logf argument outside the exact table" : e == 5 ? "record arena exhausted" : "device error";
 	rh_set_error("device reported: %s (code %u)", what, e);
 	return e == 4 ? RH_ERR_ARG : RH_ERR_NOMEM;
 }
 
 /* set up per-read state on the device; raw already resident in c->d_raw */
-int setup_reads(rh_gpu_ctx *c, const batch_in &in, const std::vector<uint64_t> &beg, const std::vector<uint64_t> &len, std::vector<uint32_t> &l_sig)
+int setup_reads(rh_worker *c, const batch_in &in, const std::vector<uint64_t> &beg, const std::vector<uint64_t> &len, std::vector<uint32_t> &l_sig)
 {
 	const uint32_t n = in.n;
 	std::vector<read_state_t> rs(n);
@@ -326,8 +376,8 @@ int setup_reads(rh_gpu_ctx *c, const batch_in &in, const std::vector<uint64_t> &
 		r.cal_scale = (double)(float)(in.range[i] / in.digitisation[i]); /* rsig.c:493: float scale */
 		if (ava && in.names) {
 			const char *q = in.names[i];
-			uint32_t lo = 0, hi = (uint32_t)c->name_order.size();
-			while (lo < hi) { uint32_t mid = (lo + hi) / 2; if (strcmp(c->idx->names[c->name_order[mid]].c_str(), q) <= 0) lo = mid + 1; else hi = mid; }
+			uint32_t lo = 0, hi = (uint32_t)c->name_order->size();
+			while (lo < hi) { uint32_t mid = (lo + hi) / 2; if (strcmp(c->idx->names[(*c->name_order)[mid]].c_str(), q) <= 0) lo = mid + 1; else hi = mid; }
 			r.name_ub = lo;
 		}
 	}
@@ -350,7 +400,7 @@ int setup_reads(rh_gpu_ctx *c, const batch_in &in, const std::vector<uint64_t> &
 	return RH_OK;
 }
 
-int map_resident(rh_gpu_ctx *c, const batch_in &in, const std::vector<uint64_t> &beg, const std::vector<uint64_t> &len, rh_map_rec_t **recs_out, uint64_t *n_recs_out)
+int map_resident(rh_worker *c, const batch_in &in, const std::vector<uint64_t> &beg, const std::vector<uint64_t> &len, rh_map_rec_t **recs_out, uint64_t *n_recs_out)
 {
 	const uint32_t n = in.n;
 	std::vector<uint32_t> l_sig;
@@ -424,11 +474,150 @@ int map_resident(rh_gpu_ctx *c, const batch_in &in, const std::vector<uint64_t> 
 	return RH_OK;
 }
 
-void begin_call(rh_gpu_ctx *c) { memset(&c->st, 0, sizeof(c->st)); c->spans.clear(); c->ev_used = 0; }
+void begin_call(rh_worker *c) { memset(&c->st, 0, sizeof(c->st)); c->spans.clear(); c->ev_used = 0; }
 
 } // namespace
 
 /* ============================================================================================ */
+namespace {
+
+void destroy_worker(rh_worker *w)
+{
+	if (!w) return;
+	w->d_ps.release(); w->d_pq.release(); w->d_t1.release(); w->d_t2.release();
+	w->d_rs.release(); w->d_slots.release(); w->d_z.release(); w->d_events.release(); w->d_peaks.release();
+	w->d_seed_hash.release(); w->d_seed_pos.release(); w->d_seed_cnt.release(); w->d_seed_dst.release(); w->d_seed_src.release();
+	w->d_arena.release(); w->d_carry[0].release(); w->d_carry[1].release(); w->d_counters.release(); w->d_err.release();
+	w->d_rec_start.release(); w->d_rec_cnt.release(); w->d_recs.release(); w->d_tie_list.release(); w->d_tie_count.release(); w->d_prof.release();
+	for (cudaEvent_t e : w->ev_pool) cudaEventDestroy(e);
+	if (w->own_stream) cudaStreamDestroy(w->own_stream);
+	delete w;
+}
+
+rh_worker *make_worker(rh_gpu_ctx *c, size_t arena_bytes)
+{
+	rh_worker *w = new rh_worker();
+	w->device = c->device; w->P = c->P; w->D = c->D; w->idx = c->idx; w->I = c->I;
+	w->d_logf = c->d_logf; w->logf_n = c->logf_n; w->d_seqlen = c->d_seqlen; w->name_order = &c->name_order; /* aliases: the context owns them */
+	w->err[0] = 0;
+	if (cudaStreamCreateWithFlags(&w->own_stream, cudaStreamNonBlocking) != cudaSuccess) { rh_set_error("cudaStreamCreate failed"); destroy_worker(w); return nullptr; }
+	w->stream = w->own_stream;
+	w->prof_on = getenv("RH_PROF") != NULL;
+	if (w->d_counters.reserve(2) || w->d_err.reserve(1) || w->d_prof.reserve(64)) { destroy_worker(w); return nullptr; }
+	cudaMemset(w->d_prof.p, 0, 64 * 8);
+	w->arena_bytes = arena_bytes;
+	const size_t carry_elems = arena_bytes / 8 / sizeof(anchor_t); /* initial size: grows on demand (run_round) */
+	w->sig_budget = std::max<size_t>(arena_bytes / 16 / 44, (size_t)1 << 20); /* ~44 B of scratch per sample */
+	if (w->d_arena.reserve(arena_bytes) || w->d_carry[0].reserve(carry_elems) || w->d_carry[1].reserve(carry_elems)) { destroy_worker(w); return nullptr; }
+	w->arena_bytes = w->d_arena.cap;
+	return w;
+}
+
+void add_stats(rh_gpu_stats_t &a, const rh_gpu_stats_t &b)
+{
+	a.n_reads += b.n_reads; a.n_chunks += b.n_chunks; a.n_rounds = std::max(a.n_rounds, b.n_rounds);
+	a.raw_samples_consumed += b.raw_samples_consumed; a.n_events += b.n_events; a.n_seeds += b.n_seeds; a.n_anchors += b.n_anchors; a.n_chains += b.n_chains;
+	a.kernel_launches += b.kernel_launches; a.event_kernel_launches += b.event_kernel_launches;
+	a.ms_total = std::max(a.ms_total, b.ms_total);
+	a.ms_event_kernel += b.ms_event_kernel; a.ms_seed += b.ms_seed; a.ms_sort += b.ms_sort; a.ms_sort_ties += b.ms_sort_ties; a.ms_chain += b.ms_chain; a.ms_post += b.ms_post;
+	a.h2d_bytes += b.h2d_bytes; a.d2h_bytes += b.d2h_bytes;
+}
+
+/* contiguous read ranges with (nearly) equal raw sample counts: b[0..k] */
+std::vector<uint32_t> split_ranges(uint32_t n, const std::vector<uint64_t> &len, uint32_t k)
+{
+	std::vector<uint32_t> b(k + 1, n);
+	b[0] = 0;
+	uint64_t total = 0;
+	for (uint32_t i = 0; i < n; ++i) total += len[i];
+	uint64_t acc = 0; uint32_t r = 1;
+	for (uint32_t i = 0; i < n && r < k; ++i) {
+		acc += len[i];
+		while (r < k && acc * k >= total * r) b[r++] = i + 1;
+	}
+	return b;
+}
+
+/* one worker's share of a batch: optional upload of its raw samples, then the chunk rounds */
+struct job_t {
+	rh_worker *w; uint32_t lo, hi;
+	const int16_t *const *raw; int16_t *d_raw;   /* host pointers + shared device buffer (null when already resident) */
+	const batch_in *in; const std::vector<uint64_t> *beg, *len;
+	rh_map_rec_t *recs = nullptr; uint64_t n_recs = 0; int rc = RH_OK;
+};
+
+void run_job(job_t *j)
+{
+	rh_worker *w = j->w;
+	if (cudaSetDevice(w->device) != cudaSuccess) { j->rc = RH_ERR_CUDA; snprintf(w->err, sizeof(w->err), "cudaSetDevice(%d) failed", w->device); return; }
+	begin_call(w);
+	cudaEvent_t t0 = get_event(w), t1 = get_event(w);
+	cudaEventRecord(t0, w->stream);
+	const uint32_t n = j->hi - j->lo;
+	int rc = RH_OK;
+	if (j->raw) {
+		for (uint32_t i = j->lo; i < j->hi && rc == RH_OK; ++i) {
+			const uint64_t l = (*j->len)[i];
+			if (!l) continue;
+			if (cudaMemcpyAsync(j->d_raw + (*j->beg)[i], j->raw[i], l * 2, cudaMemcpyHostToDevice, w->stream) != cudaSuccess) { rh_set_error("H2D copy of read %u failed: %s", i, cudaGetErrorString(cudaGetLastError())); rc = RH_ERR_CUDA; }
+			w->st.h2d_bytes += l * 2;
+		}
+	}
+	if (rc == RH_OK && n) {
+		batch_in sub = *j->in;
+		sub.n = n; sub.offset += j->lo; sub.range += j->lo; sub.digitisation += j->lo;
+		if (sub.names) sub.names += j->lo;
+		const std::vector<uint64_t> b(j->beg->begin() + j->lo, j->beg->begin() + j->hi), l(j->len->begin() + j->lo, j->len->begin() + j->hi);
+		rc = map_resident(w, sub, b, l, &j->recs, &j->n_recs);
+	}
+	cudaEventRecord(t1, w->stream);
+	cudaEventSynchronize(t1);
+	float ms = 0; cudaEventElapsedTime(&ms, t0, t1); w->st.ms_total = ms;
+	collect_spans(w);
+	j->rc = rc;
+	if (rc != RH_OK) snprintf(w->err, sizeof(w->err), "%s", rh_gpu_last_error()); /* the error text is thread local: hand it to the caller */
+}
+
+int map_batch(rh_gpu_ctx *c, const batch_in &in, const std::vector<uint64_t> &beg, const std::vector<uint64_t> &len, const int16_t *raw_dev,
+              rh_map_rec_t **recs, uint64_t *n_recs)
+{
+	const uint32_t n = in.n;
+	memset(&c->st, 0, sizeof(c->st));
+	uint32_t k = std::min<uint32_t>(c->n_active, (uint32_t)c->workers.size());
+	if (n < 64 * k) k = 1; /* tiny batches: one range */
+	if (c->user_stream) k = 1; /* the caller's stream carries the whole batch */
+	const std::vector<uint32_t> b = split_ranges(n, len, k);
+	std::vector<job_t> jobs(k);
+	for (uint32_t r = 0; r < k; ++r) {
+		job_t &j = jobs[r];
+		j.w = c->workers[r]; j.lo = b[r]; j.hi = b[r + 1];
+		j.raw = in.raw; j.d_raw = c->d_raw.p; j.in = &in; j.beg = &beg; j.len = &len;
+		j.w->raw_ptr = raw_dev;
+		j.w->stream = (c->user_stream && r == 0) ? (cudaStream_t)c->user_stream : j.w->own_stream;
+	}
+	if (k == 1) run_job(&jobs[0]);
+	else {
+		std::vector<std::thread> th;
+		for (uint32_t r = 0; r < k; ++r) th.emplace_back(run_job, &jobs[r]);
+		for (std::thread &t : th) t.join();
+	}
+	int rc = RH_OK;
+	uint64_t total = 0;
+	for (job_t &j : jobs) { if (j.rc != RH_OK && rc == RH_OK) { rc = j.rc; rh_set_error("%s", j.w->err); } total += j.n_recs; add_stats(c->st, j.w->st); }
+	if (rc == RH_OK) {
+		rh_map_rec_t *out = (rh_map_rec_t *)malloc((total ? total : 1) * sizeof(rh_map_rec_t));
+		uint64_t o = 0;
+		for (job_t &j : jobs) {
+			for (uint64_t q = 0; q < j.n_recs; ++q) { out[o] = j.recs[q]; out[o].read_idx += j.lo; ++o; } /* rank order = input order */
+		}
+		*recs = out; *n_recs = total;
+	}
+	for (job_t &j : jobs) free(j.recs);
+	return rc;
+}
+
+} // namespace
+
 extern "C" rh_gpu_ctx *rh_gpu_init(const rh_index_t *idx, const rh_params_t *p, int device, size_t arena_bytes)
 {
 	if (!idx || !p) { rh_set_error("rh_gpu_init: null argument"); return NULL; }
@@ -441,8 +630,6 @@ extern "C" rh_gpu_ctx *rh_gpu_init(const rh_index_t *idx, const rh_params_t *p, 
 	fill_dev_params(*p, c->D);
 	if (p->mid_occ <= 0) { rh_params_t q = *p; rh_index_update_mapopt(idx, &q); c->P.mid_occ = q.mid_occ; c->D.mid_occ = q.mid_occ; }
 	auto fail = [&](const char *what) -> rh_gpu_ctx * { if (what) rh_set_error("%s", what); rh_gpu_destroy(c); return NULL; };
-	if (cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) != cudaSuccess) return fail("cudaStreamCreate failed");
-	c->stream = c->own_stream;
 	/* ---- index upload ---- */
 	const size_t nk = idx->keys.size();
 	int bits = 10; while (bits < 26 && ((size_t)1 << bits) < nk) ++bits;
@@ -464,27 +651,28 @@ extern "C" rh_gpu_ctx *rh_gpu_init(const rh_index_t *idx, const rh_params_t *p, 
 	c->logf_n = 1u << 20;
 	lt.resize(c->logf_n);
 	for (uint32_t i = 0; i < c->logf_n; ++i) lt[i] = logf((float)i); /* host libm: identical to the reference's calls */
-	if (upload(c->d_keys, idx->keys, c->stream) || upload(c->d_off, idx->off, c->stream) || upload(c->d_pos, idx->pos, c->stream) ||
-	    upload(c->d_bucket, bucket, c->stream) || upload(c->d_seqlen, idx->lens, c->stream) || upload(c->d_namerank, rank, c->stream) ||
-	    upload(c->d_logf, lt, c->stream)) return fail(NULL);
+	cudaStream_t s0 = nullptr;
+	if (upload(c->d_keys, idx->keys, s0) || upload(c->d_off, idx->off, s0) || upload(c->d_pos, idx->pos, s0) ||
+	    upload(c->d_bucket, bucket, s0) || upload(c->d_seqlen, idx->lens, s0) || upload(c->d_namerank, rank, s0) ||
+	    upload(c->d_logf, lt, s0)) return fail(NULL);
 	c->I.keys = c->d_keys.p; c->I.off = c->d_off.p; c->I.pos = c->d_pos.p; c->I.bucket = c->d_bucket.p; c->I.bucket_bits = bits;
 	c->I.n_keys = nk; c->I.seq_len = c->d_seqlen.p; c->I.name_rank = c->d_namerank.p; c->I.n_seq = (uint32_t)idx->names.size();
-	if (c->d_counters.reserve(2) || c->d_err.reserve(1)) return fail(NULL);
-	c->prof_on = getenv("RH_PROF") != NULL;
-	if (c->d_prof.reserve(64)) return fail(NULL);
-	cudaMemset(c->d_prof.p, 0, 64 * 8);
 	if (cudaFuncSetAttribute(k_sort_ties, cudaFuncAttributeMaxDynamicSharedMemorySize, sizeof(tie_shared_t) + TIES_SMEM_CAP) != cudaSuccess) return fail("cudaFuncSetAttribute(k_sort_ties) failed");
-	if (cudaStreamSynchronize(c->stream) != cudaSuccess) return fail("index upload failed");
-	/* ---- work arenas ---- */
+	if (cudaDeviceSynchronize() != cudaSuccess) return fail("index upload failed");
+	/* ---- workers: the work arenas are split evenly ---- */
 	size_t free_b = 0, total_b = 0;
 	cudaMemGetInfo(&free_b, &total_b);
 	if (arena_bytes == 0) arena_bytes = free_b / 2;
 	if (arena_bytes > free_b * 7 / 10) arena_bytes = free_b * 7 / 10;
-	c->arena_bytes = arena_bytes;
-	c->carry_elems = arena_bytes / 8 / sizeof(anchor_t);
-	c->sig_budget = std::max<size_t>(arena_bytes / 16 / 44, (size_t)1 << 20); /* ~44 B of scratch per sample */
-	if (c->d_arena.reserve(arena_bytes) || c->d_carry[0].reserve(c->carry_elems) || c->d_carry[1].reserve(c->carry_elems)) return fail(NULL);
-	c->arena_bytes = c->d_arena.cap; c->carry_elems = std::min(c->d_carry[0].cap, c->d_carry[1].cap);
+	uint32_t nw = 4;
+	if (const char *e = getenv("RH_WORKERS")) nw = (uint32_t)std::max(1, std::min(16, atoi(e)));
+	while (nw > 1 && arena_bytes / nw < ((size_t)64 << 20)) --nw; /* keep every worker's arena useful */
+	for (uint32_t r = 0; r < nw; ++r) {
+		rh_worker *w = make_worker(c, (size_t)((double)arena_bytes / nw / 1.25) /* dbuf over-allocates by 25 % */);
+		if (!w) return fail(NULL);
+		c->workers.push_back(w);
+	}
+	c->n_active = nw;
 	return c;
 }
 
@@ -492,33 +680,22 @@ extern "C" void rh_gpu_destroy(rh_gpu_ctx *c)
 {
 	if (!c) return;
 	cudaSetDevice(c->device);
+	for (rh_worker *w : c->workers) destroy_worker(w);
 	c->d_keys.release(); c->d_bucket.release(); c->d_seqlen.release(); c->d_namerank.release(); c->d_off.release(); c->d_pos.release(); c->d_logf.release();
-	c->d_ps.release(); c->d_pq.release(); c->d_t1.release(); c->d_t2.release();
-	c->d_raw.release(); c->d_rs.release(); c->d_slots.release(); c->d_z.release(); c->d_events.release(); c->d_peaks.release();
-	c->d_seed_hash.release(); c->d_seed_pos.release(); c->d_seed_cnt.release(); c->d_seed_dst.release(); c->d_seed_src.release();
-	c->d_arena.release(); c->d_carry[0].release(); c->d_carry[1].release(); c->d_counters.release(); c->d_err.release();
-	c->d_rec_start.release(); c->d_rec_cnt.release(); c->d_recs.release(); c->d_tie_list.release(); c->d_tie_count.release();
-	for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
-	if (c->own_stream) cudaStreamDestroy(c->own_stream);
+	c->d_raw.release();
 	delete c;
 }
 
-extern "C" void rh_gpu_set_stream(rh_gpu_ctx *c, void *cuda_stream) { if (c) c->stream = cuda_stream ? (cudaStream_t)cuda_stream : c->own_stream; }
+extern "C" void rh_gpu_set_stream(rh_gpu_ctx *c, void *cuda_stream) { if (c) c->user_stream = cuda_stream; }
+
+extern "C" int rh_gpu_set_workers(rh_gpu_ctx *c, int n_workers)
+{
+	if (!c || n_workers < 1) { rh_set_error("rh_gpu_set_workers: bad argument"); return RH_ERR_ARG; }
+	c->n_active = std::min<uint32_t>((uint32_t)n_workers, (uint32_t)c->workers.size());
+	return (int)c->n_active;
+}
 
 extern "C" void rh_gpu_get_stats(const rh_gpu_ctx *c, rh_gpu_stats_t *st) { *st = c->st; }
-
-static int upload_raw(rh_gpu_ctx *c, uint32_t n, const int16_t *const *raw, const uint64_t *raw_len, std::vector<uint64_t> &beg, std::vector<uint64_t> &len)
-{
-	beg.assign(n, 0); len.assign(n, 0);
-	uint64_t tot = 0;
-	for (uint32_t i = 0; i < n; ++i) { beg[i] = tot; len[i] = raw_len[i]; tot += (raw_len[i] + 7) & ~7ULL; } /* 16-byte aligned starts */
-	int rc = c->d_raw.reserve(tot + 8);
-	if (rc) return rc;
-	for (uint32_t i = 0; i < n; ++i)
-		if (raw_len[i]) { CUDA_TRY(cudaMemcpyAsync(c->d_raw.p + beg[i], raw[i], raw_len[i] * 2, cudaMemcpyHostToDevice, c->stream)); c->st.h2d_bytes += raw_len[i] * 2; }
-	c->raw_ptr = c->d_raw.p;
-	return RH_OK;
-}
 
 extern "C" int rh_gpu_map_batch_raw(rh_gpu_ctx *c, uint32_t n, const int16_t *const *raw, const uint64_t *raw_len,
                                     const double *offset, const double *range, const double *digitisation,
@@ -527,20 +704,13 @@ extern "C" int rh_gpu_map_batch_raw(rh_gpu_ctx *c, uint32_t n, const int16_t *co
 	if (!c || !recs || !n_recs || (n && (!raw || !raw_len || !offset || !range || !digitisation))) { rh_set_error("rh_gpu_map_batch_raw: null argument"); return RH_ERR_ARG; }
 	if (c->D.ava && n && !names) { rh_set_error("read names are required in all-vs-all mode"); return RH_ERR_ARG; }
 	CUDA_TRY(cudaSetDevice(c->device));
-	begin_call(c);
-	cudaEvent_t t0 = get_event(c), t1 = get_event(c);
-	c->ev_used = 0; /* t0/t1 stay reserved at the front of the pool */
-	c->ev_used = 2;
-	cudaEventRecord(t0, c->stream);
-	std::vector<uint64_t> beg, len;
-	int rc = upload_raw(c, n, raw, raw_len, beg, len);
+	std::vector<uint64_t> beg(n), len(n);
+	uint64_t tot = 0;
+	for (uint32_t i = 0; i < n; ++i) { beg[i] = tot; len[i] = raw_len[i]; tot += (raw_len[i] + 7) & ~7ULL; } /* 16-byte aligned starts */
+	int rc = c->d_raw.reserve(tot + 8);
+	if (rc) return rc;
 	batch_in in{n, raw, raw_len, nullptr, nullptr, offset, range, digitisation, names};
-	if (rc == RH_OK) rc = map_resident(c, in, beg, len, recs, n_recs);
-	cudaEventRecord(t1, c->stream);
-	cudaEventSynchronize(t1);
-	float ms = 0; cudaEventElapsedTime(&ms, t0, t1); c->st.ms_total = ms;
-	collect_spans(c);
-	return rc;
+	return map_batch(c, in, beg, len, c->d_raw.p, recs, n_recs);
 }
 
 extern "C" int rh_gpu_map_batch_dev(rh_gpu_ctx *c, uint32_t n, const void *d_raw, const uint64_t *raw_off,
@@ -551,32 +721,39 @@ extern "C" int rh_gpu_map_batch_dev(rh_gpu_ctx *c, uint32_t n, const void *d_raw
 	if (((uintptr_t)d_raw & 15) != 0) { rh_set_error("device raw buffer must be 16-byte aligned"); return RH_ERR_ARG; }
 	if (c->D.ava && n && !names) { rh_set_error("read names are required in all-vs-all mode"); return RH_ERR_ARG; }
 	CUDA_TRY(cudaSetDevice(c->device));
-	begin_call(c);
-	cudaEvent_t t0 = get_event(c), t1 = get_event(c);
-	cudaEventRecord(t0, c->stream);
 	std::vector<uint64_t> beg(n), len(n);
 	for (uint32_t i = 0; i < n; ++i) { beg[i] = raw_off[i]; len[i] = raw_off[i + 1] - raw_off[i]; }
-	c->raw_ptr = (const int16_t *)d_raw;
 	batch_in in{n, nullptr, nullptr, d_raw, raw_off, offset, range, digitisation, names};
-	int rc = map_resident(c, in, beg, len, recs, n_recs);
-	cudaEventRecord(t1, c->stream);
-	cudaEventSynchronize(t1);
-	float ms = 0; cudaEventElapsedTime(&ms, t0, t1); c->st.ms_total = ms;
-	collect_spans(c);
-	return rc;
+	return map_batch(c, in, beg, len, (const int16_t *)d_raw, recs, n_recs);
+}
+
+/* raw samples of a few reads into the context's shared buffer, on one worker's stream (tap / index paths) */
+static int upload_raw(rh_gpu_ctx *ctx, rh_worker *c, uint32_t n, const int16_t *const *raw, const uint64_t *raw_len, std::vector<uint64_t> &beg, std::vector<uint64_t> &len)
+{
+	beg.assign(n, 0); len.assign(n, 0);
+	uint64_t tot = 0;
+	for (uint32_t i = 0; i < n; ++i) { beg[i] = tot; len[i] = raw_len[i]; tot += (raw_len[i] + 7) & ~7ULL; } /* 16-byte aligned starts */
+	int rc = ctx->d_raw.reserve(tot + 8);
+	if (rc) return rc;
+	for (uint32_t i = 0; i < n; ++i)
+		if (raw_len[i]) { CUDA_TRY(cudaMemcpyAsync(ctx->d_raw.p + beg[i], raw[i], raw_len[i] * 2, cudaMemcpyHostToDevice, c->stream)); c->st.h2d_bytes += raw_len[i] * 2; }
+	c->raw_ptr = ctx->d_raw.p;
+	return RH_OK;
 }
 
 /* Stage tap: one read, every chunk, no stop rules (parity tests). */
-extern "C" int rh_gpu_tap_read(rh_gpu_ctx *c, const int16_t *raw, uint64_t raw_len, double offset, double range, double digitisation,
+extern "C" int rh_gpu_tap_read(rh_gpu_ctx *ctx, const int16_t *raw, uint64_t raw_len, double offset, double range, double digitisation,
                                const char *name, rh_tap_t *tap)
 {
-	if (!c || !raw || !tap) { rh_set_error("rh_gpu_tap_read: null argument"); return RH_ERR_ARG; }
-	CUDA_TRY(cudaSetDevice(c->device));
+	if (!ctx || !raw || !tap) { rh_set_error("rh_gpu_tap_read: null argument"); return RH_ERR_ARG; }
+	CUDA_TRY(cudaSetDevice(ctx->device));
+	rh_worker *c = ctx->workers[0];
+	c->stream = c->own_stream;
 	begin_call(c);
 	std::vector<uint64_t> beg, len;
 	const int16_t *rp[1] = {raw}; const uint64_t rl[1] = {raw_len};
 	const char *nm[1] = {name ? name : ""};
-	int rc = upload_raw(c, 1, rp, rl, beg, len);
+	int rc = upload_raw(ctx, c, 1, rp, rl, beg, len);
 	if (rc) return rc;
 	batch_in in{1, rp, rl, nullptr, nullptr, &offset, &range, &digitisation, nm};
 	std::vector<uint32_t> l_sig;
@@ -654,8 +831,9 @@ extern "C" rh_index_t *rh_index_build_sig(const rh_params_t *p, uint32_t n_reads
 	rh_index_s empty;
 	rh_params_t q = *p; q.w = 0; q.mid_occ = 1; /* event detection only; w/mid_occ are irrelevant to it */
 	q.map_flag |= RH_M_NO_ADAPTIVE;
-	rh_gpu_ctx *c = rh_gpu_init(&empty, &q, 0, (size_t)256 << 20);
-	if (!c) return NULL;
+	rh_gpu_ctx *ctx = rh_gpu_init(&empty, &q, 0, (size_t)256 << 20);
+	if (!ctx) return NULL;
+	rh_worker *c = ctx->workers[0];
 	rh_index_s *idx = new rh_index_s();
 	idx->flag = p->idx_flag; idx->w = p->w; idx->e = p->e; idx->n = p->n; idx->q = p->q; idx->k = p->k;
 	idx->diff = p->diff; idx->fine_min = p->fine_min; idx->fine_max = p->fine_max; idx->fine_range = p->fine_range;
@@ -666,7 +844,7 @@ extern "C" rh_index_t *rh_index_build_sig(const rh_params_t *p, uint32_t n_reads
 		const uint32_t bn = std::min(B, n_reads - b0);
 		begin_call(c);
 		std::vector<uint64_t> beg, len;
-		rc = upload_raw(c, bn, raw + b0, raw_len + b0, beg, len);
+		rc = upload_raw(ctx, c, bn, raw + b0, raw_len + b0, beg, len);
 		if (rc) break;
 		batch_in in{bn, raw + b0, raw_len + b0, nullptr, nullptr, offset + b0, range + b0, digitisation + b0, names + b0};
 		std::vector<uint32_t> l_sig;
@@ -707,7 +885,7 @@ extern "C" rh_index_t *rh_index_build_sig(const rh_params_t *p, uint32_t n_reads
 			if (sl.n_peaks) rh_host_sketch(*p, ev.data() + sl.e_off, sl.n_peaks, b0 + i, 0, all);
 		}
 	}
-	rh_gpu_destroy(c);
+	rh_gpu_destroy(ctx);
 	if (rc != RH_OK) { delete idx; return NULL; }
 	rh_index_from_seeds(idx, all, 8);
 	return idx;
