@@ -172,7 +172,7 @@ int check_params(const rh_params_t &P)
 {
 	if (P.window_length1 > 15 || P.window_length2 > 15) { rh_set_error("segmentation windows > 15 are not supported"); return RH_ERR_ARG; }
 	if (P.e < 1 || P.q < 1 || P.e * P.q > 64) { rh_set_error("bad e/q"); return RH_ERR_ARG; }
-	if (P.w != 0) { rh_set_error("minimizer seeding (w>0) is not implemented on the GPU path yet"); return RH_ERR_ARG; }
+	if (P.w < 0 || P.w > RH_MAX_W) { rh_set_error("minimizer window w must be in [0, %d]", RH_MAX_W); return RH_ERR_ARG; }
 	if (P.n != 0) { rh_set_error("BLEND seeding (n>0) is disabled in the reference and unsupported here"); return RH_ERR_ARG; }
 	if (P.min_num_anchors < 2) { rh_set_error("min_num_anchors < 2 is not supported (chains are at least two anchors; scratch sizing relies on it)"); return RH_ERR_ARG; }
 	return RH_OK;
@@ -210,6 +210,7 @@ int run_round(rh_worker *c, round_io &io, int carry_in_idx)
 	a1.raw = c->raw_ptr; a1.rs = c->d_rs.p; a1.slots = c->d_slots.p; a1.n_slots = ns;
 	a1.z = c->d_z.p; a1.ps = c->d_ps.p; a1.pq = c->d_pq.p; a1.t1 = c->d_t1.p; a1.t2 = c->d_t2.p;
 	a1.peaks = c->d_peaks.p; a1.events = c->d_events.p; a1.seed_hash = c->d_seed_hash.p; a1.seed_pos = c->d_seed_pos.p;
+	a1.min_hash = c->d_seed_cnt.p; a1.min_pos = c->d_seed_dst.p; /* free until k_seed_count */
 	a1.prof = c->prof_on ? c->d_prof.p : nullptr;
 	{ /* the event stage: five launches back to back, timed as one span */
 		span_guard g(c, T_EVENT, 5);
@@ -864,7 +865,7 @@ extern "C" rh_index_t *rh_index_build_sig(const rh_params_t *p, uint32_t n_reads
 			if ((rc = c->d_z.reserve(zt)) || (rc = c->d_events.reserve(et)) || (rc = c->d_peaks.reserve(et)) || (rc = c->d_seed_hash.reserve(et)) ||
 			    (rc = c->d_seed_pos.reserve(et)) || (rc = upload(c->d_slots, io.slots, c->stream))) break;
 			if ((rc = c->d_ps.reserve(zt + ns)) || (rc = c->d_pq.reserve(zt + ns)) || (rc = c->d_t1.reserve(zt + ns)) || (rc = c->d_t2.reserve(zt + ns))) break;
-			sig_args_t a1; a1.prof = nullptr;
+			sig_args_t a1; a1.prof = nullptr; a1.min_hash = nullptr; a1.min_pos = nullptr;
 			a1.raw = c->raw_ptr; a1.rs = c->d_rs.p; a1.slots = c->d_slots.p; a1.n_slots = ns;
 			a1.z = c->d_z.p; a1.ps = c->d_ps.p; a1.pq = c->d_pq.p; a1.t1 = c->d_t1.p; a1.t2 = c->d_t2.p;
 			a1.peaks = c->d_peaks.p; a1.events = c->d_events.p; a1.seed_hash = c->d_seed_hash.p; a1.seed_pos = c->d_seed_pos.p;

@@ -43,6 +43,7 @@ struct sig_args_t {
 	float *events;         /* [e_off .. +e_cap)                          */
 	uint32_t *seed_hash;   /* [e_off .. +e_cap)                          */
 	uint32_t *seed_pos;    /* [e_off .. +e_cap)                          */
+	uint32_t *min_hash, *min_pos; /* [e_off .. +e_cap) minimizer output before it replaces the seed stream (w > 0) */
 	unsigned long long *prof;
 };
 
@@ -296,6 +297,51 @@ __global__ void __launch_bounds__(EV_THREADS) k_sig_events(sig_args_t A)
 }
 
 /* ------------------------------------------------------------------------------------------- */
+#define RH_MAX_W 32
+/* ri_sketch_min, rsketch.c:94-140: minimizer selection over the seed stream (one (hash, position) per window of e
+ * kept events), minimap2's window logic including the equal-minimum cases.  Seeds compare by hash (the low 6 bits
+ * of x hold the same span for all), an empty window slot is "larger than everything".  Output goes to oh/op and
+ * replaces the stream at the end.  Every stream entry is emitted at most once, so n_out <= n. */
+__device__ uint32_t minimizer_select(uint32_t *sh, uint32_t *sp, uint32_t n, int w, int e, uint32_t *oh, uint32_t *op, uint32_t cap)
+{
+	const uint64_t EMPTY = ~0ULL;
+	uint64_t wx[RH_MAX_W]; uint32_t wy[RH_MAX_W];
+	for (int j = 0; j < w; ++j) { wx[j] = EMPTY; wy[j] = 0xffffffffu; }
+	uint64_t mx = EMPTY; uint32_t my = 0xffffffffu;
+	int wp = 0, mp = 0;
+	uint32_t n_out = 0;
+#define RH_PUSH(hx, py) do { if (n_out < cap) { oh[n_out] = (uint32_t)(hx); op[n_out] = (py); } ++n_out; } while (0)
+	for (uint32_t t = 0; t < n; ++t) {
+		const uint32_t l = t + (uint32_t)e; /* kept events seen so far */
+		const uint64_t cx = sh[t]; const uint32_t cy = sp[t];
+		wx[wp] = cx; wy[wp] = cy;
+		if (l == (uint32_t)(w + e - 1) && mx != EMPTY) { /* first full window: equal minima not stored yet */
+			for (int j = wp + 1; j < w; ++j) if (mx == wx[j] && wy[j] != my) RH_PUSH(wx[j], wy[j]);
+			for (int j = 0; j < wp; ++j) if (mx == wx[j] && wy[j] != my) RH_PUSH(wx[j], wy[j]);
+		}
+		if (cx <= mx) {
+			if (l >= (uint32_t)(w + e) && mx != EMPTY) RH_PUSH(mx, my);
+			mx = cx; my = cy; mp = wp;
+		} else if (wp == mp) { /* the minimum slid out of the window */
+			if (l >= (uint32_t)(w + e - 1) && mx != EMPTY) RH_PUSH(mx, my);
+			mx = EMPTY;
+			for (int j = wp + 1; j < w; ++j) if (mx >= wx[j]) { mx = wx[j]; my = wy[j]; mp = j; }
+			for (int j = 0; j <= wp; ++j) if (mx >= wx[j]) { mx = wx[j]; my = wy[j]; mp = j; }
+			if (l >= (uint32_t)(w + e - 1) && mx != EMPTY) {
+				for (int j = wp + 1; j < w; ++j) if (mx == wx[j] && my != wy[j]) RH_PUSH(wx[j], wy[j]);
+				for (int j = 0; j <= wp; ++j) if (mx == wx[j] && my != wy[j]) RH_PUSH(wx[j], wy[j]);
+			}
+		}
+		if (++wp == w) wp = 0;
+	}
+	if (mx != EMPTY) RH_PUSH(mx, my);
+#undef RH_PUSH
+	if (n_out > cap) n_out = cap; /* cannot happen (n_out <= n <= cap); keeps the copy below in bounds */
+	for (uint32_t t = 0; t < n_out; ++t) { sh[t] = oh[t]; sp[t] = op[t]; }
+	return n_out;
+}
+
+/* ------------------------------------------------------------------------------------------- */
 __global__ void __launch_bounds__(128) k_sig_sketch(sig_args_t A, dev_params_t P)
 { /* ri_sketch_reg, rsketch.c:143-204: diff filter against the last KEPT event, quantise, pack, hash */
 	const uint32_t slot_id = blockIdx.x * blockDim.x + threadIdx.x;
@@ -319,6 +365,7 @@ __global__ void __launch_bounds__(128) k_sig_sketch(sig_args_t A, dev_params_t P
 			++kept;
 			if (kept >= (uint32_t)e) sh[n_seeds++] = (uint32_t)seed_mix(packed);
 		}
+		if (P.w > 0 && n_seeds > 0) n_seeds = minimizer_select(sh, sp, n_seeds, P.w, e, A.min_hash + S->e_off, A.min_pos + S->e_off, S->e_cap);
 	}
 	S->n_events = n_events; S->n_seeds = n_seeds; S->gated = gated ? 1u : 0u;
 }

@@ -161,3 +161,43 @@ def test_wide_sort_keys(built):
         assert len(x) and int(x.max() ^ x.min()).bit_length() > 32
     m.close()
     _check_paf(w, "sensitive")
+
+
+def test_faster_preset_minimizers(built):
+    """-x faster (w=3 minimizer seeding, ri_sketch_min): seeds and everything after, per chunk, then PAF."""
+    from rawhash_b200 import synth
+    w = World(n_contigs=3, genome_len=1_500_000, n_reads=80, read_bp=4000, seed=21)
+    api, P, idx, orc = _setup(w, "faster")
+    assert P.w > 0
+    m = api.Mapper(idx, P, 0, 1 << 30)
+    for i in range(8):
+        got = m.tap_read(w.reads["raw"][i], synth.OFFSET, synth.RANGE, synth.DIGITISATION, w.names[i])
+        exp = orc.tap_read(w.pa(i), w.names[i])
+        assert tap_equal(got, exp) == [], f"read {i}"
+    m.close()
+    _check_paf(w, "faster")
+
+
+def test_rawsamble_all_vs_all(built):
+    """-x ava: index built from the reads' own signals (event detection on the GPU), all-vs-all overlap,
+    every chain reported (RI_M_ALL_CHAINS), hits filtered by read-name order (rmap.cpp:82-86)."""
+    from rawhash_b200 import api, synth
+    from _bind import OracleLib, strip_mt
+    w = World(n_contigs=1, genome_len=60_000, n_reads=60, read_bp=4000, seed=23)
+    P = api.make_params("ava")
+    n = len(w.names)
+    cal = (np.full(n, synth.OFFSET), np.full(n, synth.RANGE), np.full(n, synth.DIGITISATION))
+    idx = api.Index.build_from_signals(P, w.names, w.reads["raw"], *cal)
+    idx.update_mapopt(P)
+    orc = OracleLib().open("ava", False, w.model)
+    sigs = [w.pa(i) for i in range(n)]
+    orc.build_index_sig(sigs, w.names, 4)
+    assert orc.mapopt_update() == P.mid_occ
+    m = api.Mapper(idx, P, 0, 1 << 30)
+    recs = m.map_batch(w.reads["raw"], *cal, w.names)
+    m.close()
+    got = strip_mt(idx.format_paf(recs, w.names)).splitlines()
+    exp, _ = orc.map_paf(sigs, w.names, 4)
+    exp = strip_mt(exp).splitlines()
+    assert len(exp) > n, "expected overlaps between reads"
+    assert got == exp

@@ -67,3 +67,18 @@ def test_klib_sort_tie_order(built):
         xy = np.stack([x, np.arange(n, dtype=np.uint64)], axis=1)
         assert np.array_equal(ref.radix_sort_128x(xy), orc.radix_sort_128x(xy))
         assert np.array_equal(ref.radix_sort_64(x), orc.radix_sort_64(x))
+
+
+def test_rawsamble_ava(built):
+    """-x ava: signal-target index built from the reads, all-vs-all overlaps (config 5 of BASELINE.json)."""
+    w = World(n_contigs=1, genome_len=60_000, n_reads=60, read_bp=4000, seed=23)
+    sigs = [w.pa(i) for i in range(len(w.names))]
+    out = []
+    for L in (_bind.RefLib, _bind.OracleLib):
+        o = L().open("ava", False, w.model)
+        o.build_index_sig(sigs, w.names, 4)
+        mid = o.mapopt_update()
+        paf, _ = o.map_paf(sigs, w.names, 2)
+        out.append((mid, _bind.strip_mt(paf)))
+    assert out[0] == out[1]
+    assert len(out[0][1].splitlines()) > len(w.names)
