@@ -34,9 +34,27 @@ struct sort_args_t {
 	uint32_t *tie_list;      /* slots (indices into `slots`) whose chunk has equal keys */
 	uint32_t *tie_count;
 	unsigned long long *prof;
+	uint32_t posbits, ridbits; /* bits that hold any target position / target id of this index (fixed key packing) */
 };
 
 __device__ __forceinline__ uint32_t lanemask_lt() { uint32_t m; asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m)); return m; }
+
+/* lanes of `act` holding the same nbits-bit digit as the caller.  Built from one ballot per digit bit: the
+ * MATCH.ANY instruction issues far too slowly to sit in the inner loop of a radix pass (measured: the passes
+ * ran at ~1 match per ~60 cycles per SM).  Every lane of `act` must call. */
+__device__ __forceinline__ uint32_t digit_peers(uint32_t act, uint32_t d, int nbits = 8)
+{
+	uint32_t peers = act;
+#pragma unroll
+	for (int b = 0; b < 8; ++b) {
+		if (b < nbits) {
+			const uint32_t bit = (d >> b) & 1u;
+			const uint32_t m = __ballot_sync(act, bit);
+			peers &= bit ? m : ~m;
+		}
+	}
+	return peers;
+}
 
 /* Stable sort of a bucket of c <= 64 (key, payload) items held two per lane (item L and item 32+L):
  * returns each item's rank.  Equivalent to klib's stable insertion sort of a small bucket
@@ -76,7 +94,7 @@ __device__ __forceinline__ void sort_scatter_pass(const KeyT *__restrict__ kin, 
 		if (ok) { key = kin[i]; ix = iin[i]; d = (uint32_t)(key >> shift) & 255; }
 		const uint32_t act = __ballot_sync(0xffffffffu, ok);
 		if (ok) {
-			peers = __match_any_sync(act, d);
+			peers = digit_peers(act, d);
 			if ((peers & lanemask_lt()) == 0) s_wcnt[warp][d] = __popc(peers);
 		}
 		__syncthreads();
@@ -107,7 +125,7 @@ __device__ __forceinline__ void sort_scan256(uint32_t v, uint32_t *s_base, uint3
 	__syncthreads();
 }
 
-__global__ void __launch_bounds__(SORT_THREADS) k_sort_block(sort_args_t A)
+__global__ void __launch_bounds__(SORT_THREADS) k_sort_block(sort_args_t A, uint32_t smem_cap)
 {
 	__shared__ uint32_t s_hist[8][256];
 	__shared__ uint32_t s_base[256];
@@ -118,7 +136,7 @@ __global__ void __launch_bounds__(SORT_THREADS) k_sort_block(sort_args_t A)
 
 	slot_t *S = &A.slots[blockIdx.x];
 	const uint32_t n = S->n_anchors;
-	if (S->gated || n == 0) return;
+	if (S->gated || n == 0 || n <= smem_cap) return; /* n <= smem_cap: k_sort_smem took this chunk */
 	slot_mem_t M = slot_mem(A.arena, S->a_off, n);
 	const anchor_t *in = M.B;
 	const uint32_t tid = threadIdx.x, lane = tid & 31;
@@ -204,6 +222,131 @@ __global__ void __launch_bounds__(SORT_THREADS) k_sort_block(sort_args_t A)
 		S->n_ties = ties_found;
 		A.tie_list[atomicAdd(A.tie_count, 1u)] = blockIdx.x;
 	}
+}
+
+/* =============================================================================================
+ * k_sort_smem — the same stable sort for chunks whose packed key fits 32 bits and whose n fits shared memory:
+ * keys K[n] stay put in shared memory, only 16-bit source indices move (ping-pong I0/I1), so a chunk costs
+ * 8 bytes of shared memory per anchor and no global traffic between the one coalesced read of anchor.x and
+ * the final gather.  One CTA of 1024 threads per chunk; warp w owns the w-th contiguous piece of the index
+ * array, counts its digits privately (no barrier inside a pass except the three around the prefix), so a
+ * pass is: private count -> CTA prefix over (digit, warp) -> private ranked scatter.  Stable because pieces,
+ * tiles inside a piece and lanes inside a tile are all taken in order.
+ * Key packing uses fixed field widths from the index (bits of the longest target, bits of the target count),
+ * so no per-chunk scan for varying bits is needed.
+ * ===========================================================================================*/
+#define SB_THREADS 1024
+#define SB_WARPS (SB_THREADS / 32)
+#define SB_FIXED_BYTES (SB_WARPS * 256 * 2 + 256 * 4 + 256 * 4 + 64)
+__host__ __device__ inline size_t sort_smem_bytes(uint32_t cap) { return (size_t)cap * 8 + SB_FIXED_BYTES; }
+
+__global__ void __launch_bounds__(SB_THREADS, 1) k_sort_smem(sort_args_t A, uint32_t cap)
+{
+	extern __shared__ __align__(16) uint8_t s_dyn[];
+	uint32_t *K = (uint32_t *)s_dyn;
+	uint16_t *I0 = (uint16_t *)(K + cap), *I1 = I0 + cap;
+	uint16_t (*wcnt)[256] = (uint16_t (*)[256])(I1 + cap);
+	uint32_t *tot = (uint32_t *)(wcnt + SB_WARPS), *dbase = tot + 256;
+	uint32_t *s_misc = dbase + 256;
+
+	slot_t *S = &A.slots[blockIdx.x];
+	const uint32_t n = S->n_anchors;
+	if (S->gated || n == 0 || n > cap) return; /* larger chunks: k_sort_block */
+	slot_mem_t M = slot_mem(A.arena, S->a_off, n);
+	const anchor_t *__restrict__ in = M.B;
+	const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	const uint32_t FULL = 0xffffffffu;
+	const uint32_t posbits = A.posbits, ridbits = A.ridbits, kbits = posbits + ridbits + 1;
+	const uint32_t pmask = posbits >= 32 ? 0xffffffffu : ((1u << posbits) - 1), rmask = ridbits ? ((1u << ridbits) - 1) : 0u;
+
+	if (tid == 0) s_misc[0] = 0;
+#pragma unroll 4
+	for (uint32_t i = tid; i < n; i += SB_THREADS) {
+		const uint64_t x = in[i].x;
+		K[i] = ((uint32_t)x & pmask) | ((((uint32_t)(x >> 32)) & rmask) << posbits) | ((uint32_t)(x >> 63) << (posbits + ridbits));
+		I0[i] = (uint16_t)i;
+	}
+	__syncthreads();
+	const uint32_t piece = (((n + SB_WARPS - 1) / SB_WARPS) + 31) & ~31u;
+	const uint32_t cb = min(warp * piece, n), ce = min(cb + piece, n);
+	uint16_t *Ia = I0, *Ib = I1;
+	const uint32_t npass = (kbits + 7) / 8;
+	for (uint32_t p = 0; p < npass; ++p) {
+		const uint32_t shift = 8 * p;
+		const int nbits = (int)min(8u, kbits - shift);
+#pragma unroll
+		for (int q = 0; q < 8; ++q) wcnt[warp][lane * 8 + q] = 0;
+		__syncwarp();
+		for (uint32_t t0 = cb; t0 < ce; t0 += 32) { /* private digit counts of this warp's piece */
+			const uint32_t i = t0 + lane;
+			const bool ok = i < ce;
+			const uint32_t act = __ballot_sync(FULL, ok);
+			if (ok) {
+				const uint32_t d = (K[Ia[i]] >> shift) & 255u;
+				const uint32_t peers = digit_peers(act, d, nbits);
+				if ((peers & lanemask_lt()) == 0) wcnt[warp][d] += (uint16_t)__popc(peers);
+			}
+			__syncwarp();
+		}
+		__syncthreads();
+		if (tid < 256) { /* per digit: exclusive prefix over the warps, and the digit total */
+			uint32_t run = 0;
+#pragma unroll 8
+			for (int w = 0; w < SB_WARPS; ++w) { const uint32_t c = wcnt[w][tid]; wcnt[w][tid] = (uint16_t)run; run += c; }
+			tot[tid] = run;
+		}
+		__syncthreads();
+		if (warp == 0) { /* exclusive prefix over the digits */
+			uint32_t c[8], sum = 0;
+#pragma unroll
+			for (int q = 0; q < 8; ++q) { c[q] = tot[lane * 8 + q]; sum += c[q]; }
+			uint32_t incl = sum;
+#pragma unroll
+			for (int o = 1; o < 32; o <<= 1) { const uint32_t u = __shfl_up_sync(FULL, incl, o); if (lane >= o) incl += u; }
+			uint32_t start = incl - sum;
+#pragma unroll
+			for (int q = 0; q < 8; ++q) { dbase[lane * 8 + q] = start; start += c[q]; }
+		}
+		__syncthreads();
+		for (uint32_t t0 = cb; t0 < ce; t0 += 32) { /* ranked scatter */
+			const uint32_t i = t0 + lane;
+			const bool ok = i < ce;
+			const uint32_t act = __ballot_sync(FULL, ok);
+			if (ok) {
+				const uint16_t ix = Ia[i];
+				const uint32_t d = (K[ix] >> shift) & 255u;
+				const uint32_t peers = digit_peers(act, d, nbits);
+				const uint32_t off = wcnt[warp][d];
+				Ib[dbase[d] + off + __popc(peers & lanemask_lt())] = ix;
+				__syncwarp(act);
+				if ((peers & lanemask_lt()) == 0) wcnt[warp][d] = (uint16_t)(off + __popc(peers));
+			}
+			__syncwarp();
+		}
+		__syncthreads();
+		{ uint16_t *t = Ia; Ia = Ib; Ib = t; }
+	}
+	/* adjacent equal keys */
+	uint32_t my = 0;
+	for (uint32_t i = tid; i + 1 < n; i += SB_THREADS) my += K[Ia[i]] == K[Ia[i + 1]];
+	if (my) atomicAdd(&s_misc[0], my);
+	__syncthreads();
+	const uint32_t ties = s_misc[0];
+	if (ties == 0 || n <= 64) { /* <=64: klib uses a stable insertion sort -> same as the stable order */
+		anchor_t *__restrict__ out = M.A;
+#pragma unroll 4
+		for (uint32_t i = tid; i < n; i += SB_THREADS) out[i] = in[Ia[i]];
+		if (tid == 0) S->n_ties = 0;
+		return;
+	}
+	/* chunk with ties: leave the stable order and the tied flags for k_sort_ties */
+	uint32_t *sidx = (uint32_t *)M.U;
+	uint8_t *tied = (uint8_t *)M.t;
+	for (uint32_t i = tid; i < n; i += SB_THREADS) { tied[i] = 0; sidx[i] = Ia[i]; }
+	__syncthreads();
+	for (uint32_t i = tid; i + 1 < n; i += SB_THREADS)
+		if (K[Ia[i]] == K[Ia[i + 1]]) { tied[Ia[i]] = 1; tied[Ia[i + 1]] = 1; }
+	if (tid == 0) { S->n_ties = ties; A.tie_list[atomicAdd(A.tie_count, 1u)] = blockIdx.x; }
 }
 
 /* =============================================================================================
@@ -323,7 +466,7 @@ __device__ void cta_klib_replay(tie_shared_t &T, uint8_t *bytes, klib_ws_t W, co
 						const uint64_t x = xs[i];
 						const uint32_t d = (uint32_t)((x & keymask) >> shift) & 255u;
 						bytes[beg + i] = (uint8_t)d;
-						const uint32_t peers = __match_any_sync(act, d);
+						const uint32_t peers = digit_peers(act, d);
 						if ((peers & lanemask_lt()) == 0) atomicAdd(&T.tab[w][d], (uint32_t)__popc(peers));
 						if (!ALL && (x & TIE_FLAG)) atomicOr(&T.tflag[w][d >> 5], 1u << (d & 31));
 					}

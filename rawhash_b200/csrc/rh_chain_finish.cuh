@@ -231,7 +231,7 @@ __device__ void fin_radix_pass(tie_shared_t &T, const KeyT *__restrict__ kin, co
 		const uint32_t act = __ballot_sync(FULL, ok);
 		if (ok) {
 			const uint32_t d = (uint32_t)(kin[i] >> shift) & 255u;
-			const uint32_t peers = __match_any_sync(act, d);
+			const uint32_t peers = digit_peers(act, d);
 			if ((peers & lanemask_lt()) == 0) atomicAdd(&hist[d], (uint32_t)__popc(peers));
 		}
 	}
@@ -257,7 +257,7 @@ __device__ void fin_radix_pass(tie_shared_t &T, const KeyT *__restrict__ kin, co
 		const uint32_t act = __ballot_sync(FULL, ok);
 		if (ok) {
 			key = kin[i]; v = vin[i]; d = (uint32_t)(key >> shift) & 255u;
-			peers = __match_any_sync(act, d);
+			peers = digit_peers(act, d);
 			if ((peers & lanemask_lt()) == 0) wcnt[warp][d] = __popc(peers);
 		}
 		__syncthreads();

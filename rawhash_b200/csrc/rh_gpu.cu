@@ -93,6 +93,7 @@ struct rh_worker {
 	dbuf<unsigned long long> d_prof; bool prof_on = false;
 	dbuf<rh_map_rec_t> d_recs;
 	size_t arena_bytes = 0, sig_budget = 0;
+	uint32_t sort_posbits = 0, sort_ridbits = 0, sort_smem_cap = 0;
 	unsigned long long carry_known = 0, carry_pending = 0; /* exact top at the last sync + upper bound of what was launched since */
 	std::vector<timed_span> spans;
 	std::vector<cudaEvent_t> ev_pool; size_t ev_used = 0;
@@ -113,6 +114,7 @@ struct rh_gpu_ctx_s {
 	uint32_t logf_n = 0;
 	std::vector<uint32_t> name_order; /* sorted target names (indices) for Rawsamble */
 	dbuf<int16_t> d_raw;              /* raw samples of the current host-buffer call, shared by the workers */
+	uint32_t sort_posbits = 0, sort_ridbits = 0, sort_smem_cap = 0;
 	std::vector<rh_worker *> workers;
 	uint32_t n_active = 1;            /* workers used per call */
 	void *user_stream = nullptr;
@@ -281,7 +283,15 @@ int run_round(rh_worker *c, round_io &io, int carry_in_idx)
 		if ((rc = c->d_tie_list.reserve(gn)) || (rc = c->d_tie_count.reserve(1))) return rc;
 		CUDA_TRY(cudaMemsetAsync(c->d_tie_count.p, 0, 4, s));
 		sort_args_t as; as.slots = a3.slots; as.n_slots = gn; as.arena = c->d_arena.p; as.tie_list = c->d_tie_list.p; as.tie_count = c->d_tie_count.p; as.prof = c->prof_on ? c->d_prof.p : nullptr;
-		{ span_guard g(c, T_SORT); k_sort_block<<<gn, SORT_THREADS, 0, s>>>(as); }
+		as.posbits = c->sort_posbits; as.ridbits = c->sort_ridbits;
+		{ /* chunks that fit shared memory (nearly all) sort there; the rest take the global-memory kernel */
+			uint32_t maxn = 0;
+			for (uint32_t q = g0; q < g1; ++q) if (!io.slots[q].gated) maxn = std::max(maxn, io.slots[q].n_anchors);
+			const uint32_t cap = std::min(c->sort_smem_cap, (maxn + 31) & ~31u); /* small groups: less shared memory, more CTAs per SM */
+			span_guard g(c, T_SORT, (cap ? 1 : 0) + (maxn > cap ? 1 : 0));
+			if (cap) k_sort_smem<<<gn, SB_THREADS, sort_smem_bytes(cap), s>>>(as, cap);
+			if (maxn > cap) k_sort_block<<<gn, SORT_THREADS, 0, s>>>(as, cap);
+		}
 		{
 			uint32_t maxn = 0;
 			for (uint32_t q = g0; q < g1; ++q) if (!io.slots[q].gated) maxn = std::max(maxn, io.slots[q].n_anchors);
@@ -499,6 +509,7 @@ rh_worker *make_worker(rh_gpu_ctx *c, size_t arena_bytes)
 {
 	rh_worker *w = new rh_worker();
 	w->device = c->device; w->P = c->P; w->D = c->D; w->idx = c->idx; w->I = c->I;
+	w->sort_posbits = c->sort_posbits; w->sort_ridbits = c->sort_ridbits; w->sort_smem_cap = c->sort_smem_cap;
 	w->d_logf = c->d_logf; w->logf_n = c->logf_n; w->d_seqlen = c->d_seqlen; w->name_order = &c->name_order; /* aliases: the context owns them */
 	w->err[0] = 0;
 	if (cudaStreamCreateWithFlags(&w->own_stream, cudaStreamNonBlocking) != cudaSuccess) { rh_set_error("cudaStreamCreate failed"); destroy_worker(w); return nullptr; }
@@ -658,6 +669,20 @@ extern "C" rh_gpu_ctx *rh_gpu_init(const rh_index_t *idx, const rh_params_t *p, 
 	    upload(c->d_logf, lt, s0)) return fail(NULL);
 	c->I.keys = c->d_keys.p; c->I.off = c->d_off.p; c->I.pos = c->d_pos.p; c->I.bucket = c->d_bucket.p; c->I.bucket_bits = bits;
 	c->I.n_keys = nk; c->I.seq_len = c->d_seqlen.p; c->I.name_rank = c->d_namerank.p; c->I.n_seq = (uint32_t)idx->names.size();
+	{ /* fixed key packing for the shared-memory anchor sort: strand | target id | target position */
+		uint32_t maxlen = 1;
+		for (uint32_t l : idx->lens) maxlen = std::max(maxlen, l);
+		uint32_t pb = 1; while (pb < 31 && (1u << pb) < maxlen) ++pb;
+		uint32_t rb = 0; while (rb < 31 && (1u << rb) < (uint32_t)idx->lens.size()) ++rb;
+		c->sort_posbits = pb; c->sort_ridbits = rb;
+		int max_smem = 0;
+		cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
+		c->sort_smem_cap = 0;
+		if (pb + rb + 1 <= 32 && (size_t)max_smem > SB_FIXED_BYTES + 8 * 1024) {
+			c->sort_smem_cap = std::min<uint32_t>(((uint32_t)max_smem - SB_FIXED_BYTES) / 8, 65535u) & ~31u;
+			if (cudaFuncSetAttribute(k_sort_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sort_smem_bytes(c->sort_smem_cap)) != cudaSuccess) return fail("cudaFuncSetAttribute(k_sort_smem) failed");
+		}
+	}
 	if (cudaFuncSetAttribute(k_sort_ties, cudaFuncAttributeMaxDynamicSharedMemorySize, sizeof(tie_shared_t) + TIES_SMEM_CAP) != cudaSuccess) return fail("cudaFuncSetAttribute(k_sort_ties) failed");
 	if (cudaDeviceSynchronize() != cudaSuccess) return fail("index upload failed");
 	/* ---- workers: the work arenas are split evenly ---- */
