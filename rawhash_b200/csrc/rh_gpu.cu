@@ -196,7 +196,7 @@ int run_round(rh_worker *c, round_io &io, int carry_in_idx)
 	/* scratch offsets */
 	uint64_t zt = 0, et = 0;
 	for (slot_t &sl : io.slots) {
-		sl.z_off = zt; zt += sl.chunk_len;
+		sl.z_off = zt; zt += ((uint64_t)sl.chunk_len + 3) & ~3ULL; /* chunks start 16-byte aligned */
 		sl.e_cap = (uint32_t)((uint64_t)sl.chunk_len * 2 / 3 + 8);
 		sl.e_off = et; et += sl.e_cap;
 	}
@@ -207,7 +207,7 @@ int run_round(rh_worker *c, round_io &io, int carry_in_idx)
 	if ((rc = upload(c->d_slots, io.slots, s))) return rc;
 	c->st.h2d_bytes += ns * sizeof(slot_t);
 
-	if ((rc = c->d_ps.reserve(zt + ns)) || (rc = c->d_pq.reserve(zt + ns)) || (rc = c->d_t1.reserve(zt + ns)) || (rc = c->d_t2.reserve(zt + ns))) return rc;
+	if ((rc = c->d_ps.reserve(zt + 4 * (uint64_t)ns + 4)) || (rc = c->d_pq.reserve(zt + 4 * (uint64_t)ns + 4)) || (rc = c->d_t1.reserve(zt + 4 * (uint64_t)ns + 4)) || (rc = c->d_t2.reserve(zt + 4 * (uint64_t)ns + 4))) return rc;
 	sig_args_t a1;
 	a1.raw = c->raw_ptr; a1.rs = c->d_rs.p; a1.slots = c->d_slots.p; a1.n_slots = ns;
 	a1.z = c->d_z.p; a1.ps = c->d_ps.p; a1.pq = c->d_pq.p; a1.t1 = c->d_t1.p; a1.t2 = c->d_t2.p;
@@ -568,11 +568,13 @@ void run_job(job_t *j)
 	const uint32_t n = j->hi - j->lo;
 	int rc = RH_OK;
 	if (j->raw) {
-		for (uint32_t i = j->lo; i < j->hi && rc == RH_OK; ++i) {
-			const uint64_t l = (*j->len)[i];
-			if (!l) continue;
-			if (cudaMemcpyAsync(j->d_raw + (*j->beg)[i], j->raw[i], l * 2, cudaMemcpyHostToDevice, w->stream) != cudaSuccess) { rh_set_error("H2D copy of read %u failed: %s", i, cudaGetErrorString(cudaGetLastError())); rc = RH_ERR_CUDA; }
-			w->st.h2d_bytes += l * 2;
+		const std::vector<uint64_t> &B = *j->beg, &L = *j->len;
+		for (uint32_t i = j->lo; i < j->hi && rc == RH_OK;) { /* one copy per run of reads contiguous on both sides */
+			uint32_t e = i; uint64_t bytes = L[i] * 2;
+			while (e + 1 < j->hi && L[e] > 0 && j->raw[e + 1] == j->raw[e] + L[e] && B[e + 1] == B[e] + L[e] && bytes < ((uint64_t)256 << 20)) { ++e; bytes += L[e] * 2; }
+			if (bytes && cudaMemcpyAsync(j->d_raw + B[i], j->raw[i], bytes, cudaMemcpyHostToDevice, w->stream) != cudaSuccess) { rh_set_error("H2D copy of reads %u..%u failed: %s", i, e, cudaGetErrorString(cudaGetLastError())); rc = RH_ERR_CUDA; }
+			w->st.h2d_bytes += bytes;
+			i = e + 1;
 		}
 	}
 	if (rc == RH_OK && n) {
@@ -732,7 +734,12 @@ extern "C" int rh_gpu_map_batch_raw(rh_gpu_ctx *c, uint32_t n, const int16_t *co
 	CUDA_TRY(cudaSetDevice(c->device));
 	std::vector<uint64_t> beg(n), len(n);
 	uint64_t tot = 0;
-	for (uint32_t i = 0; i < n; ++i) { beg[i] = tot; len[i] = raw_len[i]; tot += (raw_len[i] + 7) & ~7ULL; } /* 16-byte aligned starts */
+	for (uint32_t i = 0; i < n; ++i) { /* reads that follow each other in host memory keep doing so on the device: one copy per run */
+		len[i] = raw_len[i];
+		if (i > 0 && raw_len[i - 1] > 0 && raw[i] == raw[i - 1] + raw_len[i - 1]) beg[i] = beg[i - 1] + raw_len[i - 1];
+		else { tot = (tot + 7) & ~7ULL; beg[i] = tot; } /* a new run starts 16-byte aligned */
+		tot = beg[i] + raw_len[i];
+	}
 	int rc = c->d_raw.reserve(tot + 8);
 	if (rc) return rc;
 	batch_in in{n, raw, raw_len, nullptr, nullptr, offset, range, digitisation, names};
@@ -886,10 +893,10 @@ extern "C" rh_index_t *rh_index_build_sig(const rh_params_t *p, uint32_t n_reads
 		std::vector<float> ev; std::vector<uint32_t> ev_off(ns), ev_n(ns);
 		if (ns) {
 			uint64_t zt = 0, et = 0;
-			for (slot_t &sl : io.slots) { sl.z_off = zt; zt += sl.chunk_len; sl.e_cap = (uint32_t)((uint64_t)sl.chunk_len * 2 / 3 + 8); sl.e_off = et; et += sl.e_cap; }
+			for (slot_t &sl : io.slots) { sl.z_off = zt; zt += ((uint64_t)sl.chunk_len + 3) & ~3ULL; /* chunks start 16-byte aligned */ sl.e_cap = (uint32_t)((uint64_t)sl.chunk_len * 2 / 3 + 8); sl.e_off = et; et += sl.e_cap; }
 			if ((rc = c->d_z.reserve(zt)) || (rc = c->d_events.reserve(et)) || (rc = c->d_peaks.reserve(et)) || (rc = c->d_seed_hash.reserve(et)) ||
 			    (rc = c->d_seed_pos.reserve(et)) || (rc = upload(c->d_slots, io.slots, c->stream))) break;
-			if ((rc = c->d_ps.reserve(zt + ns)) || (rc = c->d_pq.reserve(zt + ns)) || (rc = c->d_t1.reserve(zt + ns)) || (rc = c->d_t2.reserve(zt + ns))) break;
+			if ((rc = c->d_ps.reserve(zt + 4 * (uint64_t)ns + 4)) || (rc = c->d_pq.reserve(zt + 4 * (uint64_t)ns + 4)) || (rc = c->d_t1.reserve(zt + 4 * (uint64_t)ns + 4)) || (rc = c->d_t2.reserve(zt + 4 * (uint64_t)ns + 4))) break;
 			sig_args_t a1; a1.prof = nullptr; a1.min_hash = nullptr; a1.min_pos = nullptr;
 			a1.raw = c->raw_ptr; a1.rs = c->d_rs.p; a1.slots = c->d_slots.p; a1.n_slots = ns;
 			a1.z = c->d_z.p; a1.ps = c->d_ps.p; a1.pq = c->d_pq.p; a1.t1 = c->d_t1.p; a1.t2 = c->d_t2.p;

@@ -24,7 +24,7 @@
  *   k_sig_events  CTA  / chunk     one thread per segment: sort, IQR filter, mean
  *   k_sig_sketch  lane / chunk     diff filter, quantise, pack e events, hash
  *
- * Scratch per chunk (float, chunk-major): z[len], ps/pq/t1/t2[len+1]; peaks/events/seeds[e_cap].
+ * Scratch per chunk (float, chunk-major, every chunk 16-byte aligned): z[len], ps/pq/t1/t2[len+1]; peaks/events/seeds[e_cap].
  */
 #ifndef RH_SIGNAL_CUH
 #define RH_SIGNAL_CUH
@@ -108,7 +108,7 @@ __global__ void __launch_bounds__(128) k_sig_norm(sig_args_t A)
 	/* float prefix sums: strictly sequential recurrences (revent.c:32-35, FMA as compiled).
 	 * Every lane runs the same chain on shuffled values; lane k keeps the k-th partial for a
 	 * coalesced store. */
-	float *ps = A.ps + S->z_off + slot_id, *pq = A.pq + S->z_off + slot_id;
+	float *ps = A.ps + S->z_off + 4ull * slot_id, *pq = A.pq + S->z_off + 4ull * slot_id;
 	float run_s = 0.0f, run_q = 0.0f;
 	if (lane == 0) { ps[0] = 0.0f; pq[0] = 0.0f; }
 	for (uint32_t t0 = 0; t0 < n; t0 += 32) {
@@ -146,7 +146,7 @@ __global__ void __launch_bounds__(256) k_sig_tstat(sig_args_t A, dev_params_t P)
 	const slot_t *S = &A.slots[blockIdx.x];
 	const uint32_t n = S->n_sig;
 	if (n == 0) return;
-	const uint64_t o = S->z_off + blockIdx.x;
+	const uint64_t o = S->z_off + 4ull * blockIdx.x;
 	const float *ps = A.ps + o, *pq = A.pq + o;
 	float *t1 = A.t1 + o, *t2 = A.t2 + o;
 	const uint32_t w1 = P.w1, w2 = P.w2;
@@ -161,25 +161,37 @@ __global__ void __launch_bounds__(256) k_sig_tstat(sig_args_t A, dev_params_t P)
 /* ------------------------------------------------------------------------------------------- */
 struct peak_det_t { uint32_t masked_to; int peak_pos; float peak_val; int valid; };
 
-__device__ __forceinline__ void detector_step(peak_det_t &D, peak_det_t *other /* next detector or null */, uint32_t i, float cur,
+/* One detector at one position, revent.c:100-146, written as selects so that the 32 lanes of a warp — each
+ * running the state machine of its own chunk — execute one instruction stream instead of diverging over the
+ * detector states.  `other` (the long detector, reset and masked by the short one) may be null. */
+__device__ __forceinline__ void detector_step(peak_det_t &D, peak_det_t *other, uint32_t i, float cur,
                                               float thr, uint32_t win, uint32_t win0, float height, uint32_t *__restrict__ peaks, uint32_t &n_peaks)
-{ /* one detector at one position, revent.c:100-146 */
-	if (D.masked_to >= i) return;
-	if (D.peak_pos == -1) {
-		if (cur < D.peak_val) D.peak_val = cur;
-		else if (__fsub_rn(cur, D.peak_val) > height) { D.peak_val = cur; D.peak_pos = (int)i; }
-	} else {
-		if (cur > D.peak_val) { D.peak_val = cur; D.peak_pos = (int)i; }
-		if (other && D.peak_val > thr) {
-			other->masked_to = D.peak_pos + win0;
-			other->peak_pos = -1; other->peak_val = FLT_MAX; other->valid = 0;
-		}
-		if (__fsub_rn(D.peak_val, cur) > height && D.peak_val > thr) D.valid = 1;
-		if (D.valid && (i - D.peak_pos) > win / 2) {
-			peaks[n_peaks++] = (uint32_t)D.peak_pos;
-			D.peak_pos = -1; D.peak_val = cur; D.valid = 0;
-		}
+{
+	const bool active = !(D.masked_to >= i);
+	const bool searching = active && D.peak_pos == -1, tracking = active && D.peak_pos != -1;
+	/* searching for a rise: follow the signal down, latch when it climbs more than `height` above the low */
+	const bool lower = cur < D.peak_val;
+	const bool rise = !lower && __fsub_rn(cur, D.peak_val) > height;
+	float pv = (searching && (lower || rise)) ? cur : D.peak_val;
+	int pp = (searching && rise) ? (int)i : D.peak_pos;
+	/* tracking a peak */
+	const bool higher = tracking && cur > D.peak_val;
+	pv = higher ? cur : pv;
+	pp = higher ? (int)i : pp;
+	if (other) {
+		const bool mask = tracking && pv > thr;
+		other->masked_to = mask ? (uint32_t)(pp + (int)win0) : other->masked_to;
+		other->peak_pos = mask ? -1 : other->peak_pos;
+		other->peak_val = mask ? FLT_MAX : other->peak_val;
+		other->valid = mask ? 0 : other->valid;
 	}
+	const int valid = (D.valid || (tracking && __fsub_rn(pv, cur) > height && pv > thr)) ? 1 : 0;
+	const bool emit = tracking && valid && (i - (uint32_t)pp) > win / 2;
+	if (emit) peaks[n_peaks] = (uint32_t)pp;
+	n_peaks += emit ? 1u : 0u;
+	D.peak_pos = emit ? -1 : pp;
+	D.peak_val = emit ? cur : pv;
+	D.valid = emit ? 0 : valid;
 }
 
 __global__ void __launch_bounds__(128) k_sig_peaks(sig_args_t A, dev_params_t P)
@@ -188,26 +200,27 @@ __global__ void __launch_bounds__(128) k_sig_peaks(sig_args_t A, dev_params_t P)
 	if (slot_id >= A.n_slots) return;
 	slot_t *S = &A.slots[slot_id];
 	const uint32_t n = S->n_sig;
-	const uint64_t o = S->z_off + slot_id;
-	const float *__restrict__ t1 = A.t1 + o, *__restrict__ t2 = A.t2 + o;
+	const uint64_t o = S->z_off + 4ull * slot_id; /* 16-byte aligned: z_off advances in multiples of 4 floats */
+	const float4 *__restrict__ t1 = (const float4 *)(A.t1 + o), *__restrict__ t2 = (const float4 *)(A.t2 + o);
 	uint32_t *__restrict__ peaks = A.peaks + S->e_off;
 	peak_det_t d1 = {0u, -1, FLT_MAX, 0}, d2 = {0u, -1, FLT_MAX, 0};
 	uint32_t n_peaks = 0;
 	const uint32_t w1 = P.w1, w2 = P.w2;
-	uint32_t i = 0;
-	for (; i + 4 <= n; i += 4) { /* loads for four positions issued ahead of the state machine */
-		float a[4], b[4];
-#pragma unroll
-		for (int k = 0; k < 4; ++k) { a[k] = t1[i + k]; b[k] = t2[i + k]; }
+	const float thr1 = P.thr1, thr2 = P.thr2, height = P.height;
+	const uint32_t nq = (n + 3) / 4; /* the arrays hold n+1 values padded to a multiple of 4: reading the pad is harmless */
+	float4 a = nq ? t1[0] : make_float4(0, 0, 0, 0), b = nq ? t2[0] : make_float4(0, 0, 0, 0);
+	for (uint32_t q = 0; q < nq; ++q) {
+		const float4 ca = a, cb = b;
+		if (q + 1 < nq) { a = t1[q + 1]; b = t2[q + 1]; } /* next four positions are in flight while these are consumed */
+		const float va[4] = {ca.x, ca.y, ca.z, ca.w}, vb[4] = {cb.x, cb.y, cb.z, cb.w};
 #pragma unroll
 		for (int k = 0; k < 4; ++k) {
-			detector_step(d1, &d2, i + k, a[k], P.thr1, w1, w1, P.height, peaks, n_peaks);
-			detector_step(d2, nullptr, i + k, b[k], P.thr2, w2, w1, P.height, peaks, n_peaks);
+			const uint32_t i = 4 * q + k;
+			if (i < n) {
+				detector_step(d1, &d2, i, va[k], thr1, w1, w1, height, peaks, n_peaks);
+				detector_step(d2, nullptr, i, vb[k], thr2, w2, w1, height, peaks, n_peaks);
+			}
 		}
-	}
-	for (; i < n; ++i) {
-		detector_step(d1, &d2, i, t1[i], P.thr1, w1, w1, P.height, peaks, n_peaks);
-		detector_step(d2, nullptr, i, t2[i], P.thr2, w2, w1, P.height, peaks, n_peaks);
 	}
 	S->n_peaks = n_peaks;
 }
