@@ -172,6 +172,7 @@ def main():
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=dev)
 
     mp, means, stdv, genome, data = build_world()
@@ -194,7 +195,7 @@ def main():
     free_b, _ = torch.cuda.mem_get_info()
     arena = int(float(os.environ["RH_ARENA_GB"]) * (1 << 30)) if "RH_ARENA_GB" in os.environ else int(free_b * 0.55)
     mapper = api.Mapper(idx, P, local_rank, arena)
-    n_workers = mapper.set_workers(int(os.environ.get("RH_WORKERS", "4")))   # concurrent read ranges (own CUDA stream each)
+    n_workers = mapper.set_workers(int(os.environ.get("RH_WORKERS", "2")))   # concurrent read ranges (own CUDA stream each)
 
     def step_dev():
         return mapper.map_batch_device(raw_dev.data_ptr(), raw_off, *cal, names=None)

@@ -149,7 +149,7 @@ const char *rh_gpu_last_error(void);
 void        rh_gpu_set_stream(rh_gpu_ctx *ctx, void *cuda_stream);
 /* A batch is cut into contiguous read ranges that run concurrently on their own CUDA streams (the
  * multi-threaded side of kt_for, src/kthread.c:47-65): the slow tail of one range overlaps the bulk of
- * the others and the host->device copy overlaps compute.  Default 4 (env RH_WORKERS at rh_gpu_init);
+ * the others and the host->device copy overlaps compute.  Default 2 (env RH_WORKERS at rh_gpu_init);
  * returns the count in effect.  With a caller stream set, one range is used. */
 int         rh_gpu_set_workers(rh_gpu_ctx *ctx, int n_workers);
 

@@ -515,13 +515,21 @@ __device__ void cta_klib_replay(tie_shared_t &T, uint8_t *bytes, klib_ws_t W, co
 				const bool walker = lane < nb && T.seg_kind[lane < nb ? lane : 0] == TIE_WALK;
 				uint32_t *tab = T.tab[lane < nb ? lane : 0];
 				const uint8_t *bs = bytes + T.seg_beg[lane < nb ? lane : 0];
+				/* digits in shared memory are read with ld.shared: through the generic pointer the same load goes
+				 * down the global path and costs several times the latency, and it sits on the walk's critical chain */
+				const bool bs_shared = __isShared(bytes);
+				const uint32_t bs_saddr = bs_shared ? (uint32_t)__cvta_generic_to_shared(bs) : 0u;
 				uint32_t *D = dst + T.seg_beg[lane < nb ? lane : 0];
 				uint32_t k = 0, rp = 0;
 				bool live = walker;
 				if (live) { for (;; ++k) { const uint32_t wk = tab[k]; if ((wk & 0xffffu) != (wk >> 16)) { rp = wk & 0xffffu; break; } } }
+				unsigned long long walk_iters = 0;
 				while (__any_sync(FULL, live)) {
+					++walk_iters;
 					if (live) {
-						const uint32_t d = bs[rp];
+						uint32_t d;
+						if (bs_shared) asm volatile("ld.shared.u8 %0, [%1];" : "=r"(d) : "r"(bs_saddr + rp));
+						else d = bs[rp];
 						const uint32_t wd = tab[d];
 						const uint32_t h = wd & 0xffffu;
 						const uint32_t home = d == k;
@@ -534,6 +542,7 @@ __device__ void cta_klib_replay(tie_shared_t &T, uint8_t *bytes, klib_ws_t W, co
 						}
 					}
 				}
+				if (prof && lane == 0) { atomicAdd(&prof[22], walk_iters); atomicAdd(&prof[23], 1ULL); } /* RH_PROF: loop trips of the walking warp, walk batches */
 			}
 			__syncthreads();
 			RH_PROF_MARK(prof, 18, tid == 0);

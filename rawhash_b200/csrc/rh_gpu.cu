@@ -692,7 +692,7 @@ extern "C" rh_gpu_ctx *rh_gpu_init(const rh_index_t *idx, const rh_params_t *p, 
 	cudaMemGetInfo(&free_b, &total_b);
 	if (arena_bytes == 0) arena_bytes = free_b / 2;
 	if (arena_bytes > free_b * 7 / 10) arena_bytes = free_b * 7 / 10;
-	uint32_t nw = 4;
+	uint32_t nw = 2;
 	if (const char *e = getenv("RH_WORKERS")) nw = (uint32_t)std::max(1, std::min(16, atoi(e)));
 	while (nw > 1 && arena_bytes / nw < ((size_t)64 << 20)) --nw; /* keep every worker's arena useful */
 	for (uint32_t r = 0; r < nw; ++r) {
