@@ -283,9 +283,10 @@ struct k3_args_t {
  * gaps, then its threads take segments round-robin.  (Random hits are sparse in target space, so
  * a chunk has thousands of short segments and a few long ones around true loci.) */
 #define DP_THREADS 128
+#define DP_BIG_SEG 64          /* segments at least this long are chained by a whole warp */
 __global__ void __launch_bounds__(DP_THREADS) k_chain_dp(k3_args_t A, dev_params_t P)
 {
-	__shared__ uint32_t s_nseg;
+	__shared__ uint32_t s_nseg, s_nbig, s_next;
 	slot_t *S = &A.slots[blockIdx.x];
 	if (S->gated || S->n_anchors == 0) return;
 	const int32_t n = (int32_t)S->n_anchors;
@@ -299,7 +300,8 @@ __global__ void __launch_bounds__(DP_THREADS) k_chain_dp(k3_args_t A, dev_params
 	if (max_t < bw) max_t = bw;
 	if (max_q < bw) max_q = bw;
 	const uint32_t tid = threadIdx.x;
-	if (tid == 0) s_nseg = 0;
+	uint32_t *big = starts + n; /* segments handed to whole warps (M.U holds 2n words) */
+	if (tid == 0) { s_nseg = 0; s_nbig = 0; s_next = 0; }
 	__syncthreads();
 	for (int32_t i = tid; i < n; i += DP_THREADS) {
 		t[i] = 0;
@@ -312,8 +314,13 @@ __global__ void __launch_bounds__(DP_THREADS) k_chain_dp(k3_args_t A, dev_params
 	const uint32_t n_seg = s_nseg;
 	if (tid == 0) S->n_seg = n_seg;
 	RH_PROF_BEGIN(A.prof);
-	for (uint32_t sg = tid; sg < n_seg; sg += DP_THREADS) {
+	for (uint32_t sg = atomicAdd(&s_next, 1u); sg < n_seg; sg = atomicAdd(&s_next, 1u)) { /* segments differ wildly in cost: hand them out on demand */
 		const int32_t i0 = (int32_t)starts[sg];
+		{ /* long segments (a true locus: hundreds of anchors, each with a long predecessor window) go to a whole warp */
+			int32_t e = i0 + 1;
+			while (e < n && e - i0 < DP_BIG_SEG && !is_start[e]) ++e;
+			if (e - i0 >= DP_BIG_SEG) { big[atomicAdd(&s_nbig, 1u)] = (uint32_t)i0; continue; }
+		}
 		int32_t st = i0, band_best = -1;
 		for (int32_t i = i0; i < n && (i == i0 || !is_start[i]); ++i) {
 			const uint64_t ix = a[i].x, iy = a[i].y;
@@ -343,6 +350,72 @@ __global__ void __launch_bounds__(DP_THREADS) k_chain_dp(k3_args_t A, dev_params
 		}
 	}
 	RH_PROF_MARK(A.prof, 8, true);
+	__syncthreads();
+	/* ---- long segments: one warp each, lanes take 32 predecessors at a time.  The order-dependent part of the scan
+	 *      (running maximum with "first one wins", the skip counter with its early exit: lchain.c:454-470) is resolved
+	 *      from two ballots per tile, identically on every lane. ---- */
+	const uint32_t n_big = s_nbig;
+	const uint32_t FULL = 0xffffffffu;
+	const uint32_t lane = tid & 31, warp = tid >> 5;
+	for (uint32_t bg = warp; bg < n_big; bg += DP_THREADS / 32) {
+		const int32_t i0 = (int32_t)big[bg];
+		int32_t st = i0, band_best = -1;
+		for (int32_t i = i0; i < n && (i == i0 || !is_start[i]); ++i) {
+			const uint64_t ix = a[i].x, iy = a[i].y;
+			int32_t best = (int32_t)((iy >> 32) & 63), best_j = -1, skipped = 0;
+			while (st < i && ((ix >> 32) != (a[st].x >> 32) || ix > a[st].x + (uint64_t)max_t)) ++st;
+			if (i - st > P.max_iter) st = i - P.max_iter;
+			int32_t end_j = st - 1;
+			bool broke = false;
+			for (int32_t jt = i - 1; jt >= st && !broke; jt -= 32) {
+				const int32_t j = jt - (int32_t)lane;
+				int32_t sc = INT32_MIN;
+				if (j >= st) {
+					const int32_t s0 = pair_score(ix, iy, a[j].x, a[j].y, max_t, max_q, bw, P.pen_gap, P.pen_skip);
+					if (s0 != INT32_MIN) { sc = s0 + f[j]; const int32_t pj = p[j]; if (pj >= 0) t[pj] = i; } /* marks beyond an early exit are never read */
+				}
+				__syncwarp();
+				const bool marked = sc != INT32_MIN && t[j] == i; /* only an earlier (larger) j can have marked j */
+				int32_t incl = sc;
+#pragma unroll
+				for (int o = 1; o < 32; o <<= 1) { const int32_t u = __shfl_up_sync(FULL, incl, o); if ((int)lane >= o && u > incl) incl = u; }
+				int32_t before = __shfl_up_sync(FULL, incl, 1);
+				if (lane == 0) before = INT32_MIN;
+				if (best > before) before = best;
+				const bool improve = sc != INT32_MIN && sc > before;
+				const uint32_t im = __ballot_sync(FULL, improve), sm = __ballot_sync(FULL, sc != INT32_MIN && !improve && marked);
+				uint32_t ev = im | sm; int brk = -1;
+				while (ev) {
+					const int l = __ffs(ev) - 1; ev &= ev - 1;
+					if ((im >> l) & 1u) { if (skipped > 0) --skipped; }
+					else if (++skipped > P.max_skip) { brk = l; break; }
+				}
+				const uint32_t imv = brk < 0 ? im : (im & ((1u << brk) - 1u));
+				if (imv) { const int last = 31 - __clz(imv); best = __shfl_sync(FULL, sc, last); best_j = jt - last; }
+				if (brk >= 0) { broke = true; end_j = jt - brk; }
+			}
+			if (band_best < 0 || ix - a[band_best].x > (uint64_t)(int64_t)max_t) { /* largest f in the window, the largest index among equals */
+				int32_t mx = INT32_MIN; band_best = -1;
+				for (int32_t jt = i - 1; jt >= st; jt -= 32) {
+					const int32_t j = jt - (int32_t)lane;
+					const int32_t fj = j >= st ? f[j] : INT32_MIN;
+					int32_t m = fj;
+#pragma unroll
+					for (int o = 16; o > 0; o >>= 1) { const int32_t u = __shfl_xor_sync(FULL, m, o); if (u > m) m = u; }
+					const uint32_t who = __ballot_sync(FULL, j >= st && fj == m);
+					if (who && mx < m) { mx = m; band_best = jt - (__ffs(who) - 1); }
+				}
+			}
+			if (band_best >= 0 && band_best < end_j) {
+				const int32_t sc = pair_score(ix, iy, a[band_best].x, a[band_best].y, max_t, max_q, bw, P.pen_gap, P.pen_skip);
+				if (sc != INT32_MIN && best < sc + f[band_best]) { best = sc + f[band_best]; best_j = band_best; }
+			}
+			const int32_t vi = (best_j >= 0 && v[best_j] > best) ? v[best_j] : best;
+			if (band_best < 0 || (ix - a[band_best].x <= (uint64_t)(int64_t)max_t && f[band_best] < best)) band_best = i;
+			if (lane == 0) { f[i] = best; p[i] = best_j; v[i] = vi; }
+			__syncwarp();
+		}
+	}
 }
 
 #endif
