@@ -277,16 +277,14 @@ __global__ void __launch_bounds__(SB_THREADS, 1) k_sort_smem(sort_args_t A, uint
 #pragma unroll
 		for (int q = 0; q < 8; ++q) wcnt[warp][lane * 8 + q] = 0;
 		__syncwarp();
-		for (uint32_t t0 = cb; t0 < ce; t0 += 32) { /* private digit counts of this warp's piece */
-			const uint32_t i = t0 + lane;
-			const bool ok = i < ce;
-			const uint32_t act = __ballot_sync(FULL, ok);
-			if (ok) {
+		{ /* private digit counts of this warp's piece: shared-memory atomics on the 32-bit word that holds two 16-bit
+		   * counters (a piece is far shorter than 65536, so the low half never carries into the high one) */
+			uint32_t *cw = (uint32_t *)wcnt[warp];
+#pragma unroll 4
+			for (uint32_t i = cb + lane; i < ce; i += 32) {
 				const uint32_t d = (K[Ia[i]] >> shift) & 255u;
-				const uint32_t peers = digit_peers(act, d, nbits);
-				if ((peers & lanemask_lt()) == 0) wcnt[warp][d] += (uint16_t)__popc(peers);
+				atomicAdd(&cw[d >> 1], 1u << ((d & 1u) * 16u));
 			}
-			__syncwarp();
 		}
 		__syncthreads();
 		if (tid < 256) { /* per digit: exclusive prefix over the warps, and the digit total */

@@ -340,7 +340,7 @@ __device__ __forceinline__ uint64_t fin_backtrack_one(int32_t i0, const int32_t 
 struct fin_shared_t {
 	tie_shared_t T;
 	uint8_t bytes[FIN_BYTES_CAP];
-	uint32_t wsum[TIE_WARPS];
+	uint32_t wsum[TIE_WARPS], wsum2[TIE_WARPS];
 	unsigned long long carry_off;
 };
 
@@ -402,16 +402,32 @@ __global__ void __launch_bounds__(FIN_THREADS, 8) k_chain_finish(k3_args_t A, de
 			uint32_t n_z = 0, n_runs = 0;
 			{
 				uint32_t *zseg = W.dst;
-				uint32_t seg_run = 0;
-				for (uint32_t i0 = 0; i0 < un; i0 += FIN_THREADS) {
-					const uint32_t i = i0 + tid;
-					int32_t fi = 0; bool ok = false; uint32_t st = 0;
-					if (i < un) { fi = f[i]; ok = fi >= min_sc; t[i] = 0; st = is_start[i]; }
-					uint32_t zt, stt;
-					const uint32_t zr = tie_tile_rank(ok, SH.wsum, &zt);
-					const uint32_t sincl = fin_tile_scan(st, SH.wsum, &stt);
-					if (ok) { const uint32_t j = n_z + zr; z_idx[j] = i; zseg[j] = seg_run + sincl; W.xk[j] = (uint64_t)(int64_t)fi; W.ord[j] = j; }
-					n_z += zt; seg_run += stt;
+				/* each warp owns a contiguous quarter of the anchors: count, exchange four totals, then place — two
+				 * barriers for the whole phase instead of four per 128 anchors */
+				const uint32_t piece = (((un + TIE_WARPS - 1) / TIE_WARPS) + 31) & ~31u;
+				const uint32_t cb = min(warp * piece, un), ce = min(cb + piece, un);
+				uint32_t cz = 0, cs = 0;
+				for (uint32_t i0 = cb; i0 < ce; i0 += 32) {
+					const uint32_t i = i0 + lane;
+					bool ok = false, st = false;
+					if (i < ce) { ok = f[i] >= min_sc; st = is_start[i] != 0; t[i] = 0; }
+					cz += __popc(__ballot_sync(FULL, ok)); cs += __popc(__ballot_sync(FULL, st));
+				}
+				if (lane == 0) { SH.wsum[warp] = cz; SH.wsum2[warp] = cs; }
+				__syncthreads();
+				uint32_t bz = 0, bs = 0;
+				for (uint32_t w2 = 0; w2 < TIE_WARPS; ++w2) { if (w2 < warp) { bz += SH.wsum[w2]; bs += SH.wsum2[w2]; } n_z += SH.wsum[w2]; }
+				for (uint32_t i0 = cb; i0 < ce; i0 += 32) {
+					const uint32_t i = i0 + lane;
+					int32_t fi = 0; bool ok = false, st = false;
+					if (i < ce) { fi = f[i]; ok = fi >= min_sc; st = is_start[i] != 0; }
+					const uint32_t zm = __ballot_sync(FULL, ok), sm = __ballot_sync(FULL, st);
+					if (ok) {
+						const uint32_t j = bz + __popc(zm & lanemask_lt());
+						z_idx[j] = i; zseg[j] = bs + __popc(sm & (lanemask_lt() | (1u << lane))); /* starts up to and including i */
+						W.xk[j] = (uint64_t)(int64_t)fi; W.ord[j] = j;
+					}
+					bz += __popc(zm); bs += __popc(sm);
 				}
 				__syncthreads();
 				uint32_t *runs = (uint32_t *)M.U, *runidx = runs + un; /* M.U is 8n bytes */
