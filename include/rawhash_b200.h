@@ -149,8 +149,10 @@ const char *rh_gpu_last_error(void);
 void        rh_gpu_set_stream(rh_gpu_ctx *ctx, void *cuda_stream);
 /* A batch is cut into contiguous read ranges that run concurrently on their own CUDA streams (the
  * multi-threaded side of kt_for, src/kthread.c:47-65): the slow tail of one range overlaps the bulk of
- * the others and the host->device copy overlaps compute.  Default 2 (env RH_WORKERS at rh_gpu_init);
- * returns the count in effect.  With a caller stream set, one range is used. */
+ * the others and the host->device copy overlaps compute.  The number of workers is fixed at rh_gpu_init
+ * (env RH_WORKERS, default 1: on B200 the kernels of one range already fill the GPU, and splitting the
+ * work arena costs more than the overlap wins — measured 118.6k / 115.0k / 113.5k reads/s at 1 / 2 / 4);
+ * this call lowers or restores the count in use and returns it.  With a caller stream set, one range is used. */
 int         rh_gpu_set_workers(rh_gpu_ctx *ctx, int n_workers);
 
 /*

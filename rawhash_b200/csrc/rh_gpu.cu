@@ -215,10 +215,11 @@ int run_round(rh_worker *c, round_io &io, int carry_in_idx)
 	a1.min_hash = c->d_seed_cnt.p; a1.min_pos = c->d_seed_dst.p; /* free until k_seed_count */
 	a1.prof = c->prof_on ? c->d_prof.p : nullptr;
 	{ /* the event stage: five launches back to back, timed as one span */
-		span_guard g(c, T_EVENT, 5);
+		span_guard g(c, T_EVENT, 6);
 		k_sig_norm<<<(ns * 32 + 127) / 128, 128, 0, s>>>(a1);
 		k_sig_tstat<<<ns, 256, 0, s>>>(a1, c->D);
 		k_sig_peaks<<<(ns + 127) / 128, 128, 0, s>>>(a1, c->D);
+		k_sig_events_fast<<<ns, EV_THREADS, 0, s>>>(a1);
 		k_sig_events<<<ns, EV_THREADS, 0, s>>>(a1);
 		k_sig_sketch<<<(ns + 127) / 128, 128, 0, s>>>(a1, c->D);
 	}
@@ -555,8 +556,26 @@ struct job_t {
 	rh_worker *w; uint32_t lo, hi;
 	const int16_t *const *raw; int16_t *d_raw;   /* host pointers + shared device buffer (null when already resident) */
 	const batch_in *in; const std::vector<uint64_t> *beg, *len;
-	rh_map_rec_t *recs = nullptr; uint64_t n_recs = 0; int rc = RH_OK;
+	rh_map_rec_t *recs = nullptr; uint64_t n_recs = 0; int rc = RH_OK; uint64_t h2d = 0;
 };
+
+/* H2D copies of one worker's reads on its stream; called from the submitting thread for worker 0, 1, ... in turn so
+ * that the copy engine serves the ranges in that order and worker r computes while the ranges after it still load */
+int issue_uploads(job_t *j)
+{
+	rh_worker *w = j->w;
+	int rc = RH_OK;
+	if (!j->raw) return rc;
+	const std::vector<uint64_t> &B = *j->beg, &L = *j->len;
+	for (uint32_t i = j->lo; i < j->hi && rc == RH_OK;) { /* one copy per run of reads contiguous on both sides */
+		uint32_t e = i; uint64_t bytes = L[i] * 2;
+		while (e + 1 < j->hi && L[e] > 0 && j->raw[e + 1] == j->raw[e] + L[e] && B[e + 1] == B[e] + L[e] && bytes < ((uint64_t)256 << 20)) { ++e; bytes += L[e] * 2; }
+		if (bytes && cudaMemcpyAsync(j->d_raw + B[i], j->raw[i], bytes, cudaMemcpyHostToDevice, w->stream) != cudaSuccess) { rh_set_error("H2D copy of reads %u..%u failed: %s", i, e, cudaGetErrorString(cudaGetLastError())); rc = RH_ERR_CUDA; }
+		j->h2d += bytes;
+		i = e + 1;
+	}
+	return rc;
+}
 
 void run_job(job_t *j)
 {
@@ -566,17 +585,9 @@ void run_job(job_t *j)
 	cudaEvent_t t0 = get_event(w), t1 = get_event(w);
 	cudaEventRecord(t0, w->stream);
 	const uint32_t n = j->hi - j->lo;
-	int rc = RH_OK;
-	if (j->raw) {
-		const std::vector<uint64_t> &B = *j->beg, &L = *j->len;
-		for (uint32_t i = j->lo; i < j->hi && rc == RH_OK;) { /* one copy per run of reads contiguous on both sides */
-			uint32_t e = i; uint64_t bytes = L[i] * 2;
-			while (e + 1 < j->hi && L[e] > 0 && j->raw[e + 1] == j->raw[e] + L[e] && B[e + 1] == B[e] + L[e] && bytes < ((uint64_t)256 << 20)) { ++e; bytes += L[e] * 2; }
-			if (bytes && cudaMemcpyAsync(j->d_raw + B[i], j->raw[i], bytes, cudaMemcpyHostToDevice, w->stream) != cudaSuccess) { rh_set_error("H2D copy of reads %u..%u failed: %s", i, e, cudaGetErrorString(cudaGetLastError())); rc = RH_ERR_CUDA; }
-			w->st.h2d_bytes += bytes;
-			i = e + 1;
-		}
-	}
+	const int rc0 = j->rc; /* outcome of issue_uploads (its error text is already in w->err) */
+	int rc = rc0;
+	w->st.h2d_bytes += j->h2d;
 	if (rc == RH_OK && n) {
 		batch_in sub = *j->in;
 		sub.n = n; sub.offset += j->lo; sub.range += j->lo; sub.digitisation += j->lo;
@@ -589,7 +600,7 @@ void run_job(job_t *j)
 	float ms = 0; cudaEventElapsedTime(&ms, t0, t1); w->st.ms_total = ms;
 	collect_spans(w);
 	j->rc = rc;
-	if (rc != RH_OK) snprintf(w->err, sizeof(w->err), "%s", rh_gpu_last_error()); /* the error text is thread local: hand it to the caller */
+	if (rc != RH_OK && rc0 == RH_OK) snprintf(w->err, sizeof(w->err), "%s", rh_gpu_last_error()); /* the error text is thread local: hand it to the caller */
 }
 
 int map_batch(rh_gpu_ctx *c, const batch_in &in, const std::vector<uint64_t> &beg, const std::vector<uint64_t> &len, const int16_t *raw_dev,
@@ -609,6 +620,7 @@ int map_batch(rh_gpu_ctx *c, const batch_in &in, const std::vector<uint64_t> &be
 		j.w->raw_ptr = raw_dev;
 		j.w->stream = (c->user_stream && r == 0) ? (cudaStream_t)c->user_stream : j.w->own_stream;
 	}
+	for (uint32_t r = 0; r < k; ++r) { jobs[r].rc = issue_uploads(&jobs[r]); if (jobs[r].rc != RH_OK) snprintf(jobs[r].w->err, sizeof(jobs[r].w->err), "%s", rh_gpu_last_error()); }
 	if (k == 1) run_job(&jobs[0]);
 	else {
 		std::vector<std::thread> th;
@@ -692,7 +704,7 @@ extern "C" rh_gpu_ctx *rh_gpu_init(const rh_index_t *idx, const rh_params_t *p, 
 	cudaMemGetInfo(&free_b, &total_b);
 	if (arena_bytes == 0) arena_bytes = free_b / 2;
 	if (arena_bytes > free_b * 7 / 10) arena_bytes = free_b * 7 / 10;
-	uint32_t nw = 2;
+	uint32_t nw = 1;
 	if (const char *e = getenv("RH_WORKERS")) nw = (uint32_t)std::max(1, std::min(16, atoi(e)));
 	while (nw > 1 && arena_bytes / nw < ((size_t)64 << 20)) --nw; /* keep every worker's arena useful */
 	for (uint32_t r = 0; r < nw; ++r) {
@@ -904,6 +916,7 @@ extern "C" rh_index_t *rh_index_build_sig(const rh_params_t *p, uint32_t n_reads
 			k_sig_norm<<<(ns * 32 + 127) / 128, 128, 0, c->stream>>>(a1);
 			k_sig_tstat<<<ns, 256, 0, c->stream>>>(a1, c->D);
 			k_sig_peaks<<<(ns + 127) / 128, 128, 0, c->stream>>>(a1, c->D);
+			k_sig_events_fast<<<ns, EV_THREADS, 0, c->stream>>>(a1);
 			k_sig_events<<<ns, EV_THREADS, 0, c->stream>>>(a1);
 			if (cudaMemcpyAsync(io.slots.data(), c->d_slots.p, ns * sizeof(slot_t), cudaMemcpyDeviceToHost, c->stream) != cudaSuccess) { rc = RH_ERR_CUDA; break; }
 			ev.resize(et);

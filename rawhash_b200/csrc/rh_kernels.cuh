@@ -54,6 +54,7 @@ struct slot_t {
 	uint32_t raw_used;             /* raw samples streamed by the event kernel for this chunk  */
 	uint32_t n_ties;               /* adjacent equal keys found by the anchor sort              */
 	uint32_t n_seg;                /* independent DP segments                                   */
+	uint32_t ev_done;              /* events already produced by the fast event kernel          */
 };
 
 /* layout of a slot's region in the anchor arena (n = n_anchors) */

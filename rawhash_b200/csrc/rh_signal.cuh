@@ -254,6 +254,55 @@ __device__ void heapsort_global(float *a, uint32_t n)
 	}
 }
 
+/* Fast path of gen_events for ordinary chunks (<= EVF_MAXN samples, no segment longer than EVF_LONG): the chunk's
+ * samples sit in shared memory and every THREAD ranks one SAMPLE inside its segment (count of smaller values, index
+ * as tie-break), so the lanes of a warp work on neighbouring samples of the same few segments and stay converged —
+ * the thread-per-segment insertion sort ran with 5 of 32 lanes active (ncu).  The order-dependent float sum in
+ * ascending order (revent.c:169-176) is then one short loop per segment over the sorted copy.  Chunks it cannot
+ * take are left to k_sig_events. */
+#define EVF_MAXN 4096
+#define EVF_LONG 512
+__global__ void __launch_bounds__(EV_THREADS) k_sig_events_fast(sig_args_t A)
+{
+	__shared__ float zs[EVF_MAXN], so[EVF_MAXN];
+	__shared__ uint16_t seg_of[EVF_MAXN];
+	__shared__ uint32_t s_maxlen, s_bad;
+	slot_t *S = &A.slots[blockIdx.x];
+	const uint32_t n_peaks = S->n_peaks, n = S->n_sig, tid = threadIdx.x;
+	if (n_peaks == 0) { if (tid == 0) S->ev_done = 1; return; }
+	if (n > EVF_MAXN || n_peaks >= 0xffffu) return;
+	const uint32_t *__restrict__ pk = A.peaks + S->e_off;
+	const float *__restrict__ zz = A.z + S->z_off;
+	float *__restrict__ ev = A.events + S->e_off;
+	if (tid == 0) { s_maxlen = 0; s_bad = 0; }
+	for (uint32_t i = tid; i < n; i += EV_THREADS) { zs[i] = zz[i]; seg_of[i] = 0xffffu; }
+	__syncthreads();
+	for (uint32_t j = tid; j < n_peaks; j += EV_THREADS) { /* gen_events (revent.c:193-219): segment j = z[peaks[j-1] .. peaks[j]) */
+		const uint32_t p = pk[j], start = j ? pk[j - 1] : 0u;
+		if (p > n || start > p) { s_bad = 1; continue; } /* the reference assumes increasing peaks inside the chunk */
+		const uint32_t len = p - start;
+		atomicMax(&s_maxlen, len);
+		if (len <= EVF_LONG) for (uint32_t i = start; i < p; ++i) seg_of[i] = (uint16_t)j;
+	}
+	__syncthreads();
+	if (s_bad || s_maxlen > EVF_LONG) return; /* CTA-uniform: the general kernel takes this chunk */
+	for (uint32_t i = tid; i < n; i += EV_THREADS) {
+		const uint32_t j = seg_of[i];
+		if (j == 0xffffu) continue; /* samples after the last peak produce no event */
+		const uint32_t start = j ? pk[j - 1] : 0u, end = pk[j];
+		const float v = zs[i];
+		uint32_t r = 0;
+		for (uint32_t k = start; k < end; ++k) { const float u = zs[k]; r += (u < v) || (u == v && k < i); }
+		so[start + r] = v;
+	}
+	__syncthreads();
+	for (uint32_t j = tid; j < n_peaks; j += EV_THREADS) {
+		const uint32_t p = pk[j], start = j ? pk[j - 1] : 0u, len = p - start;
+		ev[j] = len ? filtered_mean_sorted(so + start, len, 1) : 0.0f;
+	}
+	if (tid == 0) S->ev_done = 1;
+}
+
 __global__ void __launch_bounds__(EV_THREADS) k_sig_events(sig_args_t A)
 {
 	__shared__ float s_buf[EV_BIG];
@@ -261,7 +310,7 @@ __global__ void __launch_bounds__(EV_THREADS) k_sig_events(sig_args_t A)
 	__shared__ uint32_t s_nlong;
 	slot_t *S = &A.slots[blockIdx.x];
 	const uint32_t n_peaks = S->n_peaks, tid = threadIdx.x;
-	if (n_peaks == 0) return;
+	if (n_peaks == 0 || S->ev_done) return; /* ev_done: k_sig_events_fast already produced this chunk's events */
 	const uint32_t *pk = A.peaks + S->e_off;
 	float *zz = A.z + S->z_off;
 	float *ev = A.events + S->e_off;
