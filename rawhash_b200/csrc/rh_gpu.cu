@@ -215,8 +215,9 @@ int run_round(rh_worker *c, round_io &io, int carry_in_idx)
 	a1.min_hash = c->d_seed_cnt.p; a1.min_pos = c->d_seed_dst.p; /* free until k_seed_count */
 	a1.prof = c->prof_on ? c->d_prof.p : nullptr;
 	{ /* the event stage: five launches back to back, timed as one span */
-		span_guard g(c, T_EVENT, 6);
+		span_guard g(c, T_EVENT, 7);
 		k_sig_norm<<<(ns * 32 + 127) / 128, 128, 0, s>>>(a1);
+		k_sig_prefix<<<(ns + 127) / 128, 128, 0, s>>>(a1);
 		k_sig_tstat<<<ns, 256, 0, s>>>(a1, c->D);
 		k_sig_peaks<<<(ns + 127) / 128, 128, 0, s>>>(a1, c->D);
 		k_sig_events_fast<<<ns, EV_THREADS, 0, s>>>(a1);
@@ -914,6 +915,7 @@ extern "C" rh_index_t *rh_index_build_sig(const rh_params_t *p, uint32_t n_reads
 			a1.z = c->d_z.p; a1.ps = c->d_ps.p; a1.pq = c->d_pq.p; a1.t1 = c->d_t1.p; a1.t2 = c->d_t2.p;
 			a1.peaks = c->d_peaks.p; a1.events = c->d_events.p; a1.seed_hash = c->d_seed_hash.p; a1.seed_pos = c->d_seed_pos.p;
 			k_sig_norm<<<(ns * 32 + 127) / 128, 128, 0, c->stream>>>(a1);
+			k_sig_prefix<<<(ns + 127) / 128, 128, 0, c->stream>>>(a1);
 			k_sig_tstat<<<ns, 256, 0, c->stream>>>(a1, c->D);
 			k_sig_peaks<<<(ns + 127) / 128, 128, 0, c->stream>>>(a1, c->D);
 			k_sig_events_fast<<<ns, EV_THREADS, 0, c->stream>>>(a1);

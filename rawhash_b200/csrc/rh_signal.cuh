@@ -14,11 +14,12 @@
  * be re-associated without changing bits: the float prefix sums, the peak state machine and the
  * diff filter.  Everything else — pA conversion, both filters, Σx/Σx² (exact in
  * double, hence order free), the t-statistics, the per-segment sort/mean, quantise/hash — is
- * data parallel.  The stage is therefore five back-to-back launches that alternate between
+ * data parallel.  The stage is therefore a handful of back-to-back launches that alternate between
  * "all lanes on one chunk" and "one lane per chunk" work shapes, so the serial steps cost one
  * lane each instead of a whole warp:
  *
- *   k_sig_norm    warp / chunk     raw -> pA -> filter -> sums -> z -> filter -> prefix sums
+ *   k_sig_norm    warp / chunk     raw -> pA -> filter -> sums -> z -> filter
+ *   k_sig_prefix  lane / chunk     the two sequential float prefix sums
  *   k_sig_tstat   CTA  / chunk     t-statistics for both windows, one thread per position
  *   k_sig_peaks   lane / chunk     the two coupled peak detectors
  *   k_sig_events  CTA  / chunk     one thread per segment: sort, IQR filter, mean
@@ -105,25 +106,38 @@ __global__ void __launch_bounds__(128) k_sig_norm(sig_args_t A)
 	}
 	__syncwarp();
 
-	/* float prefix sums: strictly sequential recurrences (revent.c:32-35, FMA as compiled).
-	 * Every lane runs the same chain on shuffled values; lane k keeps the k-th partial for a
-	 * coalesced store. */
-	float *ps = A.ps + S->z_off + 4ull * slot_id, *pq = A.pq + S->z_off + 4ull * slot_id;
-	float run_s = 0.0f, run_q = 0.0f;
-	if (lane == 0) { ps[0] = 0.0f; pq[0] = 0.0f; }
-	for (uint32_t t0 = 0; t0 < n; t0 += 32) {
-		const float zr = (t0 + lane < n) ? xz[t0 + lane] : 0.0f; /* +0 leaves both chains unchanged */
-		float my_s = 0.0f, my_q = 0.0f;
-#pragma unroll
-		for (int k = 0; k < 32; ++k) {
-			const float v = __shfl_sync(FULL, zr, k);
-			run_s = __fadd_rn(run_s, v);
-			run_q = __fmaf_rn(v, v, run_q);
-			if ((int)lane == k) { my_s = run_s; my_q = run_q; }
-		}
-		if (t0 + lane < n) { ps[t0 + lane + 1] = my_s; pq[t0 + lane + 1] = my_q; }
-	}
 	if (lane == 0) { S->n_sig = n; S->n_peaks = 0; }
+}
+
+/* float prefix sums, comp_prefix_prefixsq (revent.c:23-36): two strictly sequential recurrences (the second one an
+ * FMA in the reference as compiled), so they cannot be re-associated.  One LANE per chunk runs them — a warp works
+ * on 32 chunks at once instead of 32 lanes repeating one chunk's chain — with 16-byte loads one group ahead and
+ * 16-byte stores. */
+__global__ void __launch_bounds__(128) k_sig_prefix(sig_args_t A)
+{
+	const uint32_t slot_id = blockIdx.x * blockDim.x + threadIdx.x;
+	if (slot_id >= A.n_slots) return;
+	const slot_t *S = &A.slots[slot_id];
+	const uint32_t n = S->n_sig;
+	const float4 *__restrict__ z4 = (const float4 *)(A.z + S->z_off);
+	const uint64_t o = S->z_off + 4ull * slot_id;
+	float4 *__restrict__ ps4 = (float4 *)(A.ps + o), *__restrict__ pq4 = (float4 *)(A.pq + o);
+	/* ps[0] = 0, ps[i+1] = ps[i] + z[i]; group g stores ps[4g .. 4g+3] and needs z[4g-1 .. 4g+2] */
+	float run_s = 0.0f, run_q = 0.0f;
+	const uint32_t ng = n / 4 + 1; /* groups covering ps[0..n] */
+	float4 cur = n ? z4[0] : make_float4(0, 0, 0, 0);
+	for (uint32_t g = 0; g < ng; ++g) {
+		const float4 zc = cur;
+		if (4 * (g + 1) < n) cur = z4[g + 1]; /* next group's samples are in flight while this one is consumed */
+		float4 s, q;
+		s.x = run_s; q.x = run_q;
+		const float v0 = 4 * g + 0 < n ? zc.x : 0.0f, v1 = 4 * g + 1 < n ? zc.y : 0.0f, v2 = 4 * g + 2 < n ? zc.z : 0.0f, v3 = 4 * g + 3 < n ? zc.w : 0.0f;
+		s.y = __fadd_rn(s.x, v0); q.y = __fmaf_rn(v0, v0, q.x);
+		s.z = __fadd_rn(s.y, v1); q.z = __fmaf_rn(v1, v1, q.y);
+		s.w = __fadd_rn(s.z, v2); q.w = __fmaf_rn(v2, v2, q.z);
+		run_s = __fadd_rn(s.w, v3); run_q = __fmaf_rn(v3, v3, q.w);
+		ps4[g] = s; pq4[g] = q; /* entries past ps[n] fall in the chunk's padding and are never read as data */
+	}
 }
 
 /* ------------------------------------------------------------------------------------------- */
