@@ -687,7 +687,7 @@ __device__ void cta_klib_replay(tie_shared_t &T, uint8_t *bytes, klib_ws_t W, co
 	__syncthreads();
 }
 
-__global__ void __launch_bounds__(TIE_THREADS, 10) k_sort_ties(sort_args_t A, uint32_t smem_cap, uint32_t n_lo, uint32_t n_hi)
+__global__ void __launch_bounds__(TIE_THREADS, 14) k_sort_ties(sort_args_t A, uint32_t smem_cap, uint32_t n_lo, uint32_t n_hi)
 {
 	extern __shared__ __align__(16) uint8_t s_dyn[];
 	tie_shared_t &T = *(tie_shared_t *)s_dyn;

@@ -352,7 +352,7 @@ struct fin_shared_t {
  *   4  compact_a (+ the copy carried to the next chunk), exact sort of chains by target, region keys
  *   5  exact sort of regions, mm_gen_regs
  * The order-dependent remainder runs in k_chain_decide. */
-__global__ void __launch_bounds__(FIN_THREADS, 8) k_chain_finish(k3_args_t A, dev_params_t P)
+__global__ void __launch_bounds__(FIN_THREADS, 10) k_chain_finish(k3_args_t A, dev_params_t P)
 {
 	__shared__ fin_shared_t SH;
 	const uint32_t FULL = 0xffffffffu;
