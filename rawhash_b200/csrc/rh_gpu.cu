@@ -394,6 +394,7 @@ int setup_reads(rh_worker *c, const batch_in &in, const std::vector<uint64_t> &b
 	c->st.h2d_bytes += n * sizeof(read_state_t);
 	if ((rc = c->d_rec_start.reserve(n)) || (rc = c->d_rec_cnt.reserve(n))) return rc;
 	CUDA_TRY(cudaMemsetAsync(c->d_rec_cnt.p, 0xff, n * 4, c->stream));
+	CUDA_TRY(cudaMemsetAsync(c->d_rec_start.p, 0, n * 4, c->stream));
 	CUDA_TRY(cudaMemsetAsync(c->d_counters.p, 0, 2 * sizeof(unsigned long long), c->stream));
 	CUDA_TRY(cudaMemsetAsync(c->d_err.p, 0, 4, c->stream));
 	{

@@ -166,7 +166,8 @@ __global__ void __launch_bounds__(256) k_sig_tstat(sig_args_t A, dev_params_t P)
 	const uint32_t w1 = P.w1, w2 = P.w2;
 	const float fw1 = (float)w1, fw2 = (float)w2;
 	const bool ok1 = w1 >= 2 && n >= 2 * w1, ok2 = w2 >= 2 && n >= 2 * w2;
-	for (uint32_t i = threadIdx.x; i <= n; i += blockDim.x) {
+	const uint32_t n_pad = (n + 4) & ~3u; /* n+1 values, padded to the 16-byte groups k_sig_peaks loads */
+	for (uint32_t i = threadIdx.x; i < n_pad; i += blockDim.x) {
 		t1[i] = (ok1 && i >= w1 && i + w1 <= n) ? tstat_at(ps, pq, i, w1, fw1) : 0.0f;
 		t2[i] = (ok2 && i >= w2 && i + w2 <= n) ? tstat_at(ps, pq, i, w2, fw2) : 0.0f;
 	}
