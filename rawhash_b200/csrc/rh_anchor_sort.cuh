@@ -521,26 +521,38 @@ __device__ void cta_klib_replay(tie_shared_t &T, uint8_t *bytes, klib_ws_t W, co
 				uint32_t k = 0, rp = 0;
 				bool live = walker;
 				if (live) { for (;; ++k) { const uint32_t wk = tab[k]; if ((wk & 0xffffu) != (wk >> 16)) { rp = wk & 0xffffu; break; } } }
-				unsigned long long walk_iters = 0;
-				while (__any_sync(FULL, live)) {
-					++walk_iters;
-					if (live) {
-						uint32_t d;
-						if (bs_shared) asm volatile("ld.shared.u8 %0, [%1];" : "=r"(d) : "r"(bs_saddr + rp));
-						else d = bs[rp];
-						const uint32_t wd = tab[d];
-						const uint32_t h = wd & 0xffffu;
-						const uint32_t home = d == k;
-						D[rp] = h;
-						tab[d] = wd + 1;
-						rp = h + home;
-						if (home && h + 1 == (wd >> 16)) { /* region k complete: next unfinished region */
+				/* a single warp issues roughly one dependent instruction every 7-10 cycles, so the walk's speed is its
+				 * instruction count per element: no vote, no counters, one load per table */
+				if (live) {
+					if (bs_shared) {
+						for (;;) {
+							uint32_t d;
+							asm volatile("ld.shared.u8 %0, [%1];" : "=r"(d) : "r"(bs_saddr + rp));
+							const uint32_t wd = tab[d];
+							const uint32_t h = wd & 0xffffu;
+							D[rp] = h;
+							tab[d] = wd + 1;
+							if (d != k) { rp = h; continue; }
+							rp = h + 1;
+							if (rp != (wd >> 16)) continue;
 							do { ++k; if (k < 256) { const uint32_t wk = tab[k]; rp = wk & 0xffffu; if (rp != (wk >> 16)) break; } } while (k < 256);
-							live = k < 256;
+							if (k >= 256) break;
+						}
+					} else {
+						for (;;) {
+							const uint32_t d = bs[rp];
+							const uint32_t wd = tab[d];
+							const uint32_t h = wd & 0xffffu;
+							D[rp] = h;
+							tab[d] = wd + 1;
+							if (d != k) { rp = h; continue; }
+							rp = h + 1;
+							if (rp != (wd >> 16)) continue;
+							do { ++k; if (k < 256) { const uint32_t wk = tab[k]; rp = wk & 0xffffu; if (rp != (wk >> 16)) break; } } while (k < 256);
+							if (k >= 256) break;
 						}
 					}
 				}
-				if (prof && lane == 0) { atomicAdd(&prof[22], walk_iters); atomicAdd(&prof[23], 1ULL); } /* RH_PROF: loop trips of the walking warp, walk batches */
 			}
 			__syncthreads();
 			RH_PROF_MARK(prof, 18, tid == 0);
