@@ -539,17 +539,22 @@ __device__ void cta_klib_replay(tie_shared_t &T, uint8_t *bytes, klib_ws_t W, co
 							if (k >= 256) break;
 						}
 					} else {
+						const uint32_t beg = T.seg_beg[lane < nb ? lane : 0]; /* uniform bases + one 32-bit index: fewer address instructions */
+						const uint8_t *__restrict__ gb = bytes; uint32_t *__restrict__ gd = dst;
+						uint32_t ip = beg + rp;
 						for (;;) {
-							const uint32_t d = bs[rp];
+							const uint32_t d = gb[ip];
 							const uint32_t wd = tab[d];
 							const uint32_t h = wd & 0xffffu;
-							D[rp] = h;
+							gd[ip] = h;
 							tab[d] = wd + 1;
-							if (d != k) { rp = h; continue; }
-							rp = h + 1;
-							if (rp != (wd >> 16)) continue;
-							do { ++k; if (k < 256) { const uint32_t wk = tab[k]; rp = wk & 0xffffu; if (rp != (wk >> 16)) break; } } while (k < 256);
+							if (d != k) { ip = beg + h; continue; }
+							ip = beg + h + 1;
+							if (h + 1 != (wd >> 16)) continue;
+							uint32_t nh = 0;
+							do { ++k; if (k < 256) { const uint32_t wk = tab[k]; nh = wk & 0xffffu; if (nh != (wk >> 16)) break; } } while (k < 256);
 							if (k >= 256) break;
+							ip = beg + nh;
 						}
 					}
 				}
