@@ -41,6 +41,13 @@ PRESET = "sensitive"
 WORKLOAD = "yeast-sized 12 Mb synthetic genome (16 contigs), -x sensitive, synthetic R9.4 4 kHz 450 bp/s reads of 5 kb (BASELINE configs[1])"
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum of the event-stage kernels in the `ncu --set full` capture
+# profiles/r01_final_event_raw.csv (one launch group of 20 000 chunks), divided by that group's algorithmic bytes.
+# The intermediates (z, prefix sums, two t-statistic arrays) round-trip through HBM between the stage's kernels.
+TRAFFIC_PER_ALG_BYTE = 17.5
+TRAFFIC_SOURCE = "profiles/r01_final_event_raw.csv: DRAM read+write bytes of the stage's kernels for a 20000-chunk launch group / its algorithmic bytes, scaled to this run's average launch"
+
+
 def _peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.isfile(p):
@@ -289,8 +296,9 @@ def main():
                     "h2d_bytes_per_step": h2d // args.steps, "d2h_bytes_per_step": d2h // args.steps, "records_equal_to_resident_run": same},
             "gpu_launches": int(cnt["kernel_launches"]),
             "clocks": clocks,
-            "roofline": {"kernel": "event stage: k_sig_norm+k_sig_tstat+k_sig_peaks+k_sig_events+k_sig_sketch (5 back-to-back launches per chunk round, timed as one span)", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak if peak else None, "traffic": None, "peak_source": peak_src,
+            "roofline": {"kernel": "event stage: k_sig_norm+k_sig_prefix+k_sig_tstat+k_sig_peaks+k_sig_events_fast(+k_sig_events)+k_sig_sketch (back-to-back launches per chunk group, timed as one span)", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak if peak else None,
+                         "traffic": TRAFFIC_PER_ALG_BYTE * alg_bytes / ev_launches, "traffic_source": TRAFFIC_SOURCE, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": alg_bytes / ev_launches, "avg_launch_ms": ev_ms / ev_launches,
                          "timing": "CUDA events on the launching stream around each event-stage launch group, in a one-worker pass of the same step right after the timed region (kernel timed alone)",
                          "achieved_in_timed_region": achieved_timed,

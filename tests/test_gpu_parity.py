@@ -201,3 +201,31 @@ def test_rawsamble_all_vs_all(built):
     exp = strip_mt(exp).splitlines()
     assert len(exp) > n, "expected overlaps between reads"
     assert got == exp
+
+
+def test_workers_and_device_resident_input(built, monkeypatch):
+    """A batch cut into concurrent read ranges (RH_WORKERS=3, own stream and arenas each) and the same batch passed as
+    one device-resident buffer give the records of the single-range host-buffer call, in input order."""
+    import torch
+    from rawhash_b200 import synth
+    w = World(n_contigs=3, genome_len=900_000, n_reads=400, read_bp=3000, seed=31)
+    api, P, idx, orc = _setup(w)
+    n = len(w.names)
+    cal = (np.full(n, synth.OFFSET), np.full(n, synth.RANGE), np.full(n, synth.DIGITISATION))
+    m1 = api.Mapper(idx, P, 0, 1 << 30)
+    ref = m1.map_batch(w.reads["raw"], *cal, w.names)
+    # device-resident variant: one concatenated buffer + offsets (arbitrary, unaligned read starts)
+    lens = np.array([len(r) for r in w.reads["raw"]], dtype=np.uint64)
+    off = np.concatenate([[0], np.cumsum(lens)]).astype(np.uint64)
+    flat = torch.from_numpy(np.concatenate(w.reads["raw"] + [np.zeros(8, np.int16)])).cuda()
+    dev = m1.map_batch_device(flat.data_ptr(), off, *cal, names=w.names)
+    m1.close()
+    assert np.array_equal(ref, dev)
+    monkeypatch.setenv("RH_WORKERS", "3")
+    m3 = api.Mapper(idx, P, 0, 1 << 30)
+    assert m3.set_workers(3) == 3
+    got = m3.map_batch(w.reads["raw"], *cal, w.names)
+    st = m3.stats()
+    m3.close()
+    assert np.array_equal(ref, got)
+    assert st["n_reads"] == n and np.array_equal(got["read_idx"], np.sort(got["read_idx"]))
