@@ -144,10 +144,31 @@ def run_reference(args, rank, world):
                          "sample": f"{n_sample} reads per step, kt_for(map_worker_for) wall time, index load and file parsing excluded"},
         "e2e": {"value": v, "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line))
+    _emit(line)
+
+
+_REAL_STDOUT = None
+
+
+def _claim_stdout():
+    """Keep stdout for the one JSON line: libraries (NCCL prints its version banner with printf when
+    NCCL_DEBUG=VERSION, the reference prints progress) write to fd 1, so fd 1 is pointed at stderr for the
+    duration of the run and the result goes to a private duplicate of the original stdout."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def _emit(line: dict):
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
 
 
 def main():
+    _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
@@ -312,7 +333,7 @@ def main():
         }
         if not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(mp, means, stdv, genome, args.ref_reads)
-        print(json.dumps(line))
+        _emit(line)
     mapper.close()
     if world > 1:
         dist.destroy_process_group()
