@@ -119,14 +119,23 @@ __device__ bool set_parent_bitset(dev_reg_t *r, uint32_t n_regs, const dev_param
 			int covered = 0;
 			if (kk > 0 && ei > si) {
 				const int w0 = si >> 5, w1 = (ei - 1) >> 5;
-				for (int w = w0 + (int)lane; w <= w1; w += 32) {
-					uint32_t m = bits[w];
-					if (w == w0) m &= 0xffffffffu << (si & 31);
-					if (w == w1) m &= 0xffffffffu >> (31 - ((ei - 1) & 31));
-					covered += __popc(m);
-				}
+				if (w1 - w0 < 4) { /* short interval (nearly all regions): every lane adds up the same few words, no reduction chain */
+					for (int w = w0; w <= w1; ++w) {
+						uint32_t m = bits[w];
+						if (w == w0) m &= 0xffffffffu << (si & 31);
+						if (w == w1) m &= 0xffffffffu >> (31 - ((ei - 1) & 31));
+						covered += __popc(m);
+					}
+				} else {
+					for (int w = w0 + (int)lane; w <= w1; w += 32) {
+						uint32_t m = bits[w];
+						if (w == w0) m &= 0xffffffffu << (si & 31);
+						if (w == w1) m &= 0xffffffffu >> (31 - ((ei - 1) & 31));
+						covered += __popc(m);
+					}
 #pragma unroll
-				for (int o = 16; o > 0; o >>= 1) covered += __shfl_xor_sync(FULL, covered, o);
+					for (int o = 16; o > 0; o >>= 1) covered += __shfl_xor_sync(FULL, covered, o);
+				}
 			}
 			int hit = -1;
 			if (covered > 0) {

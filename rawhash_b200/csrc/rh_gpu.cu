@@ -449,6 +449,14 @@ int map_resident(rh_worker *c, const batch_in &in, const std::vector<uint64_t> &
 		c->st.n_rounds++;
 		CUDA_TRY(cudaMemcpyAsync(rec_cnt.data(), c->d_rec_cnt.p, n * 4, cudaMemcpyDeviceToHost, c->stream));
 		CUDA_TRY(cudaStreamSynchronize(c->stream));
+		if (c->prof_on && getenv("RH_PROF_ROUNDS")) { /* per-round phase cycles (debug aid) */
+			unsigned long long h[64];
+			cudaMemcpy(h, c->d_prof.p, sizeof(h), cudaMemcpyDeviceToHost);
+			cudaMemset(c->d_prof.p, 0, sizeof(h));
+			fprintf(stderr, "[RH_PROF] round %u (%zu reads active) Mcycles:", round, active.size());
+			for (int i = 0; i < 64; ++i) if (h[i]) fprintf(stderr, " [%d]=%.1f", i, h[i] / 1e6);
+			fprintf(stderr, "\n");
+		}
 		c->st.d2h_bytes += n * 4;
 		std::vector<uint32_t> next;
 		for (uint32_t r : active) if (rec_cnt[r] == 0xffffffffu) next.push_back(r);
