@@ -196,6 +196,7 @@ int ref_mapopt_update(void *h)
 }
 
 void ref_set_mid_occ(void *h, int mid_occ) { ((ref_ctx *)h)->opt.mid_occ = mid_occ; }
+void ref_set_best_n(void *h, int best_n) { ((ref_ctx *)h)->opt.best_n = best_n; } /* --best-chains, src/main.cpp */
 
 uint32_t ref_n_seq(void *h) { ref_ctx *c = (ref_ctx *)h; return c->ri ? c->ri->n_seq : 0; }
 

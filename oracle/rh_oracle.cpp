@@ -1037,6 +1037,7 @@ int orc_mapopt_update(void *h) /* ri_mapopt_update, src/rindex.c:1041-1053 */
 	return m;
 }
 void orc_set_mid_occ(void *h, int v) { ((Ctx *)h)->P.mid_occ = v; }
+void orc_set_best_n(void *h, int v) { ((Ctx *)h)->P.best_n = v; }
 uint32_t orc_n_seq(void *h) { return (uint32_t)((Ctx *)h)->idx.names.size(); }
 const uint64_t *orc_idx_get(void *h, uint64_t hash, int *n) { return ((Ctx *)h)->idx.get((uint32_t)hash, n); }
 

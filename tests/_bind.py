@@ -148,6 +148,7 @@ class _CpuChecker:
         g("build_index_sig").argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
         g("mapopt_update").argtypes = [C.c_void_p]
         g("set_mid_occ").argtypes = [C.c_void_p, C.c_int]
+        g("set_best_n").argtypes = [C.c_void_p, C.c_int]
         g("set_sampling").argtypes = [C.c_void_p, C.c_uint32, C.c_uint32]
         g("set_chunks").argtypes = [C.c_void_p, C.c_uint32, C.c_uint32]
         g("idx_get").restype = C.POINTER(C.c_uint64)
@@ -202,6 +203,9 @@ class _CpuChecker:
 
     def set_mid_occ(self, v):
         self._g("set_mid_occ")(self.h, int(v))
+
+    def set_best_n(self, v):
+        self._g("set_best_n")(self.h, int(v))
 
     def set_sampling(self, sample_rate, bp_per_sec):
         self._g("set_sampling")(self.h, sample_rate, bp_per_sec)

@@ -229,3 +229,51 @@ def test_workers_and_device_resident_input(built, monkeypatch):
     m3.close()
     assert np.array_equal(ref, got)
     assert st["n_reads"] == n and np.array_equal(got["read_idx"], np.sort(got["read_idx"]))
+
+
+def test_scale_properties(built):
+    """Size-independent properties on a batch the oracle would take minutes for: two runs agree record for record,
+    host-buffer and device-resident inputs agree, every read comes back exactly once and in order, and the
+    synthetic reads land on the locus they were sampled from."""
+    import torch
+    from rawhash_b200 import api, synth
+    w = World(n_contigs=8, genome_len=6_000_000, n_reads=4000, read_bp=4000, seed=41)
+    P = api.make_params("sensitive")
+    names, seqs = w.genome_strings()
+    idx = api.Index.build(P, api.load_pore(w.model, w.k), names, seqs, 8)
+    idx.update_mapopt(P)
+    n = len(w.names)
+    cal = (np.full(n, synth.OFFSET), np.full(n, synth.RANGE), np.full(n, synth.DIGITISATION))
+    m = api.Mapper(idx, P, 0, 4 << 30)
+    a = m.map_batch(w.reads["raw"], *cal, w.names)
+    b = m.map_batch(w.reads["raw"], *cal, w.names)
+    lens = np.array([len(r) for r in w.reads["raw"]], dtype=np.uint64)
+    off = np.concatenate([[0], np.cumsum(lens)]).astype(np.uint64)
+    flat = torch.from_numpy(np.concatenate(w.reads["raw"] + [np.zeros(8, np.int16)])).cuda()
+    c = m.map_batch_device(flat.data_ptr(), off, *cal, names=w.names)
+    m.close()
+    assert np.array_equal(a, b) and np.array_equal(a, c)
+    assert np.array_equal(a["read_idx"], np.arange(n))          # -x sensitive: one record per read, input order
+    ok = 0
+    for r, (ci, st, strand) in zip(a, w.reads["truth"]):
+        if r["mapped"] and r["ref_id"] == ci and r["rev"] == strand and abs(int(r["fragment_start_position"]) - st) < 4000:
+            ok += 1
+    assert ok >= 0.97 * n, f"only {ok} of {n} reads mapped to their true locus"
+
+
+def test_secondary_reporting_best_n(built):
+    """best_n > 0 (mm_select_sub keeps secondaries, hit.c:338-367) — the general path of the decision kernel."""
+    from rawhash_b200 import synth
+    from _bind import strip_mt
+    w = World(n_contigs=2, genome_len=500_000, n_reads=80, read_bp=4000, seed=43)
+    api, P, idx, orc = _setup(w, "sensitive", best_n=3)
+    orc.set_best_n(3)
+    n = len(w.names)
+    cal = (np.full(n, synth.OFFSET), np.full(n, synth.RANGE), np.full(n, synth.DIGITISATION))
+    m = api.Mapper(idx, P, 0, 1 << 30)
+    recs = m.map_batch(w.reads["raw"], *cal, w.names)
+    m.close()
+    got = strip_mt(idx.format_paf(recs, w.names)).splitlines()
+    exp, _ = orc.map_paf([w.pa(i) for i in range(n)], w.names, 4)
+    exp = strip_mt(exp).splitlines()
+    assert got == exp

@@ -82,3 +82,19 @@ def test_rawsamble_ava(built):
         out.append((mid, _bind.strip_mt(paf)))
     assert out[0] == out[1]
     assert len(out[0][1].splitlines()) > len(w.names)
+
+
+def test_best_n_secondaries(built):
+    """best_n > 0: mm_select_sub keeps secondaries (hit.c:338-367), which changes nc/mapq of the reported chain."""
+    w = World(n_contigs=2, genome_len=500_000, n_reads=80, read_bp=4000, seed=43)
+    ref, orc = _pair(w, "sensitive")
+    ref.set_best_n(3); orc.set_best_n(3)
+    sigs = [w.pa(i) for i in range(len(w.names))]
+    for i in range(0, len(sigs), 8):
+        assert tap_equal(orc.tap_read(sigs[i], w.names[i]), ref.tap_read(sigs[i], w.names[i])) == [], f"read {i}"
+    a, _ = ref.map_paf(sigs, w.names, 2)
+    b, _ = orc.map_paf(sigs, w.names, 2)
+    assert _bind.strip_mt(a) == _bind.strip_mt(b)
+    ref.set_best_n(0)
+    c, _ = ref.map_paf(sigs, w.names, 2)
+    assert _bind.strip_mt(a) != _bind.strip_mt(c), "best_n had no observable effect in this world"
