@@ -4,21 +4,20 @@
  * The reference's klib radix sort is unstable and its tie order is observable,
  * but any two correct sorts agree on every element whose key is unique.  So:
  *
- *   k_sort_block     one CTA per chunk: stable LSD byte-radix sort of (x, source index) pairs,
- *                    skipping byte positions on which all keys of the chunk agree; then a scan
- *                    for adjacent equal keys.  Chunks without ties (the large majority) are
- *                    finished here: A[j] = B[idx[j]].
- *   k_sort_ties      one warp per chunk WITH ties: replays klib's in-place MSD pass exactly, but
- *                    only along the sub-arrays that contain a tie group — for those it needs the
- *                    true element order the reference would have at that recursion level, which
- *                    it tracks as a permutation of source indices.  Histogram/permute are
- *                    warp-parallel; the displacement-cycle walk itself is order dependent and is
- *                    done by lane 0 on a byte array.  The result patches the index order inside
- *                    the tie-containing terminal buckets, then A[j] = B[idx[j]].
+ *   k_sort_smem      one CTA (1024 threads) per chunk: stable LSD byte-radix sort with the packed 32-bit keys
+ *                    stationary in shared memory and 16-bit source indices moving; then a scan for adjacent
+ *                    equal keys.  Chunks without ties (the large majority) are finished here: A[j] = B[idx[j]].
+ *   k_sort_block     the same sort through global memory, for chunks or keys too large for k_sort_smem.
+ *   k_sort_ties      one CTA per chunk WITH ties: cta_klib_replay replays klib's in-place MSD pass exactly, but
+ *                    only along the sub-arrays that contain a tie group; the result patches the index order
+ *                    inside the tie-containing terminal bins, then A[j] = B[idx[j]].
+ *   cta_klib_replay  the replay engine (also used by k_chain_finish for full exact sorts): per level, digits of
+ *                    the pending sub-arrays, histograms, then either a closed form (two occupied bins) or the
+ *                    order-dependent displacement walk, one lane per independent sub-array.
  *
- * Slot region usage (slot_mem): B = anchors as expanded (input), A = sorted output,
- * Z/W = (x, idx) ping-pong, f = ord, p = ord scratch, v = dst, t = tied flags (n bytes) +
- * level bytes (n bytes), U/U2 = segment work lists.
+ * Slot region usage (slot_mem): B = anchors as expanded (input), A = sorted output, Z/W = keys ping-pong,
+ * f/p = source index ping-pong, v = destinations, t = tied flags (n bytes) + digit bytes (n bytes),
+ * U = stable order, U2 = closed-form scratch, regs = pending sub-array lists.
  */
 #ifndef RH_ANCHOR_SORT_CUH
 #define RH_ANCHOR_SORT_CUH

@@ -1,15 +1,21 @@
 /*
- * rh_chain_finish.cuh — everything after the chaining DP, one WARP per chunk:
+ * rh_chain_finish.cuh — everything after the chaining DP:
  *
- *   mg_chain_backtrack + compact_a          reference src/lchain.c:95-281
- *   mm_gen_regs / mm_set_parent / mm_select_sub / mm_sync_regs / mm_set_mapq
- *                                           reference src/hit.c:100-150,195-263,312-367,502-539
- *   stop rules + final record of map_worker_for   reference src/rmap.cpp:423-586
+ *   k_chain_finish (one CTA per chunk)
+ *     mg_chain_backtrack + compact_a          reference src/lchain.c:95-281
+ *     mm_gen_regs                             reference src/hit.c:100-150
+ *   k_chain_decide (one warp per chunk)
+ *     mm_set_parent / mm_select_sub / mm_sync_regs / mm_set_mapq
+ *                                             reference src/hit.c:195-263,312-367,502-539
+ *     stop rules + final record of map_worker_for   reference src/rmap.cpp:423-586
  *
- * The O(n) passes (candidate collection, mark reset, gathers, histograms, permutes) and the
- * O(n_u * n_primary) overlap tests of mm_set_parent run on all 32 lanes; only the steps whose
- * result depends on visiting order (the klib sort's displacement walk, the backtrack itself,
- * the parent assignment order) are executed by lane 0.
+ * The O(n) passes (candidate collection, gathers, radix passes, scans) run on the whole CTA.  The steps whose
+ * result depends on visiting order are cut as small as they can be: the score sort replays klib's displacement
+ * walk (cta_klib_replay, rh_anchor_sort.cuh); the backtrack runs one thread per DP segment, because chains never
+ * leave their segment and only the relative order of a segment's own candidates matters; the sorts on keys that
+ * are unique in practice (chain start, salted region key) use a parallel radix sort and fall back to the exact
+ * replay if two equal keys do show up; mm_set_parent is a sequential sweep over regions in score order with the
+ * covered query positions kept as a bitset in shared memory.
  */
 #ifndef RH_CHAIN_FINISH_CUH
 #define RH_CHAIN_FINISH_CUH
