@@ -6,10 +6,10 @@
  *   k_sig_*             src/revent.c:221-316 + src/rsketch.c:143-204   (the event stage, rh_signal.cuh)
  *   k_seed_count        src/rseed.c:60-154 + src/rindex.c:497-514      lookup, occ filter, rep_len
  *   k_seed_expand       src/rmap.cpp:74-116       anchors from position lists + previous chunk's
- *   k_sort_block/_ties  src/ksort.h:101-151       anchor sort with klib's exact tie order (rh_anchor_sort.cuh)
+ *   k_sort_smem/_block/_ties  src/ksort.h:101-151  anchor sort with klib's exact tie order (rh_anchor_sort.cuh)
  *   k_chain_dp          src/lchain.c:385-505      chaining DP
- *   k_chain_finish      src/lchain.c:95-281, src/hit.c:100-150,195-263,338-367,502-539,
- *                       src/rmap.cpp:423-586      backtrack, regions, MAPQ, stop rules (rh_chain_finish.cuh)
+ *   k_chain_finish      src/lchain.c:95-281, src/hit.c:100-150      backtrack, compact_a, regions (rh_chain_finish.cuh)
+ *   k_chain_decide      src/hit.c:195-263,338-367,502-539, src/rmap.cpp:423-586   parents, MAPQ, stop rules, records
  *
  * Work decomposition: a "slot" is one (read, chunk) pair of the current chunk round.
  */
