@@ -1,0 +1,41 @@
+"""CPU: bench.py's output contract — the reference arm prints exactly one JSON line on stdout with the agreed keys,
+and the GPU arm refuses to run (no CPU fallback) when no CUDA device is present."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_reference_arm_json_line(built):
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1", "--ref-reads", "120"],
+                       capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1, f"stdout must carry exactly one line, got {len(lines)}"
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "reads/sec mapped" and d["unit"] == "reads/s"
+    assert d["higher_is_better"] is True and d["value"] > 0 and d["steps"] == 1
+    assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"]["value"] == d["value"] and d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
+    assert "workload" in d["config"]
+
+
+def test_reference_arm_other_ranks_exit_quietly(built):
+    env = dict(os.environ, RANK="1", LOCAL_RANK="1", WORLD_SIZE="2")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "1"],
+                       capture_output=True, text=True, timeout=120, cwd=ROOT, env=env)
+    assert r.returncode == 0 and r.stdout.strip() == ""
+
+
+def test_gpu_arm_needs_a_device(built):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a CUDA device is present")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1", "--warmup", "1"],
+                       capture_output=True, text=True, timeout=300, cwd=ROOT)
+    assert r.returncode != 0 and r.stdout.strip() == ""
+    assert "no CPU fallback" in r.stderr
