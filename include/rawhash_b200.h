@@ -119,6 +119,11 @@ typedef struct rh_index_s rh_index_t;   /* flattened host-side index */
 rh_index_t *rh_index_build(const rh_params_t *p, const float *pore_vals, uint32_t n_pore_vals,
                            uint32_t n_seq, const char *const *names, const char *const *seqs,
                            const uint32_t *lens, int n_threads);
+/* Same index, built on the GPU (expected-signal generation, sketching of both strands,
+ * sort, key table).  ACGT-only references and w == 0; other inputs are handed to rh_index_build. */
+rh_index_t *rh_index_build_gpu(const rh_params_t *p, const float *pore_vals, uint32_t n_pore_vals,
+                               uint32_t n_seq, const char *const *names, const char *const *seqs,
+                               const uint32_t *lens, int device);
 /* Build from raw signals for Rawsamble (semantics of ri_idx_siggen, src/rindex.c:927-969).
  * Event detection runs on the GPU. */
 rh_index_t *rh_index_build_sig(const rh_params_t *p, uint32_t n_reads, const char *const *names,
@@ -132,6 +137,7 @@ const char *rh_index_seq_name(const rh_index_t *idx, uint32_t i);
 uint32_t    rh_index_seq_len(const rh_index_t *idx, uint32_t i);
 uint64_t    rh_index_n_keys(const rh_index_t *idx);
 uint64_t    rh_index_n_pos(const rh_index_t *idx);
+uint32_t    rh_index_key(const rh_index_t *idx, uint64_t i);   /* i-th distinct hash, ascending */
 /* ri_idx_cal_max_occ + ri_mapopt_update (src/rindex.c:1018-1053): sets p->mid_occ */
 void        rh_index_update_mapopt(const rh_index_t *idx, rh_params_t *p);
 /* ri_idx_get (src/rindex.c:497-514): returns pointer to ascending position list */

@@ -126,6 +126,7 @@ def _load():
         "rh_pore_load": (i32, [cp, i32, i32, C.POINTER(C.POINTER(C.c_float)), C.POINTER(u32)]),
         "rh_free": (None, [vp]),
         "rh_index_build": (vp, [PP, vp, u32, u32, vp, vp, vp, i32]),
+        "rh_index_build_gpu": (vp, [PP, vp, u32, u32, vp, vp, vp, i32]),
         "rh_index_build_sig": (vp, [PP, u32, vp, vp, vp, vp, vp, vp]),
         "rh_index_load": (vp, [cp, PP]),
         "rh_index_destroy": (None, [vp]),
@@ -134,6 +135,7 @@ def _load():
         "rh_index_seq_len": (u32, [vp, u32]),
         "rh_index_n_keys": (u64, [vp]),
         "rh_index_n_pos": (u64, [vp]),
+        "rh_index_key": (u32, [vp, u64]),
         "rh_index_update_mapopt": (None, [vp, PP]),
         "rh_index_get": (C.POINTER(u64), [vp, u32, C.POINTER(i32)]),
         "rh_gpu_init": (vp, [vp, PP, i32, C.c_size_t]),
@@ -206,6 +208,19 @@ class Index:
         h = _lib.rh_index_build(C.byref(params), pore_vals.ctypes.data, len(pore_vals), len(bs), _cstr_array(names),
                                 (C.c_char_p * len(bs))(*bs), lens.ctypes.data, n_threads)
         return cls(h)
+
+    @classmethod
+    def build_gpu(cls, params: Params, pore_vals: np.ndarray, names: Sequence[str], seqs: Sequence[str | bytes], device: int = 0):
+        """Same index as build(), constructed on the GPU (rh_index_build_gpu)."""
+        pore_vals = np.ascontiguousarray(pore_vals, dtype=np.float32)
+        bs = [s.encode() if isinstance(s, str) else bytes(s) for s in seqs]
+        lens = np.array([len(b) for b in bs], dtype=np.uint32)
+        h = _lib.rh_index_build_gpu(C.byref(params), pore_vals.ctypes.data, len(pore_vals), len(bs), _cstr_array(names),
+                                    (C.c_char_p * len(bs))(*bs), lens.ctypes.data, device)
+        return cls(h)
+
+    def key(self, i: int) -> int:
+        return _lib.rh_index_key(self.h, int(i))
 
     @classmethod
     def build_from_signals(cls, params: Params, names, raws, offset, rng, digitisation):

@@ -24,7 +24,7 @@ NVCC_FLAGS = [
     "-Xcompiler", "-fPIC,-ffp-contract=off,-O2",
     "-shared",
 ]
-SOURCES = ["rh_gpu.cu", "rh_host.cpp"]
+SOURCES = ["rh_gpu.cu", "rh_index_gpu.cu", "rh_host.cpp"]
 HEADERS = sorted(f for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))) + [os.path.join(ROOT, "include", "rawhash_b200.h")]
 
 

@@ -358,6 +358,7 @@ extern "C" const char *rh_index_seq_name(const rh_index_t *idx, uint32_t i) { re
 extern "C" uint32_t rh_index_seq_len(const rh_index_t *idx, uint32_t i) { return idx->lens[i]; }
 extern "C" uint64_t rh_index_n_keys(const rh_index_t *idx) { return idx->keys.size(); }
 extern "C" uint64_t rh_index_n_pos(const rh_index_t *idx) { return idx->pos.size(); }
+extern "C" uint32_t rh_index_key(const rh_index_t *idx, uint64_t i) { return i < idx->keys.size() ? idx->keys[i] : 0u; }
 
 extern "C" const uint64_t *rh_index_get(const rh_index_t *idx, uint32_t hash, int *n)
 {

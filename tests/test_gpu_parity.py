@@ -277,3 +277,25 @@ def test_secondary_reporting_best_n(built):
     exp, _ = orc.map_paf([w.pa(i) for i in range(n)], w.names, 4)
     exp = strip_mt(exp).splitlines()
     assert got == exp
+
+
+@pytest.mark.parametrize("kind,r10", [("r9.4", False), ("r10.4.1", True)])
+def test_gpu_index_build_equals_host_build(built, kind, r10):
+    """rh_index_build_gpu (events, diff filter, sketch of both strands, sort, key table on the device) against the
+    host builder, which the CPU tests pin to the reference's ri_idx_get answers: same keys, same position lists."""
+    from rawhash_b200 import api
+    w = World(n_contigs=5, genome_len=1_200_000, n_reads=1, read_bp=1000, seed=51, kind=kind)
+    P = api.make_params("sensitive", r10)
+    pore = api.load_pore(w.model, w.k)
+    names, seqs = w.genome_strings()
+    seqs = [seqs[0].lower()] + seqs[1:] + ["ACGTACG"[: w.k - 1]]   # lower case accepted; a sequence shorter than k gives no events
+    names = names + ["tiny"]
+    host = api.Index.build(P, pore, names, seqs, 8)
+    dev = api.Index.build_gpu(P, pore, names, seqs, 0)
+    assert dev.n_seq == host.n_seq and dev.n_keys == host.n_keys and dev.n_pos == host.n_pos
+    assert host.update_mapopt(api.make_params("sensitive", r10)) == dev.update_mapopt(api.make_params("sensitive", r10))
+    nk = host.n_keys
+    for i in list(range(0, nk, 37)) + [nk - 1]:
+        h = host.key(i)
+        assert dev.key(i) == h
+        assert np.array_equal(dev.get(h), host.get(h)), f"key {h:#x}"
