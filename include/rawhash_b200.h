@@ -225,6 +225,49 @@ int rh_gpu_tap_read(rh_gpu_ctx *ctx, const int16_t *raw, uint64_t raw_len,
                     double offset, double range, double digitisation,
                     const char *name, rh_tap_t *tap);
 
+/* ---- files either side of the path (SURVEY.md §8b "file surfaces kept", §8f rank 3) -------------- */
+/* Write the index in the reference's `.ind` layout (ri_idx_dump, src/rindex.c:545-648): header, pore table,
+ * sequence names/lengths, 2^14 buckets of (position array, key/value pairs).  The reference's ri_idx_load
+ * (src/rindex.c:650-776) and rh_index_load read it back.  pore_vals (z-normalised, as rh_pore_load returns
+ * them) may be NULL for a signal index. */
+int rh_index_dump(const rh_index_t *idx, const char *path, const float *pore_vals, uint32_t n_pore_vals);
+
+/* FASTA / gzipped FASTA reader (mm_bseq_open/mm_bseq_read, src/bseq.c:28-110: name = text up to the first
+ * white space).  Arrays are malloc'ed; release with rh_fasta_free. */
+int  rh_fasta_load(const char *path, uint32_t *n_seq, char ***names, char ***seqs, uint32_t **lens);
+void rh_fasta_free(uint32_t n_seq, char **names, char **seqs, uint32_t *lens);
+
+/* SLOW5 / BLOW5 signal files (ri_sig_open_slow5 + ri_read_sig_slow5, src/rsig.c:170-207,478-533; slow5lib
+ * 0.2.0 file format: ASCII, or binary with record compression none|zlib and signal compression none|svb-zd).
+ * A batch keeps the raw int16 samples of its reads back to back in ONE arena (page-locked when a CUDA device
+ * is usable) so that rh_gpu_map_batch_raw uploads it in a single copy; the pA conversion stays on the GPU. */
+typedef struct rh_sigfile_s rh_sigfile_t;
+typedef struct rh_sigbatch_s {
+	uint32_t n;                       /* reads in the batch                          */
+	uint64_t n_samples;               /* sum of raw_len                              */
+	const int16_t *const *raw;        /* raw[i] -> raw_len[i] samples in the arena   */
+	const uint64_t *raw_len;
+	const double *offset, *range, *digitisation, *sampling_rate;
+	const char *const *names;         /* read ids                                    */
+	void *priv;
+} rh_sigbatch_t;
+rh_sigfile_t *rh_sigfile_open(const char *path, int n_threads);
+void          rh_sigfile_close(rh_sigfile_t *f);
+/* Reads records until the batch holds >= max_samples raw samples (the -K mini-batch rule of
+ * ri_sig_read_frag, src/rmap.cpp:600-660, counted on raw samples) or max_reads reads (0 = no limit) or the
+ * file ends.  *out == NULL with RH_OK at end of file. */
+int  rh_sigfile_next_batch(rh_sigfile_t *f, uint64_t max_samples, uint32_t max_reads, rh_sigbatch_t **out);
+void rh_sigbatch_free(rh_sigbatch_t *b);
+/* find_sfiles (src/rsig.c:286-330): `path` itself or, for a directory, every *.slow5 / *.blow5 below it.
+ * Returns a malloc'ed array of malloc'ed strings (rh_free each, then the array). */
+int  rh_find_sigfiles(const char *path, char ***files, uint32_t *n_files);
+/* Writer used by the synthetic-data generator, bench and tests: `.slow5` (ASCII) or `.blow5`
+ * (record_press 0 none | 1 zlib, signal_press 0 none | 1 svb-zd); slow5lib reads the result. */
+int  rh_slow5_write(const char *path, uint32_t n, const char *const *names,
+                    const int16_t *const *raw, const uint64_t *raw_len,
+                    const double *offset, const double *range, const double *digitisation, double sampling_rate,
+                    int record_press, int signal_press);
+
 /* ---- PAF ------------------------------------------------------------------ */
 /* Formats records exactly like src/rmap.cpp:751-772 (mt:f: is printed as 0).
  * Returns a malloc'ed NUL-terminated string (free with rh_free). */

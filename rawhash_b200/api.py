@@ -111,6 +111,17 @@ class _TapC(C.Structure):
     ]
 
 
+class SigBatchC(C.Structure):
+    """rh_sigbatch_t: one batch of raw reads out of a SLOW5/BLOW5 file."""
+    _fields_ = [
+        ("n", C.c_uint32), ("n_samples", C.c_uint64),
+        ("raw", C.POINTER(C.POINTER(C.c_int16))), ("raw_len", C.POINTER(C.c_uint64)),
+        ("offset", C.POINTER(C.c_double)), ("range", C.POINTER(C.c_double)),
+        ("digitisation", C.POINTER(C.c_double)), ("sampling_rate", C.POINTER(C.c_double)),
+        ("names", C.POINTER(C.c_char_p)), ("priv", C.c_void_p),
+    ]
+
+
 def _load():
     if not os.path.isfile(LIB_PATH):
         raise RawHashError(
@@ -148,6 +159,15 @@ def _load():
         "rh_gpu_get_stats": (None, [vp, C.POINTER(GpuStats)]),
         "rh_gpu_tap_read": (i32, [vp, vp, u64, dbl, dbl, dbl, cp, C.POINTER(_TapC)]),
         "rh_format_paf": (vp, [vp, vp, u64, vp]),
+        "rh_index_dump": (i32, [vp, cp, vp, u32]),
+        "rh_fasta_load": (i32, [cp, C.POINTER(u32), C.POINTER(C.POINTER(cp)), C.POINTER(C.POINTER(cp)), C.POINTER(C.POINTER(u32))]),
+        "rh_fasta_free": (None, [u32, vp, vp, vp]),
+        "rh_sigfile_open": (vp, [cp, i32]),
+        "rh_sigfile_close": (None, [vp]),
+        "rh_sigfile_next_batch": (i32, [vp, u64, u32, C.POINTER(C.POINTER(SigBatchC))]),
+        "rh_sigbatch_free": (None, [C.POINTER(SigBatchC)]),
+        "rh_find_sigfiles": (i32, [cp, C.POINTER(C.POINTER(vp)), C.POINTER(u32)]),
+        "rh_slow5_write": (i32, [cp, u32, vp, vp, vp, vp, vp, vp, dbl, i32, i32]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)  # AttributeError if the library does not export a declared symbol
@@ -236,6 +256,13 @@ class Index:
     @classmethod
     def load(cls, path: str, params: Params):
         return cls(_lib.rh_index_load(path.encode(), C.byref(params)))
+
+    def dump(self, path: str, pore_vals: np.ndarray | None = None):
+        """Write the reference's `.ind` layout (ri_idx_dump, src/rindex.c:545-648)."""
+        pv = None if pore_vals is None else np.ascontiguousarray(pore_vals, dtype=np.float32)
+        rc = _lib.rh_index_dump(self.h, path.encode(), None if pv is None else pv.ctypes.data, 0 if pv is None else len(pv))
+        if rc != 0:
+            raise _err("rh_index_dump")
 
     def __del__(self):
         if getattr(self, "h", None):
@@ -390,3 +417,86 @@ class Mapper:
             })
             o["ev"] += ne; o["seed"] += nsd; o["anc"] += na; o["u"] += nu; o["ca"] += nv; o["reg"] += nr
         return out
+
+
+# ---- files either side of the path (csrc/rh_io.cpp) -------------------------------------------------------------
+def read_fasta(path: str):
+    """(names, sequences) of a FASTA / FASTA.gz file, read like mm_bseq_read (src/bseq.c)."""
+    n = C.c_uint32(0)
+    names, seqs, lens = C.POINTER(C.c_char_p)(), C.POINTER(C.c_char_p)(), C.POINTER(C.c_uint32)()
+    if _lib.rh_fasta_load(path.encode(), C.byref(n), C.byref(names), C.byref(seqs), C.byref(lens)) != 0:
+        raise _err("rh_fasta_load")
+    out_n = [names[i].decode() for i in range(n.value)]
+    out_s = [C.string_at(seqs[i], lens[i]) for i in range(n.value)]
+    _lib.rh_fasta_free(n, names, seqs, lens)
+    return out_n, out_s
+
+
+def find_signal_files(path: str):
+    files, n = C.POINTER(C.c_void_p)(), C.c_uint32(0)
+    if _lib.rh_find_sigfiles(path.encode(), C.byref(files), C.byref(n)) != 0:
+        raise _err("rh_find_sigfiles")
+    out = [C.string_at(files[i]).decode() for i in range(n.value)]
+    for i in range(n.value):
+        _lib.rh_free(files[i])
+    _lib.rh_free(C.cast(files, C.c_void_p))
+    return out
+
+
+class SignalFile:
+    """SLOW5/BLOW5 reader (stands where ri_sig_open_slow5/ri_read_sig_slow5 do, src/rsig.c:170-207,478-533)."""
+
+    def __init__(self, path: str, n_threads: int = 4):
+        self._h = _lib.rh_sigfile_open(path.encode(), n_threads)
+        if not self._h:
+            raise _err("rh_sigfile_open")
+
+    def close(self):
+        if self._h:
+            _lib.rh_sigfile_close(self._h)
+            self._h = None
+
+    def __del__(self):
+        self.close()
+
+    def next_batch(self, max_samples: int = 0, max_reads: int = 0):
+        """dict(names, raw=[int16 arrays], offset, range, digitisation, sampling_rate) or None at end of file."""
+        b = C.POINTER(SigBatchC)()
+        if _lib.rh_sigfile_next_batch(self._h, max_samples, max_reads, C.byref(b)) != 0:
+            raise _err("rh_sigfile_next_batch")
+        if not b:
+            return None
+        c = b.contents
+        n = c.n
+        out = {
+            "names": [c.names[i].decode() for i in range(n)],
+            "raw": [np.ctypeslib.as_array(c.raw[i], shape=(c.raw_len[i],)).copy() if c.raw_len[i] else np.zeros(0, np.int16) for i in range(n)],
+            "offset": np.array([c.offset[i] for i in range(n)]), "range": np.array([c.range[i] for i in range(n)]),
+            "digitisation": np.array([c.digitisation[i] for i in range(n)]),
+            "sampling_rate": np.array([c.sampling_rate[i] for i in range(n)]),
+            "contiguous": all(C.addressof(c.raw[i].contents) + 2 * c.raw_len[i] == C.addressof(c.raw[i + 1].contents) for i in range(n - 1) if c.raw_len[i] and c.raw_len[i + 1]),
+        }
+        _lib.rh_sigbatch_free(b)
+        return out
+
+    def __iter__(self):
+        while True:
+            b = self.next_batch()
+            if b is None:
+                return
+            yield b
+
+
+def write_slow5(path: str, names, raws, offset, rng, digitisation, sampling_rate: float = 4000.0, record_press: int = 1, signal_press: int = 1):
+    """Write `.slow5` (ASCII) or `.blow5` (record_press 0 none | 1 zlib, signal_press 0 none | 1 svb-zd)."""
+    n = len(raws)
+    raws = [np.ascontiguousarray(r, dtype=np.int16) for r in raws]
+    ptrs = (C.c_void_p * max(n, 1))(*[r.ctypes.data for r in raws])
+    lens = np.array([len(r) for r in raws], dtype=np.uint64)
+    off = np.ascontiguousarray(np.broadcast_to(np.asarray(offset, dtype=np.float64), (n,)))
+    rg = np.ascontiguousarray(np.broadcast_to(np.asarray(rng, dtype=np.float64), (n,)))
+    dg = np.ascontiguousarray(np.broadcast_to(np.asarray(digitisation, dtype=np.float64), (n,)))
+    nm = _cstr_array(list(names))
+    rc = _lib.rh_slow5_write(path.encode(), n, nm, ptrs, lens.ctypes.data, off.ctypes.data, rg.ctypes.data, dg.ctypes.data, float(sampling_rate), record_press, signal_press)
+    if rc != 0:
+        raise _err("rh_slow5_write")

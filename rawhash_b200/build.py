@@ -15,6 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "librawhash_b200.so")
+CLI = os.path.join(HERE, "rawhash2_b200")
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -22,9 +23,10 @@ NVCC_FLAGS = [
     "--fmad=false",            # no implicit FMA: every fused op in the kernels is an explicit __fmaf_rn/__fma_rn
     "-prec-div=true", "-prec-sqrt=true", "-ftz=false",
     "-Xcompiler", "-fPIC,-ffp-contract=off,-O2",
-    "-shared",
 ]
-SOURCES = ["rh_gpu.cu", "rh_index_gpu.cu", "rh_host.cpp"]
+COMPILE_FLAGS = NVCC_FLAGS
+LINK_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-shared"]
+SOURCES = ["rh_gpu.cu", "rh_index_gpu.cu", "rh_host.cpp", "rh_io.cpp"]
 HEADERS = sorted(f for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))) + [os.path.join(ROOT, "include", "rawhash_b200.h")]
 
 
@@ -36,19 +38,39 @@ def _newer(target, deps):
 
 
 def build_lib(force: bool = False, verbose: bool = False) -> str:
-    srcs = [os.path.join(CSRC, s) for s in SOURCES]
-    deps = srcs + [h if os.path.isabs(h) else os.path.join(CSRC, h) for h in HEADERS] + [os.path.abspath(__file__)]
-    if not force and not _newer(LIB, deps):
-        return LIB
+    """One object per source under csrc/_obj/ (rebuilt when the source or any header is newer), then one link."""
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + srcs
+    hdrs = [h if os.path.isabs(h) else os.path.join(CSRC, h) for h in HEADERS] + [os.path.abspath(__file__)]
+    obj_dir = os.path.join(CSRC, "_obj")
+    os.makedirs(obj_dir, exist_ok=True)
+    objs, relink = [], force or not os.path.isfile(LIB)
+    for s in SOURCES:
+        src, obj = os.path.join(CSRC, s), os.path.join(obj_dir, os.path.splitext(s)[0] + ".o")
+        objs.append(obj)
+        if force or _newer(obj, [src] + hdrs):
+            _run([nvcc] + COMPILE_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj], verbose)
+            relink = True
+    if relink or _newer(LIB, objs):
+        _run([nvcc] + LINK_FLAGS + ["-o", LIB] + objs + ["-lz"], verbose)
+    return LIB
+
+
+def build_cli(force: bool = False) -> str:
+    """rawhash_b200/rawhash2_b200: the `rawhash2` command line (src/main.cpp) on top of the C-ABI library."""
+    src = os.path.join(CSRC, "rh_main.cpp")
+    if force or _newer(CLI, [src, LIB, os.path.join(ROOT, "include", "rawhash_b200.h")]):
+        gxx = os.environ.get("CXX") or shutil.which("g++") or "g++"
+        _run([gxx, "-std=c++17", "-O2", "-pthread", "-Wall", "-o", CLI, src, "-L" + HERE, "-lrawhash_b200", "-Wl,-rpath,$ORIGIN"], False)
+    return CLI
+
+
+def _run(cmd, verbose):
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         sys.stderr.write(r.stdout + r.stderr)
-        raise RuntimeError("nvcc failed building librawhash_b200.so")
+        raise RuntimeError("build failed: " + " ".join(cmd[:1] + cmd[-3:]))
     if verbose:
         sys.stderr.write(r.stdout + r.stderr)
-    return LIB
 
 
 def stage_models() -> None:

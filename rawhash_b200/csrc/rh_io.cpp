@@ -1,0 +1,721 @@
+/*
+ * rh_io.cpp — the file surfaces either side of the mapping path (SURVEY.md §8b "file surfaces kept", §8f rank 3):
+ *
+ *   rh_index_dump      `.ind` writer            (ri_idx_dump,  src/rindex.c:545-648; read back by ri_idx_load 650-776)
+ *   rh_fasta_load      FASTA / FASTA.gz reader  (mm_bseq_open/mm_bseq_read, src/bseq.c:38-128)
+ *   rh_sigfile_*       SLOW5 / BLOW5 reader     (ri_sig_open_slow5 / ri_read_sig_slow5, src/rsig.c:170-207,478-533;
+ *                                                file format of slow5lib 0.2.0, extern/slow5lib/src/slow5.c)
+ *   rh_find_sigfiles   directory scan           (find_sfiles, src/rsig.c:286-330)
+ *   rh_slow5_write     SLOW5 / BLOW5 writer     (synthetic data for bench and tests)
+ *
+ * Unlike the reference's reader this one never converts to pA: a batch is the raw int16 samples of its reads laid
+ * back to back in one page-locked arena plus the calibration triples, which is what rh_gpu_map_batch_raw uploads
+ * in one copy (the conversion of rsig.c:496-503 runs on the GPU).  Records are inflated and their signals decoded
+ * by a pool of threads; the file itself is read sequentially.
+ *
+ * Host code only; nothing here is on the per-read hot path.  Citations are relative to the RawHash tree.
+ */
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <errno.h>
+#include <dirent.h>
+#include <sys/stat.h>
+#include <math.h>
+#include <zlib.h>
+#include <algorithm>
+#include <atomic>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include <cuda_runtime_api.h>
+
+#include "rh_host.h"
+
+/* ================================================================================================================
+ * `.ind` writer
+ * ================================================================================================================ */
+namespace {
+
+struct file_out {
+	FILE *f; bool ok = true;
+	explicit file_out(FILE *fp) : f(fp) {}
+	void put(const void *p, size_t bytes) { if (ok && bytes && fwrite(p, 1, bytes, f) != bytes) ok = false; }
+	template <class T> void val(T v) { put(&v, sizeof(T)); }
+};
+
+uint32_t revcomp_code(uint32_t x, int k)
+{ /* rev_complement of a 2-bit packed k-mer (src/rutils.c:71-82) */
+	uint32_t y = 0;
+	for (int i = 0; i < k; ++i) { y = (y << 2) | (3u - (x & 3u)); x >>= 2; }
+	return y;
+}
+
+const int IND_BUCKET_BITS = 14; /* ri_idx_load hard-codes b = 14 (src/rindex.c:669) */
+
+/* The reference writes a bucket's (key, value) pairs in the slot order of its khash table (src/rindex.c:622-627), so
+ * a byte-identical `.ind` needs that order: an open-addressing table of 2^m slots, slot = (key>>1) & mask with
+ * triangular probing, created with room for n keys (kh_resize, src/khash.h:232-290), filled in ascending key order
+ * (worker_post, src/rindex.c:334-352) and doubled in place — entries re-seated in slot order, displacing not yet
+ * moved ones — whenever the load reaches 0.77 (kh_put, src/khash.h:291-300).  No deletions occur. */
+struct slot_table {
+	std::vector<uint64_t> key, val; std::vector<uint8_t> used;
+	uint32_t n_slots = 0, size = 0, limit = 0;
+	static uint32_t pow2_at_least(uint32_t x) { uint32_t p = 4; while (p < x) p <<= 1; return p; }
+	uint32_t probe(const std::vector<uint8_t> &occ, uint64_t k, uint32_t mask) const
+	{
+		uint32_t i = (uint32_t)(k >> 1) & mask, step = 0;
+		while (occ[i]) i = (i + (++step)) & mask;
+		return i;
+	}
+	void reserve(uint32_t want)
+	{
+		const uint32_t nn = pow2_at_least(want);
+		if (size >= (uint32_t)(nn * 0.77 + 0.5)) return;
+		std::vector<uint8_t> occ(nn, 0);
+		key.resize(std::max<size_t>(key.size(), nn)); val.resize(key.size());
+		for (uint32_t j = 0; j < n_slots; ++j) {
+			if (!used[j]) continue;
+			uint64_t k = key[j], v = val[j];
+			used[j] = 0;
+			for (;;) {
+				const uint32_t i = probe(occ, k, nn - 1);
+				occ[i] = 1;
+				if (i < n_slots && used[i]) { std::swap(k, key[i]); std::swap(v, val[i]); used[i] = 0; }
+				else { key[i] = k; val[i] = v; break; }
+			}
+		}
+		used.swap(occ); n_slots = nn; limit = (uint32_t)(nn * 0.77 + 0.5);
+	}
+	void insert(uint64_t k, uint64_t v)
+	{
+		if (size >= limit) reserve(n_slots + 1);
+		const uint32_t i = probe(used, k, n_slots - 1);
+		key[i] = k; val[i] = v; used[i] = 1; ++size;
+	}
+};
+
+} // namespace
+
+extern "C" int rh_index_dump(const rh_index_t *idx, const char *path, const float *pore_vals, uint32_t n_pore_vals)
+{
+	if (!idx || !path) { rh_set_error("rh_index_dump: bad arguments"); return RH_ERR_ARG; }
+	for (const std::string &nm : idx->names)
+		if (nm.size() > 255) { rh_set_error("rh_index_dump: sequence name longer than 255 bytes: %s", nm.c_str()); return RH_ERR_ARG; }
+	FILE *fp = fopen(path, "wb");
+	if (!fp) { rh_set_error("cannot create %s: %s", path, strerror(errno)); return RH_ERR_IO; }
+	file_out o(fp);
+	/* header: magic, w e n q k n_seq flag, diff fine_min fine_max fine_range (src/rindex.c:547-558) */
+	o.put("RI", 2);
+	const uint32_t pars[7] = {(uint32_t)idx->w, (uint32_t)idx->e, (uint32_t)idx->n, (uint32_t)idx->q, (uint32_t)idx->k, (uint32_t)idx->names.size(), (uint32_t)idx->flag};
+	o.put(pars, sizeof(pars));
+	o.val(idx->diff); o.val(idx->fine_min); o.val(idx->fine_max); o.val(idx->fine_range);
+	/* ri_pore_t written raw (src/rutils.h:26): two pointers (meaningless in a file; zero here), n_pore_vals, k,
+	 * padding, max_val, min_val; then pore_vals[] and the value-sorted pore_inds[] (src/rutils.c:84-114) */
+	if (!pore_vals) n_pore_vals = 0;
+	{
+		unsigned char raw[32]; memset(raw, 0, sizeof(raw));
+		const int16_t k16 = (int16_t)idx->k; const float mx = -5000.0f, mn = 5000.0f; /* as main() initialises them (src/main.cpp:573-576) */
+		memcpy(raw + 16, &n_pore_vals, 4); memcpy(raw + 20, &k16, 2); memcpy(raw + 24, &mx, 4); memcpy(raw + 28, &mn, 4);
+		o.put(raw, 32);
+		o.put(pore_vals, (size_t)n_pore_vals * 4);
+		struct porei { float v; uint32_t ind, rev; };
+		std::vector<porei> pi(n_pore_vals);
+		/* create_sorted_pairs normalises the already normalised levels once more (src/rutils.c:89-110; variance as
+		 * fma(-mean, mean, E[x^2]), the contraction the reference is built with) */
+		double sum = 0, sum2 = 0;
+		for (uint32_t i = 0; i < n_pore_vals; ++i) { sum += pore_vals[i]; sum2 += pore_vals[i] * pore_vals[i]; }
+		const double mean = n_pore_vals ? sum / n_pore_vals : 0, sd = n_pore_vals ? sqrt(fma(-mean, mean, sum2 / n_pore_vals)) : 1;
+		for (uint32_t i = 0; i < n_pore_vals; ++i) pi[i] = {(float)((pore_vals[i] - mean) / sd), i, revcomp_code(i, idx->k)};
+		std::stable_sort(pi.begin(), pi.end(), [](const porei &a, const porei &b) { return a.v < b.v; });
+		o.put(pi.data(), pi.size() * sizeof(porei));
+	}
+	for (size_t i = 0; i < idx->names.size(); ++i) {
+		const uint8_t l = (uint8_t)idx->names[i].size();
+		o.val(l); o.put(idx->names[i].data(), l); o.val(idx->lens[i]);
+	}
+	/* buckets: key h lives in bucket h & (2^14-1) under the khash key (h>>14)<<1 | singleton; a singleton's value
+	 * is the position itself, otherwise offset<<32 | count into the bucket's position array (src/rindex.c:334-352) */
+	const uint32_t nb = 1u << IND_BUCKET_BITS, bmask = nb - 1;
+	const size_t nk = idx->keys.size();
+	std::vector<uint32_t> cnt(nb + 1, 0);
+	for (size_t i = 0; i < nk; ++i) ++cnt[(idx->keys[i] & bmask) + 1];
+	for (uint32_t b = 0; b < nb; ++b) cnt[b + 1] += cnt[b];
+	std::vector<uint32_t> order(nk);
+	{
+		std::vector<uint32_t> cur(cnt.begin(), cnt.end() - 1);
+		for (size_t i = 0; i < nk; ++i) order[cur[idx->keys[i] & bmask]++] = (uint32_t)i; /* keys ascending inside a bucket */
+	}
+	std::vector<uint64_t> kv;
+	slot_table tab;
+	for (uint32_t b = 0; b < nb && o.ok; ++b) {
+		uint64_t np = 0;
+		for (uint32_t j = cnt[b]; j < cnt[b + 1]; ++j) { const uint64_t c = idx->off[order[j] + 1] - idx->off[order[j]]; if (c > 1) np += c; }
+		if (np > 0x7fffffffULL) { rh_set_error("rh_index_dump: bucket %u holds %llu positions (> 2^31-1)", b, (unsigned long long)np); fclose(fp); return RH_ERR_FORMAT; }
+		o.val((int32_t)np);
+		const uint32_t n_keys = cnt[b + 1] - cnt[b];
+		tab = slot_table();
+		if (n_keys) tab.reserve(n_keys);
+		uint64_t at = 0;
+		for (uint32_t j = cnt[b]; j < cnt[b + 1]; ++j) {
+			const uint32_t ki = order[j];
+			const uint64_t c = idx->off[ki + 1] - idx->off[ki], key = (uint64_t)(idx->keys[ki] >> IND_BUCKET_BITS) << 1;
+			if (c == 1) tab.insert(key | 1, idx->pos[idx->off[ki]]);
+			else { o.put(&idx->pos[idx->off[ki]], c * 8); tab.insert(key, at << 32 | c); at += c; }
+		}
+		kv.clear();
+		for (uint32_t i = 0; i < tab.n_slots; ++i) if (tab.used[i]) { kv.push_back(tab.key[i]); kv.push_back(tab.val[i]); }
+		o.val(n_keys);
+		o.put(kv.data(), kv.size() * 8);
+	}
+	const bool ok = o.ok && fflush(fp) == 0;
+	fclose(fp);
+	if (!ok) { rh_set_error("write to %s failed", path); return RH_ERR_IO; }
+	return RH_OK;
+}
+
+/* ================================================================================================================
+ * FASTA
+ * ================================================================================================================ */
+extern "C" int rh_fasta_load(const char *path, uint32_t *n_seq, char ***names, char ***seqs, uint32_t **lens)
+{
+	if (!path || !n_seq || !names || !seqs || !lens) { rh_set_error("rh_fasta_load: bad arguments"); return RH_ERR_ARG; }
+	gzFile g = gzopen(path, "rb"); /* transparent for plain files, like the reference's gzdopen (src/bseq.c:38-50) */
+	if (!g) { rh_set_error("cannot open %s: %s", path, strerror(errno)); return RH_ERR_IO; }
+	gzbuffer(g, 1 << 20);
+	std::vector<std::string> nm, sq;
+	std::vector<char> buf(1 << 20);
+	/* kseq semantics (src/kseq.h): '>' or '@' opens a record, the name ends at the first white space, sequence lines
+	 * run until a line starting with '>', '@' or '+'; after '+' as many quality characters as bases are skipped */
+	enum { HEADER, SEQ, PLUS, QUAL } mode = SEQ;
+	bool line_start = true, name_done = false;
+	size_t qual_left = 0;
+	int n;
+	while ((n = gzread(g, buf.data(), (unsigned)buf.size())) > 0) {
+		for (int i = 0; i < n; ++i) {
+			const char c = buf[i];
+			const bool nl = c == '\n';
+			switch (mode) {
+			case HEADER:
+				if (nl) mode = SEQ;
+				else if (!name_done) { if (c == ' ' || c == '\t' || c == '\r') name_done = true; else nm.back().push_back(c); }
+				break;
+			case SEQ:
+				if (line_start && (c == '>' || c == '@')) { nm.emplace_back(); sq.emplace_back(); mode = HEADER; name_done = false; }
+				else if (line_start && c == '+' && !sq.empty()) mode = PLUS;
+				else if (!nl && c != '\r' && c != ' ' && c != '\t' && !sq.empty()) sq.back().push_back(c);
+				break;
+			case PLUS:
+				if (nl) { qual_left = sq.back().size(); mode = qual_left ? QUAL : SEQ; }
+				break;
+			case QUAL:
+				if (!nl && c != '\r' && --qual_left == 0) mode = SEQ;
+				break;
+			}
+			line_start = nl;
+		}
+	}
+	const bool bad = n < 0;
+	gzclose(g);
+	if (bad) { rh_set_error("%s: read error", path); return RH_ERR_IO; }
+	for (const std::string &s : sq) if (s.size() > 0xffffffffULL) { rh_set_error("%s: sequence longer than 2^32-1", path); return RH_ERR_FORMAT; }
+	const uint32_t N = (uint32_t)nm.size();
+	*names = (char **)malloc(sizeof(char *) * std::max(1u, N)); *seqs = (char **)malloc(sizeof(char *) * std::max(1u, N));
+	*lens = (uint32_t *)malloc(sizeof(uint32_t) * std::max(1u, N));
+	for (uint32_t i = 0; i < N; ++i) {
+		(*names)[i] = strdup(nm[i].c_str());
+		(*seqs)[i] = (char *)malloc(sq[i].size() + 1); memcpy((*seqs)[i], sq[i].c_str(), sq[i].size() + 1);
+		(*lens)[i] = (uint32_t)sq[i].size();
+		std::string().swap(sq[i]);
+	}
+	*n_seq = N;
+	return RH_OK;
+}
+
+extern "C" void rh_fasta_free(uint32_t n_seq, char **names, char **seqs, uint32_t *lens)
+{
+	for (uint32_t i = 0; i < n_seq; ++i) { if (names) free(names[i]); if (seqs) free(seqs[i]); }
+	free(names); free(seqs); free(lens);
+}
+
+/* ================================================================================================================
+ * SLOW5 / BLOW5
+ * ================================================================================================================ */
+namespace {
+
+const char BLOW5_MAGIC[6] = {'B', 'L', 'O', 'W', '5', '\1'};  /* extern/slow5lib/include/slow5/slow5_defs.h:132 */
+const char BLOW5_EOF[5] = {'5', 'W', 'O', 'L', 'B'};           /* :133 */
+const long BLOW5_HDR_SIZE_AT = 64;                              /* :134 */
+enum { PRESS_NONE = 0, PRESS_ZLIB = 1, PRESS_ZSTD = 2, SIG_NONE = 0, SIG_SVB_ZD = 1 }; /* slow5_press.c:51-145 */
+
+/* ---- streamvbyte + zig-zag delta (extern/slow5lib/thirdparty/streamvbyte; slow5_press.c:1054-1135) ------------- */
+/* layout: u32 count | ceil(count/4) control bytes (2 bits per value: 1..4 data bytes) | little-endian data bytes */
+bool svbzd_decode(const uint8_t *in, size_t in_bytes, int16_t *out, uint32_t expect)
+{
+	if (in_bytes < 4) return false;
+	uint32_t count; memcpy(&count, in, 4);
+	if (count != expect) return false;
+	const size_t nctl = ((size_t)count + 3) / 4;
+	if (in_bytes < 4 + nctl) return false;
+	const uint8_t *ctl = in + 4, *dat = ctl + nctl, *end = in + in_bytes;
+	int32_t prev = 0;
+	for (uint32_t i = 0; i < count; ++i) {
+		const unsigned code = (ctl[i >> 2] >> ((i & 3) * 2)) & 3u;
+		if (dat + code + 1 > end) return false;
+		uint32_t v = 0;
+		memcpy(&v, dat, code + 1);
+		dat += code + 1;
+		const int32_t d = (int32_t)(v >> 1) ^ -(int32_t)(v & 1);
+		prev += d;
+		out[i] = (int16_t)prev;
+	}
+	return dat == end;
+}
+
+uint32_t svbzd_count(const uint8_t *in, size_t in_bytes) { uint32_t c = 0; if (in_bytes >= 4) memcpy(&c, in, 4); return c; }
+
+void svbzd_encode(const int16_t *in, uint32_t count, std::vector<uint8_t> &out)
+{
+	const size_t nctl = ((size_t)count + 3) / 4;
+	out.assign(4 + nctl, 0);
+	memcpy(out.data(), &count, 4);
+	int32_t prev = 0;
+	for (uint32_t i = 0; i < count; ++i) {
+		const int32_t d = (int32_t)in[i] - prev; prev = in[i];
+		const uint32_t v = ((uint32_t)d << 1) ^ (uint32_t)(d >> 31);
+		const unsigned code = v < (1u << 8) ? 0 : v < (1u << 16) ? 1 : v < (1u << 24) ? 2 : 3;
+		out[4 + (i >> 2)] |= (uint8_t)(code << ((i & 3) * 2));
+		for (unsigned b = 0; b <= code; ++b) out.push_back((uint8_t)(v >> (8 * b)));
+	}
+}
+
+bool zlib_inflate(const uint8_t *in, size_t in_bytes, std::vector<uint8_t> &out)
+{ /* one zlib stream per record (ptr_depress_zlib_solo, slow5_press.c:945-982) */
+	z_stream s; memset(&s, 0, sizeof(s));
+	if (inflateInit2(&s, MAX_WBITS) != Z_OK) return false;
+	out.resize(std::max<size_t>(in_bytes * 4, 1 << 12));
+	s.next_in = (Bytef *)in; s.avail_in = (uInt)in_bytes;
+	size_t done = 0; int rc;
+	do {
+		if (done == out.size()) out.resize(out.size() * 2);
+		s.next_out = out.data() + done; s.avail_out = (uInt)std::min<size_t>(out.size() - done, 1u << 30);
+		const size_t before = s.avail_out;
+		rc = inflate(&s, Z_NO_FLUSH);
+		done += before - s.avail_out;
+	} while (rc == Z_OK || (rc == Z_BUF_ERROR && s.avail_in > 0 && done == out.size()));
+	inflateEnd(&s);
+	out.resize(done);
+	return rc == Z_STREAM_END;
+}
+
+bool zlib_deflate(const uint8_t *in, size_t in_bytes, std::vector<uint8_t> &out)
+{
+	uLongf cap = compressBound((uLong)in_bytes);
+	out.resize(cap);
+	if (compress2(out.data(), &cap, in, (uLong)in_bytes, Z_DEFAULT_COMPRESSION) != Z_OK) return false;
+	out.resize(cap);
+	return true;
+}
+
+/* ---- one record between the file and the arena ------------------------------------------------------------------ */
+struct rec_t {
+	std::vector<uint8_t> mem;       /* the record as stored (binary: after record decompression; ASCII: the line) */
+	std::string name;
+	double digitisation = 0, offset = 0, range = 0, sampling_rate = 0;
+	uint64_t n_samples = 0;         /* decoded sample count */
+	size_t sig_at = 0, sig_bytes = 0; /* where the signal payload sits inside mem */
+	bool ok = false;
+};
+
+bool parse_binary_record(rec_t &r, int rec_method, int sig_method)
+{ /* slow5_rec_parse, binary branch (slow5.c:2806-2925): u16 id_len, id, u32 read_group, 4 doubles, u64 length, signal */
+	if (rec_method == PRESS_ZLIB) {
+		std::vector<uint8_t> plain;
+		if (!zlib_inflate(r.mem.data(), r.mem.size(), plain)) return false;
+		r.mem.swap(plain);
+	}
+	const uint8_t *p = r.mem.data(); const size_t n = r.mem.size(); size_t at = 0;
+	uint16_t idl;
+	if (n < 2) return false;
+	memcpy(&idl, p, 2); at = 2;
+	if (at + idl + 4 + 32 + 8 > n) return false;
+	r.name.assign((const char *)p + at, idl); at += idl;
+	at += 4; /* read_group */
+	memcpy(&r.digitisation, p + at, 8); at += 8;
+	memcpy(&r.offset, p + at, 8); at += 8;
+	memcpy(&r.range, p + at, 8); at += 8;
+	memcpy(&r.sampling_rate, p + at, 8); at += 8;
+	uint64_t len; memcpy(&len, p + at, 8); at += 8;
+	r.sig_at = at;
+	if (sig_method == SIG_NONE) { r.sig_bytes = len * 2; r.n_samples = len; }
+	else { r.sig_bytes = len; r.n_samples = svbzd_count(p + at, std::min<size_t>(len, n - at)); } /* length field = compressed bytes */
+	return r.sig_at + r.sig_bytes <= n; /* auxiliary fields after the signal are not needed */
+}
+
+bool parse_ascii_record(rec_t &r)
+{ /* slow5_rec_parse, ASCII branch (slow5.c:2648-2770): read_id read_group digitisation offset range sampling_rate len signal[,..] */
+	char *s = (char *)r.mem.data(); /* NUL-terminated by the reader */
+	char *f[8]; int nf = 0;
+	f[nf++] = s;
+	for (char *c = s; *c && nf < 8; ++c) if (*c == '\t') { *c = 0; f[nf++] = c + 1; }
+	if (nf < 8) return false;
+	r.name = f[0];
+	char *e;
+	r.digitisation = strtod(f[2], &e); if (e == f[2]) return false;
+	r.offset = strtod(f[3], &e); if (e == f[3]) return false;
+	r.range = strtod(f[4], &e); if (e == f[4]) return false;
+	r.sampling_rate = strtod(f[5], &e); if (e == f[5]) return false;
+	r.n_samples = strtoull(f[6], &e, 10); if (e == f[6]) return false;
+	r.sig_at = (size_t)(f[7] - s);
+	char *t = strchr(f[7], '\t'); /* auxiliary columns follow */
+	r.sig_bytes = t ? (size_t)(t - f[7]) : strlen(f[7]);
+	return true;
+}
+
+bool decode_signal(const rec_t &r, bool binary, int sig_method, int16_t *out)
+{
+	const uint8_t *p = r.mem.data() + r.sig_at;
+	if (binary) {
+		if (sig_method == SIG_NONE) { memcpy(out, p, r.sig_bytes); return true; }
+		return svbzd_decode(p, r.sig_bytes, out, (uint32_t)r.n_samples);
+	}
+	const char *c = (const char *)p, *end = c + r.sig_bytes;
+	uint64_t i = 0;
+	while (c < end && i < r.n_samples) {
+		bool neg = false; int v = 0;
+		if (*c == '-') { neg = true; ++c; }
+		if (c >= end || *c < '0' || *c > '9') return false;
+		while (c < end && *c >= '0' && *c <= '9') { v = v * 10 + (*c - '0'); if (v > 40000) return false; ++c; }
+		v = neg ? -v : v;
+		if (v < -32768 || v > 32767) return false;
+		out[i++] = (int16_t)v;
+		if (c < end) { if (*c != ',') return false; ++c; }
+	}
+	return i == r.n_samples && c >= end;
+}
+
+template <class F> void parallel_for(size_t n, int n_threads, F fn)
+{
+	if (n_threads <= 1 || n < 2) { for (size_t i = 0; i < n; ++i) fn(i); return; }
+	std::atomic<size_t> next(0);
+	auto work = [&]() { for (size_t i; (i = next.fetch_add(16)) < n;) for (size_t j = i; j < std::min(n, i + 16); ++j) fn(j); };
+	std::vector<std::thread> th;
+	const int nt = (int)std::min<size_t>((size_t)n_threads, (n + 15) / 16);
+	for (int t = 1; t < nt; ++t) th.emplace_back(work);
+	work();
+	for (auto &t : th) t.join();
+}
+
+struct arena_t { int16_t *p = nullptr; size_t cap = 0; bool pinned = false; };
+
+arena_t arena_alloc(size_t samples)
+{
+	arena_t a; a.cap = std::max<size_t>(samples, 1);
+	static std::atomic<int> pin_state(-1); /* -1 unknown, 0 no usable device, 1 page-lock */
+	const char *env = getenv("RH_PIN");
+	if (pin_state.load() != 0 && !(env && env[0] == '0')) {
+		void *p = nullptr;
+		if (cudaHostAlloc(&p, a.cap * 2, cudaHostAllocPortable) == cudaSuccess) { a.p = (int16_t *)p; a.pinned = true; pin_state = 1; return a; }
+		(void)cudaGetLastError();
+		pin_state = 0;
+	}
+	a.p = (int16_t *)malloc(a.cap * 2);
+	return a;
+}
+
+void arena_free(arena_t &a) { if (a.p) { if (a.pinned) cudaFreeHost(a.p); else free(a.p); } a = arena_t(); }
+
+} // namespace
+
+struct rh_sigfile_s {
+	FILE *fp = nullptr; std::string path;
+	bool binary = false; int rec_method = PRESS_NONE, sig_method = SIG_NONE;
+	int n_threads = 1; bool eof = false;
+	std::mutex mu; std::vector<arena_t> pool; /* arenas handed back by freed batches */
+	std::atomic<int> live_batches{0}; bool closed = false;
+	char *line = nullptr; size_t line_cap = 0;
+	std::vector<rec_t> pending; size_t pending_at = 0; /* parsed records not yet handed out */
+};
+
+namespace {
+struct batch_impl {
+	rh_sigbatch_t pub;
+	rh_sigfile_s *owner = nullptr;
+	arena_t arena;
+	std::vector<const int16_t *> raw; std::vector<uint64_t> len;
+	std::vector<double> offset, range, digitisation, sampling_rate;
+	std::vector<std::string> name_store; std::vector<const char *> names;
+};
+
+void sigfile_destroy(rh_sigfile_s *f)
+{
+	for (arena_t &a : f->pool) arena_free(a);
+	if (f->fp) fclose(f->fp);
+	free(f->line);
+	delete f;
+}
+
+bool has_suffix(const std::string &s, const char *suf) { const size_t n = strlen(suf); return s.size() >= n && s.compare(s.size() - n, n, suf) == 0; }
+} // namespace
+
+extern "C" rh_sigfile_t *rh_sigfile_open(const char *path, int n_threads)
+{ /* slow5_open + slow5_hdr_init (slow5.c:636-900): the format follows the extension */
+	if (!path) { rh_set_error("rh_sigfile_open: no path"); return NULL; }
+	const std::string p(path);
+	const bool bin = has_suffix(p, ".blow5");
+	if (!bin && !has_suffix(p, ".slow5")) { rh_set_error("%s: only .slow5 and .blow5 signal files are supported (FAST5/POD5 need HDF5/Arrow)", path); return NULL; }
+	FILE *fp = fopen(path, "rb");
+	if (!fp) { rh_set_error("cannot open %s: %s", path, strerror(errno)); return NULL; }
+	rh_sigfile_s *f = new rh_sigfile_s();
+	f->fp = fp; f->path = p; f->binary = bin; f->n_threads = std::max(1, n_threads);
+	setvbuf(fp, NULL, _IOFBF, 4 << 20);
+	bool ok = true;
+	if (bin) {
+		unsigned char h[BLOW5_HDR_SIZE_AT + 4];
+		ok = fread(h, 1, sizeof(h), fp) == sizeof(h) && memcmp(h, BLOW5_MAGIC, 6) == 0;
+		if (!ok) rh_set_error("%s: not a BLOW5 file (bad magic number)", path);
+		else {
+			const unsigned major = h[6], minor = h[7];
+			f->rec_method = h[9];
+			f->sig_method = (major > 0 || minor >= 2) ? h[14] : SIG_NONE; /* signal compression byte exists from 0.2.0 (slow5.c:824) */
+			if (major > 0 || minor > 2) { rh_set_error("%s: BLOW5 version %u.%u.%u is newer than 0.2.0", path, major, minor, (unsigned)h[8]); ok = false; }
+			else if (f->rec_method == PRESS_ZSTD) { rh_set_error("%s: zstd record compression is not available in this build (zlib and none are)", path); ok = false; }
+			else if (f->rec_method > PRESS_ZSTD || f->sig_method > SIG_SVB_ZD) { rh_set_error("%s: unknown compression method (record %d, signal %d)", path, f->rec_method, f->sig_method); ok = false; }
+			uint32_t hdr_bytes; memcpy(&hdr_bytes, h + BLOW5_HDR_SIZE_AT, 4);
+			if (ok) { /* the ASCII header block must end with the column-name line */
+				std::vector<char> hb((size_t)hdr_bytes + 1, 0);
+				ok = fread(hb.data(), 1, hdr_bytes, fp) == hdr_bytes && strstr(hb.data(), "#read_id\t") != NULL;
+				if (!ok) rh_set_error("%s: malformed BLOW5 header", path);
+			}
+		}
+	} else {
+		bool seen_cols = false;
+		for (;;) {
+			const int c = fgetc(fp);
+			if (c == EOF) break;
+			if (c != '#' && c != '@') { ungetc(c, fp); break; }
+			ungetc(c, fp);
+			if (getline(&f->line, &f->line_cap, fp) < 0) break;
+			if (strncmp(f->line, "#read_id\t", 9) == 0) { seen_cols = true; break; }
+		}
+		ok = seen_cols;
+		if (!ok) rh_set_error("%s: malformed SLOW5 header (no #read_id column line)", path);
+	}
+	if (!ok) { sigfile_destroy(f); return NULL; }
+	return f;
+}
+
+extern "C" void rh_sigfile_close(rh_sigfile_t *f)
+{
+	if (!f) return;
+	bool destroy;
+	{ std::lock_guard<std::mutex> g(f->mu); f->closed = true; destroy = f->live_batches.load() == 0; }
+	if (destroy) sigfile_destroy(f); /* otherwise the last rh_sigbatch_free does it */
+}
+
+/* next stored record -> r.mem; returns 1 record, 0 end of file, <0 error */
+static int read_stored_record(rh_sigfile_s *f, rec_t &r)
+{
+	if (f->binary) { /* slow5_get_next_mem (slow5.c:3191-3270): u64 size, then the bytes; "5WOLB" closes the file */
+		uint64_t sz; unsigned char b[8];
+		const size_t got = fread(b, 1, 8, f->fp);
+		if (got != 8) {
+			if (got == 5 && memcmp(b, BLOW5_EOF, 5) == 0) return 0;
+			rh_set_error("%s: truncated BLOW5 (no end-of-file marker)", f->path.c_str());
+			return RH_ERR_FORMAT;
+		}
+		memcpy(&sz, b, 8);
+		if (sz > ((uint64_t)1 << 33)) { rh_set_error("%s: implausible record size %llu", f->path.c_str(), (unsigned long long)sz); return RH_ERR_FORMAT; }
+		r.mem.resize(sz);
+		if (sz && fread(r.mem.data(), 1, sz, f->fp) != sz) { rh_set_error("%s: truncated BLOW5 record", f->path.c_str()); return RH_ERR_FORMAT; }
+		return 1;
+	}
+	const ssize_t n = getline(&f->line, &f->line_cap, f->fp);
+	if (n < 0) return 0;
+	size_t l = (size_t)n;
+	while (l && (f->line[l - 1] == '\n' || f->line[l - 1] == '\r')) --l;
+	r.mem.assign((const uint8_t *)f->line, (const uint8_t *)f->line + l);
+	r.mem.push_back(0);
+	return 1;
+}
+
+extern "C" int rh_sigfile_next_batch(rh_sigfile_t *f, uint64_t max_samples, uint32_t max_reads, rh_sigbatch_t **out)
+{
+	if (!f || !out) { rh_set_error("rh_sigfile_next_batch: bad arguments"); return RH_ERR_ARG; }
+	*out = NULL;
+	if (max_samples == 0) max_samples = 500000000ULL; /* mini_batch_size default (src/roptions.c:88) */
+	std::vector<rec_t> recs;
+	uint64_t total = 0;
+	const size_t group = 4096; /* the reference pulls 4096 records at a time (src/rsig.c:186) */
+	/* ri_sig_read_frag (src/rmap.cpp:600-660): reads are appended until the running sample count reaches the limit */
+	while (total < max_samples && (max_reads == 0 || recs.size() < max_reads)) {
+		if (f->pending_at == f->pending.size()) {
+			f->pending.clear(); f->pending_at = 0;
+			if (f->eof) break;
+			for (size_t i = 0; i < group; ++i) {
+				rec_t r;
+				const int rc = read_stored_record(f, r);
+				if (rc < 0) return rc;
+				if (rc == 0) { f->eof = true; break; }
+				if (!f->binary && r.mem.size() <= 1) continue; /* blank line */
+				f->pending.emplace_back(std::move(r));
+			}
+			const bool binary = f->binary; const int rm = f->rec_method, sm = f->sig_method;
+			std::vector<rec_t> &P = f->pending;
+			parallel_for(P.size(), f->n_threads, [&](size_t i) { P[i].ok = binary ? parse_binary_record(P[i], rm, sm) : parse_ascii_record(P[i]); });
+			for (size_t i = 0; i < P.size(); ++i)
+				if (!P[i].ok) { rh_set_error("%s: a record cannot be parsed (record %zu of the current group)", f->path.c_str(), i); return RH_ERR_FORMAT; }
+			if (P.empty()) break;
+		}
+		total += f->pending[f->pending_at].n_samples;
+		recs.emplace_back(std::move(f->pending[f->pending_at++]));
+	}
+	if (recs.empty()) return RH_OK;
+	batch_impl *b = new batch_impl();
+	b->owner = f;
+	{
+		std::lock_guard<std::mutex> g(f->mu);
+		for (size_t i = 0; i < f->pool.size(); ++i)
+			if (f->pool[i].cap >= total) { b->arena = f->pool[i]; f->pool.erase(f->pool.begin() + i); break; }
+		if (!b->arena.p && !f->pool.empty()) { arena_free(f->pool.back()); f->pool.pop_back(); } /* too small: replace */
+		++f->live_batches;
+	}
+	if (!b->arena.p) b->arena = arena_alloc(total + total / 8);
+	if (!b->arena.p) { rh_set_error("out of host memory for a %llu-sample batch", (unsigned long long)total); --f->live_batches; delete b; return RH_ERR_NOMEM; }
+	const size_t n = recs.size();
+	b->raw.resize(n); b->len.resize(n); b->offset.resize(n); b->range.resize(n); b->digitisation.resize(n); b->sampling_rate.resize(n);
+	b->name_store.resize(n); b->names.resize(n);
+	uint64_t at = 0;
+	for (size_t i = 0; i < n; ++i) {
+		b->raw[i] = b->arena.p + at; b->len[i] = recs[i].n_samples; at += recs[i].n_samples;
+		b->offset[i] = recs[i].offset; b->range[i] = recs[i].range; b->digitisation[i] = recs[i].digitisation; b->sampling_rate[i] = recs[i].sampling_rate;
+		b->name_store[i].swap(recs[i].name);
+	}
+	for (size_t i = 0; i < n; ++i) b->names[i] = b->name_store[i].c_str();
+	std::atomic<bool> bad(false);
+	{
+		const bool binary = f->binary; const int sm = f->sig_method;
+		parallel_for(n, f->n_threads, [&](size_t i) {
+			if (!decode_signal(recs[i], binary, sm, const_cast<int16_t *>(b->raw[i]))) bad = true;
+			std::vector<uint8_t>().swap(recs[i].mem);
+		});
+	}
+	b->pub.n = (uint32_t)n; b->pub.n_samples = total;
+	b->pub.raw = b->raw.data(); b->pub.raw_len = b->len.data();
+	b->pub.offset = b->offset.data(); b->pub.range = b->range.data(); b->pub.digitisation = b->digitisation.data(); b->pub.sampling_rate = b->sampling_rate.data();
+	b->pub.names = b->names.data(); b->pub.priv = b;
+	if (bad) { rh_set_error("%s: a raw signal cannot be decoded", f->path.c_str()); rh_sigbatch_free(&b->pub); return RH_ERR_FORMAT; }
+	*out = &b->pub;
+	return RH_OK;
+}
+
+extern "C" void rh_sigbatch_free(rh_sigbatch_t *pub)
+{
+	if (!pub) return;
+	batch_impl *b = (batch_impl *)pub->priv;
+	rh_sigfile_s *f = b->owner;
+	bool destroy = false;
+	{
+		std::lock_guard<std::mutex> g(f->mu);
+		if (!f->closed && f->pool.size() < 3) f->pool.push_back(b->arena); else arena_free(b->arena);
+		destroy = --f->live_batches == 0 && f->closed;
+	}
+	delete b;
+	if (destroy) sigfile_destroy(f);
+}
+
+/* ---- directory scan -------------------------------------------------------------------------------------------- */
+static bool is_sigfile_name(const char *s) { return strstr(s, ".slow5") || strstr(s, ".blow5"); }
+static bool is_directory(const std::string &p) { struct stat st; return stat(p.c_str(), &st) == 0 && S_ISDIR(st.st_mode); }
+static void scan_sigfiles(const std::string &p, std::vector<std::string> &out)
+{
+	if (!is_directory(p)) { if (is_sigfile_name(p.c_str())) out.push_back(p); return; }
+	DIR *d = opendir(p.c_str());
+	if (!d) return;
+	std::vector<std::string> here;
+	for (struct dirent *e; (e = readdir(d)) != NULL;) {
+		if (!strcmp(e->d_name, ".") || !strcmp(e->d_name, "..")) continue;
+		here.push_back(p + "/" + e->d_name);
+	}
+	closedir(d);
+	std::sort(here.begin(), here.end()); /* readdir order is file-system dependent; sorted = reproducible output order */
+	for (const std::string &c : here) { if (is_directory(c)) scan_sigfiles(c, out); else if (is_sigfile_name(c.c_str())) out.push_back(c); }
+}
+
+extern "C" int rh_find_sigfiles(const char *path, char ***files, uint32_t *n_files)
+{
+	if (!path || !files || !n_files) { rh_set_error("rh_find_sigfiles: bad arguments"); return RH_ERR_ARG; }
+	std::vector<std::string> v;
+	scan_sigfiles(path, v);
+	*files = (char **)malloc(sizeof(char *) * std::max<size_t>(1, v.size()));
+	for (size_t i = 0; i < v.size(); ++i) (*files)[i] = strdup(v[i].c_str());
+	*n_files = (uint32_t)v.size();
+	return RH_OK;
+}
+
+/* ---- writer ------------------------------------------------------------------------------------------------------ */
+extern "C" int rh_slow5_write(const char *path, uint32_t n, const char *const *names,
+                              const int16_t *const *raw, const uint64_t *raw_len,
+                              const double *offset, const double *range, const double *digitisation, double sampling_rate,
+                              int record_press, int signal_press)
+{ /* slow5_hdr_to_mem + slow5_rec_to_mem (slow5.c:940-1150, 3900-4050) */
+	if (!path || (n && (!names || !raw || !raw_len || !offset || !range || !digitisation))) { rh_set_error("rh_slow5_write: bad arguments"); return RH_ERR_ARG; }
+	const std::string p(path);
+	const bool bin = has_suffix(p, ".blow5");
+	if (!bin && !has_suffix(p, ".slow5")) { rh_set_error("rh_slow5_write: %s must end in .slow5 or .blow5", path); return RH_ERR_ARG; }
+	if (record_press < 0 || record_press > PRESS_ZLIB || signal_press < 0 || signal_press > SIG_SVB_ZD) { rh_set_error("rh_slow5_write: unsupported compression"); return RH_ERR_ARG; }
+	FILE *fp = fopen(path, "wb");
+	if (!fp) { rh_set_error("cannot create %s: %s", path, strerror(errno)); return RH_ERR_IO; }
+	file_out o(fp);
+	char num[64];
+	snprintf(num, sizeof(num), "%.0f", sampling_rate);
+	const std::string attrs = std::string("@asic_id\t0\n@exp_start_time\t0\n@flow_cell_id\tsynthetic\n@run_id\trawhash_b200\n@sample_frequency\t") + num + "\n";
+	const std::string cols = "#char*\tuint32_t\tdouble\tdouble\tdouble\tdouble\tuint64_t\tint16_t*\n"
+	                         "#read_id\tread_group\tdigitisation\toffset\trange\tsampling_rate\tlen_raw_signal\traw_signal\n";
+	if (bin) {
+		unsigned char h[BLOW5_HDR_SIZE_AT]; memset(h, 0, sizeof(h));
+		memcpy(h, BLOW5_MAGIC, 6); h[6] = 0; h[7] = 2; h[8] = 0; h[9] = (unsigned char)record_press;
+		const uint32_t groups = 1; memcpy(h + 10, &groups, 4); h[14] = (unsigned char)signal_press;
+		o.put(h, sizeof(h));
+		const std::string body = attrs + cols;
+		o.val((uint32_t)body.size()); o.put(body.data(), body.size());
+	} else {
+		const std::string top = "#slow5_version\t0.2.0\n#num_read_groups\t1\n";
+		o.put(top.data(), top.size()); o.put(attrs.data(), attrs.size()); o.put(cols.data(), cols.size());
+	}
+	std::vector<uint8_t> rec, sig, packed;
+	std::string line;
+	for (uint32_t i = 0; i < n && o.ok; ++i) {
+		if (bin) {
+			const size_t idl = strlen(names[i]);
+			if (idl > 0xffff) { fclose(fp); rh_set_error("rh_slow5_write: read id too long"); return RH_ERR_ARG; }
+			rec.clear();
+			auto push = [&](const void *q, size_t b) { const uint8_t *c = (const uint8_t *)q; rec.insert(rec.end(), c, c + b); };
+			const uint16_t l16 = (uint16_t)idl; const uint32_t rg = 0;
+			push(&l16, 2); push(names[i], idl); push(&rg, 4);
+			push(&digitisation[i], 8); push(&offset[i], 8); push(&range[i], 8); push(&sampling_rate, 8);
+			if (signal_press == SIG_SVB_ZD) {
+				svbzd_encode(raw[i], (uint32_t)raw_len[i], sig);
+				const uint64_t sb = sig.size(); push(&sb, 8); push(sig.data(), sig.size());
+			} else { const uint64_t sl = raw_len[i]; push(&sl, 8); push(raw[i], raw_len[i] * 2); }
+			const std::vector<uint8_t> *body = &rec;
+			if (record_press == PRESS_ZLIB) { if (!zlib_deflate(rec.data(), rec.size(), packed)) { o.ok = false; break; } body = &packed; }
+			o.val((uint64_t)body->size()); o.put(body->data(), body->size());
+		} else {
+			line.clear();
+			char head[512];
+			snprintf(head, sizeof(head), "%s\t0\t%.17g\t%.17g\t%.17g\t%.17g\t%llu\t", names[i], digitisation[i], offset[i], range[i], sampling_rate, (unsigned long long)raw_len[i]);
+			line = head;
+			for (uint64_t j = 0; j < raw_len[i]; ++j) { snprintf(num, sizeof(num), j ? ",%d" : "%d", (int)raw[i][j]); line += num; }
+			line += '\n';
+			o.put(line.data(), line.size());
+		}
+	}
+	if (bin) o.put(BLOW5_EOF, 5);
+	const bool ok = o.ok && fflush(fp) == 0;
+	fclose(fp);
+	if (!ok) { rh_set_error("write to %s failed", path); return RH_ERR_IO; }
+	return RH_OK;
+}
