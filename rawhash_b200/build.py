@@ -97,5 +97,6 @@ def build_oracle() -> None:
 
 if __name__ == "__main__":
     build_lib(force="--force" in sys.argv, verbose="-v" in sys.argv)
+    build_cli(force="--force" in sys.argv)
     stage_models()
     print(LIB)

@@ -1,0 +1,148 @@
+"""CPU: the `rawhash2_b200` command line (csrc/rh_main.cpp) next to the unmodified reference binary
+(oracle/_ref/rawhash2 = src/main.cpp + slow5lib, built by oracle/Makefile): option handling, `-d` index files,
+and the end-to-end file path that pins the GPU CLI test (tests/test_zz_cli_gpu.py): the reference binary, fed the
+FASTA / BLOW5 / `.ind` files OUR writers produce, prints the committed golden PAF."""
+import os
+import shutil
+import subprocess
+
+import numpy as np
+import pytest
+
+import _bind
+from common import World
+from golden_util import CASES, GoldenCase
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CLI = os.path.join(ROOT, "rawhash_b200", "rawhash2_b200")
+REF_CLI = os.path.join(ROOT, "oracle", "_ref", "rawhash2")
+needs_ref_cli = pytest.mark.skipif(not os.path.isfile(REF_CLI), reason="oracle/_ref/rawhash2 not built")
+
+
+def run(cmd, **kw):
+    return subprocess.run(cmd, capture_output=True, text=True, timeout=600, **kw)
+
+
+def have_gpu():
+    return shutil.which("nvidia-smi") is not None and subprocess.run(["nvidia-smi", "-L"], capture_output=True).returncode == 0
+
+
+def golden_cli_options(g):
+    opts = ["-x", g.preset] + (["--r10"] if g.r10 else [])
+    if g.non_default_sampling():
+        opts += ["--sample-rate", str(g.sample_rate), "--bp-per-sec", str(g.bp_per_sec)]
+    return opts
+
+
+def test_cli_is_built_and_reports_usage(built):
+    assert os.path.isfile(CLI), "rawhash_b200/rawhash2_b200 missing: python -m rawhash_b200.build"
+    r = run([CLI])
+    assert r.returncode == 1 and "Usage: rawhash2_b200" in r.stderr
+    r = run([CLI, "-h"])
+    assert r.returncode == 0 and "--max-chunks" in r.stdout and "[10]" in r.stdout
+    assert run([CLI, "--version"]).stdout.startswith("2.1")
+    r = run([CLI, "-x", "viral", "-h"])  # the preset is applied before the help text prints its defaults
+    assert "--max-chunks INT [5]" in r.stdout
+
+
+@pytest.mark.parametrize("args,msg", [
+    (["-x", "nope", "t.fa"], "unknown preset 'nope'"),
+    (["--no-such-option", "t.fa"], "unknown option"),
+    (["-t"], "missing option argument"),
+    (["--rmq", "t.fa"], "outside the mapping path"),
+    (["--dtw-evaluate-chains", "t.fa"], "outside the mapping path"),
+    (["--sequence-until", "t.fa"], "outside the mapping path"),
+    (["-t", "1", "--io-thread", "2", "t.fa"], "must NOT be smaller"),
+    (["-w", "3", "-n", "2", "t.fa"], "cannot be set together"),
+    (["/no/such/file.fa", "q.blow5"], "failed to open file"),
+])
+def test_cli_option_errors(built, args, msg):
+    r = run([CLI] + args)
+    assert r.returncode == 1 and msg in r.stderr, r.stderr
+
+
+def test_cli_missing_inputs(built, tmp_path):
+    w = World(n_contigs=1, genome_len=20_000, n_reads=1, read_bp=500, seed=3)
+    r = run([CLI, w.fasta])
+    assert r.returncode == 1 and "missing input: please specify a query" in r.stderr
+    r = run([CLI, "-d", str(tmp_path / "x.ind"), w.fasta])
+    assert r.returncode == 1 and "pore model file with -p" in r.stderr
+
+
+@needs_ref_cli
+@pytest.mark.parametrize("opts", [["-x", "sensitive"], ["-x", "faster"], ["-x", "fast", "-e", "7", "--sig-diff", "0.3", "--fine-range", "0.5"]])
+def test_cli_index_dump_equals_reference_binary(built, tmp_path, opts):
+    """`rawhash2_b200 -d` (host builder here, GPU builder on a GPU box) vs `rawhash2 -d`: same bytes but the two
+    stale pointers; options given AFTER the positional argument are honoured like ketopt's permutation does."""
+    w = World(n_contigs=3, genome_len=240_000, n_reads=1, read_bp=500, seed=17)
+    mine, theirs = str(tmp_path / "mine.ind"), str(tmp_path / "ref.ind")
+    r = run([REF_CLI] + opts + ["-t", "4", "-p", w.model, "-d", theirs, w.fasta])
+    assert r.returncode == 0, r.stderr
+    r = run([CLI] + opts + ["-t", "4", "-p", w.model, w.fasta, "-d", mine])
+    assert r.returncode == 0 and "Only the index is constructed" in r.stderr, r.stderr
+    a, b = np.fromfile(mine, np.uint8), np.fromfile(theirs, np.uint8)
+    assert a.size == b.size
+    d = np.nonzero(a != b)[0]
+    assert d.size <= 16 and (d.size == 0 or (d.min() >= 46 and d.max() < 62))
+
+
+@needs_ref_cli
+@pytest.mark.parametrize("case", CASES)
+def test_reference_binary_on_our_files_prints_the_golden_paf(built, tmp_path, case):
+    """The chain of custody for the GPU CLI test: golden reads written by rh_slow5_write, the index written by
+    rh_index_dump, both consumed by the UNMODIFIED reference binary -> the committed golden PAF."""
+    from rawhash_b200 import api
+    g = GoldenCase(case, str(tmp_path))
+    reads = str(tmp_path / "reads.blow5")
+    api.write_slow5(reads, g.names, g.raws, *g.cal, float(g.sample_rate))
+    opts = golden_cli_options(g)
+    r = run([REF_CLI] + opts + ["-t", "2", "-p", g.model, g.fasta, reads])
+    assert r.returncode == 0, r.stderr
+    assert _bind.strip_mt(r.stdout) == _bind.strip_mt(g.paf)
+    ind = str(tmp_path / "ours.ind")
+    r = run([CLI] + opts + ["-t", "2", "-p", g.model, "-d", ind, g.fasta])
+    assert r.returncode == 0, r.stderr
+    r = run([REF_CLI] + opts + ["-t", "2", ind, reads])
+    assert r.returncode == 0, r.stderr
+    assert _bind.strip_mt(r.stdout) == _bind.strip_mt(g.paf)
+
+
+@needs_ref_cli
+def test_reference_binary_rawsamble_equals_oracle(built, tmp_path):
+    """-x ava through files: the reference binary (index from the reads' own BLOW5, then all-vs-all) prints what the
+    oracle's in-memory path prints — the expected output of the GPU CLI's Rawsamble test."""
+    from rawhash_b200 import api, synth
+    w = ava_world()
+    reads = str(tmp_path / "reads.blow5")
+    api.write_slow5(reads, w.names, w.reads["raw"], synth.OFFSET, synth.RANGE, synth.DIGITISATION)
+    ind = str(tmp_path / "ava.ind")
+    r = run([REF_CLI, "-x", "ava", "-t", "2", "-p", w.model, "-d", ind, reads])  # ri_idx_siggen refuses to run without a pore model
+    assert r.returncode == 0, r.stderr
+    r = run([REF_CLI, "-x", "ava", "-t", "2", ind, reads])
+    assert r.returncode == 0, r.stderr
+    exp = ava_expected(w)
+    assert len(exp) > len(w.names)
+    assert _bind.strip_mt(r.stdout).splitlines() == exp
+
+
+def ava_world():
+    return World(n_contigs=1, genome_len=60_000, n_reads=60, read_bp=4000, seed=23)
+
+
+def ava_expected(w):
+    orc = _bind.OracleLib().open("ava", False, w.model)
+    sigs = [w.pa(i) for i in range(len(w.names))]
+    orc.build_index_sig(sigs, w.names, 4)
+    orc.mapopt_update()
+    exp, _ = orc.map_paf(sigs, w.names, 4)
+    return _bind.strip_mt(exp).splitlines()
+
+
+@pytest.mark.skipif(have_gpu(), reason="a GPU is present: the CLI maps instead of refusing")
+def test_cli_refuses_to_map_without_a_gpu(built, tmp_path):
+    from rawhash_b200 import api
+    g = GoldenCase("r94_sensitive", str(tmp_path))
+    reads = str(tmp_path / "reads.blow5")
+    api.write_slow5(reads, g.names, g.raws, *g.cal)
+    r = run([CLI, "-x", "sensitive", "-p", g.model, g.fasta, reads])
+    assert r.returncode == 1 and "there is no CPU mapping path" in r.stderr and r.stdout == ""
