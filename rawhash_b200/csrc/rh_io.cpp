@@ -20,7 +20,9 @@
 #include <string.h>
 #include <errno.h>
 #include <dirent.h>
+#include <sys/mman.h>
 #include <sys/stat.h>
+#include <unistd.h>
 #include <math.h>
 #include <zlib.h>
 #include <algorithm>
@@ -261,14 +263,27 @@ bool svbzd_decode(const uint8_t *in, size_t in_bytes, int16_t *out, uint32_t exp
 	if (in_bytes < 4 + nctl) return false;
 	const uint8_t *ctl = in + 4, *dat = ctl + nctl, *end = in + in_bytes;
 	int32_t prev = 0;
-	for (uint32_t i = 0; i < count; ++i) {
+	uint32_t i = 0;
+	static const uint32_t KEEP[4] = {0xffu, 0xffffu, 0xffffffu, 0xffffffffu};
+	/* four values per control byte; a 4-byte load per value is safe while 16 bytes of input remain */
+	for (; i + 4 <= count && dat + 16 <= end; i += 4) {
+		const unsigned c = ctl[i >> 2];
+		for (int j = 0; j < 4; ++j) {
+			const unsigned code = (c >> (2 * j)) & 3u;
+			uint32_t v; memcpy(&v, dat, 4);
+			v &= KEEP[code];
+			dat += code + 1;
+			prev += (int32_t)(v >> 1) ^ -(int32_t)(v & 1);
+			out[i + j] = (int16_t)prev;
+		}
+	}
+	for (; i < count; ++i) {
 		const unsigned code = (ctl[i >> 2] >> ((i & 3) * 2)) & 3u;
 		if (dat + code + 1 > end) return false;
 		uint32_t v = 0;
-		memcpy(&v, dat, code + 1);
+		for (unsigned b = 0; b <= code; ++b) v |= (uint32_t)dat[b] << (8 * b);
 		dat += code + 1;
-		const int32_t d = (int32_t)(v >> 1) ^ -(int32_t)(v & 1);
-		prev += d;
+		prev += (int32_t)(v >> 1) ^ -(int32_t)(v & 1);
 		out[i] = (int16_t)prev;
 	}
 	return dat == end;
@@ -279,16 +294,19 @@ uint32_t svbzd_count(const uint8_t *in, size_t in_bytes) { uint32_t c = 0; if (i
 void svbzd_encode(const int16_t *in, uint32_t count, std::vector<uint8_t> &out)
 {
 	const size_t nctl = ((size_t)count + 3) / 4;
-	out.assign(4 + nctl, 0);
+	out.assign(4 + nctl + (size_t)count * 4, 0);
 	memcpy(out.data(), &count, 4);
+	uint8_t *ctl = out.data() + 4, *dat = ctl + nctl;
 	int32_t prev = 0;
 	for (uint32_t i = 0; i < count; ++i) {
 		const int32_t d = (int32_t)in[i] - prev; prev = in[i];
 		const uint32_t v = ((uint32_t)d << 1) ^ (uint32_t)(d >> 31);
 		const unsigned code = v < (1u << 8) ? 0 : v < (1u << 16) ? 1 : v < (1u << 24) ? 2 : 3;
-		out[4 + (i >> 2)] |= (uint8_t)(code << ((i & 3) * 2));
-		for (unsigned b = 0; b <= code; ++b) out.push_back((uint8_t)(v >> (8 * b)));
+		ctl[i >> 2] |= (uint8_t)(code << ((i & 3) * 2));
+		memcpy(dat, &v, 4); /* little endian; the buffer has room for 4 bytes per value */
+		dat += code + 1;
 	}
+	out.resize((size_t)(dat - out.data()));
 }
 
 bool zlib_inflate(const uint8_t *in, size_t in_bytes, std::vector<uint8_t> &out)
@@ -321,7 +339,9 @@ bool zlib_deflate(const uint8_t *in, size_t in_bytes, std::vector<uint8_t> &out)
 
 /* ---- one record between the file and the arena ------------------------------------------------------------------ */
 struct rec_t {
-	std::vector<uint8_t> mem;       /* the record as stored (binary: after record decompression; ASCII: the line) */
+	const uint8_t *src = nullptr; size_t src_bytes = 0; /* binary: the stored record inside the file mapping */
+	std::vector<uint8_t> mem;       /* binary: the inflated record when records are compressed; ASCII: the line */
+	const uint8_t *body = nullptr; size_t body_bytes = 0; /* what the fields are parsed from (src or mem) */
 	std::string name;
 	double digitisation = 0, offset = 0, range = 0, sampling_rate = 0;
 	uint64_t n_samples = 0;         /* decoded sample count */
@@ -331,12 +351,12 @@ struct rec_t {
 
 bool parse_binary_record(rec_t &r, int rec_method, int sig_method)
 { /* slow5_rec_parse, binary branch (slow5.c:2806-2925): u16 id_len, id, u32 read_group, 4 doubles, u64 length, signal */
+	r.body = r.src; r.body_bytes = r.src_bytes;
 	if (rec_method == PRESS_ZLIB) {
-		std::vector<uint8_t> plain;
-		if (!zlib_inflate(r.mem.data(), r.mem.size(), plain)) return false;
-		r.mem.swap(plain);
+		if (!zlib_inflate(r.src, r.src_bytes, r.mem)) return false;
+		r.body = r.mem.data(); r.body_bytes = r.mem.size();
 	}
-	const uint8_t *p = r.mem.data(); const size_t n = r.mem.size(); size_t at = 0;
+	const uint8_t *p = r.body; const size_t n = r.body_bytes; size_t at = 0;
 	uint16_t idl;
 	if (n < 2) return false;
 	memcpy(&idl, p, 2); at = 2;
@@ -351,12 +371,14 @@ bool parse_binary_record(rec_t &r, int rec_method, int sig_method)
 	r.sig_at = at;
 	if (sig_method == SIG_NONE) { r.sig_bytes = len * 2; r.n_samples = len; }
 	else { r.sig_bytes = len; r.n_samples = svbzd_count(p + at, std::min<size_t>(len, n - at)); } /* length field = compressed bytes */
-	return r.sig_at + r.sig_bytes <= n; /* auxiliary fields after the signal are not needed */
+	if (r.sig_bytes > n - r.sig_at) return false; /* auxiliary fields after the signal are not needed */
+	return sig_method == SIG_NONE || r.n_samples + (r.n_samples + 3) / 4 + 4 <= r.sig_bytes; /* every value has >= 1 data byte */
 }
 
 bool parse_ascii_record(rec_t &r)
 { /* slow5_rec_parse, ASCII branch (slow5.c:2648-2770): read_id read_group digitisation offset range sampling_rate len signal[,..] */
 	char *s = (char *)r.mem.data(); /* NUL-terminated by the reader */
+	r.body = r.mem.data(); r.body_bytes = r.mem.size();
 	char *f[8]; int nf = 0;
 	f[nf++] = s;
 	for (char *c = s; *c && nf < 8; ++c) if (*c == '\t') { *c = 0; f[nf++] = c + 1; }
@@ -371,16 +393,17 @@ bool parse_ascii_record(rec_t &r)
 	r.sig_at = (size_t)(f[7] - s);
 	char *t = strchr(f[7], '\t'); /* auxiliary columns follow */
 	r.sig_bytes = t ? (size_t)(t - f[7]) : strlen(f[7]);
-	return true;
+	return r.n_samples <= (r.sig_bytes + 1) / 2; /* "d,d,...,d" */
 }
 
 bool decode_signal(const rec_t &r, bool binary, int sig_method, int16_t *out)
 {
-	const uint8_t *p = r.mem.data() + r.sig_at;
+	const uint8_t *p = r.body + r.sig_at;
 	if (binary) {
 		if (sig_method == SIG_NONE) { memcpy(out, p, r.sig_bytes); return true; }
 		return svbzd_decode(p, r.sig_bytes, out, (uint32_t)r.n_samples);
 	}
+	if (r.n_samples == 0) return true; /* an empty signal is written as "" or "." */
 	const char *c = (const char *)p, *end = c + r.sig_bytes;
 	uint64_t i = 0;
 	while (c < end && i < r.n_samples) {
@@ -436,6 +459,7 @@ struct rh_sigfile_s {
 	std::mutex mu; std::vector<arena_t> pool; /* arenas handed back by freed batches */
 	std::atomic<int> live_batches{0}; bool closed = false;
 	char *line = nullptr; size_t line_cap = 0;
+	const uint8_t *map = nullptr; size_t map_bytes = 0, map_at = 0; /* binary files are read through a mapping: no copies */
 	std::vector<rec_t> pending; size_t pending_at = 0; /* parsed records not yet handed out */
 };
 
@@ -452,6 +476,7 @@ struct batch_impl {
 void sigfile_destroy(rh_sigfile_s *f)
 {
 	for (arena_t &a : f->pool) arena_free(a);
+	if (f->map) munmap((void *)f->map, f->map_bytes);
 	if (f->fp) fclose(f->fp);
 	free(f->line);
 	delete f;
@@ -473,8 +498,15 @@ extern "C" rh_sigfile_t *rh_sigfile_open(const char *path, int n_threads)
 	setvbuf(fp, NULL, _IOFBF, 4 << 20);
 	bool ok = true;
 	if (bin) {
-		unsigned char h[BLOW5_HDR_SIZE_AT + 4];
-		ok = fread(h, 1, sizeof(h), fp) == sizeof(h) && memcmp(h, BLOW5_MAGIC, 6) == 0;
+		struct stat st;
+		ok = fstat(fileno(fp), &st) == 0 && (size_t)st.st_size >= BLOW5_HDR_SIZE_AT + 4;
+		if (ok) {
+			void *m = mmap(NULL, (size_t)st.st_size, PROT_READ, MAP_PRIVATE, fileno(fp), 0);
+			ok = m != MAP_FAILED;
+			if (ok) { f->map = (const uint8_t *)m; f->map_bytes = (size_t)st.st_size; madvise(m, f->map_bytes, MADV_SEQUENTIAL); }
+		}
+		const uint8_t *h = f->map;
+		ok = ok && memcmp(h, BLOW5_MAGIC, 6) == 0;
 		if (!ok) rh_set_error("%s: not a BLOW5 file (bad magic number)", path);
 		else {
 			const unsigned major = h[6], minor = h[7];
@@ -485,9 +517,11 @@ extern "C" rh_sigfile_t *rh_sigfile_open(const char *path, int n_threads)
 			else if (f->rec_method > PRESS_ZSTD || f->sig_method > SIG_SVB_ZD) { rh_set_error("%s: unknown compression method (record %d, signal %d)", path, f->rec_method, f->sig_method); ok = false; }
 			uint32_t hdr_bytes; memcpy(&hdr_bytes, h + BLOW5_HDR_SIZE_AT, 4);
 			if (ok) { /* the ASCII header block must end with the column-name line */
-				std::vector<char> hb((size_t)hdr_bytes + 1, 0);
-				ok = fread(hb.data(), 1, hdr_bytes, fp) == hdr_bytes && strstr(hb.data(), "#read_id\t") != NULL;
+				const size_t body_at = BLOW5_HDR_SIZE_AT + 4;
+				ok = hdr_bytes <= f->map_bytes - body_at;
+				if (ok) { const std::string hb((const char *)h + body_at, hdr_bytes); ok = hb.find("#read_id\t") != std::string::npos; }
 				if (!ok) rh_set_error("%s: malformed BLOW5 header", path);
+				f->map_at = body_at + hdr_bytes;
 			}
 		}
 	} else {
@@ -515,21 +549,20 @@ extern "C" void rh_sigfile_close(rh_sigfile_t *f)
 	if (destroy) sigfile_destroy(f); /* otherwise the last rh_sigbatch_free does it */
 }
 
-/* next stored record -> r.mem; returns 1 record, 0 end of file, <0 error */
+/* next stored record -> r.src (binary) or r.mem (ASCII); returns 1 record, 0 end of file, <0 error */
 static int read_stored_record(rh_sigfile_s *f, rec_t &r)
 {
 	if (f->binary) { /* slow5_get_next_mem (slow5.c:3191-3270): u64 size, then the bytes; "5WOLB" closes the file */
-		uint64_t sz; unsigned char b[8];
-		const size_t got = fread(b, 1, 8, f->fp);
-		if (got != 8) {
-			if (got == 5 && memcmp(b, BLOW5_EOF, 5) == 0) return 0;
+		const size_t left = f->map_bytes - f->map_at;
+		if (left < 8) {
+			if (left == 5 && memcmp(f->map + f->map_at, BLOW5_EOF, 5) == 0) return 0;
 			rh_set_error("%s: truncated BLOW5 (no end-of-file marker)", f->path.c_str());
 			return RH_ERR_FORMAT;
 		}
-		memcpy(&sz, b, 8);
-		if (sz > ((uint64_t)1 << 33)) { rh_set_error("%s: implausible record size %llu", f->path.c_str(), (unsigned long long)sz); return RH_ERR_FORMAT; }
-		r.mem.resize(sz);
-		if (sz && fread(r.mem.data(), 1, sz, f->fp) != sz) { rh_set_error("%s: truncated BLOW5 record", f->path.c_str()); return RH_ERR_FORMAT; }
+		uint64_t sz; memcpy(&sz, f->map + f->map_at, 8);
+		if (sz > left - 8) { rh_set_error("%s: truncated BLOW5 record", f->path.c_str()); return RH_ERR_FORMAT; }
+		r.src = f->map + f->map_at + 8; r.src_bytes = sz;
+		f->map_at += 8 + sz;
 		return 1;
 	}
 	const ssize_t n = getline(&f->line, &f->line_cap, f->fp);
