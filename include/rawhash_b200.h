@@ -249,6 +249,7 @@ typedef struct rh_sigbatch_s {
 	const uint64_t *raw_len;
 	const double *offset, *range, *digitisation, *sampling_rate;
 	const char *const *names;         /* read ids                                    */
+	int32_t arena_pinned;             /* 1 if the arena is page-locked (cudaHostAlloc) */
 	void *priv;
 } rh_sigbatch_t;
 rh_sigfile_t *rh_sigfile_open(const char *path, int n_threads);

@@ -3,7 +3,7 @@
 BLOW5 (svb-zd signals), then `rawhash2_b200 -d` (index build + dump) and `rawhash2_b200 idx reads.blow5 > paf`.
 Reports what the CLI itself prints: pipeline reads/s (file decode + H2D + map + PAF) and the mapping step alone.
 
-    python profiles/tools/cli_bench.py [n_reads] [record_press]
+    python profiles/tools/cli_bench.py [n_reads] [record_press] [-K value ...]
 """
 import json
 import os
@@ -44,15 +44,18 @@ out["index_cmd_s"] = round(time.time() - t0, 2)
 out["index_rc"] = r.returncode
 out["ind_mb"] = round(os.path.getsize(ind) / 1e6, 1) if os.path.isfile(ind) else None
 paf = os.path.join(tmp, "out.paf")
-for attempt in ("cold", "warm"):
+ks = sys.argv[3:] or ["500M", "500M"]
+for attempt in ks:
     t0 = time.time()
-    r = subprocess.run([CLI, "-x", "sensitive", "-t", str(os.cpu_count()), "-o", paf, ind, blow5], capture_output=True, text=True)
+    r = subprocess.run([CLI, "-x", "sensitive", "-t", str(os.cpu_count()), "-K", attempt, "-o", paf, ind, blow5], capture_output=True, text=True, env=dict(os.environ, RH_CLI_VERBOSE="1"))
+    attempt = "K" + attempt + ("_again" if "K" + attempt in out else "")
     wall = time.time() - t0
-    m = re.search(r"mapped (\d+) of (\d+) reads .*pipeline: ([\d.]+) sec \((\d+) reads/s\); mapping step alone: ([\d.]+) sec \((\d+) reads/s\); real time: ([\d.]+)", r.stderr)
+    m = re.search(r"mapped (\d+) of (\d+) reads .*pipeline: ([\d.]+) sec \((\d+) reads/s\); mapping step alone: ([\d.]+) sec \((\d+) reads/s\); file decode alone: ([\d.]+) sec; real time: ([\d.]+)", r.stderr)
     out[attempt] = {"rc": r.returncode, "wall_s": round(wall, 2)}
     if m:
         out[attempt] |= {"mapped": int(m.group(1)), "pipeline_s": float(m.group(3)), "pipeline_reads_per_s": int(m.group(4)),
-                         "map_step_s": float(m.group(5)), "map_step_reads_per_s": int(m.group(6)), "process_real_s": float(m.group(7))}
+                         "map_step_s": float(m.group(5)), "map_step_reads_per_s": int(m.group(6)), "decode_s": float(m.group(7)), "process_real_s": float(m.group(8)),
+                         "batch_map_s": [float(x) for x in re.findall(r"map ([\d.]+) sec", r.stderr)]}
     else:
         out[attempt]["stderr"] = r.stderr[-500:]
 lines = open(paf).read().splitlines() if os.path.isfile(paf) else []

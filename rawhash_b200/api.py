@@ -118,7 +118,7 @@ class SigBatchC(C.Structure):
         ("raw", C.POINTER(C.POINTER(C.c_int16))), ("raw_len", C.POINTER(C.c_uint64)),
         ("offset", C.POINTER(C.c_double)), ("range", C.POINTER(C.c_double)),
         ("digitisation", C.POINTER(C.c_double)), ("sampling_rate", C.POINTER(C.c_double)),
-        ("names", C.POINTER(C.c_char_p)), ("priv", C.c_void_p),
+        ("names", C.POINTER(C.c_char_p)), ("arena_pinned", C.c_int32), ("priv", C.c_void_p),
     ]
 
 

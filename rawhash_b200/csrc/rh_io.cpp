@@ -638,7 +638,7 @@ extern "C" int rh_sigfile_next_batch(rh_sigfile_t *f, uint64_t max_samples, uint
 	b->pub.n = (uint32_t)n; b->pub.n_samples = total;
 	b->pub.raw = b->raw.data(); b->pub.raw_len = b->len.data();
 	b->pub.offset = b->offset.data(); b->pub.range = b->range.data(); b->pub.digitisation = b->digitisation.data(); b->pub.sampling_rate = b->sampling_rate.data();
-	b->pub.names = b->names.data(); b->pub.priv = b;
+	b->pub.names = b->names.data(); b->pub.arena_pinned = b->arena.pinned ? 1 : 0; b->pub.priv = b;
 	if (bad) { rh_set_error("%s: a raw signal cannot be decoded", f->path.c_str()); rh_sigbatch_free(&b->pub); return RH_ERR_FORMAT; }
 	*out = &b->pub;
 	return RH_OK;

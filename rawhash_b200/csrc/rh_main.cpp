@@ -381,7 +381,8 @@ int main(int argc, char **argv)
 	int status = 0; std::mutex status_mu;
 	auto fail = [&](const std::string &msg) { std::lock_guard<std::mutex> l(status_mu); if (!status) fprintf(stderr, "[ERROR] %s\n", msg.c_str()); status = 1; };
 	uint64_t n_reads = 0, n_mapped = 0, n_samples = 0;
-	double t_map = 0;
+	double t_map = 0, t_read = 0;
+	uint64_t n_batches = 0;
 	const double t_pipe0 = now_s();
 
 	std::thread reader([&]() { /* step 0: ri_sig_read_frag, src/rmap.cpp:600-660 */
@@ -394,8 +395,10 @@ int main(int argc, char **argv)
 				if (!f) { fail(rh_gpu_last_error()); break; }
 				for (;;) {
 					rh_sigbatch_t *b = NULL;
+					const double t1 = now_s();
 					if (rh_sigfile_next_batch(f, (uint64_t)S.mini_batch, 0, &b) != RH_OK) { fail(rh_gpu_last_error()); break; }
 					if (!b || status) { if (b) rh_sigbatch_free(b); break; }
+					t_read += now_s() - t1;
 					to_map.push(b);
 				}
 				rh_sigfile_close(f);
@@ -424,6 +427,12 @@ int main(int argc, char **argv)
 		t_map += now_s() - t1;
 		if (rc != RH_OK) { fail(std::string("mapping failed: ") + rh_gpu_last_error()); rh_free(recs); rh_sigbatch_free(b); continue; }
 		n_reads += b->n; n_samples += b->n_samples;
+		if (getenv("RH_CLI_VERBOSE")) {
+			rh_gpu_stats_t st; rh_gpu_get_stats(ctx[0], &st);
+			fprintf(stderr, "[M::batch %llu] %u reads, %llu samples (arena %s): map %.3f sec; GPU 0: %.1f ms on the stream (events %.1f seed %.1f sort %.1f chain %.1f post %.1f), %llu chunks in %llu rounds, H2D %.1f MB, %llu launches\n",
+			        (unsigned long long)++n_batches, b->n, (unsigned long long)b->n_samples, b->arena_pinned ? "page-locked" : "pageable", now_s() - t1,
+			        st.ms_total, st.ms_event_kernel, st.ms_seed, st.ms_sort, st.ms_chain, st.ms_post, (unsigned long long)st.n_chunks, (unsigned long long)st.n_rounds, st.h2d_bytes / 1e6, (unsigned long long)st.kernel_launches);
+		}
 		to_print.push({b, recs, n_recs});
 	}
 	to_print.close();
@@ -433,7 +442,7 @@ int main(int argc, char **argv)
 	rh_index_destroy(idx);
 	if (status) { fprintf(stderr, "ERROR: failed to map the query file\n"); return 1; }
 	if (fflush(stdout) == EOF) { perror("[ERROR] failed to write the results"); return 1; }
-	fprintf(stderr, "[M::%s] Version: %s\n[M::%s] mapped %llu of %llu reads (%llu raw samples); read+map+print pipeline: %.3f sec (%.0f reads/s); mapping step alone: %.3f sec (%.0f reads/s); real time: %.3f sec\n", __func__, RH_VERSION, __func__,
-	        (unsigned long long)n_mapped, (unsigned long long)n_reads, (unsigned long long)n_samples, t_pipe, t_pipe > 0 ? n_reads / t_pipe : 0.0, t_map, t_map > 0 ? n_reads / t_map : 0.0, now_s() - g_t0);
+	fprintf(stderr, "[M::%s] Version: %s\n[M::%s] mapped %llu of %llu reads (%llu raw samples); read+map+print pipeline: %.3f sec (%.0f reads/s); mapping step alone: %.3f sec (%.0f reads/s); file decode alone: %.3f sec; real time: %.3f sec\n", __func__, RH_VERSION, __func__,
+	        (unsigned long long)n_mapped, (unsigned long long)n_reads, (unsigned long long)n_samples, t_pipe, t_pipe > 0 ? n_reads / t_pipe : 0.0, t_map, t_map > 0 ? n_reads / t_map : 0.0, t_read, now_s() - g_t0);
 	return 0;
 }
