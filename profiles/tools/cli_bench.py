@@ -3,7 +3,7 @@
 BLOW5 (svb-zd signals), then `rawhash2_b200 -d` (index build + dump) and `rawhash2_b200 idx reads.blow5 > paf`.
 Reports what the CLI itself prints: pipeline reads/s (file decode + H2D + map + PAF) and the mapping step alone.
 
-    python profiles/tools/cli_bench.py [n_reads] [record_press] [-K value ...]
+    python profiles/tools/cli_bench.py [n_reads] [record_press] [-K value[@threads] ...]
 """
 import json
 import os
@@ -47,9 +47,13 @@ paf = os.path.join(tmp, "out.paf")
 ks = sys.argv[3:] or ["500M", "500M"]
 for attempt in ks:
     t0 = time.time()
-    r = subprocess.run([CLI, "-x", "sensitive", "-t", str(os.cpu_count()), "-K", attempt, "-o", paf, ind, blow5], capture_output=True, text=True, env=dict(os.environ, RH_CLI_VERBOSE="1"))
+    kval, _, nthr = attempt.partition("@")  # "500M@8" = -K 500M -t 8
+    r = subprocess.run([CLI, "-x", "sensitive", "-t", nthr or str(os.cpu_count()), "-K", kval, "-o", paf, ind, blow5], capture_output=True, text=True, env=dict(os.environ, RH_CLI_VERBOSE="1"))
     attempt = "K" + attempt + ("_again" if "K" + attempt in out else "")
     wall = time.time() - t0
+    log_dir = os.path.join(ROOT, "gpurun_out")
+    if os.path.isdir(log_dir):
+        open(os.path.join(log_dir, f"cli_bench_K{attempt}.stderr"), "w").write(r.stderr)
     m = re.search(r"mapped (\d+) of (\d+) reads .*pipeline: ([\d.]+) sec \((\d+) reads/s\); mapping step alone: ([\d.]+) sec \((\d+) reads/s\); file decode alone: ([\d.]+) sec; real time: ([\d.]+)", r.stderr)
     out[attempt] = {"rc": r.returncode, "wall_s": round(wall, 2)}
     if m:

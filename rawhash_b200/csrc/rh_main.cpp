@@ -20,6 +20,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <sys/time.h>
+#include <atomic>
 #include <condition_variable>
 #include <deque>
 #include <mutex>
@@ -281,6 +282,28 @@ int map_on_gpus(std::vector<rh_gpu_ctx *> &ctx, const rh_sigbatch_t *b, rh_map_r
 	return bad;
 }
 
+/* One small batch of noise through every GPU while step 0 decodes the first real mini-batch: first-use costs of
+ * the CUDA runtime (scratch allocations, stream/event pools) are paid here instead of inside the first batch. */
+void warm_up(std::vector<rh_gpu_ctx *> &ctx)
+{
+	const uint32_t n = 256, len = 9000;
+	std::vector<int16_t> raw((size_t)n * len);
+	uint32_t x = 12345;
+	for (size_t i = 0; i < raw.size(); ++i) {
+		x = x * 1664525u + 1013904223u;
+		if (i % 9 == 0 || i % len == 0) raw[i] = (int16_t)(350 + (x >> 16) % 350); /* a new level about every 9 samples */
+		else raw[i] = (int16_t)(raw[i - 1] + (int)((x >> 24) % 9) - 4);
+	}
+	std::vector<const int16_t *> ptr(n); std::vector<uint64_t> l(n, len); std::vector<double> off(n, 10.0), rng(n, 1400.0), dig(n, 8192.0);
+	std::vector<std::string> nm(n); std::vector<const char *> names(n);
+	for (uint32_t i = 0; i < n; ++i) { ptr[i] = raw.data() + (size_t)i * len; nm[i] = "warmup_" + std::to_string(i); names[i] = nm[i].c_str(); }
+	for (rh_gpu_ctx *c : ctx) {
+		rh_map_rec_t *recs = NULL; uint64_t nr = 0;
+		rh_gpu_map_batch_raw(c, n, ptr.data(), l.data(), off.data(), rng.data(), dig.data(), names.data(), &recs, &nr);
+		rh_free(recs);
+	}
+}
+
 } // namespace
 
 int main(int argc, char **argv)
@@ -310,11 +333,55 @@ int main(int argc, char **argv)
 		return 1;
 	}
 
+	/* ---- pipeline state; step 0 starts right away so that decoding the first mini-batches (and page-locking their
+	 * arenas) overlaps index loading and GPU initialisation ------------------------------------------------------ */
+	setenv("CUDA_MODULE_LOADING", "EAGER", 0); /* load every kernel at context creation, not inside the first batch */
+	const bool have_queries = pos.size() >= 2;
+	handoff<rh_sigbatch_t *> to_map(2);
+	handoff<mapped_batch> to_print(2);
+	std::atomic<int> status(0); std::mutex status_mu;
+	auto fail = [&](const std::string &msg) { std::lock_guard<std::mutex> l(status_mu); if (!status) fprintf(stderr, "[ERROR] %s\n", msg.c_str()); status = 1; };
+	uint64_t n_reads = 0, n_mapped = 0, n_samples = 0;
+	double t_map = 0, t_read = 0;
+	uint64_t n_batches = 0;
+	const double t_pipe0 = now_s();
+	const int decode_threads = std::max(1, S.n_threads - 2); /* one thread drives the GPU, one prints */
+	std::thread reader;
+	if (have_queries) reader = std::thread([&]() { /* step 0: ri_sig_read_frag, src/rmap.cpp:600-660 */
+		for (size_t q = 1; q < pos.size() && !status; ++q) {
+			char **files = NULL; uint32_t nf = 0;
+			rh_find_sigfiles(pos[q], &files, &nf);
+			if (nf == 0) fail(std::string("failed to open file '") + pos[q] + "': no .slow5/.blow5 signal file");
+			for (uint32_t i = 0; i < nf && !status; ++i) {
+				rh_sigfile_t *f = rh_sigfile_open(files[i], decode_threads);
+				if (!f) { fail(rh_gpu_last_error()); break; }
+				for (;;) {
+					rh_sigbatch_t *b = NULL;
+					const double t1 = now_s();
+					if (rh_sigfile_next_batch(f, (uint64_t)S.mini_batch, 0, &b) != RH_OK) { fail(rh_gpu_last_error()); break; }
+					if (!b || status) { if (b) rh_sigbatch_free(b); break; }
+					t_read += now_s() - t1;
+					to_map.push(b);
+				}
+				rh_sigfile_close(f);
+			}
+			for (uint32_t i = 0; i < nf; ++i) rh_free(files[i]);
+			rh_free(files);
+		}
+		to_map.close();
+	});
+	auto quit = [&](int code) { /* leave before the mapping loop: stop step 0 and drop what it has queued */
+		status = 1;
+		rh_sigbatch_t *q;
+		if (reader.joinable()) { while (to_map.pop(q)) rh_sigbatch_free(q); reader.join(); }
+		return code;
+	};
+
 	/* ---- index ---------------------------------------------------------------------------------------------------- */
 	float *pore = NULL; uint32_t n_pore = 0;
 	if (!target_is_idx && S.pore && rh_pore_load(S.pore, P.k, P.lev_col, &pore, &n_pore) != RH_OK) {
 		fprintf(stderr, "[ERROR] cannot parse the k-mer pore model file: %s\n", rh_gpu_last_error());
-		return 1;
+		return quit(1);
 	}
 	rh_index_t *idx = NULL;
 	if (target_is_idx) {
@@ -346,7 +413,7 @@ int main(int argc, char **argv)
 		rh_free(files);
 	} else {
 		uint32_t n_seq = 0; char **names = NULL, **seqs = NULL; uint32_t *lens = NULL;
-		if (rh_fasta_load(target, &n_seq, &names, &seqs, &lens) != RH_OK) { fprintf(stderr, "[ERROR] %s\n", rh_gpu_last_error()); return 1; }
+		if (rh_fasta_load(target, &n_seq, &names, &seqs, &lens) != RH_OK) { fprintf(stderr, "[ERROR] %s\n", rh_gpu_last_error()); return quit(1); }
 		if (!S.index_on_host) {
 			idx = rh_index_build_gpu(&P, pore, n_pore, n_seq, names, seqs, lens, S.device);
 			if (!idx) { fprintf(stderr, "[M::%s] GPU index build not possible (%s); using the host builder with %d threads\n", __func__, rh_gpu_last_error(), S.n_threads); }
@@ -354,60 +421,31 @@ int main(int argc, char **argv)
 		if (!idx) idx = rh_index_build(&P, pore, n_pore, n_seq, names, seqs, lens, S.n_threads);
 		rh_fasta_free(n_seq, names, seqs, lens);
 	}
-	if (!idx) { fprintf(stderr, "[ERROR] failed to load/build the index from '%s': %s\n", target, rh_gpu_last_error()); return 1; }
+	if (!idx) { fprintf(stderr, "[ERROR] failed to load/build the index from '%s': %s\n", target, rh_gpu_last_error()); return quit(1); }
 	fprintf(stderr, "[M::%s::%.3f] loaded/built the index for %u target sequence(s)\n", __func__, now_s() - g_t0, rh_index_n_seq(idx));
 	if (S.dump && !target_is_idx) {
-		if (rh_index_dump(idx, S.dump, pore, n_pore) != RH_OK) { fprintf(stderr, "[ERROR] %s\n", rh_gpu_last_error()); return 1; }
+		if (rh_index_dump(idx, S.dump, pore, n_pore) != RH_OK) { fprintf(stderr, "[ERROR] %s\n", rh_gpu_last_error()); return quit(1); }
 	}
 	rh_free(pore);
 	if (pos.size() < 2) {
 		fprintf(stderr, "[INFO] No files to query index on. Only the index is constructed.\n");
 		rh_index_destroy(idx);
-		return 0;
+		return quit(0);
 	}
 	rh_index_update_mapopt(idx, &P); /* ri_mapopt_update, src/main.cpp:606 */
 	fprintf(stderr, "[M::%s::%.3f] mid_occ = %d, min_mid_occ = %d, max_mid_occ = %d; distinct seeds: %llu, positions: %llu\n", __func__, now_s() - g_t0,
 	        P.mid_occ, P.min_mid_occ, P.max_mid_occ, (unsigned long long)rh_index_n_keys(idx), (unsigned long long)rh_index_n_pos(idx));
 
-	/* ---- mapping pipeline ------------------------------------------------------------------------------------------ */
+	/* ---- GPUs ------------------------------------------------------------------------------------------------------ */
 	std::vector<rh_gpu_ctx *> ctx;
 	for (int g = 0; g < S.n_gpus; ++g) {
 		rh_gpu_ctx *c = rh_gpu_init(idx, &P, S.device + g, 0);
-		if (!c) { fprintf(stderr, "[ERROR] cannot initialise GPU %d: %s (there is no CPU mapping path)\n", S.device + g, rh_gpu_last_error()); return 1; }
+		if (!c) { fprintf(stderr, "[ERROR] cannot initialise GPU %d: %s (there is no CPU mapping path)\n", S.device + g, rh_gpu_last_error()); return quit(1); }
 		ctx.push_back(c);
 	}
-	handoff<rh_sigbatch_t *> to_map(2);
-	handoff<mapped_batch> to_print(2);
-	int status = 0; std::mutex status_mu;
-	auto fail = [&](const std::string &msg) { std::lock_guard<std::mutex> l(status_mu); if (!status) fprintf(stderr, "[ERROR] %s\n", msg.c_str()); status = 1; };
-	uint64_t n_reads = 0, n_mapped = 0, n_samples = 0;
-	double t_map = 0, t_read = 0;
-	uint64_t n_batches = 0;
-	const double t_pipe0 = now_s();
+	if (!getenv("RH_NO_WARMUP")) warm_up(ctx);
+	const double t_ready = now_s() - g_t0;
 
-	std::thread reader([&]() { /* step 0: ri_sig_read_frag, src/rmap.cpp:600-660 */
-		for (size_t q = 1; q < pos.size() && !status; ++q) {
-			char **files = NULL; uint32_t nf = 0;
-			rh_find_sigfiles(pos[q], &files, &nf);
-			if (nf == 0) fail(std::string("failed to open file '") + pos[q] + "': no .slow5/.blow5 signal file");
-			for (uint32_t i = 0; i < nf && !status; ++i) {
-				rh_sigfile_t *f = rh_sigfile_open(files[i], std::max(1, S.n_threads));
-				if (!f) { fail(rh_gpu_last_error()); break; }
-				for (;;) {
-					rh_sigbatch_t *b = NULL;
-					const double t1 = now_s();
-					if (rh_sigfile_next_batch(f, (uint64_t)S.mini_batch, 0, &b) != RH_OK) { fail(rh_gpu_last_error()); break; }
-					if (!b || status) { if (b) rh_sigbatch_free(b); break; }
-					t_read += now_s() - t1;
-					to_map.push(b);
-				}
-				rh_sigfile_close(f);
-			}
-			for (uint32_t i = 0; i < nf; ++i) rh_free(files[i]);
-			rh_free(files);
-		}
-		to_map.close();
-	});
 	std::thread printer([&]() { /* step 2: src/rmap.cpp:745-800 */
 		mapped_batch m;
 		while (to_print.pop(m)) {
@@ -442,7 +480,7 @@ int main(int argc, char **argv)
 	rh_index_destroy(idx);
 	if (status) { fprintf(stderr, "ERROR: failed to map the query file\n"); return 1; }
 	if (fflush(stdout) == EOF) { perror("[ERROR] failed to write the results"); return 1; }
-	fprintf(stderr, "[M::%s] Version: %s\n[M::%s] mapped %llu of %llu reads (%llu raw samples); read+map+print pipeline: %.3f sec (%.0f reads/s); mapping step alone: %.3f sec (%.0f reads/s); file decode alone: %.3f sec; real time: %.3f sec\n", __func__, RH_VERSION, __func__,
-	        (unsigned long long)n_mapped, (unsigned long long)n_reads, (unsigned long long)n_samples, t_pipe, t_pipe > 0 ? n_reads / t_pipe : 0.0, t_map, t_map > 0 ? n_reads / t_map : 0.0, t_read, now_s() - g_t0);
+	fprintf(stderr, "[M::%s] Version: %s\n[M::%s] mapped %llu of %llu reads (%llu raw samples); read+map+print pipeline: %.3f sec (%.0f reads/s); mapping step alone: %.3f sec (%.0f reads/s); file decode alone: %.3f sec; index + GPU ready after %.3f sec; real time: %.3f sec\n", __func__, RH_VERSION, __func__,
+	        (unsigned long long)n_mapped, (unsigned long long)n_reads, (unsigned long long)n_samples, t_pipe, t_pipe > 0 ? n_reads / t_pipe : 0.0, t_map, t_map > 0 ? n_reads / t_map : 0.0, t_read, t_ready, now_s() - g_t0);
 	return 0;
 }
