@@ -335,7 +335,6 @@ int main(int argc, char **argv)
 
 	/* ---- pipeline state; step 0 starts right away so that decoding the first mini-batches (and page-locking their
 	 * arenas) overlaps index loading and GPU initialisation ------------------------------------------------------ */
-	setenv("CUDA_MODULE_LOADING", "EAGER", 0); /* load every kernel at context creation, not inside the first batch */
 	const bool have_queries = pos.size() >= 2;
 	handoff<rh_sigbatch_t *> to_map(2);
 	handoff<mapped_batch> to_print(2);

@@ -146,3 +146,32 @@ def test_cli_refuses_to_map_without_a_gpu(built, tmp_path):
     api.write_slow5(reads, g.names, g.raws, *g.cal)
     r = run([CLI, "-x", "sensitive", "-p", g.model, g.fasta, reads])
     assert r.returncode == 1 and "there is no CPU mapping path" in r.stderr and r.stdout == ""
+
+
+# ---- the drop-in itself: the reference's own binary with step 1 replaced (integration/build_dropin.py) ----------------
+DROPIN = os.path.join(ROOT, "oracle", "_ref", "rawhash2_gpu")
+needs_dropin = pytest.mark.skipif(not os.path.isfile(DROPIN), reason="oracle/_ref/rawhash2_gpu not built (integration/build_dropin.py)")
+
+
+@needs_dropin
+@pytest.mark.skipif(have_gpu(), reason="a GPU is present: the patched reference maps instead of refusing")
+def test_patched_reference_fails_loudly_without_a_gpu(built, tmp_path):
+    """The reference binary with `kt_for(map_worker_for)` replaced by rh_gpu_map_batch_raw has no CPU path left."""
+    from rawhash_b200 import api
+    g = GoldenCase("r94_sensitive", str(tmp_path))
+    reads = str(tmp_path / "reads.blow5")
+    api.write_slow5(reads, g.names, g.raws, *g.cal)
+    r = run([DROPIN, "-x", "sensitive", "-t", "2", "-p", g.model, g.fasta, reads])
+    assert r.returncode == 1 and "no usable CUDA device" in r.stderr and r.stdout == ""
+
+
+@needs_dropin
+@needs_ref_cli
+def test_patched_reference_index_only_mode_is_untouched(built, tmp_path):
+    w = World(n_contigs=2, genome_len=100_000, n_reads=1, read_bp=500, seed=21)
+    a, b = str(tmp_path / "a.ind"), str(tmp_path / "b.ind")
+    assert run([DROPIN, "-x", "sensitive", "-t", "2", "-p", w.model, "-d", a, w.fasta]).returncode == 0
+    assert run([REF_CLI, "-x", "sensitive", "-t", "2", "-p", w.model, "-d", b, w.fasta]).returncode == 0
+    x, y = np.fromfile(a, np.uint8), np.fromfile(b, np.uint8)
+    d = np.nonzero(x != y)[0]
+    assert x.size == y.size and d.size <= 16
