@@ -54,14 +54,29 @@ for attempt in ks:
     log_dir = os.path.join(ROOT, "gpurun_out")
     if os.path.isdir(log_dir):
         open(os.path.join(log_dir, f"cli_bench_K{attempt}.stderr"), "w").write(r.stderr)
-    m = re.search(r"mapped (\d+) of (\d+) reads .*pipeline: ([\d.]+) sec \((\d+) reads/s\); mapping step alone: ([\d.]+) sec \((\d+) reads/s\); file decode alone: ([\d.]+) sec; real time: ([\d.]+)", r.stderr)
+    m = re.search(r"mapped (\d+) of (\d+) reads .*pipeline: ([\d.]+) sec \((\d+) reads/s\); mapping step alone: ([\d.]+) sec \((\d+) reads/s\); file decode alone: ([\d.]+) sec; index \+ GPU ready after ([\d.]+) sec; real time: ([\d.]+)", r.stderr)
     out[attempt] = {"rc": r.returncode, "wall_s": round(wall, 2)}
     if m:
         out[attempt] |= {"mapped": int(m.group(1)), "pipeline_s": float(m.group(3)), "pipeline_reads_per_s": int(m.group(4)),
-                         "map_step_s": float(m.group(5)), "map_step_reads_per_s": int(m.group(6)), "decode_s": float(m.group(7)), "process_real_s": float(m.group(8)),
+                         "map_step_s": float(m.group(5)), "map_step_reads_per_s": int(m.group(6)), "decode_s": float(m.group(7)), "ready_s": float(m.group(8)), "process_real_s": float(m.group(9)),
                          "batch_map_s": [float(x) for x in re.findall(r"map ([\d.]+) sec", r.stderr)]}
     else:
         out[attempt]["stderr"] = r.stderr[-500:]
+# the same files through the reference's own binary (CPU, all host threads) and through the drop-in build of it
+# (oracle/_ref/rawhash2_gpu: reference main/reader/printer, our library at the kt_for line); PAFs must be identical
+strip = lambda txt: re.sub(r"mt:f:[^\t]*\t", "", txt)
+if os.environ.get("RH_WITH_REFERENCE"):
+    mine = strip(open(paf).read())
+    for tag, exe in (("reference_cpu", "rawhash2"), ("reference_dropin_gpu", "rawhash2_gpu")):
+        exe = os.path.join(ROOT, "oracle", "_ref", exe)
+        if not os.path.isfile(exe):
+            continue
+        t0 = time.time()
+        r = subprocess.run([exe, "-x", "sensitive", "-t", str(os.cpu_count()), ind, blow5], capture_output=True, text=True)
+        wall = time.time() - t0
+        out[tag] = {"rc": r.returncode, "wall_s": round(wall, 2), "reads_per_s_whole_program": round(n_reads / wall), "threads": os.cpu_count(),
+                    "paf_identical_to_rawhash2_b200": strip(r.stdout) == mine, "paf_lines": len(r.stdout.splitlines()),
+                    "stderr_tail": r.stderr[-300:]}
 lines = open(paf).read().splitlines() if os.path.isfile(paf) else []
 ok = 0
 clen = [len(s) for _, s in genome]
