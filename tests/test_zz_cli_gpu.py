@@ -62,3 +62,34 @@ def test_cli_rawsamble(built, tmp_path):
     exp = ava_expected(w)
     assert len(exp) > len(w.names)
     assert _bind.strip_mt(r.stdout).splitlines() == exp
+
+
+def _n_gpus():
+    import shutil
+    if shutil.which("nvidia-smi") is None:
+        return 0
+    r = subprocess.run(["nvidia-smi", "-L"], capture_output=True, text=True)
+    return sum(1 for ln in r.stdout.splitlines() if ln.startswith("GPU ")) if r.returncode == 0 else 0
+
+
+@pytest.mark.skipif(_n_gpus() < 2, reason="needs two GPUs")
+def test_cli_two_gpus_same_paf(built, tmp_path):
+    """--gpus 2: every mini-batch is cut into two sample-balanced read ranges mapped on their own GPU (index
+    replicated), records concatenated in range order — the PAF must not change."""
+    from rawhash_b200 import api, synth
+    from common import World
+    g = GoldenCase("r94_sensitive", str(tmp_path))
+    reads = str(tmp_path / "reads.blow5")
+    api.write_slow5(reads, g.names, g.raws, *g.cal)
+    r = run([CLI, "-x", "sensitive", "--gpus", "2", "-p", g.model, g.fasta, reads])
+    assert r.returncode == 0, r.stderr
+    assert _bind.strip_mt(r.stdout) == _bind.strip_mt(g.paf)
+    w = World(n_contigs=3, genome_len=900_000, n_reads=600, read_bp=3000, seed=31)
+    big = str(tmp_path / "big.blow5")
+    api.write_slow5(big, w.names, w.reads["raw"], synth.OFFSET, synth.RANGE, synth.DIGITISATION)
+    ind = str(tmp_path / "w.ind")
+    assert run([CLI, "-x", "sensitive", "-p", w.model, "-d", ind, w.fasta]).returncode == 0
+    one = run([CLI, "-x", "sensitive", "-K", "8M", ind, big])
+    two = run([CLI, "-x", "sensitive", "-K", "8M", "--gpus", "2", ind, big])
+    assert one.returncode == 0 and two.returncode == 0, one.stderr + two.stderr
+    assert len(one.stdout.splitlines()) >= 600 and _bind.strip_mt(one.stdout) == _bind.strip_mt(two.stdout)
