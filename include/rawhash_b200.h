@@ -259,6 +259,9 @@ void          rh_sigfile_close(rh_sigfile_t *f);
  * file ends.  *out == NULL with RH_OK at end of file. */
 int  rh_sigfile_next_batch(rh_sigfile_t *f, uint64_t max_samples, uint32_t max_reads, rh_sigbatch_t **out);
 void rh_sigbatch_free(rh_sigbatch_t *b);
+/* One zlib stream -> malloc'ed bytes (rh_free): the record decompression of slow5lib's ptr_depress_zlib_solo
+ * (extern/slow5lib/src/slow5_press.c:945-982) through this library's own inflate (csrc/rh_inflate.h, Adler-32 checked). */
+int  rh_zlib_inflate(const void *in, size_t in_bytes, void **out, size_t *out_bytes);
 /* find_sfiles (src/rsig.c:286-330): `path` itself or, for a directory, every *.slow5 / *.blow5 below it.
  * Returns a malloc'ed array of malloc'ed strings (rh_free each, then the array). */
 int  rh_find_sigfiles(const char *path, char ***files, uint32_t *n_files);

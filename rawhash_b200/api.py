@@ -166,6 +166,7 @@ def _load():
         "rh_sigfile_close": (None, [vp]),
         "rh_sigfile_next_batch": (i32, [vp, u64, u32, C.POINTER(C.POINTER(SigBatchC))]),
         "rh_sigbatch_free": (None, [C.POINTER(SigBatchC)]),
+        "rh_zlib_inflate": (i32, [vp, C.c_size_t, C.POINTER(vp), C.POINTER(C.c_size_t)]),
         "rh_find_sigfiles": (i32, [cp, C.POINTER(C.POINTER(vp)), C.POINTER(u32)]),
         "rh_slow5_write": (i32, [cp, u32, vp, vp, vp, vp, vp, vp, dbl, i32, i32]),
     }
@@ -430,6 +431,17 @@ def read_fasta(path: str):
     out_s = [C.string_at(seqs[i], lens[i]) for i in range(n.value)]
     _lib.rh_fasta_free(n, names, seqs, lens)
     return out_n, out_s
+
+
+def zlib_inflate(data: bytes) -> bytes:
+    """One zlib stream through the library's own inflate (csrc/rh_inflate.h)."""
+    out, n = C.c_void_p(), C.c_size_t(0)
+    buf = (C.c_char * max(len(data), 1)).from_buffer_copy(data or b"\0")
+    if _lib.rh_zlib_inflate(C.cast(buf, C.c_void_p), len(data), C.byref(out), C.byref(n)) != 0:
+        raise _err("rh_zlib_inflate")
+    res = C.string_at(out, n.value)
+    _lib.rh_free(out)
+    return res
 
 
 def find_signal_files(path: str):

@@ -35,6 +35,7 @@
 #include <cuda_runtime_api.h>
 
 #include "rh_host.h"
+#include "rh_inflate.h"
 
 /* ================================================================================================================
  * `.ind` writer
@@ -328,6 +329,22 @@ bool zlib_inflate(const uint8_t *in, size_t in_bytes, std::vector<uint8_t> &out)
 	return rc == Z_STREAM_END;
 }
 
+/* records go through the table-driven decoder of rh_inflate.h (it needs readable bytes after the input: the file
+ * mapping provides them except for the last records of a file, which are copied); RH_ZLIB=1 selects zlib's inflate */
+bool inflate_record(const uint8_t *in, size_t in_bytes, size_t readable_after, std::vector<uint8_t> &out)
+{
+	static const bool use_zlib = []() { const char *e = getenv("RH_ZLIB"); return e && e[0] == '1'; }();
+	if (use_zlib) return zlib_inflate(in, in_bytes, out);
+	bool ok;
+	if (readable_after >= rhz::RH_INFLATE_SLACK) ok = rhz::inflate_zlib(in, in_bytes, out);
+	else {
+		std::vector<uint8_t> padded(in_bytes + rhz::RH_INFLATE_SLACK, 0);
+		memcpy(padded.data(), in, in_bytes);
+		ok = rhz::inflate_zlib(padded.data(), in_bytes, out);
+	}
+	return ok || zlib_inflate(in, in_bytes, out); /* second opinion: zlib decides what is malformed */
+}
+
 bool zlib_deflate(const uint8_t *in, size_t in_bytes, std::vector<uint8_t> &out)
 {
 	uLongf cap = compressBound((uLong)in_bytes);
@@ -339,7 +356,7 @@ bool zlib_deflate(const uint8_t *in, size_t in_bytes, std::vector<uint8_t> &out)
 
 /* ---- one record between the file and the arena ------------------------------------------------------------------ */
 struct rec_t {
-	const uint8_t *src = nullptr; size_t src_bytes = 0; /* binary: the stored record inside the file mapping */
+	const uint8_t *src = nullptr; size_t src_bytes = 0, src_slack = 0; /* binary: the stored record inside the file mapping (+ readable bytes after it) */
 	std::vector<uint8_t> mem;       /* binary: the inflated record when records are compressed; ASCII: the line */
 	const uint8_t *body = nullptr; size_t body_bytes = 0; /* what the fields are parsed from (src or mem) */
 	std::string name;
@@ -353,7 +370,7 @@ bool parse_binary_record(rec_t &r, int rec_method, int sig_method)
 { /* slow5_rec_parse, binary branch (slow5.c:2806-2925): u16 id_len, id, u32 read_group, 4 doubles, u64 length, signal */
 	r.body = r.src; r.body_bytes = r.src_bytes;
 	if (rec_method == PRESS_ZLIB) {
-		if (!zlib_inflate(r.src, r.src_bytes, r.mem)) return false;
+		if (!inflate_record(r.src, r.src_bytes, r.src_slack, r.mem)) return false;
 		r.body = r.mem.data(); r.body_bytes = r.mem.size();
 	}
 	const uint8_t *p = r.body; const size_t n = r.body_bytes; size_t at = 0;
@@ -511,7 +528,7 @@ extern "C" rh_sigfile_t *rh_sigfile_open(const char *path, int n_threads)
 		else {
 			const unsigned major = h[6], minor = h[7];
 			f->rec_method = h[9];
-			f->sig_method = (major > 0 || minor >= 2) ? h[14] : SIG_NONE; /* signal compression byte exists from 0.2.0 (slow5.c:824) */
+			f->sig_method = (major > 0 || minor >= 2) ? (int)h[14] : (int)SIG_NONE; /* signal compression byte exists from 0.2.0 (slow5.c:824) */
 			if (major > 0 || minor > 2) { rh_set_error("%s: BLOW5 version %u.%u.%u is newer than 0.2.0", path, major, minor, (unsigned)h[8]); ok = false; }
 			else if (f->rec_method == PRESS_ZSTD) { rh_set_error("%s: zstd record compression is not available in this build (zlib and none are)", path); ok = false; }
 			else if (f->rec_method > PRESS_ZSTD || f->sig_method > SIG_SVB_ZD) { rh_set_error("%s: unknown compression method (record %d, signal %d)", path, f->rec_method, f->sig_method); ok = false; }
@@ -561,7 +578,7 @@ static int read_stored_record(rh_sigfile_s *f, rec_t &r)
 		}
 		uint64_t sz; memcpy(&sz, f->map + f->map_at, 8);
 		if (sz > left - 8) { rh_set_error("%s: truncated BLOW5 record", f->path.c_str()); return RH_ERR_FORMAT; }
-		r.src = f->map + f->map_at + 8; r.src_bytes = sz;
+		r.src = f->map + f->map_at + 8; r.src_bytes = sz; r.src_slack = left - 8 - sz;
 		f->map_at += 8 + sz;
 		return 1;
 	}
@@ -657,6 +674,19 @@ extern "C" void rh_sigbatch_free(rh_sigbatch_t *pub)
 	}
 	delete b;
 	if (destroy) sigfile_destroy(f);
+}
+
+extern "C" int rh_zlib_inflate(const void *in, size_t in_bytes, void **out, size_t *out_bytes)
+{
+	if (!in || !out || !out_bytes) { rh_set_error("rh_zlib_inflate: bad arguments"); return RH_ERR_ARG; }
+	std::vector<uint8_t> padded(in_bytes + rhz::RH_INFLATE_SLACK, 0), plain;
+	memcpy(padded.data(), in, in_bytes);
+	if (!rhz::inflate_zlib(padded.data(), in_bytes, plain)) { rh_set_error("rh_zlib_inflate: malformed zlib stream"); return RH_ERR_FORMAT; }
+	*out = malloc(plain.size() ? plain.size() : 1);
+	if (!*out) return RH_ERR_NOMEM;
+	memcpy(*out, plain.data(), plain.size());
+	*out_bytes = plain.size();
+	return RH_OK;
 }
 
 /* ---- directory scan -------------------------------------------------------------------------------------------- */

@@ -232,3 +232,44 @@ def test_ind_writer_signal_index_without_pore(built, tmp_path):
     assert back.n_keys == idx.n_keys and back.n_pos == idx.n_pos
     for i in range(0, idx.n_keys, 97):
         assert np.array_equal(back.get(idx.key(i)), idx.get(idx.key(i)))
+
+
+def test_own_inflate_equals_zlib(built):
+    """csrc/rh_inflate.h (the BLOW5 record decompressor) against Python's zlib: stored, fixed and dynamic blocks, long
+    codes (sub-tables), every level/strategy, small windows, multi-block streams; damaged streams are errors."""
+    import random
+    import zlib
+    from rawhash_b200 import api
+    rng = np.random.default_rng(5)
+    random.seed(5)
+    skew = np.array([1.6 ** -i for i in range(1, 256)])
+    skew /= skew.sum()
+    datas = [b"", b"a", b"hello hello hello hello hello", bytes(70000), bytes(rng.integers(0, 256, 200000, dtype=np.uint8)),
+             bytes(rng.integers(0, 4, 300000, dtype=np.uint8)), open(__file__, "rb").read() * 3,
+             np.cumsum(rng.integers(-40, 40, 200000)).astype(np.int16).tobytes(), (b"abc" * 7 + b"Z") * 9000,
+             bytes(rng.choice(255, size=600000, p=skew).astype(np.uint8))]
+    datas += [bytes(rng.integers(0, 256, n, dtype=np.uint8)) for n in (2, 3, 257, 258, 259, 65535, 65536, 65537)]
+    n = 0
+    for data in datas:
+        for level in (0, 1, 6, 9):
+            for strategy in (zlib.Z_DEFAULT_STRATEGY, zlib.Z_HUFFMAN_ONLY, zlib.Z_FIXED, zlib.Z_RLE):
+                for wbits in (15, 9):
+                    c = zlib.compressobj(level, zlib.DEFLATED, wbits, 8, strategy)
+                    assert api.zlib_inflate(c.compress(data) + c.flush()) == data, (len(data), level, strategy, wbits)
+                    n += 1
+    assert n >= 500
+    c, parts, blob = zlib.compressobj(6), [], b""
+    for i in range(40):
+        d = bytes(rng.integers(0, 256, int(rng.integers(1, 5000)), dtype=np.uint8)) if i % 2 else b"run" * int(rng.integers(1, 3000))
+        blob += d
+        parts += [c.compress(d), c.flush(random.choice([zlib.Z_SYNC_FLUSH, zlib.Z_FULL_FLUSH, zlib.Z_NO_FLUSH, zlib.Z_BLOCK]))]
+    assert api.zlib_inflate(b"".join(parts) + c.flush()) == blob
+    z = zlib.compress(open(__file__, "rb").read(), 6)
+    for k in range(400):
+        b = bytearray(z)
+        b[random.randrange(len(b))] ^= 1 << random.randrange(8)
+        with pytest.raises(api.RawHashError):
+            api.zlib_inflate(bytes(b))
+    for cut in range(0, len(z), 211):
+        with pytest.raises(api.RawHashError):
+            api.zlib_inflate(z[:cut])
