@@ -175,3 +175,55 @@ def test_patched_reference_index_only_mode_is_untouched(built, tmp_path):
     x, y = np.fromfile(a, np.uint8), np.fromfile(b, np.uint8)
     d = np.nonzero(x != y)[0]
     assert x.size == y.size and d.size <= 16
+
+
+# ---- option parsing next to the reference's: both programs print the values in effect in their help text -------------
+_NUM = r"\[(-?[0-9][0-9.e+-]*(?:, ?-?[0-9][0-9.e+-]*)?)\]"
+_SHOWN = ["-k", "-e", "-q", "-w", "-t", "--level_column", "--sig-diff", "--q-mid-occ", "--min-events", "--bw", "--max-target-gap", "--max-query-gap",
+          "--min-anchors", "--best-chains", "--min-score", "--chain-gap-scale", "--chain-skip-scale", "--primary-ratio", "--primary-length",
+          "--max-skips", "--max-iterations", "--max-chunks", "--min-mapq", "--bp-per-sec", "--sample-rate", "--chunk-size",
+          "--seg-window-length1", "--seg-window-length2", "--seg-threshold1", "--seg-threshold2", "--seg-peak-height", "--io-thread"]
+
+
+def _values_in_help(text):
+    import re
+    out = {}
+    for name in _SHOWN:
+        m = re.search(r"(?m)^\s+" + re.escape(name) + r" [A-Z][^\n]*", text) if not name.startswith("--") else re.search(re.escape(name) + r" [A-Z][^\n]*", text)
+        assert m, name
+        seg = m.group(0)
+        nxt = re.search(r"\s--[a-z]", seg[len(name):])  # our help lists several options on one line
+        if nxt:
+            seg = seg[:len(name) + nxt.start()]
+        v = re.search(_NUM, seg)
+        assert v, (name, seg)
+        out[name] = [float(x) for x in v.group(1).replace(" ", "").split(",")]
+    return out
+
+
+@needs_ref_cli
+@pytest.mark.parametrize("args", [
+    [],
+    ["-x", "viral"], ["-x", "sensitive"], ["-x", "fast"], ["-x", "faster"], ["-x", "ava"], ["-x", "ava-sensitive"], ["-x", "ava-viral"], ["-x", "ava-large"],
+    ["--r10"], ["--depletion"], ["-x", "fast", "--r10", "--depletion"],
+    ["--bw", "77", "-x", "viral"],  # the preset is applied first wherever it stands
+    ["-k", "9", "-e", "7", "-q", "3", "-w", "5", "-t", "12", "--io-thread", "4", "--level_column", "2", "--sig-diff", "0.3"],
+    ["--q-mid-occ", "40,9000", "--min-events", "33", "--max-target-gap", "1234", "--max-query-gap", "4321", "--min-anchors", "4", "--best-chains", "3"],
+    ["--q-mid-occ", "60", "--min-score", "21", "--chain-gap-scale", "0.75", "--chain-skip-scale", "0.125", "--primary-ratio", "0.25", "--primary-length", "5000"],
+    ["--max-skips", "9", "--max-iterations", "150", "--max-chunks", "3", "--min-mapq", "7", "--chunk-size", "5000"],
+    ["--bp-per-sec", "400", "--sample-rate", "5000"], ["--sample-rate", "5000", "--bp-per-sec", "400"],
+    ["--seg-window-length1", "4", "--seg-window-length2", "8", "--seg-threshold1", "5.5", "--seg-threshold2", "2.25", "--seg-peak-height", "0.3"],
+    ["-k9", "-e7", "--bw=99"],
+])
+def test_cli_options_take_effect_like_the_reference(built, args):
+    """`<options> -h` prints the values in effect in both programs (the reference prints its help after parsing,
+    src/main.cpp:421-520): every option shown by both must agree, for presets, macros and single options."""
+    if "--bw=99" in args:  # ketopt also accepts --name=value; give the reference the spaced form of the same options
+        ref_args = ["-k", "9", "-e", "7", "--bw", "99"]
+    else:
+        ref_args = args
+    mine = run([CLI] + args + ["-h"])
+    ref = run([REF_CLI] + ref_args + ["-h"])
+    assert mine.returncode == 0 and ref.returncode == 0
+    a, b = _values_in_help(mine.stdout), _values_in_help(ref.stdout)
+    assert a == b, {k: (a[k], b[k]) for k in a if a[k] != b[k]}
