@@ -319,32 +319,60 @@ extern "C" rh_index_t *rh_index_load(const char *path, rh_params_t *pp)
 			if (ok && !(idx->flag & 0x40)) { ok = fread(&nf, 4, 1, f) == 1 && fseek(f, (long)nf * 4, SEEK_CUR) == 0; }
 		}
 	}
-	/* 2^14 buckets (the bucket-bit count is not stored; the reference hard-codes 14, rindex.c:669) */
-	struct ent { uint32_t hash; uint64_t val; bool single; uint32_t bucket; };
+	/* 2^14 buckets (the bucket-bit count is not stored; the reference hard-codes 14, rindex.c:669).  Two passes so that a
+	 * human-size index (≈42 GB of positions) is never held twice: pass 1 reads the (key, value) pairs and skips the
+	 * position arrays, pass 2 reads one bucket's positions at a time and drops each list at its final place. */
+	struct ent { uint32_t hash; uint32_t bucket; uint64_t val; bool single; };
 	std::vector<ent> ents;
-	std::vector<std::vector<uint64_t>> bp(1 << 14);
+	std::vector<int64_t> p_at(1 << 14, 0); std::vector<int32_t> p_n(1 << 14, 0);
+	std::vector<uint32_t> first_ent((1 << 14) + 1, 0);
 	for (uint32_t b = 0; ok && b < (1u << 14); ++b) {
 		int32_t n; uint32_t size;
-		ok = ok && fread(&n, 4, 1, f) == 1;
+		ok = ok && fread(&n, 4, 1, f) == 1 && n >= 0;
 		if (!ok) break;
-		bp[b].resize(n);
-		if (n) ok = fread(bp[b].data(), 8, n, f) == (size_t)n;
-		ok = ok && fread(&size, 4, 1, f) == 1;
+		p_n[b] = n; p_at[b] = (int64_t)ftello(f);
+		ok = fseeko(f, (off_t)n * 8, SEEK_CUR) == 0 && fread(&size, 4, 1, f) == 1;
+		first_ent[b] = (uint32_t)ents.size();
 		for (uint32_t j = 0; ok && j < size; ++j) {
 			uint64_t kv[2];
 			ok = fread(kv, 8, 2, f) == 2;
-			ents.push_back({(uint32_t)(((kv[0] >> 1) << 14) | b), kv[1], (kv[0] & 1) != 0, b});
+			const bool single = (kv[0] & 1) != 0;
+			if (ok && !single && ((kv[1] >> 32) + (uint32_t)kv[1] > (uint64_t)n || (uint32_t)kv[1] == 0)) ok = false; /* list outside the bucket's array */
+			ents.push_back({(uint32_t)(((kv[0] >> 1) << 14) | b), b, kv[1], single});
+		}
+	}
+	first_ent[1 << 14] = (uint32_t)ents.size();
+	if (ok) {
+		const size_t nk = ents.size();
+		std::vector<uint32_t> order(nk);
+		for (size_t i = 0; i < nk; ++i) order[i] = (uint32_t)i;
+		std::sort(order.begin(), order.end(), [&](uint32_t x, uint32_t y) { return ents[x].hash < ents[y].hash; });
+		idx->keys.resize(nk); idx->off.resize(nk + 1);
+		std::vector<uint32_t> rank(nk);
+		uint64_t total = 0;
+		for (size_t i = 0; i < nk; ++i) {
+			const ent &e = ents[order[i]];
+			if (i && e.hash == ents[order[i - 1]].hash) { ok = false; break; } /* a key stored twice */
+			idx->keys[i] = e.hash; idx->off[i] = total; rank[order[i]] = (uint32_t)i;
+			total += e.single ? 1 : (uint32_t)e.val;
+		}
+		idx->off[nk] = total;
+		if (ok) idx->pos.resize(total);
+		std::vector<uint64_t> bucket_pos;
+		for (uint32_t b = 0; ok && b < (1u << 14); ++b) {
+			if (first_ent[b] == first_ent[b + 1]) continue;
+			bucket_pos.resize((size_t)p_n[b]);
+			if (p_n[b]) ok = fseeko(f, (off_t)p_at[b], SEEK_SET) == 0 && fread(bucket_pos.data(), 8, (size_t)p_n[b], f) == (size_t)p_n[b];
+			for (uint32_t j = first_ent[b]; ok && j < first_ent[b + 1]; ++j) {
+				const ent &e = ents[j];
+				uint64_t *dst = &idx->pos[idx->off[rank[j]]];
+				if (e.single) *dst = e.val;
+				else memcpy(dst, &bucket_pos[e.val >> 32], (size_t)(uint32_t)e.val * 8);
+			}
 		}
 	}
 	fclose(f);
-	if (!ok) { delete idx; rh_set_error("%s: truncated index", path); return NULL; }
-	std::sort(ents.begin(), ents.end(), [](const ent &a, const ent &b) { return a.hash < b.hash; });
-	for (const ent &e : ents) {
-		idx->keys.push_back(e.hash); idx->off.push_back(idx->pos.size());
-		if (e.single) idx->pos.push_back(e.val);
-		else { const uint64_t *src = &bp[e.bucket][e.val >> 32]; idx->pos.insert(idx->pos.end(), src, src + (uint32_t)e.val); }
-	}
-	idx->off.push_back(idx->pos.size());
+	if (!ok) { delete idx; rh_set_error("%s: truncated or inconsistent index", path); return NULL; }
 	if (pp) {
 		pp->w = idx->w; pp->e = idx->e; pp->n = idx->n; pp->q = idx->q; pp->k = idx->k; pp->idx_flag = idx->flag;
 		pp->diff = idx->diff; pp->fine_min = idx->fine_min; pp->fine_max = idx->fine_max; pp->fine_range = idx->fine_range;

@@ -215,6 +215,12 @@ def test_ind_writer_equals_reference_dump(built, tmp_path, preset, seed, glen):
         exp = idx.get(h)
         assert np.array_equal(ref_on_mine.idx_get(h), exp) and np.array_equal(back.get(h), exp)
     assert ref_on_mine.mapopt_update() == ref.mapopt_update()
+    # the loader, exhaustively: the reference's own file read by rh_index_load and written back gives the same bytes
+    again = str(tmp_path / "again.ind")
+    api.Index.load(theirs, api.make_params(preset)).dump(again, pore)
+    c = np.fromfile(again, np.uint8)
+    d2 = np.nonzero(c != b)[0]
+    assert c.size == b.size and d2.size <= 16 and (d2.size == 0 or (d2.min() >= 46 and d2.max() < 62))
 
 
 @needs_ref
