@@ -274,8 +274,15 @@ def test_own_inflate_equals_zlib(built):
     for k in range(400):
         b = bytearray(z)
         b[random.randrange(len(b))] ^= 1 << random.randrange(8)
-        with pytest.raises(api.RawHashError):
-            api.zlib_inflate(bytes(b))
+        try:  # same verdict as zlib: a flipped padding bit before the Adler-32 trailer is harmless, anything else is an error
+            want = zlib.decompress(bytes(b))
+        except zlib.error:
+            want = None
+        if want is None:
+            with pytest.raises(api.RawHashError):
+                api.zlib_inflate(bytes(b))
+        else:
+            assert api.zlib_inflate(bytes(b)) == want
     for cut in range(0, len(z), 211):
         with pytest.raises(api.RawHashError):
             api.zlib_inflate(z[:cut])
