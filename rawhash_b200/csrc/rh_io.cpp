@@ -467,13 +467,42 @@ arena_t arena_alloc(size_t samples)
 
 void arena_free(arena_t &a) { if (a.p) { if (a.pinned) cudaFreeHost(a.p); else free(a.p); } a = arena_t(); }
 
+/* Page-locking a 1 GB arena costs a few hundred milliseconds, so arenas are recycled: a process-wide pool of at most
+ * three (one being decoded into, one queued, one being mapped), shared by all signal files that are read one after
+ * the other.  What is still pooled at exit is left to the operating system. */
+std::mutex g_pool_mu;
+std::vector<arena_t> g_pool;
+
+arena_t arena_take(size_t samples)
+{
+	arena_t drop;
+	{
+		std::lock_guard<std::mutex> g(g_pool_mu);
+		for (size_t i = 0; i < g_pool.size(); ++i)
+			if (g_pool[i].cap >= samples) { arena_t a = g_pool[i]; g_pool.erase(g_pool.begin() + i); return a; }
+		if (!g_pool.empty()) { drop = g_pool.back(); g_pool.pop_back(); } /* too small for this batch: replace it */
+	}
+	arena_free(drop);
+	return arena_alloc(samples + samples / 8);
+}
+
+void arena_give_back(arena_t &a)
+{
+	if (!a.p) return;
+	{
+		std::lock_guard<std::mutex> g(g_pool_mu);
+		if (g_pool.size() < 3) { g_pool.push_back(a); a = arena_t(); return; }
+	}
+	arena_free(a);
+}
+
 } // namespace
 
 struct rh_sigfile_s {
 	FILE *fp = nullptr; std::string path;
 	bool binary = false; int rec_method = PRESS_NONE, sig_method = SIG_NONE;
 	int n_threads = 1; bool eof = false;
-	std::mutex mu; std::vector<arena_t> pool; /* arenas handed back by freed batches */
+	std::mutex mu;
 	std::atomic<int> live_batches{0}; bool closed = false;
 	char *line = nullptr; size_t line_cap = 0;
 	const uint8_t *map = nullptr; size_t map_bytes = 0, map_at = 0; /* binary files are read through a mapping: no copies */
@@ -492,7 +521,6 @@ struct batch_impl {
 
 void sigfile_destroy(rh_sigfile_s *f)
 {
-	for (arena_t &a : f->pool) arena_free(a);
 	if (f->map) munmap((void *)f->map, f->map_bytes);
 	if (f->fp) fclose(f->fp);
 	free(f->line);
@@ -625,14 +653,8 @@ extern "C" int rh_sigfile_next_batch(rh_sigfile_t *f, uint64_t max_samples, uint
 	if (recs.empty()) return RH_OK;
 	batch_impl *b = new batch_impl();
 	b->owner = f;
-	{
-		std::lock_guard<std::mutex> g(f->mu);
-		for (size_t i = 0; i < f->pool.size(); ++i)
-			if (f->pool[i].cap >= total) { b->arena = f->pool[i]; f->pool.erase(f->pool.begin() + i); break; }
-		if (!b->arena.p && !f->pool.empty()) { arena_free(f->pool.back()); f->pool.pop_back(); } /* too small: replace */
-		++f->live_batches;
-	}
-	if (!b->arena.p) b->arena = arena_alloc(total + total / 8);
+	b->arena = arena_take(total);
+	++f->live_batches;
 	if (!b->arena.p) { rh_set_error("out of host memory for a %llu-sample batch", (unsigned long long)total); --f->live_batches; delete b; return RH_ERR_NOMEM; }
 	const size_t n = recs.size();
 	b->raw.resize(n); b->len.resize(n); b->offset.resize(n); b->range.resize(n); b->digitisation.resize(n); b->sampling_rate.resize(n);
@@ -666,10 +688,10 @@ extern "C" void rh_sigbatch_free(rh_sigbatch_t *pub)
 	if (!pub) return;
 	batch_impl *b = (batch_impl *)pub->priv;
 	rh_sigfile_s *f = b->owner;
+	arena_give_back(b->arena);
 	bool destroy = false;
 	{
 		std::lock_guard<std::mutex> g(f->mu);
-		if (!f->closed && f->pool.size() < 3) f->pool.push_back(b->arena); else arena_free(b->arena);
 		destroy = --f->live_batches == 0 && f->closed;
 	}
 	delete b;
