@@ -185,6 +185,11 @@ int rh_gpu_map_batch_dev(rh_gpu_ctx *ctx, uint32_t n,
                          const char *const *names,
                          rh_map_rec_t **recs, uint64_t *n_recs);
 
+/* Multi-GPU sharding of a mini-batch: boundaries cut[0..parts] of contiguous read ranges with nearly
+ * equal raw sample counts; range r = reads [cut[r], cut[r+1]).  Order preserving, every read in exactly one range.
+ * The same rule cuts a batch into worker ranges inside one context. */
+void rh_split_by_samples(uint32_t n, const uint64_t *raw_len, uint32_t parts, uint32_t *cut);
+
 /* Per-stage statistics of the last rh_gpu_map_batch_* call. */
 typedef struct rh_gpu_stats_s {
 	uint64_t n_reads, n_chunks, n_rounds;

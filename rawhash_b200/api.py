@@ -166,6 +166,7 @@ def _load():
         "rh_sigfile_close": (None, [vp]),
         "rh_sigfile_next_batch": (i32, [vp, u64, u32, C.POINTER(C.POINTER(SigBatchC))]),
         "rh_sigbatch_free": (None, [C.POINTER(SigBatchC)]),
+        "rh_split_by_samples": (None, [u32, vp, u32, vp]),
         "rh_zlib_inflate": (i32, [vp, C.c_size_t, C.POINTER(vp), C.POINTER(C.c_size_t)]),
         "rh_find_sigfiles": (i32, [cp, C.POINTER(C.POINTER(vp)), C.POINTER(u32)]),
         "rh_slow5_write": (i32, [cp, u32, vp, vp, vp, vp, vp, vp, dbl, i32, i32]),
@@ -431,6 +432,14 @@ def read_fasta(path: str):
     out_s = [C.string_at(seqs[i], lens[i]) for i in range(n.value)]
     _lib.rh_fasta_free(n, names, seqs, lens)
     return out_n, out_s
+
+
+def split_by_samples(lens, parts: int) -> np.ndarray:
+    """rh_split_by_samples: boundaries of `parts` contiguous read ranges balanced by sample count."""
+    lens = np.ascontiguousarray(lens, dtype=np.uint64)
+    cut = np.zeros(parts + 1, dtype=np.uint32)
+    _lib.rh_split_by_samples(len(lens), lens.ctypes.data, parts, cut.ctypes.data)
+    return cut
 
 
 def zlib_inflate(data: bytes) -> bytes:

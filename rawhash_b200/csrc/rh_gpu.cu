@@ -545,14 +545,7 @@ void add_stats(rh_gpu_stats_t &a, const rh_gpu_stats_t &b)
 std::vector<uint32_t> split_ranges(uint32_t n, const std::vector<uint64_t> &len, uint32_t k)
 {
 	std::vector<uint32_t> b(k + 1, n);
-	b[0] = 0;
-	uint64_t total = 0;
-	for (uint32_t i = 0; i < n; ++i) total += len[i];
-	uint64_t acc = 0; uint32_t r = 1;
-	for (uint32_t i = 0; i < n && r < k; ++i) {
-		acc += len[i];
-		while (r < k && acc * k >= total * r) b[r++] = i + 1;
-	}
+	rh_split_by_samples(n, len.data(), k, b.data());
 	return b;
 }
 

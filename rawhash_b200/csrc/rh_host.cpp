@@ -415,6 +415,21 @@ extern "C" void rh_index_update_mapopt(const rh_index_t *idx, rh_params_t *p)
 	p->mid_occ = thres;
 }
 
+/* ---- sharding ------------------------------------------------------------------------------------ */
+extern "C" void rh_split_by_samples(uint32_t n, const uint64_t *raw_len, uint32_t parts, uint32_t *cut)
+{ /* range r ends after the first read at which the running sample count reaches r/parts of the total */
+	if (!cut || parts == 0) return;
+	for (uint32_t r = 0; r <= parts; ++r) cut[r] = n;
+	cut[0] = 0;
+	unsigned __int128 total = 0;
+	for (uint32_t i = 0; i < n; ++i) total += raw_len[i];
+	unsigned __int128 acc = 0; uint32_t r = 1;
+	for (uint32_t i = 0; i < n && r < parts; ++i) {
+		acc += raw_len[i];
+		while (r < parts && acc * parts >= total * r) cut[r++] = i + 1;
+	}
+}
+
 /* ---- PAF ---------------------------------------------------------------------------------------- */
 extern "C" char *rh_format_paf(const rh_index_t *idx, const rh_map_rec_t *recs, uint64_t n_recs, const char *const *names)
 { /* line formats of src/rmap.cpp:751-764 (mapped) and 768-772 (unmapped); tags of 527-570 */

@@ -256,11 +256,7 @@ int map_on_gpus(std::vector<rh_gpu_ctx *> &ctx, const rh_sigbatch_t *b, rh_map_r
 	const size_t G = ctx.size();
 	if (G == 1) return rh_gpu_map_batch_raw(ctx[0], b->n, b->raw, b->raw_len, b->offset, b->range, b->digitisation, b->names, recs, n_recs);
 	std::vector<uint32_t> cut(G + 1, b->n);
-	cut[0] = 0;
-	{
-		uint64_t acc = 0; size_t g = 1;
-		for (uint32_t i = 0; i < b->n && g < G; ++i) { acc += b->raw_len[i]; if (acc * G >= b->n_samples * g) cut[g++] = i + 1; }
-	}
+	rh_split_by_samples(b->n, b->raw_len, (uint32_t)G, cut.data());
 	std::vector<rh_map_rec_t *> part(G, nullptr); std::vector<uint64_t> pn(G, 0); std::vector<int> rc(G, RH_OK); std::vector<std::string> err(G);
 	std::vector<std::thread> th;
 	for (size_t g = 0; g < G; ++g) th.emplace_back([&, g]() {

@@ -21,6 +21,26 @@ def test_split_is_a_balanced_partition():
             assert per.max() - per.min() <= 2 * lens.max()
 
 
+def test_library_split_is_a_balanced_partition(built):
+    """rh_split_by_samples — what the command line (--gpus N) and the in-context worker ranges use — obeys the same
+    contract as shard.split_by_samples: ordered, complete, balanced to within one read either side of every cut."""
+    from rawhash_b200 import api
+    rng = np.random.Generator(np.random.PCG64(4))
+    for n, parts in [(0, 2), (1, 4), (7, 8), (1000, 2), (1000, 8), (5, 8), (3000, 3), (64, 1)]:
+        lens = rng.integers(1, 90_000, n).astype(np.uint64)
+        b = api.split_by_samples(lens, parts).astype(np.int64)
+        assert len(b) == parts + 1 and b[0] == 0 and b[-1] == n and np.all(np.diff(b) >= 0)
+        if n:
+            cs = np.concatenate([[0], np.cumsum(lens)]).astype(np.float64)
+            for r in range(1, parts):  # each cut sits at the first read where the running count reaches r/parts of the total
+                target = cs[-1] * r / parts
+                assert cs[b[r]] >= target and (b[r] == 0 or cs[b[r] - 1] < target)
+    # degenerate shapes: one huge read, zero-length reads, more parts than reads
+    assert list(api.split_by_samples([10**12, 1, 1, 1], 4)) == [0, 1, 1, 1, 4]
+    assert list(api.split_by_samples([0, 0, 0], 2)) == [0, 1, 3]
+    assert list(api.split_by_samples([5], 3)) == [0, 1, 1, 1]
+
+
 def _worker(rank, world, port, lens, q):
     import torch.distributed as dist
     os.environ["MASTER_ADDR"] = "127.0.0.1"
