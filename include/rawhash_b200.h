@@ -243,7 +243,8 @@ int  rh_fasta_load(const char *path, uint32_t *n_seq, char ***names, char ***seq
 void rh_fasta_free(uint32_t n_seq, char **names, char **seqs, uint32_t *lens);
 
 /* SLOW5 / BLOW5 signal files (ri_sig_open_slow5 + ri_read_sig_slow5, src/rsig.c:170-207,478-533; slow5lib
- * 0.2.0 file format: ASCII, or binary with record compression none|zlib and signal compression none|svb-zd).
+ * 0.2.0 file format: ASCII, or binary with record compression none|zlib|zstd and signal compression none|svb-zd;
+ * zstd is bound from libzstd.so.1 at run time and refused by name when that library is absent).
  * A batch keeps the raw int16 samples of its reads back to back in ONE arena (page-locked when a CUDA device
  * is usable) so that rh_gpu_map_batch_raw uploads it in a single copy; the pA conversion stays on the GPU. */
 typedef struct rh_sigfile_s rh_sigfile_t;
@@ -271,7 +272,7 @@ int  rh_zlib_inflate(const void *in, size_t in_bytes, void **out, size_t *out_by
  * Returns a malloc'ed array of malloc'ed strings (rh_free each, then the array). */
 int  rh_find_sigfiles(const char *path, char ***files, uint32_t *n_files);
 /* Writer used by the synthetic-data generator, bench and tests: `.slow5` (ASCII) or `.blow5`
- * (record_press 0 none | 1 zlib, signal_press 0 none | 1 svb-zd); slow5lib reads the result. */
+ * (record_press 0 none | 1 zlib | 2 zstd, signal_press 0 none | 1 svb-zd); slow5lib reads the result. */
 int  rh_slow5_write(const char *path, uint32_t n, const char *const *names,
                     const int16_t *const *raw, const uint64_t *raw_len,
                     const double *offset, const double *range, const double *digitisation, double sampling_rate,

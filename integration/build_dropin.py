@@ -87,7 +87,8 @@ def main():
             subprocess.run([cxx] + flags + ["-c", os.path.join(src, name + ext), "-o", obj], check=True)
             objs.append(obj)
         os.makedirs(os.path.dirname(OUT), exist_ok=True)
-        subprocess.run([cxx, "-pthread", "-o", OUT] + objs + s5_objs + ["-L" + LIBDIR, "-lrawhash_b200", "-Wl,-rpath,$ORIGIN/../../rawhash_b200", "-lz", "-lm", "-ldl"], check=True)
+        zstd = [p for p in ("/lib/x86_64-linux-gnu/libzstd.so.1", "/usr/lib/x86_64-linux-gnu/libzstd.so.1", "/usr/lib64/libzstd.so.1") if os.path.isfile(p)][:1]  # as oracle/Makefile
+        subprocess.run([cxx, "-pthread", "-o", OUT] + objs + s5_objs + zstd + ["-L" + LIBDIR, "-lrawhash_b200", "-Wl,-rpath,$ORIGIN/../../rawhash_b200", "-lz", "-lm", "-ldl"], check=True)
     print(OUT)
     return 0
 

@@ -38,3 +38,32 @@ void s5tap_close(void *h)
 	slow5_close(t->sp);
 	free(t);
 }
+
+/* Re-writes `in` as BLOW5 with the given compression (record: 0 none, 1 zlib, 2 zstd; signal: 0 none, 1 svb-zd)
+ * through slow5lib's own writer.  Returns the number of records, -100 when zstd was asked for but not compiled in. */
+int s5tap_convert(const char *in, const char *out, int record_press, int signal_press)
+{
+#ifndef SLOW5_USE_ZSTD
+	if (record_press == 2) return -100;
+#endif
+	slow5_file_t *src = slow5_open(in, "r");
+	if (!src) return -1;
+	slow5_file_t *dst = slow5_open(out, "w");
+	if (!dst) { slow5_close(src); return -2; }
+	/* same header: attributes of every read group, auxiliary field table */
+	slow5_hdr_t *tmp = dst->header;
+	dst->header = src->header;
+	enum slow5_press_method rp = record_press == 2 ? SLOW5_COMPRESS_ZSTD : record_press == 1 ? SLOW5_COMPRESS_ZLIB : SLOW5_COMPRESS_NONE;
+	enum slow5_press_method sp = signal_press == 1 ? SLOW5_COMPRESS_SVB_ZD : SLOW5_COMPRESS_NONE;
+	int n = -3;
+	if (slow5_set_press(dst, rp, sp) == 0 && slow5_hdr_write(dst) >= 0) {
+		slow5_rec_t *rec = NULL;
+		n = 0;
+		while (slow5_get_next(&rec, src) >= 0) { if (slow5_write(rec, dst) < 0) { n = -4; break; } ++n; }
+		slow5_rec_free(rec);
+	}
+	dst->header = tmp;
+	slow5_close(dst);
+	slow5_close(src);
+	return n;
+}

@@ -51,7 +51,7 @@ def build_lib(force: bool = False, verbose: bool = False) -> str:
             _run([nvcc] + COMPILE_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj], verbose)
             relink = True
     if relink or _newer(LIB, objs):
-        _run([nvcc] + LINK_FLAGS + ["-o", LIB] + objs + ["-lz"], verbose)
+        _run([nvcc] + LINK_FLAGS + ["-o", LIB] + objs + ["-lz", "-ldl"], verbose)
     return LIB
 
 

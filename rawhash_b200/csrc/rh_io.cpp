@@ -20,6 +20,7 @@
 #include <string.h>
 #include <errno.h>
 #include <dirent.h>
+#include <dlfcn.h>
 #include <sys/mman.h>
 #include <sys/stat.h>
 #include <unistd.h>
@@ -329,6 +330,46 @@ bool zlib_inflate(const uint8_t *in, size_t in_bytes, std::vector<uint8_t> &out)
 	return rc == Z_STREAM_END;
 }
 
+/* zstd records (slow5lib built with zstd=1: ptr_compress_zstd / ptr_depress_zstd, slow5_press.c:1146-1200).  This image
+ * ships libzstd.so.1 without headers, so the four stable entry points are bound at run time; without the library zstd
+ * files are refused by name. */
+struct zstd_api {
+	size_t (*decompress)(void *, size_t, const void *, size_t) = nullptr;
+	unsigned long long (*frame_content_size)(const void *, size_t) = nullptr;
+	unsigned (*is_error)(size_t) = nullptr;
+	size_t (*compress)(void *, size_t, const void *, size_t, int) = nullptr;
+	size_t (*compress_bound)(size_t) = nullptr;
+	bool ok = false;
+};
+const zstd_api &zstd()
+{
+	static const zstd_api api = []() {
+		zstd_api a;
+		void *h = dlopen("libzstd.so.1", RTLD_NOW | RTLD_LOCAL);
+		if (!h) h = dlopen("libzstd.so", RTLD_NOW | RTLD_LOCAL);
+		if (!h) return a;
+		a.decompress = (size_t (*)(void *, size_t, const void *, size_t))dlsym(h, "ZSTD_decompress");
+		a.frame_content_size = (unsigned long long (*)(const void *, size_t))dlsym(h, "ZSTD_getFrameContentSize");
+		a.is_error = (unsigned (*)(size_t))dlsym(h, "ZSTD_isError");
+		a.compress = (size_t (*)(void *, size_t, const void *, size_t, int))dlsym(h, "ZSTD_compress");
+		a.compress_bound = (size_t (*)(size_t))dlsym(h, "ZSTD_compressBound");
+		a.ok = a.decompress && a.frame_content_size && a.is_error && a.compress && a.compress_bound;
+		return a;
+	}();
+	return api;
+}
+
+bool zstd_inflate(const uint8_t *in, size_t in_bytes, std::vector<uint8_t> &out)
+{
+	const zstd_api &z = zstd();
+	if (!z.ok) return false;
+	const unsigned long long n = z.frame_content_size(in, in_bytes);
+	if (n >= 0xfffffffffffffffeULL || n > ((unsigned long long)1 << 34)) return false; /* unknown / error / implausible */
+	out.resize((size_t)n);
+	const size_t got = z.decompress(out.data(), out.size(), in, in_bytes);
+	return !z.is_error(got) && got == n;
+}
+
 /* records go through the table-driven decoder of rh_inflate.h (it needs readable bytes after the input: the file
  * mapping provides them except for the last records of a file, which are copied); RH_ZLIB=1 selects zlib's inflate */
 bool inflate_record(const uint8_t *in, size_t in_bytes, size_t readable_after, std::vector<uint8_t> &out)
@@ -369,8 +410,8 @@ struct rec_t {
 bool parse_binary_record(rec_t &r, int rec_method, int sig_method)
 { /* slow5_rec_parse, binary branch (slow5.c:2806-2925): u16 id_len, id, u32 read_group, 4 doubles, u64 length, signal */
 	r.body = r.src; r.body_bytes = r.src_bytes;
-	if (rec_method == PRESS_ZLIB) {
-		if (!inflate_record(r.src, r.src_bytes, r.src_slack, r.mem)) return false;
+	if (rec_method == PRESS_ZLIB || rec_method == PRESS_ZSTD) {
+		if (!(rec_method == PRESS_ZLIB ? inflate_record(r.src, r.src_bytes, r.src_slack, r.mem) : zstd_inflate(r.src, r.src_bytes, r.mem))) return false;
 		r.body = r.mem.data(); r.body_bytes = r.mem.size();
 	}
 	const uint8_t *p = r.body; const size_t n = r.body_bytes; size_t at = 0;
@@ -558,7 +599,7 @@ extern "C" rh_sigfile_t *rh_sigfile_open(const char *path, int n_threads)
 			f->rec_method = h[9];
 			f->sig_method = (major > 0 || minor >= 2) ? (int)h[14] : (int)SIG_NONE; /* signal compression byte exists from 0.2.0 (slow5.c:824) */
 			if (major > 0 || minor > 2) { rh_set_error("%s: BLOW5 version %u.%u.%u is newer than 0.2.0", path, major, minor, (unsigned)h[8]); ok = false; }
-			else if (f->rec_method == PRESS_ZSTD) { rh_set_error("%s: zstd record compression is not available in this build (zlib and none are)", path); ok = false; }
+			else if (f->rec_method == PRESS_ZSTD && !zstd().ok) { rh_set_error("%s: zstd record compression needs libzstd.so.1 at run time, which is not installed (zlib and none are built in)", path); ok = false; }
 			else if (f->rec_method > PRESS_ZSTD || f->sig_method > SIG_SVB_ZD) { rh_set_error("%s: unknown compression method (record %d, signal %d)", path, f->rec_method, f->sig_method); ok = false; }
 			uint32_t hdr_bytes; memcpy(&hdr_bytes, h + BLOW5_HDR_SIZE_AT, 4);
 			if (ok) { /* the ASCII header block must end with the column-name line */
@@ -750,7 +791,8 @@ extern "C" int rh_slow5_write(const char *path, uint32_t n, const char *const *n
 	const std::string p(path);
 	const bool bin = has_suffix(p, ".blow5");
 	if (!bin && !has_suffix(p, ".slow5")) { rh_set_error("rh_slow5_write: %s must end in .slow5 or .blow5", path); return RH_ERR_ARG; }
-	if (record_press < 0 || record_press > PRESS_ZLIB || signal_press < 0 || signal_press > SIG_SVB_ZD) { rh_set_error("rh_slow5_write: unsupported compression"); return RH_ERR_ARG; }
+	if (record_press < 0 || record_press > PRESS_ZSTD || signal_press < 0 || signal_press > SIG_SVB_ZD) { rh_set_error("rh_slow5_write: unsupported compression"); return RH_ERR_ARG; }
+	if (record_press == PRESS_ZSTD && !zstd().ok) { rh_set_error("rh_slow5_write: libzstd.so.1 is not installed"); return RH_ERR_ARG; }
 	FILE *fp = fopen(path, "wb");
 	if (!fp) { rh_set_error("cannot create %s: %s", path, strerror(errno)); return RH_ERR_IO; }
 	file_out o(fp);
@@ -787,6 +829,13 @@ extern "C" int rh_slow5_write(const char *path, uint32_t n, const char *const *n
 			} else { const uint64_t sl = raw_len[i]; push(&sl, 8); push(raw[i], raw_len[i] * 2); }
 			const std::vector<uint8_t> *body = &rec;
 			if (record_press == PRESS_ZLIB) { if (!zlib_deflate(rec.data(), rec.size(), packed)) { o.ok = false; break; } body = &packed; }
+			else if (record_press == PRESS_ZSTD) {
+				const zstd_api &z = zstd();
+				packed.resize(z.compress_bound(rec.size()));
+				const size_t got = z.compress(packed.data(), packed.size(), rec.data(), rec.size(), 1); /* SLOW5_ZSTD_COMPRESS_LEVEL */
+				if (z.is_error(got)) { o.ok = false; break; }
+				packed.resize(got); body = &packed;
+			}
 			o.val((uint64_t)body->size()); o.put(body->data(), body->size());
 		} else {
 			line.clear();

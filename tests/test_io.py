@@ -96,7 +96,8 @@ def test_reader_equals_slow5lib_on_the_reference_files(built):
 
 
 @needs_s5
-@pytest.mark.parametrize("fname,rec,sig", [("a.slow5", 0, 0), ("b.blow5", 0, 0), ("c.blow5", 1, 0), ("d.blow5", 0, 1), ("e.blow5", 1, 1)])
+@pytest.mark.parametrize("fname,rec,sig", [("a.slow5", 0, 0), ("b.blow5", 0, 0), ("c.blow5", 1, 0), ("d.blow5", 0, 1), ("e.blow5", 1, 1),
+                                           ("f.blow5", 2, 0), ("g.blow5", 2, 1)])  # 2 = zstd records (libzstd.so.1 bound at run time)
 def test_writer_is_read_by_slow5lib_and_round_trips(built, tmp_path, fname, rec, sig):
     from rawhash_b200 import api
     names, raws, off, rg, dg = _edge_reads()
@@ -286,3 +287,24 @@ def test_own_inflate_equals_zlib(built):
     for cut in range(0, len(z), 211):
         with pytest.raises(api.RawHashError):
             api.zlib_inflate(z[:cut])
+
+
+@needs_s5
+@pytest.mark.skipif(not os.path.isdir(S5LIB), reason="reference tree not present")
+def test_reader_takes_zstd_files_written_by_slow5lib(built, tmp_path):
+    """The other direction for zstd: a file written by the reference's slow5lib (zstd records + svb-zd signals, the
+    combination slow5tools calls `-c zstd -s svb-zd`) read by rh_sigfile_*."""
+    src = os.path.join(ROOT, "oracle", "slow5_tap.c")
+    if "s5tap_convert" not in open(src).read():
+        pytest.skip("slow5_tap.c has no converter")
+    T = C.CDLL(S5TAP)
+    T.s5tap_convert.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.c_int]
+    out = str(tmp_path / "z.blow5")
+    rc = T.s5tap_convert(f"{S5LIB}/examples/example.slow5".encode(), out.encode(), 2, 1)
+    if rc == -100:
+        pytest.skip("slow5lib built without zstd")
+    assert rc == 5
+    exp = Slow5Lib().read(f"{S5LIB}/examples/example.slow5")
+    got, _ = read_mine(out)
+    assert same_records(got, exp)
+    assert open(out, "rb").read()[9] == 2  # record compression byte: zstd
