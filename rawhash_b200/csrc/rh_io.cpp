@@ -209,7 +209,21 @@ extern "C" int rh_fasta_load(const char *path, uint32_t *n_seq, char ***names, c
 			case SEQ:
 				if (line_start && (c == '>' || c == '@')) { nm.emplace_back(); sq.emplace_back(); mode = HEADER; name_done = false; }
 				else if (line_start && c == '+' && !sq.empty()) mode = PLUS;
-				else if (!nl && c != '\r' && c != ' ' && c != '\t' && !sq.empty()) sq.back().push_back(c);
+				else if (!nl) { /* the rest of this line (as far as it is buffered) in one append */
+					const char *e = (const char *)memchr(buf.data() + i, '\n', (size_t)(n - i));
+					const int end = e ? (int)(e - buf.data()) : n;
+					if (!sq.empty()) {
+						std::string &dst = sq.back();
+						const size_t before = dst.size();
+						dst.append(buf.data() + i, (size_t)(end - i));
+						if (memchr(buf.data() + i, '\r', (size_t)(end - i)) || memchr(buf.data() + i, ' ', (size_t)(end - i)) || memchr(buf.data() + i, '\t', (size_t)(end - i))) {
+							size_t w = before;
+							for (size_t r = before; r < dst.size(); ++r) if (dst[r] != '\r' && dst[r] != ' ' && dst[r] != '\t') dst[w++] = dst[r];
+							dst.resize(w);
+						}
+					}
+					i = end - 1; /* the newline (if buffered) is seen by the next iteration */
+				}
 				break;
 			case PLUS:
 				if (nl) { qual_left = sq.back().size(); mode = qual_left ? QUAL : SEQ; }
