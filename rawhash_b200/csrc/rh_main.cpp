@@ -20,6 +20,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <sys/time.h>
+#include <algorithm>
 #include <atomic>
 #include <condition_variable>
 #include <deque>
@@ -109,7 +110,9 @@ int64_t parse_num(const char *s)
 struct settings {
 	rh_params_t P;
 	const char *dump = NULL, *pore = NULL;
-	int n_threads = 3, io_threads = 1, n_gpus = 1, device = 0;
+	/* -t: the reference defaults to 3 mapping threads; here -t only sizes the host side (signal decoding, host index
+	 * builder), which has to keep up with a GPU, so the default is every hardware thread */
+	int n_threads = (int)std::max(3u, std::thread::hardware_concurrency()), io_threads = 1, n_gpus = 1, device = 0;
 	bool index_on_host = false, help = false;
 	int64_t mini_batch = 500000000; /* src/roptions.c:88 */
 };

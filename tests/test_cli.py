@@ -226,4 +226,6 @@ def test_cli_options_take_effect_like_the_reference(built, args):
     ref = run([REF_CLI] + ref_args + ["-h"])
     assert mine.returncode == 0 and ref.returncode == 0
     a, b = _values_in_help(mine.stdout), _values_in_help(ref.stdout)
+    if "-t" not in args:  # deliberate difference: the reference defaults to 3 mapping threads, rawhash2_b200 to all hardware threads (host-side decode)
+        assert b.pop("-t") == [3.0] and a.pop("-t")[0] >= 3
     assert a == b, {k: (a[k], b[k]) for k in a if a[k] != b[k]}
