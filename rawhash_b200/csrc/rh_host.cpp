@@ -243,12 +243,84 @@ static const unsigned char *base_code()
 	return t;
 }
 
+uint64_t rh_index_group_bases(uint64_t dflt)
+{
+	const char *e = getenv("RH_INDEX_GROUP_BASES");
+	if (!e || !*e) return dflt;
+	const unsigned long long v = strtoull(e, NULL, 10);
+	return v ? (uint64_t)v : dflt;
+}
+
+rh_index_t *rh_index_build_grouped(rh_index_builder_fn one, uint64_t group_bases, const rh_params_t *p, const float *pore_vals, uint32_t n_pore_vals,
+                                   uint32_t n_seq, const char *const *names, const char *const *seqs, const uint32_t *lens, int arg)
+{
+	std::vector<uint32_t> start; /* first sequence of every group */
+	uint64_t in_group = 0;
+	for (uint32_t i = 0; i < n_seq; ++i) {
+		if (i == 0 || in_group + lens[i] > group_bases) { start.push_back(i); in_group = 0; }
+		in_group += lens[i];
+	}
+	start.push_back(n_seq);
+	const size_t G = start.size() - 1;
+	std::vector<rh_index_s *> part(G, nullptr);
+	auto drop = [&]() { for (rh_index_s *q : part) delete q; };
+	for (size_t g = 0; g < G; ++g) {
+		const uint32_t a = start[g], m = start[g + 1] - a;
+		part[g] = one(p, pore_vals, n_pore_vals, m, names + a, seqs + a, lens + a, arg);
+		if (!part[g]) { drop(); return NULL; }
+	}
+	rh_index_s *idx = new rh_index_s();
+	index_set_params(idx, p);
+	for (uint32_t i = 0; i < n_seq; ++i) { idx->names.emplace_back(names[i]); idx->lens.push_back(lens[i]); }
+	/* sweep 1: union of the sorted key arrays with the summed list lengths */
+	std::vector<size_t> at(G, 0);
+	uint64_t total = 0;
+	for (;;) {
+		uint64_t key = UINT64_MAX;
+		for (size_t g = 0; g < G; ++g) if (at[g] < part[g]->keys.size() && part[g]->keys[at[g]] < key) key = part[g]->keys[at[g]];
+		if (key == UINT64_MAX) break;
+		idx->keys.push_back((uint32_t)key); idx->off.push_back(total);
+		for (size_t g = 0; g < G; ++g) if (at[g] < part[g]->keys.size() && part[g]->keys[at[g]] == key) { total += part[g]->off[at[g] + 1] - part[g]->off[at[g]]; ++at[g]; }
+	}
+	idx->off.push_back(total);
+	idx->pos.resize(total);
+	/* sweep 2: lists in group order, sequence ids rebased to the whole reference */
+	std::fill(at.begin(), at.end(), 0);
+	for (size_t ki = 0; ki < idx->keys.size(); ++ki) {
+		uint64_t w = idx->off[ki];
+		for (size_t g = 0; g < G; ++g) {
+			const rh_index_s *q = part[g];
+			if (at[g] >= q->keys.size() || q->keys[at[g]] != idx->keys[ki]) continue;
+			const uint64_t rebase = (uint64_t)start[g] << 32;
+			for (uint64_t j = q->off[at[g]]; j < q->off[at[g] + 1]; ++j) idx->pos[w++] = q->pos[j] + rebase;
+			++at[g];
+		}
+	}
+	drop();
+	return idx;
+}
+
+static rh_index_t *index_build_host_one(const rh_params_t *p, const float *pore_vals, uint32_t n_pore_vals,
+                                        uint32_t n_seq, const char *const *names, const char *const *seqs,
+                                        const uint32_t *lens, int n_threads);
+
 extern "C" rh_index_t *rh_index_build(const rh_params_t *p, const float *pore_vals, uint32_t n_pore_vals,
                                        uint32_t n_seq, const char *const *names, const char *const *seqs,
                                        const uint32_t *lens, int n_threads)
+{
+	if (!p || !pore_vals || n_pore_vals < (1u << (2 * p->k)) || (n_seq && (!names || !seqs || !lens))) { rh_set_error("rh_index_build: bad arguments"); return NULL; }
+	uint64_t total = 0;
+	for (uint32_t i = 0; i < n_seq; ++i) total += lens[i];
+	const uint64_t group = rh_index_group_bases(UINT64_MAX); /* the host builder needs no grouping; the env knob exists to test the merge */
+	if (n_seq > 1 && total > group) return rh_index_build_grouped(index_build_host_one, group, p, pore_vals, n_pore_vals, n_seq, names, seqs, lens, n_threads);
+	return index_build_host_one(p, pore_vals, n_pore_vals, n_seq, names, seqs, lens, n_threads);
+}
+
+static rh_index_t *index_build_host_one(const rh_params_t *p, const float *pore_vals, uint32_t n_pore_vals,
+                                        uint32_t n_seq, const char *const *names, const char *const *seqs,
+                                        const uint32_t *lens, int n_threads)
 { /* ri_idx_gen, src/rindex.c:900-925: expected signal of both strands (ri_seq_to_sig,
      src/rsig.c:13-40) -> sketch -> grouped by hash */
-	if (!p || !pore_vals || n_pore_vals < (1u << (2 * p->k))) { rh_set_error("rh_index_build: bad arguments"); return NULL; }
 	rh_index_s *idx = new rh_index_s();
 	index_set_params(idx, p);
 	std::vector<std::vector<rh_seed_t>> per(n_seq);

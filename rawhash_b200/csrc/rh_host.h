@@ -28,4 +28,12 @@ void rh_host_sketch(const rh_params_t &P, const float *ev, uint32_t len, uint32_
 void rh_index_from_seeds(rh_index_s *idx, std::vector<rh_seed_t> &seeds, int n_threads);
 void rh_set_error(const char *fmt, ...);
 
+/* Index construction over contig groups (human-size references): consecutive sequences are grouped up to `group_bases`
+ * bases (at least one sequence per group), `one` builds the index of a group with local sequence ids, and the parts
+ * are merged key by key with ids rebased — position lists stay ascending because groups are in sequence order. */
+typedef rh_index_t *(*rh_index_builder_fn)(const rh_params_t *, const float *, uint32_t, uint32_t, const char *const *, const char *const *, const uint32_t *, int);
+rh_index_t *rh_index_build_grouped(rh_index_builder_fn one, uint64_t group_bases, const rh_params_t *p, const float *pore_vals, uint32_t n_pore_vals,
+                                   uint32_t n_seq, const char *const *names, const char *const *seqs, const uint32_t *lens, int arg);
+uint64_t rh_index_group_bases(uint64_t dflt); /* env RH_INDEX_GROUP_BASES or the default */
+
 #endif

@@ -133,15 +133,33 @@ template <class T> T *dmalloc(dev_free &F, size_t n)
 
 /* Same result as rh_index_build (ri_idx_gen semantics), computed on `device`.  Falls back to the host builder for
  * inputs the kernels do not cover (non-ACGT bases, minimizers). */
+static rh_index_t *index_build_gpu_one(const rh_params_t *p, const float *pore_vals, uint32_t n_pore_vals,
+                                       uint32_t n_seq, const char *const *names, const char *const *seqs,
+                                       const uint32_t *lens, int device);
+
 extern "C" rh_index_t *rh_index_build_gpu(const rh_params_t *p, const float *pore_vals, uint32_t n_pore_vals,
                                            uint32_t n_seq, const char *const *names, const char *const *seqs,
                                            const uint32_t *lens, int device)
 {
 	if (!p || !pore_vals || n_pore_vals < (1u << (2 * p->k)) || (n_seq && (!names || !seqs || !lens))) { rh_set_error("rh_index_build_gpu: bad arguments"); return NULL; }
 	bool plain = p->w == 0 && p->n == 0 && p->k >= 1 && p->k <= 15 && p->e >= 1 && p->e * p->q <= 64;
-	for (uint32_t i = 0; i < n_seq && plain; ++i)
+	uint64_t total = 0;
+	for (uint32_t i = 0; i < n_seq && plain; ++i) {
+		total += lens[i];
 		for (uint32_t j = 0; j < lens[i]; ++j) { const char c = seqs[i][j]; if (!(c == 'A' || c == 'C' || c == 'G' || c == 'T' || c == 'a' || c == 'c' || c == 'g' || c == 't')) { plain = false; break; } }
+	}
 	if (!plain) return rh_index_build(p, pore_vals, n_pore_vals, n_seq, names, seqs, lens, 8);
+	/* one pass sorts every seed of its sequences on the device (≈50 B of buffers per base); references beyond the group
+	 * size are built contig group by contig group and merged on the host (rh_index_build_grouped) */
+	const uint64_t group = rh_index_group_bases((uint64_t)512 << 20);
+	if (n_seq > 1 && total > group) return rh_index_build_grouped(index_build_gpu_one, group, p, pore_vals, n_pore_vals, n_seq, names, seqs, lens, device);
+	return index_build_gpu_one(p, pore_vals, n_pore_vals, n_seq, names, seqs, lens, device);
+}
+
+static rh_index_t *index_build_gpu_one(const rh_params_t *p, const float *pore_vals, uint32_t n_pore_vals,
+                                       uint32_t n_seq, const char *const *names, const char *const *seqs,
+                                       const uint32_t *lens, int device)
+{
 	int ndev = 0;
 	if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0 || device >= ndev) { rh_set_error("no usable CUDA device (count=%d, asked %d)", ndev, device); return NULL; }
 	IDX_TRY(cudaSetDevice(device));

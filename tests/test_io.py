@@ -308,3 +308,23 @@ def test_reader_takes_zstd_files_written_by_slow5lib(built, tmp_path):
     got, _ = read_mine(out)
     assert same_records(got, exp)
     assert open(out, "rb").read()[9] == 2  # record compression byte: zstd
+
+
+@pytest.mark.parametrize("preset,group", [("sensitive", 120_000), ("sensitive", 250_000), ("faster", 120_000), ("sensitive", 1)])
+def test_index_built_over_contig_groups_equals_one_pass(built, tmp_path, monkeypatch, preset, group):
+    """rh_index_build_grouped (how references beyond one GPU pass are built: contig groups, host merge with rebased
+    sequence ids) gives the very same index as a single pass — compared through the `.ind` bytes."""
+    from rawhash_b200 import api
+    w = World(n_contigs=5, genome_len=500_000, n_reads=1, read_bp=500, seed=29)
+    P = api.make_params(preset)
+    pore = api.load_pore(w.model, w.k)
+    names, seqs = w.genome_strings()
+    monkeypatch.delenv("RH_INDEX_GROUP_BASES", raising=False)
+    whole = api.Index.build(P, pore, names, seqs, 4)
+    monkeypatch.setenv("RH_INDEX_GROUP_BASES", str(group))
+    parts = api.Index.build(P, pore, names, seqs, 4)
+    assert parts.n_keys == whole.n_keys and parts.n_pos == whole.n_pos and parts.n_seq == whole.n_seq == 5
+    a, b = str(tmp_path / "whole.ind"), str(tmp_path / "parts.ind")
+    whole.dump(a, pore)
+    parts.dump(b, pore)
+    assert open(a, "rb").read() == open(b, "rb").read()
