@@ -1,6 +1,6 @@
 """GPU: references larger than one device pass are indexed contig group by contig group (rh_index_build_grouped);
-forced here with a small RH_INDEX_GROUP_BASES.  Sorted last: it was written after this round's GPU budget was spent and
-has only run on CPU through the host builder (tests/test_io.py::test_index_built_over_contig_groups_equals_one_pass)."""
+forced here with a small RH_INDEX_GROUP_BASES; the CPU twin through the host builder is
+tests/test_io.py::test_index_built_over_contig_groups_equals_one_pass."""
 import pytest
 
 from common import World
