@@ -186,7 +186,8 @@ extern "C" int rh_index_dump(const rh_index_t *idx, const char *path, const floa
 extern "C" int rh_fasta_load(const char *path, uint32_t *n_seq, char ***names, char ***seqs, uint32_t **lens)
 {
 	if (!path || !n_seq || !names || !seqs || !lens) { rh_set_error("rh_fasta_load: bad arguments"); return RH_ERR_ARG; }
-	gzFile g = gzopen(path, "rb"); /* transparent for plain files, like the reference's gzdopen (src/bseq.c:38-50) */
+	/* transparent for plain files; "-" is standard input, like the reference's gzdopen(0) (src/bseq.c:38-50) */
+	gzFile g = strcmp(path, "-") == 0 ? gzdopen(dup(0), "rb") : gzopen(path, "rb");
 	if (!g) { rh_set_error("cannot open %s: %s", path, strerror(errno)); return RH_ERR_IO; }
 	gzbuffer(g, 1 << 20);
 	std::vector<std::string> nm, sq;

@@ -322,7 +322,7 @@ int main(int argc, char **argv)
 	const char *target = pos[0];
 	const bool sig_target = (P.idx_flag & RH_I_SIG_TARGET) != 0;
 	const bool target_is_idx = is_index_file(target);
-	if (!target_is_idx) { FILE *f = fopen(target, "rb"); if (!f) { fprintf(stderr, "[ERROR] failed to open file '%s': %s\n", target, strerror(errno)); return 1; } fclose(f); }
+	if (!target_is_idx && strcmp(target, "-") != 0) { FILE *f = fopen(target, "rb"); if (!f) { fprintf(stderr, "[ERROR] failed to open file '%s': %s\n", target, strerror(errno)); return 1; } fclose(f); }
 	if (!target_is_idx && !S.dump && pos.size() < 2) {
 		fprintf(stderr, "[ERROR] missing input: please specify a query SLOW5/BLOW5 file(s) to map or option -d to store the index in a file before running the mapping\n");
 		return 1;

@@ -126,3 +126,36 @@ def test_gpu_entry_points_fail_loudly_without_a_device(built):
     idx.update_mapopt(P)
     with pytest.raises(api.RawHashError, match="CUDA|device"):
         api.Mapper(idx, P, 0, 1 << 20)
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_format_paf_reprints_the_golden_paf(built, case):
+    """rh_format_paf (the fprintf block of src/rmap.cpp:751-772) on CPU: the records parsed back out of the committed
+    golden PAF — which the reference printed — must print to the same text, mapped and unmapped lines alike."""
+    from rawhash_b200 import api
+    g = GoldenCase(case)
+    P = api.make_params(g.preset, g.r10)
+    pore = api.load_pore(g.model, g.k)
+    names, seqs = g.genome_strings()
+    idx = api.Index.build(P, pore, names, seqs, 2)
+    lines = _bind.strip_mt(g.paf).splitlines()
+    recs = np.zeros(len(lines), dtype=api.MAPREC_DTYPE)
+    order = {n: i for i, n in enumerate(g.names)}
+    n_unmapped = 0
+    for i, ln in enumerate(lines):
+        f = ln.split("\t")
+        tags = dict(t.split(":", 2)[::2] for t in f[12:])
+        r = recs[i]
+        r["read_idx"], r["read_length"] = order[f[0]], int(f[1])
+        r["ci"], r["sl"], r["cm"], r["nc"], r["s1"] = (int(tags[k]) for k in ("ci", "sl", "cm", "nc", "s1"))
+        if f[2] == "*":
+            n_unmapped += 1
+            r["mapq"] = int(f[11])
+            continue
+        r["mapped"], r["rev"], r["ref_id"] = 1, f[4] == "-", names.index(f[5])
+        r["read_start_position"], r["read_end_position"] = int(f[2]), int(f[3])
+        r["fragment_start_position"], r["fragment_length"], r["mapq"] = int(f[7]), int(f[10]), int(f[11])
+        assert int(f[6]) == idx.seq_len(names.index(f[5])) and int(f[8]) == int(f[7]) + int(f[10]) and int(f[9]) == int(f[3]) - int(f[2]) - 1
+    got = _bind.strip_mt(idx.format_paf(recs, g.names)).splitlines()
+    assert got == lines
+    assert len(lines) >= len(g.names)
