@@ -284,17 +284,31 @@ rh_index_t *rh_index_build_grouped(rh_index_builder_fn one, uint64_t group_bases
 	}
 	idx->off.push_back(total);
 	idx->pos.resize(total);
-	/* sweep 2: lists in group order, sequence ids rebased to the whole reference */
-	std::fill(at.begin(), at.end(), 0);
-	for (size_t ki = 0; ki < idx->keys.size(); ++ki) {
-		uint64_t w = idx->off[ki];
-		for (size_t g = 0; g < G; ++g) {
-			const rh_index_s *q = part[g];
-			if (at[g] >= q->keys.size() || q->keys[at[g]] != idx->keys[ki]) continue;
-			const uint64_t rebase = (uint64_t)start[g] << 32;
-			for (uint64_t j = q->off[at[g]]; j < q->off[at[g] + 1]; ++j) idx->pos[w++] = q->pos[j] + rebase;
-			++at[g];
-		}
+	/* sweep 2: lists in group order, sequence ids rebased to the whole reference; key ranges are independent, so the
+	 * copy (tens of GB at human size) runs on all host threads */
+	{
+		const size_t nk = idx->keys.size();
+		const unsigned T = (unsigned)std::max<size_t>(1, std::min<size_t>(std::thread::hardware_concurrency(), nk / 4096 + 1));
+		auto work = [&](unsigned t) {
+			const size_t k0 = nk * t / T, k1 = nk * (t + 1) / T;
+			if (k0 == k1) return;
+			std::vector<size_t> cur(G);
+			for (size_t g = 0; g < G; ++g) cur[g] = (size_t)(std::lower_bound(part[g]->keys.begin(), part[g]->keys.end(), idx->keys[k0]) - part[g]->keys.begin());
+			for (size_t ki = k0; ki < k1; ++ki) {
+				uint64_t w = idx->off[ki];
+				for (size_t g = 0; g < G; ++g) {
+					const rh_index_s *q = part[g];
+					if (cur[g] >= q->keys.size() || q->keys[cur[g]] != idx->keys[ki]) continue;
+					const uint64_t rebase = (uint64_t)start[g] << 32;
+					for (uint64_t j = q->off[cur[g]]; j < q->off[cur[g] + 1]; ++j) idx->pos[w++] = q->pos[j] + rebase;
+					++cur[g];
+				}
+			}
+		};
+		std::vector<std::thread> th;
+		for (unsigned t = 1; t < T; ++t) th.emplace_back(work, t);
+		work(0);
+		for (auto &x : th) x.join();
 	}
 	drop();
 	return idx;
