@@ -159,3 +159,30 @@ def test_format_paf_reprints_the_golden_paf(built, case):
     got = _bind.strip_mt(idx.format_paf(recs, g.names)).splitlines()
     assert got == lines
     assert len(lines) >= len(g.names)
+
+
+def test_c99_example_compiles_links_and_fails_loudly_without_a_gpu(built, tmp_path):
+    """examples/map_blow5.c: the boundary is usable from plain C99 (the reference's language) — compile with
+    -pedantic, link against the library, and (on a box without a GPU) see rh_gpu_init refuse."""
+    import shutil
+    import subprocess
+    from rawhash_b200 import api
+    exe = str(tmp_path / "map_blow5")
+    libdir = os.path.dirname(api.LIB_PATH)
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-O2", "-I" + os.path.join(ROOT, "include"),
+                        os.path.join(ROOT, "examples", "map_blow5.c"), "-L" + libdir, "-lrawhash_b200", "-Wl,-rpath," + libdir, "-o", exe],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    g = GoldenCase("r94_sensitive", str(tmp_path))
+    P = api.make_params(g.preset)
+    pore = api.load_pore(g.model, g.k)
+    names, seqs = g.genome_strings()
+    ind, reads = str(tmp_path / "t.ind"), str(tmp_path / "reads.blow5")
+    api.Index.build(P, pore, names, seqs, 2).dump(ind, pore)
+    api.write_slow5(reads, g.names, g.raws, *g.cal)
+    r = subprocess.run([exe, ind, reads], capture_output=True, text=True, timeout=300)
+    has_gpu = shutil.which("nvidia-smi") is not None and subprocess.run(["nvidia-smi", "-L"], capture_output=True).returncode == 0
+    if has_gpu:
+        assert r.returncode == 0 and _bind.strip_mt(r.stdout) == _bind.strip_mt(g.paf)
+    else:
+        assert r.returncode == 1 and "no usable CUDA device" in r.stderr and r.stdout == ""
