@@ -691,7 +691,7 @@ extern "C" int rh_sigfile_next_batch(rh_sigfile_t *f, uint64_t max_samples, uint
 			for (size_t i = 0; i < group; ++i) {
 				rec_t r;
 				const int rc = read_stored_record(f, r);
-				if (rc < 0) return rc;
+				if (rc < 0) { f->pending.clear(); f->eof = true; return rc; } /* a damaged file ends here: later calls report end of file */
 				if (rc == 0) { f->eof = true; break; }
 				if (!f->binary && r.mem.size() <= 1) continue; /* blank line */
 				f->pending.emplace_back(std::move(r));
@@ -700,7 +700,7 @@ extern "C" int rh_sigfile_next_batch(rh_sigfile_t *f, uint64_t max_samples, uint
 			std::vector<rec_t> &P = f->pending;
 			parallel_for(P.size(), f->n_threads, [&](size_t i) { P[i].ok = binary ? parse_binary_record(P[i], rm, sm) : parse_ascii_record(P[i]); });
 			for (size_t i = 0; i < P.size(); ++i)
-				if (!P[i].ok) { rh_set_error("%s: a record cannot be parsed (record %zu of the current group)", f->path.c_str(), i); return RH_ERR_FORMAT; }
+				if (!P[i].ok) { rh_set_error("%s: a record cannot be parsed (record %zu of the current group)", f->path.c_str(), i); f->pending.clear(); f->eof = true; return RH_ERR_FORMAT; }
 			if (P.empty()) break;
 		}
 		total += f->pending[f->pending_at].n_samples;
