@@ -328,3 +328,37 @@ def test_index_built_over_contig_groups_equals_one_pass(built, tmp_path, monkeyp
     whole.dump(a, pore)
     parts.dump(b, pore)
     assert open(a, "rb").read() == open(b, "rb").read()
+
+
+@needs_s5
+def test_random_files_round_trip_and_match_slow5lib(built, tmp_path):
+    """40 seeded random files: read count, lengths (incl. empty reads), sample statistics (noise, steps, saturated),
+    calibration, every compression pair, random mini-batch limits — our reader == slow5lib == what was written."""
+    from rawhash_b200 import api
+    rng = np.random.default_rng(77)
+    s5 = Slow5Lib()
+    for t in range(40):
+        n = int(rng.integers(0, 12))
+        raws = []
+        for _ in range(n):
+            ln = int(rng.choice([0, 1, 2, 7, 100, 5000, 40000]))
+            kind = int(rng.integers(0, 4))
+            if kind == 0:
+                r = rng.integers(-32768, 32768, ln)
+            elif kind == 1:
+                r = np.cumsum(rng.integers(-30, 31, ln)) + 500
+            elif kind == 2:
+                r = np.repeat(rng.integers(200, 900, ln // 9 + 1), 9)[:ln] + rng.integers(-3, 4, ln)
+            else:
+                r = np.full(ln, int(rng.choice([-32768, 32767, 0])))
+            raws.append(np.clip(r, -32768, 32767).astype(np.int16))
+        names = [f"r{t}_{i}_{'x' * int(rng.integers(0, 40))}" for i in range(n)]
+        off, rg, dg = rng.uniform(-300, 300, n), rng.uniform(200, 3000, n), rng.choice([2048.0, 8192.0], n)
+        rec, sig = int(rng.integers(0, 3)), int(rng.integers(0, 2))
+        ext = "slow5" if (rec == 0 and sig == 0 and t % 3 == 0) else "blow5"
+        p = str(tmp_path / f"f{t}.{ext}")
+        api.write_slow5(p, names, raws, off, rg, dg, 5000.0, rec, sig)
+        want = [(nm, r, g, o, q, 5000.0) for nm, r, o, q, g in zip(names, raws, off, rg, dg)]
+        assert same_records(s5.read(p), want), (t, ext, rec, sig)
+        got, _ = read_mine(p, threads=int(rng.integers(1, 5)), max_samples=int(rng.choice([1, 1000, 10**9])), max_reads=int(rng.choice([0, 1, 3])))
+        assert same_records(got, want), (t, ext, rec, sig)
