@@ -17,6 +17,7 @@ def built():
     """Build the CUDA library and the CPU checkers once per session (no-ops when up to date)."""
     from rawhash_b200 import build
     build.build_lib()
+    build.build_cli()
     build.stage_models()
     build.build_oracle()
     return True
