@@ -33,6 +33,7 @@
 #include <thread>
 #include <vector>
 
+#include <immintrin.h>
 #include <cuda_runtime_api.h>
 
 #include "rh_host.h"
@@ -270,6 +271,53 @@ const long BLOW5_HDR_SIZE_AT = 64;                              /* :134 */
 enum { PRESS_NONE = 0, PRESS_ZLIB = 1, PRESS_ZSTD = 2, SIG_NONE = 0, SIG_SVB_ZD = 1 }; /* slow5_press.c:51-145 */
 
 /* ---- streamvbyte + zig-zag delta (extern/slow5lib/thirdparty/streamvbyte; slow5_press.c:1054-1135) ------------- */
+/* SSSE3 path: one control byte = four values.  A 16-byte shuffle spreads their 4..16 data bytes over four 32-bit
+ * lanes; zig-zag, the running sum of the deltas and the narrowing to int16 stay in registers.  Selected at run time. */
+struct svb_tables_t {
+	alignas(16) uint8_t shuffle[256][16];
+	uint8_t length[256];
+	bool ssse3;
+	svb_tables_t()
+	{
+		for (unsigned c = 0; c < 256; ++c) {
+			unsigned at = 0;
+			for (unsigned j = 0; j < 4; ++j) {
+				const unsigned n = ((c >> (2 * j)) & 3u) + 1;
+				for (unsigned b = 0; b < 4; ++b) shuffle[c][4 * j + b] = b < n ? (uint8_t)(at + b) : 0x80; /* 0x80: zero the byte */
+				at += n;
+			}
+			length[c] = (uint8_t)at;
+		}
+		const char *e = getenv("RH_NO_SIMD");
+		ssse3 = __builtin_cpu_supports("ssse3") && !(e && e[0] == '1');
+	}
+};
+const svb_tables_t &svb_tables() { static const svb_tables_t t; return t; }
+
+__attribute__((target("ssse3")))
+void svbzd_decode_ssse3(const uint8_t *ctl, const uint8_t *&dat, const uint8_t *end, int16_t *out, uint32_t count, uint32_t &i, int32_t &prev)
+{
+	const svb_tables_t &T = svb_tables();
+	const __m128i one = _mm_set1_epi32(1), zero = _mm_setzero_si128();
+	const __m128i narrow = _mm_setr_epi8(0, 1, 4, 5, 8, 9, 12, 13, (char)0x80, (char)0x80, (char)0x80, (char)0x80, (char)0x80, (char)0x80, (char)0x80, (char)0x80);
+	__m128i run = _mm_set1_epi32(prev); /* the last decoded sample in every lane */
+	const uint8_t *d = dat;
+	uint32_t k = i;
+	for (; k + 4 <= count && d + 16 <= end; k += 4) {
+		const unsigned c = ctl[k >> 2];
+		__m128i v = _mm_shuffle_epi8(_mm_loadu_si128((const __m128i *)d), _mm_load_si128((const __m128i *)T.shuffle[c]));
+		d += T.length[c];
+		v = _mm_xor_si128(_mm_srli_epi32(v, 1), _mm_sub_epi32(zero, _mm_and_si128(v, one))); /* zig-zag */
+		v = _mm_add_epi32(v, _mm_slli_si128(v, 4));                                             /* prefix sum over the four deltas */
+		v = _mm_add_epi32(v, _mm_slli_si128(v, 8));
+		v = _mm_add_epi32(v, run);
+		run = _mm_shuffle_epi32(v, 0xff);
+		_mm_storel_epi64((__m128i *)(out + k), _mm_shuffle_epi8(v, narrow));                    /* low 16 bits of each lane, like (int16_t) */
+	}
+	prev = _mm_cvtsi128_si32(run);
+	dat = d; i = k;
+}
+
 /* layout: u32 count | ceil(count/4) control bytes (2 bits per value: 1..4 data bytes) | little-endian data bytes */
 bool svbzd_decode(const uint8_t *in, size_t in_bytes, int16_t *out, uint32_t expect)
 {
@@ -281,6 +329,7 @@ bool svbzd_decode(const uint8_t *in, size_t in_bytes, int16_t *out, uint32_t exp
 	const uint8_t *ctl = in + 4, *dat = ctl + nctl, *end = in + in_bytes;
 	int32_t prev = 0;
 	uint32_t i = 0;
+	if (svb_tables().ssse3) svbzd_decode_ssse3(ctl, dat, end, out, count, i, prev); /* whole control bytes while 16 input bytes remain */
 	static const uint32_t KEEP[4] = {0xffu, 0xffffu, 0xffffffu, 0xffffffffu};
 	/* four values per control byte; a 4-byte load per value is safe while 16 bytes of input remain */
 	for (; i + 4 <= count && dat + 16 <= end; i += 4) {
