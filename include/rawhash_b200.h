@@ -124,6 +124,16 @@ rh_index_t *rh_index_build(const rh_params_t *p, const float *pore_vals, uint32_
 rh_index_t *rh_index_build_gpu(const rh_params_t *p, const float *pore_vals, uint32_t n_pore_vals,
                                uint32_t n_seq, const char *const *names, const char *const *seqs,
                                const uint32_t *lens, int device);
+/* Same index from 2-bit base codes (one per byte, 0..3 = A,C,G,T; sequences back to back) that already lie in the
+ * memory of `device`.  The result is device-resident: rh_gpu_init on that device maps from it without a copy, and the
+ * host accessors below download it on first use.  (ri_idx_gen, src/rindex.c:900-925; w == 0 only.) */
+rh_index_t *rh_index_build_dev(const rh_params_t *p, const float *pore_vals, uint32_t n_pore_vals,
+                               uint32_t n_seq, const char *const *names, const void *d_codes,
+                               const uint32_t *lens, int device);
+/* device the flattened index currently lives on, or -1 */
+int         rh_index_on_device(const rh_index_t *idx);
+/* host arrays of the flattened index: keys[n_keys] ascending, off[n_keys+1], pos[n_pos] (valid until rh_index_destroy) */
+int         rh_index_flat(const rh_index_t *idx, const uint32_t **keys, const uint64_t **off, const uint64_t **pos);
 /* Build from raw signals for Rawsamble (semantics of ri_idx_siggen, src/rindex.c:927-969).
  * Event detection runs on the GPU. */
 rh_index_t *rh_index_build_sig(const rh_params_t *p, uint32_t n_reads, const char *const *names,

@@ -142,6 +142,77 @@ int ref_build_index(void *h, const char *fasta, const char *dump_path, int n_thr
 	return 0;
 }
 
+/* The reference's in-memory index (ri_idx_t: 2^14 buckets of khash + position arrays, src/rindex.c:311-363) filled
+ * from a flattened key -> ascending-positions table instead of from a FASTA or an `.ind` file.  Every bucket is
+ * built with the reference's own khash instantiation and the same calls worker_post makes (kh_resize, kh_put,
+ * singleton keys tagged with bit 0, lists as start<<32|n into b->p), so ri_idx_get answers from the structure it
+ * would have after ri_idx_load.  Used for human-size worlds, where a 13-minute host index build (or a 42 GB file
+ * round trip) per bench run is not an option; tests/test_oracle_vs_ref.py checks it against ri_idx_gen. */
+#define rt_idx_hash(a) ((a)>>1)
+#define rt_idx_eq(a, b) ((a)>>1 == (b)>>1)
+KHASH_INIT(idx, uint64_t, uint64_t, 1, rt_idx_hash, rt_idx_eq) /* same parameters as src/rindex.c:17-19 */
+
+struct flat_fill_t {
+	ri_idx_t *ri; const uint32_t *keys; const uint64_t *off, *pos;
+	const uint32_t *order; const uint64_t *bstart; /* keys of bucket b: order[bstart[b] .. bstart[b+1]) */
+	int bad;
+};
+
+static void flat_fill_bucket(void *g, long b, int tid)
+{
+	flat_fill_t *F = (flat_fill_t *)g;
+	ri_idx_bucket_t *B = &F->ri->B[b];
+	const uint64_t k0 = F->bstart[b], k1 = F->bstart[b + 1];
+	if (k0 == k1) return;
+	uint64_t np = 0;
+	for (uint64_t j = k0; j < k1; ++j) { const uint64_t c = F->off[F->order[j] + 1] - F->off[F->order[j]]; if (c > 1) np += c; }
+	if (np > 0x7fffffffULL) { F->bad = 1; return; }
+	khash_t(idx) *h = kh_init(idx);
+	kh_resize(idx, h, (khint_t)(k1 - k0));
+	B->n = (int32_t)np;
+	B->p = (uint64_t *)calloc(np ? np : 1, 8);
+	uint64_t start_p = 0;
+	for (uint64_t j = k0; j < k1; ++j) {
+		const uint32_t ki = F->order[j];
+		const uint64_t c = F->off[ki + 1] - F->off[ki];
+		int absent;
+		khint_t itr = kh_put(idx, h, (uint64_t)(F->keys[ki] >> F->ri->b) << 1, &absent);
+		if (c == 1) { kh_key(h, itr) |= 1; kh_val(h, itr) = F->pos[F->off[ki]]; }
+		else { memcpy(B->p + start_p, F->pos + F->off[ki], c * 8); kh_val(h, itr) = start_p << 32 | c; start_p += c; }
+	}
+	B->h = h;
+}
+
+int ref_index_from_flat(void *hd, uint32_t n_seq, const char *const *names, const uint32_t *lens,
+                        uint64_t n_keys, const uint32_t *keys, const uint64_t *off, const uint64_t *pos, int n_threads)
+{
+	ref_ctx *c = (ref_ctx *)hd;
+	if (c->ri) { ri_idx_destroy(c->ri); c->ri = 0; }
+	const ri_idxopt_t &o = c->ipt;
+	ri_idx_t *ri = ri_idx_init(o.diff, o.b, o.w, o.e, o.n, o.q, o.k, o.fine_min, o.fine_max, o.fine_range, o.flag);
+	ri->window_length1 = o.window_length1; ri->window_length2 = o.window_length2;
+	ri->threshold1 = o.threshold1; ri->threshold2 = o.threshold2; ri->peak_height = o.peak_height;
+	ri->seq = (ri_idx_seq_t *)ri_kcalloc(ri->km, n_seq ? n_seq : 1, sizeof(ri_idx_seq_t));
+	uint64_t sum_len = 0;
+	for (uint32_t i = 0; i < n_seq; ++i) {
+		ri->seq[i].name = (char *)ri_kmalloc(ri->km, strlen(names[i]) + 1);
+		strcpy(ri->seq[i].name, names[i]);
+		ri->seq[i].len = lens[i]; ri->seq[i].offset = sum_len; sum_len += lens[i];
+	}
+	ri->n_seq = n_seq;
+	const uint32_t nb = 1u << ri->b, mask = nb - 1;
+	std::vector<uint64_t> bstart(nb + 1, 0);
+	for (uint64_t i = 0; i < n_keys; ++i) ++bstart[(keys[i] & mask) + 1];
+	for (uint32_t b = 0; b < nb; ++b) bstart[b + 1] += bstart[b];
+	std::vector<uint32_t> order(n_keys);
+	{ std::vector<uint64_t> cur(bstart.begin(), bstart.end() - 1); for (uint64_t i = 0; i < n_keys; ++i) order[cur[keys[i] & mask]++] = (uint32_t)i; }
+	flat_fill_t F = {ri, keys, off, pos, order.data(), bstart.data(), 0};
+	kt_for(n_threads > 0 ? n_threads : 1, flat_fill_bucket, &F, nb);
+	if (F.bad) { ri_idx_destroy(ri); return -2; }
+	c->ri = ri;
+	return 0;
+}
+
 int ref_load_index(void *h, const char *path)
 {
 	ref_ctx *c = (ref_ctx *)h;

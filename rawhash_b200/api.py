@@ -139,6 +139,9 @@ def _load():
         "rh_index_build": (vp, [PP, vp, u32, u32, vp, vp, vp, i32]),
         "rh_index_build_gpu": (vp, [PP, vp, u32, u32, vp, vp, vp, i32]),
         "rh_index_build_sig": (vp, [PP, u32, vp, vp, vp, vp, vp, vp]),
+        "rh_index_build_dev": (vp, [PP, vp, u32, u32, vp, vp, vp, i32]),
+        "rh_index_on_device": (i32, [vp]),
+        "rh_index_flat": (i32, [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]),
         "rh_index_load": (vp, [cp, PP]),
         "rh_index_destroy": (None, [vp]),
         "rh_index_n_seq": (u32, [vp]),
@@ -241,6 +244,29 @@ class Index:
                                     (C.c_char_p * len(bs))(*bs), lens.ctypes.data, device)
         return cls(h)
 
+    @classmethod
+    def build_dev(cls, params: Params, pore_vals: np.ndarray, names: Sequence[str], d_codes_ptr: int, lens, device: int = 0):
+        """Index from 2-bit base codes (uint8 0..3, sequences back to back) already in the memory of `device`
+        (rh_index_build_dev); the result stays on the device."""
+        pore_vals = np.ascontiguousarray(pore_vals, dtype=np.float32)
+        lens = np.ascontiguousarray(lens, dtype=np.uint32)
+        h = _lib.rh_index_build_dev(C.byref(params), pore_vals.ctypes.data, len(pore_vals), len(lens), _cstr_array(names),
+                                    C.c_void_p(int(d_codes_ptr)), lens.ctypes.data, device)
+        return cls(h)
+
+    @property
+    def on_device(self) -> int:
+        return _lib.rh_index_on_device(self.h)
+
+    def flat(self):
+        """(keys u32[n_keys], off u64[n_keys+1], pos u64[n_pos]) numpy views of the host mirror (no copy)."""
+        k, o, p = C.c_void_p(), C.c_void_p(), C.c_void_p()
+        if _lib.rh_index_flat(self.h, C.byref(k), C.byref(o), C.byref(p)) != 0:
+            raise _err("rh_index_flat")
+        nk, npos = self.n_keys, self.n_pos
+        mk = lambda ptr, n, ct: np.ctypeslib.as_array(C.cast(ptr, C.POINTER(ct)), shape=(max(n, 1),))[:n]
+        return mk(k, nk, C.c_uint32), mk(o, nk + 1, C.c_uint64), mk(p, npos, C.c_uint64)
+
     def key(self, i: int) -> int:
         return _lib.rh_index_key(self.h, int(i))
 
@@ -267,7 +293,7 @@ class Index:
             raise _err("rh_index_dump")
 
     def __del__(self):
-        if getattr(self, "h", None):
+        if getattr(self, "h", None) and _lib is not None:  # _lib is None while the interpreter shuts down
             _lib.rh_index_destroy(self.h)
             self.h = None
 

@@ -105,9 +105,10 @@ struct rh_gpu_ctx_s {
 	dev_params_t D;
 	const rh_index_s *idx = nullptr;
 	dev_index_t I;
-	/* index storage */
-	dbuf<uint32_t> d_keys, d_bucket, d_seqlen, d_namerank;
-	dbuf<uint64_t> d_off, d_pos;
+	/* index storage: the flattened index lives with the index handle (rh_index_s::dev) unless that one is resident on
+	 * another GPU, in which case this context owns a private copy */
+	rh_index_dev_t own_dev; bool own_dev_valid = false;
+	dbuf<uint32_t> d_seqlen, d_namerank;
 	dbuf<float> d_logf;
 	uint32_t logf_n = 0;
 	std::vector<uint32_t> name_order; /* sorted target names (indices) for Rawsamble */
@@ -652,20 +653,37 @@ extern "C" rh_gpu_ctx *rh_gpu_init(const rh_index_t *idx, const rh_params_t *p, 
 	rh_gpu_ctx *c = new rh_gpu_ctx();
 	c->device = device; c->P = *p; c->idx = idx;
 	fill_dev_params(*p, c->D);
-	if (p->mid_occ <= 0) { rh_params_t q = *p; rh_index_update_mapopt(idx, &q); c->P.mid_occ = q.mid_occ; c->D.mid_occ = q.mid_occ; }
 	auto fail = [&](const char *what) -> rh_gpu_ctx * { if (what) rh_set_error("%s", what); rh_gpu_destroy(c); return NULL; };
-	/* ---- index upload ---- */
-	const size_t nk = idx->keys.size();
-	int bits = 10; while (bits < 26 && ((size_t)1 << bits) < nk) ++bits;
-	std::vector<uint32_t> bucket(((size_t)1 << bits) + 1);
-	{
-		size_t ki = 0;
-		for (size_t b = 0; b <= ((size_t)1 << bits); ++b) {
-			const uint64_t lo = (uint64_t)b << (32 - bits);
-			while (ki < nk && (uint64_t)idx->keys[ki] < lo) ++ki;
-			bucket[b] = (uint32_t)ki;
-		}
+	/* ---- index: a device-resident index on this device is used in place; a host index is uploaded once and becomes
+	 *      device-resident (several contexts on one GPU share it) ---- */
+	rh_index_s *midx = const_cast<rh_index_s *>(idx);
+	if (midx->dev.device >= 0 && midx->dev.device != device) {
+		if (rh_index_sync_host(idx) != RH_OK) return fail(NULL);
 	}
+	if (midx->dev.device != device) { /* upload the host arrays */
+		rh_index_dev_t V; V.device = device; V.n_keys = idx->keys.size(); V.n_pos = idx->pos.size();
+		if (midx->dev.device >= 0) { /* lives on another GPU: this context keeps a private copy (c->own_dev) */ }
+		if (cudaMalloc((void **)&V.keys, std::max<size_t>(V.n_keys, 1) * 4) != cudaSuccess || cudaMalloc((void **)&V.off, (V.n_keys + 1) * 8) != cudaSuccess ||
+		    cudaMalloc((void **)&V.pos, std::max<size_t>(V.n_pos, 1) * 8) != cudaSuccess) {
+			if (V.keys) cudaFree(V.keys); if (V.off) cudaFree(V.off); if (V.pos) cudaFree(V.pos);
+			return fail("index upload: out of device memory");
+		}
+		const uint64_t zero = 0;
+		cudaMemcpy(V.keys, idx->keys.data(), V.n_keys * 4, cudaMemcpyHostToDevice);
+		if (idx->off.size() == V.n_keys + 1) cudaMemcpy(V.off, idx->off.data(), (V.n_keys + 1) * 8, cudaMemcpyHostToDevice);
+		else cudaMemcpy(V.off, &zero, 8, cudaMemcpyHostToDevice);
+		cudaMemcpy(V.pos, idx->pos.data(), V.n_pos * 8, cudaMemcpyHostToDevice);
+		if (midx->dev.device < 0) midx->dev = V; /* the index handle owns it from here on */
+		else { c->own_dev = V; c->own_dev_valid = true; }
+	}
+	rh_index_dev_t *V = c->own_dev_valid ? &c->own_dev : &midx->dev;
+	if (!V->bucket) {
+		rh_index_s tmp_holder; /* rh_index_dev_make_buckets works on an index handle */
+		if (c->own_dev_valid) { tmp_holder.dev = c->own_dev; if (rh_index_dev_make_buckets(&tmp_holder) != RH_OK) { tmp_holder.dev = rh_index_dev_t(); return fail(NULL); } c->own_dev = tmp_holder.dev; tmp_holder.dev = rh_index_dev_t(); }
+		else if (rh_index_dev_make_buckets(midx) != RH_OK) return fail(NULL);
+	}
+	const size_t nk = (size_t)V->n_keys;
+	const int bits = V->bucket_bits;
 	std::vector<uint32_t> rank(idx->names.size());
 	c->name_order.resize(idx->names.size());
 	std::iota(c->name_order.begin(), c->name_order.end(), 0u);
@@ -676,11 +694,10 @@ extern "C" rh_gpu_ctx *rh_gpu_init(const rh_index_t *idx, const rh_params_t *p, 
 	lt.resize(c->logf_n);
 	for (uint32_t i = 0; i < c->logf_n; ++i) lt[i] = logf((float)i); /* host libm: identical to the reference's calls */
 	cudaStream_t s0 = nullptr;
-	if (upload(c->d_keys, idx->keys, s0) || upload(c->d_off, idx->off, s0) || upload(c->d_pos, idx->pos, s0) ||
-	    upload(c->d_bucket, bucket, s0) || upload(c->d_seqlen, idx->lens, s0) || upload(c->d_namerank, rank, s0) ||
-	    upload(c->d_logf, lt, s0)) return fail(NULL);
-	c->I.keys = c->d_keys.p; c->I.off = c->d_off.p; c->I.pos = c->d_pos.p; c->I.bucket = c->d_bucket.p; c->I.bucket_bits = bits;
+	if (upload(c->d_seqlen, idx->lens, s0) || upload(c->d_namerank, rank, s0) || upload(c->d_logf, lt, s0)) return fail(NULL);
+	c->I.keys = V->keys; c->I.off = V->off; c->I.pos = V->pos; c->I.bucket = V->bucket; c->I.bucket_bits = bits;
 	c->I.n_keys = nk; c->I.seq_len = c->d_seqlen.p; c->I.name_rank = c->d_namerank.p; c->I.n_seq = (uint32_t)idx->names.size();
+	if (p->mid_occ <= 0) { rh_params_t q = *p; rh_index_update_mapopt(idx, &q); c->P.mid_occ = q.mid_occ; c->D.mid_occ = q.mid_occ; }
 	{ /* fixed key packing for the shared-memory anchor sort: strand | target id | target position */
 		uint32_t maxlen = 1;
 		for (uint32_t l : idx->lens) maxlen = std::max(maxlen, l);
@@ -718,7 +735,8 @@ extern "C" void rh_gpu_destroy(rh_gpu_ctx *c)
 	if (!c) return;
 	cudaSetDevice(c->device);
 	for (rh_worker *w : c->workers) destroy_worker(w);
-	c->d_keys.release(); c->d_bucket.release(); c->d_seqlen.release(); c->d_namerank.release(); c->d_off.release(); c->d_pos.release(); c->d_logf.release();
+	if (c->own_dev_valid) { rh_index_s h; h.dev = c->own_dev; /* released by ~rh_index_s */ }
+	c->d_seqlen.release(); c->d_namerank.release(); c->d_logf.release();
 	c->d_raw.release();
 	delete c;
 }

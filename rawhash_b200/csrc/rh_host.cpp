@@ -457,6 +457,15 @@ extern "C" rh_index_t *rh_index_load(const char *path, rh_params_t *pp)
 			}
 		}
 	}
+	if (ok) { /* ri_idx_reader_read writes one part per 4 G bases/samples and ri_idx_load is called until EOF (rindex.c:795-830):
+	           * a second part would silently be a missing piece of the reference, so it is refused by name */
+		if (fseeko(f, 0, SEEK_END) == 0) {
+			const off_t fsize = ftello(f);
+			/* end of the part = end of the last bucket's (key, value) pairs */
+			const off_t at = p_at[(1 << 14) - 1] + (off_t)p_n[(1 << 14) - 1] * 8 + 4 + (off_t)(first_ent[1 << 14] - first_ent[(1 << 14) - 1]) * 16;
+			if (fsize > at) { fclose(f); delete idx; rh_set_error("%s: multi-part index files (references above 4 G bases or samples) are not supported: %lld bytes follow the first part", path, (long long)(fsize - at)); return NULL; }
+		}
+	}
 	fclose(f);
 	if (!ok) { delete idx; rh_set_error("%s: truncated or inconsistent index", path); return NULL; }
 	if (pp) {
@@ -466,16 +475,28 @@ extern "C" rh_index_t *rh_index_load(const char *path, rh_params_t *pp)
 	return idx;
 }
 
+rh_index_s::~rh_index_s() { rh_index_dev_release(this); }
+int rh_host_threads(void) { const unsigned n = std::thread::hardware_concurrency(); return n ? (int)n : 1; }
+
 extern "C" void rh_index_destroy(rh_index_t *idx) { delete idx; }
 extern "C" uint32_t rh_index_n_seq(const rh_index_t *idx) { return (uint32_t)idx->names.size(); }
 extern "C" const char *rh_index_seq_name(const rh_index_t *idx, uint32_t i) { return idx->names[i].c_str(); }
 extern "C" uint32_t rh_index_seq_len(const rh_index_t *idx, uint32_t i) { return idx->lens[i]; }
-extern "C" uint64_t rh_index_n_keys(const rh_index_t *idx) { return idx->keys.size(); }
-extern "C" uint64_t rh_index_n_pos(const rh_index_t *idx) { return idx->pos.size(); }
-extern "C" uint32_t rh_index_key(const rh_index_t *idx, uint64_t i) { return i < idx->keys.size() ? idx->keys[i] : 0u; }
+extern "C" uint64_t rh_index_n_keys(const rh_index_t *idx) { return idx->host_valid ? idx->keys.size() : idx->dev.n_keys; }
+extern "C" uint64_t rh_index_n_pos(const rh_index_t *idx) { return idx->host_valid ? idx->pos.size() : idx->dev.n_pos; }
+extern "C" uint32_t rh_index_key(const rh_index_t *idx, uint64_t i) { if (rh_index_sync_host(idx)) return 0u; return i < idx->keys.size() ? idx->keys[i] : 0u; }
+extern "C" int rh_index_on_device(const rh_index_t *idx) { return idx->dev.device; }
+extern "C" int rh_index_flat(const rh_index_t *idx, const uint32_t **keys, const uint64_t **off, const uint64_t **pos)
+{ /* host arrays of the flattened index (downloaded first when the index lives on a device) */
+	const int rc = rh_index_sync_host(idx);
+	if (rc) return rc;
+	*keys = idx->keys.data(); *off = idx->off.data(); *pos = idx->pos.data();
+	return RH_OK;
+}
 
 extern "C" const uint64_t *rh_index_get(const rh_index_t *idx, uint32_t hash, int *n)
 {
+	if (rh_index_sync_host(idx)) { *n = 0; return NULL; }
 	auto it = std::lower_bound(idx->keys.begin(), idx->keys.end(), hash);
 	if (it == idx->keys.end() || *it != hash) { *n = 0; return NULL; }
 	size_t i = it - idx->keys.begin();
@@ -487,8 +508,13 @@ extern "C" void rh_index_update_mapopt(const rh_index_t *idx, rh_params_t *p)
 { /* ri_mapopt_update + ri_idx_cal_max_occ, src/rindex.c:1018-1053 */
 	if (p->mid_occ > 0) return;
 	int32_t thres = INT32_MAX;
-	const size_t n = idx->keys.size();
-	if (p->mid_occ_frac > 0. && n > 0) {
+	const size_t n = idx->host_valid ? idx->keys.size() : (size_t)idx->dev.n_keys;
+	if (p->mid_occ_frac > 0. && n > 0 && !idx->host_valid) { /* device-resident index: radix select over the CSR offsets in HBM */
+		size_t kth = (uint32_t)((1. - p->mid_occ_frac) * n);
+		if (kth >= n) kth = n - 1;
+		uint32_t v = 0;
+		if (rh_index_dev_kth_occ(idx, kth, &v) == RH_OK) thres = (int32_t)std::min<uint32_t>(v, 0x7ffffffeu) + 1;
+	} else if (p->mid_occ_frac > 0. && n > 0) {
 		std::vector<uint32_t> occ(n);
 		for (size_t i = 0; i < n; ++i) occ[i] = (uint32_t)(idx->off[i + 1] - idx->off[i]);
 		size_t kth = (uint32_t)((1. - p->mid_occ_frac) * n);

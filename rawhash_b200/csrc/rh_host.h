@@ -10,7 +10,19 @@
 /* Flattened index: key -> ascending position list (the mapping ri_idx_get returns,
  * reference src/rindex.c:497-514), stored as sorted keys + CSR offsets so it can be copied
  * to HBM verbatim. */
+/* device-resident copy of the flattened index (rh_index_build_dev leaves the index here; rh_gpu_init on the same
+ * device maps straight from it) */
+struct rh_index_dev_t {
+	int device = -1;
+	uint32_t *keys = nullptr; uint64_t *off = nullptr; uint64_t *pos = nullptr;
+	uint32_t *bucket = nullptr; int bucket_bits = 0;
+	uint64_t n_keys = 0, n_pos = 0;
+};
+
 struct rh_index_s {
+	~rh_index_s();
+	rh_index_dev_t dev;
+	bool host_valid = true;       /* false: keys/off/pos below are empty until rh_index_sync_host() */
 	std::vector<uint32_t> keys;   /* distinct 32-bit seed hashes, ascending            */
 	std::vector<uint64_t> off;    /* keys.size()+1 offsets into pos                    */
 	std::vector<uint64_t> pos;    /* id<<32 | pos<<1 | strand, ascending within a key  */
@@ -27,6 +39,11 @@ struct rh_seed_t { uint64_t x, y; };
 void rh_host_sketch(const rh_params_t &P, const float *ev, uint32_t len, uint32_t id, int strand, std::vector<rh_seed_t> &out);
 void rh_index_from_seeds(rh_index_s *idx, std::vector<rh_seed_t> &seeds, int n_threads);
 void rh_set_error(const char *fmt, ...);
+int  rh_host_threads(void);                           /* hardware threads of the host (>= 1) */
+int  rh_index_sync_host(const rh_index_s *idx);       /* download the device-resident index once */
+void rh_index_dev_release(rh_index_s *idx);
+int  rh_index_dev_make_buckets(rh_index_s *idx);
+int  rh_index_dev_kth_occ(const rh_index_s *idx, uint64_t kth, uint32_t *out);
 
 /* Index construction over contig groups (human-size references): consecutive sequences are grouped up to `group_bases`
  * bases (at least one sequence per group), `one` builds the index of a group with local sequence ids, and the parts

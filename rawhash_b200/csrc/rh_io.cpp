@@ -107,6 +107,7 @@ struct slot_table {
 extern "C" int rh_index_dump(const rh_index_t *idx, const char *path, const float *pore_vals, uint32_t n_pore_vals)
 {
 	if (!idx || !path) { rh_set_error("rh_index_dump: bad arguments"); return RH_ERR_ARG; }
+	if (rh_index_sync_host(idx) != RH_OK) return RH_ERR_CUDA; /* a device-resident index is downloaded first */
 	for (const std::string &nm : idx->names)
 		if (nm.size() > 255) { rh_set_error("rh_index_dump: sequence name longer than 255 bytes: %s", nm.c_str()); return RH_ERR_ARG; }
 	FILE *fp = fopen(path, "wb");

@@ -167,17 +167,55 @@ def raw_to_pa(raw: np.ndarray, offset: float, rng_: float, digitisation: float) 
     return pa[(pa > np.float32(30.0)) & (pa < np.float32(200.0))]
 
 
+# GRCh38 primary assembly chromosome lengths (chr1..22, X, Y): the contig layout of the human-size synthetic genome
+GRCH38_LENS = [248956422, 242193529, 198295559, 190214555, 181538259, 170805979, 159345973, 145138636, 138394717,
+               133797422, 135086622, 133275309, 114364328, 107043718, 101991189, 90338345, 83257441, 80373285,
+               58617616, 64444167, 46709983, 50818468, 156040895, 57227415]
+GRCH38_NAMES = [f"chr{i}" for i in range(1, 23)] + ["chrX", "chrY"]
+
+
+class DeviceGenome:
+    """i.i.d. uniform ACGT genome generated in device memory (2-bit codes, one per byte, contigs back to back).
+
+    Human-size inputs (3.1 Gb) are generated where they are consumed; nothing of this size exists on the boxes."""
+
+    def __init__(self, names, lens, device="cuda", seed: int = 1):
+        import torch
+        self.names = list(names)
+        self.lens = np.asarray(lens, dtype=np.int64)
+        self.total = int(self.lens.sum())
+        gen = torch.Generator(device=device)
+        gen.manual_seed(seed)
+        self.codes = torch.empty(self.total, dtype=torch.uint8, device=device)
+        step = 1 << 28
+        for a in range(0, self.total, step):  # bounded temporaries
+            b = min(a + step, self.total)
+            self.codes[a:b] = torch.randint(0, 4, (b - a,), dtype=torch.uint8, device=device, generator=gen)
+        self.starts = np.concatenate([[0], np.cumsum(self.lens)[:-1]]).astype(np.int64)
+
+    def host_contigs(self):
+        """[(name, uint8 codes)] on the host (small genomes only: parity checks against the host builders)."""
+        h = self.codes.cpu().numpy()
+        return [(n, h[s:s + l]) for n, s, l in zip(self.names, self.starts, self.lens)]
+
+
 def make_reads_torch(genome, n_reads: int, read_len_bp: int, k: int, means, stdv, device="cuda",
                      sample_rate: float = 4000.0, bp_per_sec: float = 450.0, seed: int = 2, batch: int = 4000):
     """Same recipe as make_reads, generated on the GPU with torch (bench-sized inputs: 10^5 reads).
 
+    `genome` is a list of (name, uint8 codes) or a DeviceGenome.
     Returns (raw int16 tensor on `device`, reads concatenated back to back; raw_off uint64 numpy
     [n+1]; lens uint64 numpy [n]; truth list).  Read i is raw[raw_off[i] : raw_off[i+1]]."""
     import torch
     gen = torch.Generator(device=device)
     gen.manual_seed(seed)
-    G = torch.from_numpy(np.concatenate([s for _, s in genome])).to(device)
-    clen = np.array([len(s) for _, s in genome], dtype=np.int64)
+    if isinstance(genome, DeviceGenome):
+        G = genome.codes
+        clen = genome.lens.copy()
+        genome = [None] * len(clen)
+    else:
+        G = torch.from_numpy(np.concatenate([s for _, s in genome])).to(device)
+        clen = np.array([len(s) for _, s in genome], dtype=np.int64)
     cstart = np.concatenate([[0], np.cumsum(clen)[:-1]])
     M = torch.from_numpy(np.asarray(means, dtype=np.float32)).to(device)
     SD = torch.from_numpy(np.asarray(stdv, dtype=np.float32)).to(device)

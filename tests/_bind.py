@@ -279,6 +279,19 @@ class RefLib(_CpuChecker):
 
     def __init__(self):
         super().__init__(REF_SO)
+        self.lib.ref_index_from_flat.restype = C.c_int
+        self.lib.ref_index_from_flat.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+
+    def index_from_flat(self, names, lens, keys, off, pos, n_threads=4):
+        """Fill the reference's ri_idx_t (khash buckets + position arrays) from a flattened key -> positions table."""
+        lens = np.ascontiguousarray(lens, dtype=np.uint32)
+        keys = np.ascontiguousarray(keys, dtype=np.uint32)
+        off = np.ascontiguousarray(off, dtype=np.uint64)
+        pos = np.ascontiguousarray(pos, dtype=np.uint64)
+        assert len(off) == len(keys) + 1
+        rc = self.lib.ref_index_from_flat(self.h, len(lens), _names(names), lens.ctypes.data, len(keys), keys.ctypes.data,
+                                          off.ctypes.data, pos.ctypes.data, n_threads)
+        assert rc == 0, rc
 
 
 class OracleLib(_CpuChecker):

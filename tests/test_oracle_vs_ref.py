@@ -98,3 +98,27 @@ def test_best_n_secondaries(built):
     ref.set_best_n(0)
     c, _ = ref.map_paf(sigs, w.names, 2)
     assert _bind.strip_mt(a) != _bind.strip_mt(c), "best_n had no observable effect in this world"
+
+
+def test_reference_index_filled_from_flat_table(built):
+    """ref_index_from_flat (the reference's ri_idx_t filled from keys/off/pos, used for human-size worlds) serves the
+    same ri_idx_get answers and the same PAF as the index the reference builds itself from the FASTA."""
+    from rawhash_b200 import api
+    w = World(n_contigs=3, genome_len=500_000, n_reads=16, read_bp=3000, seed=61)
+    P = api.make_params("fast")
+    names, seqs = w.genome_strings()
+    idx = api.Index.build(P, api.load_pore(w.model, w.k), names, seqs, 4)
+    keys, off, pos = idx.flat()
+    a = _bind.RefLib().open("fast", False, w.model)
+    a.build_index(w.fasta, "", 4)
+    b = _bind.RefLib().open("fast", False, w.model)
+    b.index_from_flat(names, [len(s) for s in seqs], keys, off, pos, 4)
+    assert a.mapopt_update() == b.mapopt_update()
+    rng = np.random.Generator(np.random.PCG64(3))
+    probe = list(keys[rng.integers(0, len(keys), 3000)]) + list(rng.integers(0, 1 << 32, 500))
+    for h in probe:
+        assert np.array_equal(a.idx_get(int(h)), b.idx_get(int(h)))
+    sigs = [w.pa(i) for i in range(len(w.names))]
+    pa, _ = a.map_paf(sigs, w.names, 2)
+    pb, _ = b.map_paf(sigs, w.names, 2)
+    assert _bind.strip_mt(pa) == _bind.strip_mt(pb)
