@@ -368,20 +368,45 @@ __global__ void __launch_bounds__(SB_THREADS, 1) k_sort_smem(sort_args_t A, uint
  * one slot right, and z_j falls into the hole m_j.  Elements past z_J and bin-0 elements of R0
  * stay.  (Derived from ksort.h:126-138; checked against the walk in tests.)
  * ===========================================================================================*/
-#define TIE_THREADS 128
+#define TIE_THREADS 256
 #define TIE_WARPS (TIE_THREADS / 32)
 #define TIE_WALKERS 8
+#define TIE_TAB_ROWS (2 + TIE_WARPS > TIE_WALKERS ? 2 + TIE_WARPS : TIE_WALKERS)
 #define TIE_CLOSED_MIN 256        /* two-bin sub-arrays at least this long use the closed form */
 
 struct tie_shared_t {
-	uint32_t tab[TIE_WALKERS][256];   /* per walker: (end << 16 | head), relative to the sub-array start */
+	uint32_t tab[TIE_TAB_ROWS][256];  /* per walker: (end << 16 | head), relative to the sub-array start; rows 2.. double as the per-warp digit counts of fin_radix_pass */
 	uint32_t tflag[TIE_WALKERS][8];   /* per walker: bins that hold a tied element (bitmask)              */
 	uint32_t wsum[TIE_WARPS];
 	uint32_t seg_beg[TIE_WALKERS], seg_len[TIE_WALKERS], seg_kind[TIE_WALKERS], seg_b0[TIE_WALKERS], seg_b1[TIE_WALKERS], seg_c0[TIE_WALKERS];
 	uint32_t n_nxt, n_term;
 	unsigned long long diff;
+	uint32_t big_left;                /* long sub-arrays of the current round still walking */
+	uint32_t big_list[TIE_WALKERS];   /* long sub-arrays of the current batch               */
+};
+/* tables of one long sub-array while its level is replayed (cta_big_*) */
+struct big_tab_t {
+	uint32_t rs[257];                 /* region starts; rs[256] = len                                      */
+	uint32_t qb[257];                 /* first displaced element (index into P/Q) of every region          */
+	uint4 st[256];                    /* per region: .x = next displaced element (index into Q), .y = its digit (or BIG_ND_UNKNOWN),
+	                                   * .z = end of what the region's ring holds, .w = byte offset of the region's ring */
+	uint32_t ja[256];                 /* arrivals a region received before it became the one being closed  */
+	uint16_t cid[256];                /* ring slot of every occupied bin                                   */
+	uint32_t done, nact, M, RW;
+	uint32_t beg, len;
+	const uint8_t *Q;                 /* digits of the displaced elements (global)                         */
+	uint32_t *arr;                    /* out: where every displaced element arrives                        */
+	uint8_t *ring;                    /* TIE_RING_BYTES of shared memory                                   */
 };
 enum { TIE_IDENT = 0, TIE_WALK = 1, TIE_TWO = 2, TIE_BIG = 3 };
+#define BIG_ND_UNKNOWN 0xffffffffu
+__device__ __forceinline__ uint4 lds_v4(uint32_t saddr) { uint4 v; asm volatile("ld.volatile.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(saddr)); return v; }
+__device__ __forceinline__ uint32_t lds_u32(uint32_t saddr) { uint32_t v; asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(v) : "r"(saddr)); return v; }
+__device__ __forceinline__ uint32_t lds_u8(uint32_t saddr) { uint32_t v; asm volatile("ld.volatile.shared.u8 %0, [%1];" : "=r"(v) : "r"(saddr)); return v; }
+__device__ __forceinline__ void sts_v2(uint32_t saddr, uint32_t a, uint32_t b) { asm volatile("st.volatile.shared.v2.u32 [%0], {%1,%2};" :: "r"(saddr), "r"(a), "r"(b) : "memory"); }
+__device__ __forceinline__ void sts_u32(uint32_t saddr, uint32_t a) { asm volatile("st.volatile.shared.u32 [%0], %1;" :: "r"(saddr), "r"(a) : "memory"); }
+#define TIE_BIG_MIN 4096u         /* sub-arrays at least this long take cta_big_level instead of a lane's walk */
+#define TIE_RING_BYTES 8192u      /* shared-memory ring space of cta_big_level: 256 regions x 32 entries       */
 
 /* exclusive rank of `flag` over one tile of TIE_THREADS elements; returns rank within the tile, *total = tile count */
 __device__ __forceinline__ uint32_t tie_tile_rank(bool flag, uint32_t *wsum, uint32_t *total)
@@ -409,7 +434,254 @@ struct klib_ws_t {
 	uint32_t *zlist, *mlist; /* closed-form scratch, n words each                                       */
 	uint2 *term;             /* terminal bins of a level, <= n/2 entries (may alias zlist/mlist)         */
 	uint2 *wl0, *wl1;        /* pending sub-arrays (> 64 elements), n/64+2 entries each                 */
+	uint8_t *qbytes;         /* cta_big_level: digits of the displaced elements, n + 32 bytes, 16-byte aligned */
+	big_tab_t *big;          /* cta_big_*: n_big table sets in shared memory ...                                    */
+	uint8_t *ring;           /* ... and n_big x TIE_RING_BYTES of shared-memory rings (free while a long level runs)  */
+	uint32_t n_big;          /* long sub-arrays that can walk side by side (<= warps - 1)                          */
 };
+
+
+/* =============================================================================================
+ * cta_big_prepare / big_walk / big_feed / cta_big_place — one level of klib's in-place MSD pass (ksort.h:117-138) on ONE long sub-array, by the whole CTA.
+ *
+ * The displacement walk only ever touches elements that sit outside the region of their own bin ("displaced"
+ * elements); everything else keeps its place or moves one slot to the right.  So the level is replayed as
+ *   1  ranks: for every position, the number of displaced elements before it; the displaced ones are compacted,
+ *      in position order, into P (positions) and Q (their digits) — region b owns the slice [qb[b], qb[b+1])
+ *   2  the walk over the displaced elements only: "take the next displaced element of the region I am in; it belongs
+ *      to region d; go there" — a rotor walk whose only state is one head counter per region.  Region k, the lowest
+ *      unfinished one, is special: an element that returns to k closes the cycle and fills the hole the cycle
+ *      started from.  Each step records at which rank the moved element ARRIVES in its own region.
+ *      One thread walks; the other three warps keep a 32-entry ring of every region's queue filled from Q, so the
+ *      walk's dependent chain is shared-memory loads only.
+ *   3  placement, closed form: while region d is not the one being closed, its a-th arrival lands right behind the
+ *      (a-1)-th displaced slot of d (the region start for a = 1) and the d-elements between there and the a-th
+ *      displaced slot shift one to the right; once d is being closed, an arrival fills the displaced slot itself.
+ * Checked against klib for 2..256 bins and skewed histograms (tests: klib tie orders at chunk sizes > 65535).
+ * On entry T.tab[w] holds the raw bin counts; on exit dst[beg + i] = new position of element i, relative to beg.
+ * Several long sub-arrays of a level walk side by side: one walking thread per warp, one feeder warp for all.
+ * ===========================================================================================*/
+__device__ void cta_big_prepare(tie_shared_t &T, big_tab_t &B, const uint32_t w, const uint8_t *__restrict__ bytes, const uint32_t beg, const uint32_t len,
+                                uint32_t *__restrict__ dst, uint32_t *__restrict__ Pz, uint32_t *__restrict__ arr, uint8_t *__restrict__ Q, uint8_t *ring)
+{
+	const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	const uint32_t FULL = 0xffffffffu;
+	const uint8_t *__restrict__ dg = bytes + beg;
+	uint32_t *__restrict__ D = dst + beg;
+	__syncthreads();
+	if (warp == 0) { /* region starts */
+		uint32_t c[8], tot = 0;
+#pragma unroll
+		for (int q = 0; q < 8; ++q) { c[q] = T.tab[w][lane * 8 + q]; tot += c[q]; }
+		uint32_t incl = tot;
+#pragma unroll
+		for (int o = 1; o < 32; o <<= 1) { const uint32_t u = __shfl_up_sync(FULL, incl, o); if (lane >= o) incl += u; }
+		uint32_t start = incl - tot;
+#pragma unroll
+		for (int q = 0; q < 8; ++q) { B.rs[lane * 8 + q] = start; start += c[q]; }
+		if (lane == 31) B.rs[256] = start;
+		/* occupied bins get consecutive ring slots */
+		uint32_t nz = 0;
+#pragma unroll
+		for (int q = 0; q < 8; ++q) nz += c[q] != 0;
+		uint32_t nincl = nz;
+#pragma unroll
+		for (int o = 1; o < 32; o <<= 1) { const uint32_t u = __shfl_up_sync(FULL, nincl, o); if (lane >= o) nincl += u; }
+		uint32_t id = nincl - nz;
+#pragma unroll
+		for (int q = 0; q < 8; ++q) { B.cid[lane * 8 + q] = (uint16_t)id; id += c[q] != 0; }
+		if (lane == 31) B.nact = nincl;
+	}
+	for (uint32_t b = tid; b < 257; b += TIE_THREADS) B.qb[b] = 0xffffffffu;
+	__syncthreads();
+	const uint32_t na = B.nact;
+	const uint32_t RW = na > 128 ? 32u : na > 64 ? 64u : na > 32 ? 128u : 256u; /* ring entries per region: 32 with all 256 bins occupied */
+	/* ---- ranks of the displaced elements; each warp owns a contiguous piece ---- */
+	const uint32_t piece = (((len + TIE_WARPS - 1) / TIE_WARPS) + 31) & ~31u;
+	const uint32_t cb = min(warp * piece, len), ce = min(cb + piece, len);
+	uint32_t hb0 = 0;
+	{ /* region of position cb */
+		uint32_t lo = 0, hi = 256;
+		while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (B.rs[mid + 1] <= cb) lo = mid + 1; else hi = mid; }
+		hb0 = lo;
+	}
+	uint32_t cz = 0;
+	{
+		uint32_t hb = hb0;
+		for (uint32_t i0 = cb; i0 < ce; i0 += 32) {
+			const uint32_t i = i0 + lane;
+			bool out = false;
+			if (i < ce) { while (i >= B.rs[hb + 1]) ++hb; out = dg[i] != hb; }
+			cz += __popc(__ballot_sync(FULL, out));
+			hb = __shfl_sync(FULL, hb, 0); /* lane 0 holds the smallest position of the next group as well */
+		}
+	}
+	if (lane == 0) T.wsum[warp] = cz;
+	__syncthreads();
+	uint32_t run = 0, M = 0;
+	for (uint32_t w2 = 0; w2 < TIE_WARPS; ++w2) { if (w2 < warp) run += T.wsum[w2]; M += T.wsum[w2]; }
+	{
+		uint32_t hb = hb0;
+		for (uint32_t i0 = cb; i0 < ce; i0 += 32) {
+			const uint32_t i = i0 + lane;
+			bool out = false; uint32_t d = 0;
+			if (i < ce) { while (i >= B.rs[hb + 1]) ++hb; d = dg[i]; out = d != hb; }
+			const uint32_t m = __ballot_sync(FULL, out);
+			const uint32_t r = run + __popc(m & lanemask_lt());
+			if (i < ce) {
+				D[i] = r;
+				if (out) { Pz[r] = i; Q[r] = (uint8_t)d; }
+				if (i == B.rs[hb]) B.qb[hb] = r; /* first position of a non-empty region */
+			}
+			run += __popc(m);
+			hb = __shfl_sync(FULL, hb, 0);
+		}
+	}
+	__syncthreads();
+	if (tid == 0) { /* empty regions inherit the next region's start */
+		uint32_t nxt = M;
+		B.qb[256] = M;
+		for (int b = 255; b >= 0; --b) { if (B.qb[b] == 0xffffffffu) B.qb[b] = nxt; else nxt = B.qb[b]; }
+		B.done = 0; B.M = M; B.RW = RW; B.beg = beg; B.len = len; B.Q = Q; B.arr = arr; B.ring = ring;
+	}
+	__syncthreads();
+	for (uint32_t b = tid; b < 256; b += TIE_THREADS) {
+		B.st[b] = make_uint4(B.qb[b], BIG_ND_UNKNOWN, B.qb[b] & ~15u, (uint32_t)B.cid[b] * RW);
+		B.ja[b] = B.qb[b + 1] - B.qb[b];
+	}
+	__syncthreads();
+}
+
+/* the walk of one long sub-array, by ONE thread.  One step = one displaced element taken from the head of the region the
+ * walk is in.  The dependent chain of a step is ONE shared-memory load: a region's state word carries the digit of its
+ * head element, written there when the element before it was taken. */
+__device__ void big_walk(big_tab_t &B, unsigned long long *prof)
+{
+	const uint32_t M = B.M;
+	if (M > 0) {
+		uint32_t *__restrict__ arr = B.arr;
+		const uint32_t rmask = B.RW - 1; /* a power of two */
+		uint32_t st_s = (uint32_t)__cvta_generic_to_shared(B.st), ring_s = (uint32_t)__cvta_generic_to_shared(B.ring);
+		asm volatile("" : "+r"(st_s), "+r"(ring_s)); /* opaque: otherwise the shared window base is re-derived (S2UR) on every step */
+		uint32_t k = 0;
+		while (k < 256 && B.qb[k + 1] == B.qb[k]) ++k;
+		B.ja[k] = 0;
+		uint4 sk = lds_v4(st_s + k * 16);          /* region k's state lives in registers */
+		uint32_t ek = B.qb[k + 1];
+		for (;;) {
+			/* a cycle starts: take k's next displaced element */
+			uint32_t d = sk.y;
+			if (d == BIG_ND_UNKNOWN) { while (sk.z <= sk.x) sk.z = lds_u32(st_s + k * 16 + 8); d = lds_u8(ring_s + sk.w + (sk.x & rmask)); }
+			uint32_t ab = sk.x;
+			uint4 sc = lds_v4(st_s + d * 16);      /* d != k: a displaced element never belongs to its own region */
+			sk.x = ab + 1;
+			if (sk.x >= sk.z) sk.z = lds_u32(st_s + k * 16 + 8);
+			sk.y = sk.x < sk.z ? lds_u8(ring_s + sk.w + (sk.x & rmask)) : BIG_ND_UNKNOWN;
+			sts_u32(st_s + k * 16, sk.x);
+			arr[ab] = sc.x | 0x80000000u;          /* lands behind d's previous displaced slot */
+			uint32_t cur = d;
+			for (;;) { /* follow the cycle until an element of region k turns up */
+				d = sc.y;
+				if (d == BIG_ND_UNKNOWN) { while (sc.z <= sc.x) sc.z = lds_u32(st_s + cur * 16 + 8); d = lds_u8(ring_s + sc.w + (sc.x & rmask)); }
+				ab = sc.x;
+				const uint32_t nh = ab + 1;
+				if (d == k) {
+					const uint32_t nd = nh < sc.z ? lds_u8(ring_s + sc.w + (nh & rmask)) : BIG_ND_UNKNOWN;
+					sts_v2(st_s + cur * 16, nh, nd);
+					arr[ab] = sk.x;                /* fills the hole opened by k's own last pop: displaced slot sk.x - 1 */
+					break;
+				}
+				const uint4 s2 = lds_v4(st_s + d * 16);
+				const uint32_t nd = nh < sc.z ? lds_u8(ring_s + sc.w + (nh & rmask)) : BIG_ND_UNKNOWN;
+				sts_v2(st_s + cur * 16, nh, nd);
+				arr[ab] = s2.x | 0x80000000u;
+				cur = d; sc = s2;
+			}
+			if (sk.x == ek) { /* region k is complete: the next unfinished region takes over */
+				do { ++k; } while (k < 256 && lds_u32(st_s + k * 16) == B.qb[k + 1]);
+				if (k == 256) break;
+				sk = lds_v4(st_s + k * 16);
+				ek = B.qb[k + 1];
+				B.ja[k] = sk.x - B.qb[k];
+			}
+		}
+		if (prof) { atomicAdd(&prof[27], (unsigned long long)M); atomicAdd(&prof[29], 1ULL); }
+	}
+	__threadfence_block();
+	*(volatile uint32_t *)&B.done = 1;
+}
+
+/* ring feeder of up to m concurrent walks, by ONE warp: lane l serves regions l, l+32, ... of every walk.  Straight-line
+ * and predicated, so the loads of all needy regions of a walk are in flight together; sleeps between polls so that its
+ * shared-memory traffic stays out of the walks' way. */
+__device__ void big_feed(big_tab_t *Bs, const uint32_t m, volatile uint32_t *left)
+{
+	const uint32_t lane = threadIdx.x & 31;
+	const uint32_t FULL = 0xffffffffu;
+	for (;;) {
+		bool any = false;
+		for (uint32_t j = 0; j < m; ++j) {
+			big_tab_t &B = Bs[j];
+			if (B.M == 0 || *(volatile uint32_t *)&B.done) continue;
+			const uint32_t RW = B.RW, rmask = RW - 1;
+			const uint32_t st_s = (uint32_t)__cvta_generic_to_shared(B.st);
+			const uint8_t *__restrict__ Q = B.Q;
+			uint8_t *ring = B.ring;
+#pragma unroll
+			for (int q = 0; q < 8; ++q) {
+				const uint32_t b = lane + 32u * q;
+				const uint32_t qe = B.qb[b + 1];
+				bool need = false; uint32_t f = 0;
+				if (qe > B.qb[b]) {
+					f = lds_u32(st_s + b * 16 + 8);
+					need = f < qe && f + 16 <= lds_u32(st_s + b * 16) + RW;
+				}
+				uint4 v = make_uint4(0, 0, 0, 0);
+				if (need) v = *(const uint4 *)(Q + f);
+				if (need) { *(uint4 *)(ring + (uint32_t)B.cid[b] * RW + (f & rmask)) = v; __threadfence_block(); sts_u32(st_s + b * 16 + 8, f + 16); }
+				any |= need;
+			}
+		}
+		if (*left == 0) break;
+		if (!__any_sync(FULL, any)) __nanosleep(300);
+	}
+}
+
+__device__ void cta_big_place(tie_shared_t &T, big_tab_t &B, const uint8_t *__restrict__ bytes, uint32_t *__restrict__ dst, const uint32_t *__restrict__ Pz)
+{
+	const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	const uint32_t FULL = 0xffffffffu;
+	const uint32_t beg = B.beg, len = B.len;
+	const uint8_t *__restrict__ dg = bytes + beg;
+	uint32_t *__restrict__ D = dst + beg;
+	const uint32_t *__restrict__ arr = B.arr;
+	const uint32_t piece = (((len + TIE_WARPS - 1) / TIE_WARPS) + 31) & ~31u;
+	const uint32_t cb = min(warp * piece, len), ce = min(cb + piece, len);
+	uint32_t hb = 0;
+	{
+		uint32_t lo = 0, hi = 256;
+		while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (B.rs[mid + 1] <= cb) lo = mid + 1; else hi = mid; }
+		hb = lo;
+	}
+	for (uint32_t i0 = cb; i0 < ce; i0 += 32) {
+		const uint32_t i = i0 + lane;
+		if (i < ce) {
+			while (i >= B.rs[hb + 1]) ++hb;
+			const uint32_t d = dg[i], r = D[i];
+			uint32_t np;
+			if (d == hb) np = i + ((r - B.qb[hb]) < B.ja[hb] ? 1u : 0u);
+			else {
+				const uint32_t a = arr[r];
+				const uint32_t ai = a & 0x7fffffffu; /* index into P/Q */
+				if (a & 0x80000000u) np = ai == B.qb[d] ? B.rs[d] : Pz[ai - 1] + 1;
+				else np = Pz[ai - 1];
+			}
+			D[i] = np;
+		}
+		hb = __shfl_sync(FULL, hb, 0);
+	}
+	__syncthreads();
+}
 
 /* Exact replay of klib's radix_sort on the n > 64 (key, payload) pairs in W.xk/W.ord, by one CTA of
  * TIE_THREADS threads.  ALL = false: only bins that hold a TIE_FLAGged element are followed and only
@@ -493,7 +765,7 @@ __device__ void cta_klib_replay(tie_shared_t &T, uint8_t *bytes, klib_ws_t W, co
 				const uint32_t g_first = __shfl_sync(FULL, first, m2 ? __ffs(m2) - 1 : 0);
 				const uint32_t b0 = f_first, b1 = f_second != 0xffffffffu ? f_second : g_first;
 				const uint32_t c0 = __shfl_sync(FULL, first_cnt, l1);
-				const uint32_t kind = nzt <= 1 ? TIE_IDENT : ((nzt == 2 && len >= TIE_CLOSED_MIN) ? TIE_TWO : (len > 65535u ? TIE_BIG : TIE_WALK));
+				const uint32_t kind = nzt <= 1 ? TIE_IDENT : ((nzt == 2 && len >= TIE_CLOSED_MIN) ? TIE_TWO : (len >= TIE_BIG_MIN ? TIE_BIG : TIE_WALK));
 				uint32_t start = incl - tot;
 				if (kind != TIE_BIG) {
 #pragma unroll
@@ -560,27 +832,34 @@ __device__ void cta_klib_replay(tie_shared_t &T, uint8_t *bytes, klib_ws_t W, co
 			}
 			__syncthreads();
 			RH_PROF_MARK(prof, 18, tid == 0);
-			/* ---- sub-arrays longer than the packed tables can address: one thread, plain 32-bit tables ---- */
-			for (uint32_t w = 0; w < nb; ++w) {
-				if (T.seg_kind[w] != TIE_BIG) continue;
-				const uint32_t beg = T.seg_beg[w];
-				uint32_t *cnt = T.tab[w];                 /* counts (unscanned)   */
-				uint32_t *head = (uint32_t *)mlist;       /* 256 words of scratch */
-				if (tid == 0) {
-					uint32_t acc = 0;
-					for (uint32_t b = 0; b < 256; ++b) { head[b] = acc; acc += cnt[b]; }
-					uint32_t region_end = 0;
-					for (uint32_t k = 0; k < 256; ++k) {
-						region_end += cnt[k];
-						uint32_t hk = head[k];
-						while (hk != region_end) {
-							uint32_t e = hk, d = bytes[beg + e];
-							while (d != k) { const uint32_t hd = head[d]; dst[beg + e] = hd; head[d] = hd + 1; e = hd; d = bytes[beg + e]; }
-							dst[beg + e] = hk; ++hk;
-						}
-					}
-				}
+			/* ---- long sub-arrays: compacted displaced elements, rotor walks from shared-memory rings (up to W.n_big side by
+			 *      side: warp 1 feeds the rings, one thread of each other warp walks), closed-form placement ---- */
+			{
+				if (tid == 0) { uint32_t nbg = 0; for (uint32_t w = 0; w < nb; ++w) if (T.seg_kind[w] == TIE_BIG) T.big_list[nbg++] = w; T.big_left = 0; if (nbg < TIE_WALKERS) T.big_list[nbg] = 0xffffffffu; }
 				__syncthreads();
+				uint32_t nbg = 0;
+				while (nbg < nb && nbg < TIE_WALKERS && T.big_list[nbg] != 0xffffffffu) ++nbg;
+				const uint32_t side = min(W.n_big, (uint32_t)TIE_WARPS - 1u);
+				for (uint32_t r0 = 0; r0 < nbg; r0 += side) {
+					const uint32_t m = min(side, nbg - r0);
+					RH_PROF_BEGIN(prof);
+					for (uint32_t j = 0; j < m; ++j) {
+						const uint32_t w = T.big_list[r0 + j], beg = T.seg_beg[w];
+						cta_big_prepare(T, W.big[j], w, bytes, beg, T.seg_len[w], dst, zlist + beg, mlist + beg, W.qbytes + ((beg + 15u) & ~15u), W.ring + j * TIE_RING_BYTES);
+					}
+					if (tid == 0) T.big_left = m;
+					__syncthreads();
+					RH_PROF_MARK(prof, 24, tid == 0);
+					if (warp == 1) big_feed(W.big, m, (volatile uint32_t *)&T.big_left);
+					else if (lane == 0) {
+						const uint32_t j = warp == 0 ? 0u : warp - 1u;
+						if (j < m) { big_walk(W.big[j], prof); __threadfence_block(); atomicSub(&T.big_left, 1u); }
+					}
+					__syncthreads();
+					RH_PROF_MARK(prof, 25, tid == 0);
+					for (uint32_t j = 0; j < m; ++j) cta_big_place(T, W.big[j], bytes, dst, zlist + W.big[j].beg);
+					RH_PROF_MARK(prof, 26, tid == 0);
+				}
 			}
 			/* ---- two occupied bins: closed form, all threads ---- */
 			for (uint32_t w = 0; w < nb; ++w) {
@@ -703,11 +982,15 @@ __device__ void cta_klib_replay(tie_shared_t &T, uint8_t *bytes, klib_ws_t W, co
 	__syncthreads();
 }
 
-__global__ void __launch_bounds__(TIE_THREADS, 14) k_sort_ties(sort_args_t A, uint32_t smem_cap, uint32_t n_lo, uint32_t n_hi)
+#define TIE_SIDE_WALKS 7           /* long sub-arrays of a tie chunk that walk side by side (warps - 1) */
+__host__ __device__ inline size_t tie_smem_bytes(uint32_t smem_cap) { return ((sizeof(tie_shared_t) + 15) & ~(size_t)15) + TIE_SIDE_WALKS * (sizeof(big_tab_t) + TIE_RING_BYTES) + smem_cap; }
+__global__ void __launch_bounds__(TIE_THREADS, 1) k_sort_ties(sort_args_t A, uint32_t smem_cap, uint32_t n_lo, uint32_t n_hi)
 {
 	extern __shared__ __align__(16) uint8_t s_dyn[];
 	tie_shared_t &T = *(tie_shared_t *)s_dyn;
-	uint8_t *s_bytes = s_dyn + sizeof(tie_shared_t);
+	big_tab_t *s_big = (big_tab_t *)(s_dyn + ((sizeof(tie_shared_t) + 15) & ~(size_t)15));
+	uint8_t *s_ring = (uint8_t *)(s_big + TIE_SIDE_WALKS);
+	uint8_t *s_bytes = s_ring + TIE_SIDE_WALKS * TIE_RING_BYTES;
 	const uint32_t tid = threadIdx.x;
 	if (blockIdx.x >= *A.tie_count) return;
 	slot_t *S = &A.slots[A.tie_list[blockIdx.x]];
@@ -724,6 +1007,8 @@ __global__ void __launch_bounds__(TIE_THREADS, 14) k_sort_ties(sort_args_t A, ui
 	W.term = (uint2 *)((uint64_t *)M.W + n);        /* M.W is 16n bytes: the upper half */
 	W.wl0 = (uint2 *)M.regs; W.wl1 = W.wl0 + (n / 64 + 2);
 	uint8_t *bytes = n <= smem_cap ? s_bytes : (uint8_t *)M.t + n;
+	W.qbytes = (uint8_t *)(((uintptr_t)((uint8_t *)M.t + 2 * (size_t)n) + 15) & ~(uintptr_t)15); /* M.t is 4n bytes: flags, digits, displaced digits */
+	W.big = s_big; W.ring = s_ring; W.n_big = TIE_SIDE_WALKS;
 	for (uint32_t i = tid; i < n; i += TIE_THREADS) { W.xk[i] = in[i].x | (tied[i] ? TIE_FLAG : 0ULL); W.ord[i] = i; }
 	cta_klib_replay<false>(T, bytes, W, n, A.prof);
 	RH_PROF_BEGIN(A.prof);

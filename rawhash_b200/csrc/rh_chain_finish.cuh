@@ -24,7 +24,8 @@
 #include "rh_anchor_sort.cuh"
 
 #define FIN_THREADS TIE_THREADS
-#define FIN_BYTES_CAP 8192        /* sorts of up to this many elements keep their digit bytes in shared memory */
+#define FIN_SHORT_RUN 12          /* runs of up to this many candidates are ordered by their own thread */
+#define FIN_BYTES_CAP TIE_RING_BYTES /* shared-memory bytes: digit bytes of short sorts, or the rings of cta_big_level */
 
 __device__ __forceinline__ float logf_tab(const k3_args_t &A, int32_t x, uint32_t *flag)
 { /* glibc logf of an integer argument, tabulated on the host so MAPQ is bit-identical */
@@ -103,84 +104,75 @@ __device__ void set_parent_general(dev_reg_t *r, uint32_t n_regs, const dev_para
 
 /* Same function for the common case (query coordinates < FIN_BITS, few primaries): the union of
  * the primaries' query intervals is a bitset in shared memory, so the uncovered length of region
- * i is a popcount, and the primaries' fields live in shared memory instead of behind two
- * dependent global loads.  The uncovered length equals the reference's sorted-interval sweep
- * because all coordinates are integers. */
+ * i is a popcount, and the primaries' fields live in shared memory.  The uncovered length equals
+ * the reference's sorted-interval sweep because all coordinates are integers.
+ *
+ * Regions are taken 32 at a time, one per lane.  The sweep is sequential only through the set of
+ * primaries, and new primaries are rare (a chunk has 10^4..10^5 regions and a handful of primaries):
+ * every lane evaluates its region against the current set; the lowest lane that turns out to be a
+ * NEW primary ends the batch's valid prefix — the lanes below it saw exactly the set the sequential
+ * sweep would have shown them and are committed (subsc is a max, n_sub a count: order free), the new
+ * primary is added, and the lanes above it are evaluated again. */
 __device__ bool set_parent_bitset(dev_reg_t *r, uint32_t n_regs, const dev_params_t &P, uint32_t *bits, prim_cache_t *pc, uint32_t lane)
 {
 	const uint32_t FULL = 0xffffffffu;
 	for (uint32_t w = lane; w < FIN_BITS / 32; w += 32) bits[w] = 0;
 	__syncwarp();
 	int kk = 0;
-	for (uint32_t i0 = 0; i0 < n_regs; i0 += 32) { /* 32 regions' fields are fetched at once */
+	for (uint32_t i0 = 0; i0 < n_regs; i0 += 32) {
 		const uint32_t ii = i0 + lane;
-		int my_qs = 0, my_qe = 0, my_score = 0, my_cnt = 0;
-		if (ii < n_regs) { const dev_reg_t g = r[ii]; my_qs = g.qs; my_qe = g.qe; my_score = g.score; my_cnt = g.cnt; }
-		const uint32_t nb = min(32u, n_regs - i0);
-		for (uint32_t b = 0; b < nb; ++b) {
-			const int i = (int)(i0 + b);
-			const int si = __shfl_sync(FULL, my_qs, b), ei = __shfl_sync(FULL, my_qe, b);
-			const int sci = __shfl_sync(FULL, my_score, b), cni = __shfl_sync(FULL, my_cnt, b);
-			/* covered positions of [si, ei) */
-			int covered = 0;
-			if (kk > 0 && ei > si) {
-				const int w0 = si >> 5, w1 = (ei - 1) >> 5;
-				if (w1 - w0 < 4) { /* short interval (nearly all regions): every lane adds up the same few words, no reduction chain */
+		int si = 0, ei = 0, sci = 0, cni = 0;
+		if (ii < n_regs) { const dev_reg_t g = r[ii]; si = g.qs; ei = g.qe; sci = g.score; cni = g.cnt; }
+		uint32_t pending = __ballot_sync(FULL, ii < n_regs);
+		while (pending) {
+			int hit = -1; bool is_new = false;
+			if ((pending >> lane) & 1u) {
+				int covered = 0;
+				if (kk > 0 && ei > si) {
+					const int w0 = si >> 5, w1 = (ei - 1) >> 5;
 					for (int w = w0; w <= w1; ++w) {
 						uint32_t m = bits[w];
 						if (w == w0) m &= 0xffffffffu << (si & 31);
 						if (w == w1) m &= 0xffffffffu >> (31 - ((ei - 1) & 31));
 						covered += __popc(m);
 					}
-				} else {
-					for (int w = w0 + (int)lane; w <= w1; w += 32) {
-						uint32_t m = bits[w];
-						if (w == w0) m &= 0xffffffffu << (si & 31);
-						if (w == w1) m &= 0xffffffffu >> (31 - ((ei - 1) & 31));
-						covered += __popc(m);
+				}
+				if (covered > 0) {
+					const int uncov = (ei - si) - covered;
+					for (int j = 0; j < kk; ++j) {
+						const int sj = pc->qs[j], ej = pc->qe[j];
+						if (ej <= si || sj >= ei) continue;
+						const int mn = ej - sj < ei - si ? ej - sj : ei - si;
+						const int mx = ej - sj > ei - si ? ej - sj : ei - si;
+						const int ol = si < sj ? (ei < sj ? 0 : ei < ej ? ei - sj : ej - sj) : (ej < si ? 0 : ej < ei ? ej - si : ei - si);
+						if (__fsub_rn(__fdiv_rn((float)ol, (float)mn), __fdiv_rn((float)uncov, (float)mx)) > P.mask_level && uncov <= P.mask_len) { hit = j; break; }
 					}
-#pragma unroll
-					for (int o = 16; o > 0; o >>= 1) covered += __shfl_xor_sync(FULL, covered, o);
 				}
+				is_new = hit < 0;
 			}
-			int hit = -1;
-			if (covered > 0) {
-				const int uncov = (ei - si) - covered;
-				for (int j0 = 0; j0 < kk && hit < 0; j0 += 32) {
-					const int j = j0 + (int)lane;
-					bool sec = false;
-					if (j < kk) {
-						int sj, ej;
-						sj = pc->qs[j]; ej = pc->qe[j];
-						if (!(ej <= si || sj >= ei)) {
-							const int mn = ej - sj < ei - si ? ej - sj : ei - si;
-							const int mx = ej - sj > ei - si ? ej - sj : ei - si;
-							const int ol = si < sj ? (ei < sj ? 0 : ei < ej ? ei - sj : ej - sj) : (ej < si ? 0 : ej < ei ? ej - si : ei - si);
-							sec = __fsub_rn(__fdiv_rn((float)ol, (float)mn), __fdiv_rn((float)uncov, (float)mx)) > P.mask_level && uncov <= P.mask_len;
-						}
-					}
-					const uint32_t m = __ballot_sync(FULL, sec);
-					if (m) hit = j0 + __ffs(m) - 1;
-				}
+			const uint32_t newm = __ballot_sync(FULL, is_new);
+			const int first_new = newm ? __ffs(newm) - 1 : 32;
+			const uint32_t commit = first_new < 32 ? (pending & ((1u << first_new) - 1u)) : pending;
+			if ((commit >> lane) & 1u) { /* secondary of primary `hit` */
+				r[ii].parent = pc->idx[hit]; /* a primary's parent is itself */
+				atomicMax(&pc->subsc[hit], sci);
+				if (cni >= pc->cnt[hit]) atomicAdd(&pc->nsub[hit], 1);
 			}
-			if (hit >= 0) {
-				if (lane == 0) {
-					r[i].parent = pc->idx[hit]; /* a primary's parent is itself */
-					pc->subsc[hit] = pc->subsc[hit] > sci ? pc->subsc[hit] : sci;
-					if (cni >= pc->cnt[hit]) ++pc->nsub[hit];
-				}
-			} else {
-				if (lane == 0) { pc->qs[kk] = si; pc->qe[kk] = ei; pc->idx[kk] = i; pc->subsc[kk] = 0; pc->nsub[kk] = 0; pc->cnt[kk] = cni; r[i].parent = i; }
-				if (ei > si) {
-					const int w0 = si >> 5, w1 = (ei - 1) >> 5;
+			pending &= ~commit;
+			if (first_new < 32) {
+				const int ps = __shfl_sync(FULL, si, first_new), pe = __shfl_sync(FULL, ei, first_new);
+				if ((int)lane == first_new) { pc->qs[kk] = si; pc->qe[kk] = ei; pc->idx[kk] = (int)ii; pc->subsc[kk] = 0; pc->nsub[kk] = 0; pc->cnt[kk] = cni; r[ii].parent = (int)ii; }
+				if (pe > ps) {
+					const int w0 = ps >> 5, w1 = (pe - 1) >> 5;
 					for (int w = w0 + (int)lane; w <= w1; w += 32) {
 						uint32_t m = 0xffffffffu;
-						if (w == w0) m &= 0xffffffffu << (si & 31);
-						if (w == w1) m &= 0xffffffffu >> (31 - ((ei - 1) & 31));
+						if (w == w0) m &= 0xffffffffu << (ps & 31);
+						if (w == w1) m &= 0xffffffffu >> (31 - ((pe - 1) & 31));
 						bits[w] |= m;
 					}
 				}
 				++kk;
+				pending &= ~(1u << first_new);
 			}
 			__syncwarp();
 			if (kk >= FIN_PCAP) return false; /* primary cache full: caller redoes the chunk with the general form */
@@ -213,7 +205,7 @@ __device__ __forceinline__ uint32_t fin_tile_scan(uint32_t v, uint32_t *wsum, ui
 /* exact klib sort of m (key, payload) pairs already placed in W.xk/W.ord; W.sidx[pos] = payload at sorted position pos */
 __device__ __forceinline__ void fin_sort(tie_shared_t &T, uint8_t *s_bytes, uint8_t *g_bytes, const klib_ws_t &W, uint32_t m, unsigned long long *prof)
 {
-	if (m > 64) { cta_klib_replay<true>(T, m <= FIN_BYTES_CAP ? s_bytes : g_bytes, W, m, prof); return; }
+	if (m > 64) { cta_klib_replay<true>(T, m < TIE_BIG_MIN ? s_bytes : g_bytes, W, m, prof); return; } /* from TIE_BIG_MIN on, s_bytes is cta_big_level's ring */
 	__syncthreads();
 	if (threadIdx.x < 32 && m > 0) { /* klib: insertion sort (stable) */
 		const uint32_t lane = threadIdx.x;
@@ -354,7 +346,8 @@ __device__ __forceinline__ uint64_t fin_backtrack_one(int32_t i0, const int32_t 
 
 struct fin_shared_t {
 	tie_shared_t T;
-	uint8_t bytes[FIN_BYTES_CAP];
+	big_tab_t big;
+	__align__(16) uint8_t bytes[FIN_BYTES_CAP];
 	uint32_t wsum[TIE_WARPS], wsum2[TIE_WARPS];
 	unsigned long long carry_off;
 };
@@ -367,7 +360,7 @@ struct fin_shared_t {
  *   4  compact_a (+ the copy carried to the next chunk), exact sort of chains by target, region keys
  *   5  exact sort of regions, mm_gen_regs
  * The order-dependent remainder runs in k_chain_decide. */
-__global__ void __launch_bounds__(FIN_THREADS, 10) k_chain_finish(k3_args_t A, dev_params_t P)
+__global__ void __launch_bounds__(FIN_THREADS, 5) k_chain_finish(k3_args_t A, dev_params_t P)
 {
 	__shared__ fin_shared_t SH;
 	const uint32_t FULL = 0xffffffffu;
@@ -410,6 +403,8 @@ __global__ void __launch_bounds__(FIN_THREADS, 10) k_chain_finish(k3_args_t A, d
 			W.zlist = (uint32_t *)M.U2; W.mlist = W.zlist + un; W.term = (uint2 *)M.U2;
 			W.wl0 = (uint2 *)M.regs; W.wl1 = W.wl0 + (un / 64 + 2);
 			uint8_t *g_bytes = (uint8_t *)(W.wl1 + (un / 64 + 2));
+			W.qbytes = (uint8_t *)(((uintptr_t)(g_bytes + un) + 15) & ~(uintptr_t)15); /* 2.25 n + 128 bytes of the 6 n + 256 byte sort scratch so far */
+			W.big = &SH.big; W.ring = SH.bytes; W.n_big = 1;
 			uint32_t *z_idx = (uint32_t *)M.v;
 			RH_PROF_BEGIN(A.prof);
 
@@ -458,28 +453,52 @@ __global__ void __launch_bounds__(FIN_THREADS, 10) k_chain_finish(k3_args_t A, d
 			RH_PROF_MARK(A.prof, 32, tid == 0);
 			if (n_z > 0) {
 				/* ---- 2: z sorted by score exactly as klib leaves it ---- */
-				fin_sort(SH.T, SH.bytes, g_bytes, W, n_z, nullptr);
+				fin_sort(SH.T, SH.bytes, g_bytes, W, n_z, A.prof);
 				RH_PROF_MARK(A.prof, 33, tid == 0);
-				/* ---- 3: backtrack, best score first inside every run.  Positions of the sorted z are grouped by run
-				 *      (stable radix sort on the run index), so each run walks its own candidates in sorted order ---- */
+				/* ---- 3: backtrack, best score first inside every run.  A run's candidates are contiguous in index order
+				 *      (a DP segment is a contiguous anchor range); what is needed is their order by position in the sorted z.
+				 *      inv[] = position of every candidate; short runs (nearly all: 2-3 candidates) pick their next-best candidate
+				 *      by a scan of their own few positions, long runs are rank-sorted by a warp first ---- */
 				const uint32_t *__restrict__ sidx = W.sidx;
 				uint64_t *acc = W.xk2;
 				const uint32_t *runs = (const uint32_t *)M.U, *runidx = runs + un;
-				uint32_t *ka = (uint32_t *)W.xk, *kb = ka + un, *va = W.ord, *vb = W.ord2;
-				for (uint32_t pos = tid; pos < n_z; pos += FIN_THREADS) { ka[pos] = runidx[sidx[pos]]; va[pos] = pos; acc[pos] = 0ULL; }
+				uint32_t *inv = (uint32_t *)W.xk, *longs = inv + un, *grouped = W.ord;
+				(void)runidx;
+				if (tid == 0) SH.T.n_nxt = 0;
+				for (uint32_t pos = tid; pos < n_z; pos += FIN_THREADS) { inv[sidx[pos]] = pos; acc[pos] = 0ULL; }
 				__syncthreads();
-				for (uint32_t sh = 0; sh < 32 && (sh == 0 || ((n_runs - 1) >> sh) != 0); sh += 8) {
-					fin_radix_pass<uint32_t>(SH.T, ka, va, kb, vb, n_z, sh);
-					{ uint32_t *t2 = ka; ka = kb; kb = t2; } { uint32_t *t2 = va; va = vb; vb = t2; }
+				for (uint32_t rr = tid; rr < n_runs; rr += FIN_THREADS) {
+					const uint32_t lo = runs[rr], hi = rr + 1 < n_runs ? runs[rr + 1] : n_z;
+					const uint32_t L = hi - lo;
+					if (L > FIN_SHORT_RUN) { longs[atomicAdd(&SH.T.n_nxt, 1u)] = rr; continue; }
+					uint32_t bound = 0xffffffffu;
+					for (uint32_t s2 = 0; s2 < L; ++s2) {
+						uint32_t best = 0, bj = lo; bool any = false;
+						for (uint32_t j = lo; j < hi; ++j) { const uint32_t v = inv[j]; if (v < bound && (!any || v > best)) { best = v; bj = j; any = true; } }
+						bound = best;
+						const uint64_t res = fin_backtrack_one((int32_t)z_idx[bj], f, p, t, min_sc, min_cnt, max_drop);
+						if (res) acc[best] = res;
+					}
 				}
+				__syncthreads();
 				{
-					const uint32_t *__restrict__ grouped = va; /* run rr owns grouped[runs[rr] .. runs[rr+1]) in ascending position */
-					for (uint32_t rr = tid; rr < n_runs; rr += FIN_THREADS) {
+					const uint32_t n_long = SH.T.n_nxt;
+					for (uint32_t q = warp; q < n_long; q += TIE_WARPS) {
+						const uint32_t rr = longs[q];
 						const uint32_t lo = runs[rr], hi = rr + 1 < n_runs ? runs[rr + 1] : n_z;
-						for (uint32_t k = hi; k-- > lo;) {
-							const uint32_t pos = grouped[k];
-							const uint64_t res = fin_backtrack_one((int32_t)z_idx[sidx[pos]], f, p, t, min_sc, min_cnt, max_drop);
-							if (res) acc[pos] = res;
+						for (uint32_t j = lo + lane; j < hi; j += 32) { /* rank = candidates of the run at a lower position */
+							const uint32_t v = inv[j];
+							uint32_t rank = 0;
+							for (uint32_t j2 = lo; j2 < hi; ++j2) rank += inv[j2] < v;
+							grouped[lo + rank] = j;
+						}
+						__syncwarp();
+						if (lane == 0) {
+							for (uint32_t k = hi; k-- > lo;) {
+								const uint32_t j = grouped[k];
+								const uint64_t res = fin_backtrack_one((int32_t)z_idx[j], f, p, t, min_sc, min_cnt, max_drop);
+								if (res) acc[inv[j]] = res;
+							}
 						}
 					}
 				}

@@ -92,7 +92,7 @@ struct rh_worker {
 	dbuf<rh_map_rec_t> d_recs;
 	size_t arena_bytes = 0, sig_budget = 0;
 	uint32_t sort_posbits = 0, sort_ridbits = 0, sort_smem_cap = 0;
-	unsigned long long carry_known = 0, carry_pending = 0; /* exact top at the last sync + upper bound of what was launched since */
+	unsigned long long carry_known = 0; /* carry_top of the round's output arena at the last sync */
 	std::vector<timed_span> spans;
 	std::vector<cudaEvent_t> ev_pool; size_t ev_used = 0;
 	rh_gpu_stats_t st;
@@ -235,7 +235,6 @@ int run_round(rh_worker *c, round_io &io, int carry_in_idx)
 	CUDA_TRY(cudaMemcpyAsync(io.slots.data(), c->d_slots.p, ns * sizeof(slot_t), cudaMemcpyDeviceToHost, s));
 	CUDA_TRY(cudaMemcpyAsync(&c->carry_known, c->d_counters.p, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
 	CUDA_TRY(cudaStreamSynchronize(s));
-	c->carry_pending = 0;
 	c->st.d2h_bytes += ns * sizeof(slot_t) + 8;
 	dbuf<anchor_t> &carry_out = c->d_carry[carry_in_idx ^ 1];
 
@@ -257,24 +256,6 @@ int run_round(rh_worker *c, round_io &io, int carry_in_idx)
 			io.slots[g1].a_off = used; used += need; ++g1;
 		}
 		const uint32_t gn = g1 - g0;
-		{ /* the chains of this group carry at most all of its anchors into the next round: make room first */
-			unsigned long long need = 0;
-			for (uint32_t q = g0; q < g1; ++q) need += io.slots[q].n_anchors;
-			if (c->carry_known + c->carry_pending + need > carry_out.cap) {
-				CUDA_TRY(cudaStreamSynchronize(s));
-				CUDA_TRY(cudaMemcpy(&c->carry_known, c->d_counters.p, sizeof(unsigned long long), cudaMemcpyDeviceToHost));
-				c->carry_pending = 0;
-				if (c->carry_known + need > carry_out.cap) {
-					dbuf<anchor_t> bigger;
-					if ((rc = bigger.reserve((size_t)((c->carry_known + need) * 3 / 2)))) return rc;
-					if (c->carry_known) CUDA_TRY(cudaMemcpy(bigger.p, carry_out.p, c->carry_known * sizeof(anchor_t), cudaMemcpyDeviceToDevice));
-					carry_out.release();
-					carry_out = bigger;
-					a2.carry_out = carry_out.p; a3.carry_out = carry_out.p; a3.carry_cap = carry_out.cap;
-				}
-			}
-			c->carry_pending += need;
-		}
 		CUDA_TRY(cudaMemcpyAsync(c->d_slots.p + g0, io.slots.data() + g0, gn * sizeof(slot_t), cudaMemcpyHostToDevice, s));
 		c->st.h2d_bytes += gn * sizeof(slot_t);
 		a2.slots = c->d_slots.p + g0; a2.n_slots = gn;
@@ -298,7 +279,7 @@ int run_round(rh_worker *c, round_io &io, int carry_in_idx)
 			 * than keeping the bytes in shared memory (149 vs 184 ms per 100 k reads) because twice as many chunks are
 			 * resident per SM and the walk is latency bound either way */
 			span_guard g(c, T_TIES, 1);
-			k_sort_ties<<<gn, TIE_THREADS, sizeof(tie_shared_t), s>>>(as, 0u, 0u, 0xffffffffu);
+			k_sort_ties<<<gn, TIE_THREADS, tie_smem_bytes(0), s>>>(as, 0u, 0u, 0xffffffffu);
 		}
 		if (io.tap) { /* sorted anchor list of the single tapped slot */
 			rh_tap_t *T = io.tap_out; const slot_t &sl = io.slots[0];
@@ -321,6 +302,27 @@ int run_round(rh_worker *c, round_io &io, int carry_in_idx)
 			        gn, na.size(), pc(na, .5), pc(na, .9), pc(na, .99), pc(na, 1.0), nt.size(), pc(nt, .5), pc(nt, .9), pc(nt, 1.0));
 		}
 		{ span_guard g(c, T_CHAIN); k_chain_dp<<<gn, DP_THREADS, 0, s>>>(a3, c->D); }
+		{ /* room for what this group's chains carry into the next round.  A chain of m anchors uses m-1 distinct anchors that
+		   * have a DP predecessor, so a chunk carries at most min(n_anchors, 2 n_link) anchors (a gated chunk: its prev_n) */
+			std::vector<slot_t> after(gn);
+			CUDA_TRY(cudaMemcpyAsync(after.data(), c->d_slots.p + g0, gn * sizeof(slot_t), cudaMemcpyDeviceToHost, s));
+			CUDA_TRY(cudaMemcpyAsync(&c->carry_known, c->d_counters.p, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+			CUDA_TRY(cudaStreamSynchronize(s));
+			c->st.d2h_bytes += gn * sizeof(slot_t) + 8;
+			unsigned long long need = 0;
+			for (uint32_t q = 0; q < gn; ++q) {
+				const slot_t &sl = after[q];
+				need += (sl.gated || sl.n_anchors == 0) ? sl.n_anchors : std::min<unsigned long long>(sl.n_anchors, 2ULL * sl.n_link);
+			}
+			if (c->carry_known + need > carry_out.cap) {
+				dbuf<anchor_t> bigger;
+				if ((rc = bigger.reserve((size_t)((c->carry_known + need) * 5 / 4)))) return rc;
+				if (c->carry_known) CUDA_TRY(cudaMemcpy(bigger.p, carry_out.p, c->carry_known * sizeof(anchor_t), cudaMemcpyDeviceToDevice));
+				carry_out.release();
+				carry_out = bigger;
+				a2.carry_out = carry_out.p; a3.carry_out = carry_out.p; a3.carry_cap = carry_out.cap;
+			}
+		}
 		{ span_guard g(c, T_POST, 2); k_chain_finish<<<gn, FIN_THREADS, 0, s>>>(a3, c->D); k_chain_decide<<<(gn + DEC_WARPS - 1) / DEC_WARPS, DEC_WARPS * 32, 0, s>>>(a3, c->D); }
 		if (io.tap) {
 			CUDA_TRY(cudaMemcpyAsync(io.slots.data(), c->d_slots.p, sizeof(slot_t), cudaMemcpyDeviceToHost, s));
@@ -712,6 +714,7 @@ extern "C" rh_gpu_ctx *rh_gpu_init(const rh_index_t *idx, const rh_params_t *p, 
 			if (cudaFuncSetAttribute(k_sort_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sort_smem_bytes(c->sort_smem_cap)) != cudaSuccess) return fail("cudaFuncSetAttribute(k_sort_smem) failed");
 		}
 	}
+	if (cudaFuncSetAttribute(k_sort_ties, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tie_smem_bytes(0)) != cudaSuccess) return fail("cudaFuncSetAttribute(k_sort_ties) failed");
 	if (cudaDeviceSynchronize() != cudaSuccess) return fail("index upload failed");
 	/* ---- workers: the work arenas are split evenly ---- */
 	size_t free_b = 0, total_b = 0;

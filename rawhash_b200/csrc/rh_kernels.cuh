@@ -55,6 +55,7 @@ struct slot_t {
 	uint32_t n_ties;               /* adjacent equal keys found by the anchor sort              */
 	uint32_t n_seg;                /* independent DP segments                                   */
 	uint32_t ev_done;              /* events already produced by the fast event kernel          */
+	uint32_t n_link;               /* anchors with a DP predecessor: chains carry at most 2 n_link anchors to the next chunk */
 };
 
 /* layout of a slot's region in the anchor arena (n = n_anchors) */
@@ -283,11 +284,11 @@ struct k3_args_t {
  * array falls apart into independent DP segments at every such gap: one CTA per chunk marks the
  * gaps, then its threads take segments round-robin.  (Random hits are sparse in target space, so
  * a chunk has thousands of short segments and a few long ones around true loci.) */
-#define DP_THREADS 128
+#define DP_THREADS 256
 #define DP_BIG_SEG 64          /* segments at least this long are chained by a whole warp */
 __global__ void __launch_bounds__(DP_THREADS) k_chain_dp(k3_args_t A, dev_params_t P)
 {
-	__shared__ uint32_t s_nseg, s_nbig, s_next;
+	__shared__ uint32_t s_nseg, s_nbig, s_next, s_nlink;
 	slot_t *S = &A.slots[blockIdx.x];
 	if (S->gated || S->n_anchors == 0) return;
 	const int32_t n = (int32_t)S->n_anchors;
@@ -302,8 +303,9 @@ __global__ void __launch_bounds__(DP_THREADS) k_chain_dp(k3_args_t A, dev_params
 	if (max_q < bw) max_q = bw;
 	const uint32_t tid = threadIdx.x;
 	uint32_t *big = starts + n; /* segments handed to whole warps (M.U holds 2n words) */
-	if (tid == 0) { s_nseg = 0; s_nbig = 0; s_next = 0; }
+	if (tid == 0) { s_nseg = 0; s_nbig = 0; s_next = 0; s_nlink = 0; }
 	__syncthreads();
+	uint32_t my_links = 0;
 	for (int32_t i = tid; i < n; i += DP_THREADS) {
 		t[i] = 0;
 		bool st = true;
@@ -346,6 +348,7 @@ __global__ void __launch_bounds__(DP_THREADS) k_chain_dp(k3_args_t A, dev_params
 				if (sc != INT32_MIN && best < sc + f[band_best]) { best = sc + f[band_best]; best_j = band_best; }
 			}
 			f[i] = best; p[i] = best_j;
+			my_links += best_j >= 0;
 			v[i] = (best_j >= 0 && v[best_j] > best) ? v[best_j] : best;
 			if (band_best < 0 || (ix - a[band_best].x <= (uint64_t)(int64_t)max_t && f[band_best] < f[i])) band_best = i;
 		}
@@ -413,10 +416,13 @@ __global__ void __launch_bounds__(DP_THREADS) k_chain_dp(k3_args_t A, dev_params
 			}
 			const int32_t vi = (best_j >= 0 && v[best_j] > best) ? v[best_j] : best;
 			if (band_best < 0 || (ix - a[band_best].x <= (uint64_t)(int64_t)max_t && f[band_best] < best)) band_best = i;
-			if (lane == 0) { f[i] = best; p[i] = best_j; v[i] = vi; }
+			if (lane == 0) { f[i] = best; p[i] = best_j; v[i] = vi; my_links += best_j >= 0; }
 			__syncwarp();
 		}
 	}
+	if (my_links) atomicAdd(&s_nlink, my_links);
+	__syncthreads();
+	if (tid == 0) S->n_link = s_nlink;
 }
 
 #endif

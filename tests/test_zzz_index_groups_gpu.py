@@ -1,23 +1,30 @@
-"""GPU: references larger than one device pass are indexed contig group by contig group (rh_index_build_grouped);
-forced here with a small RH_INDEX_GROUP_BASES; the CPU twin through the host builder is
-tests/test_io.py::test_index_built_over_contig_groups_equals_one_pass."""
+"""GPU: the device-resident index builder (rh_index_build_dev) on a reference of tens of Mb — many filter segments per
+strand, so the speculative incoming states and their fix-up rounds are exercised — against the host builder, through
+the byte-exact `.ind` writer; and the device-side mid_occ (radix select over the CSR offsets) against the host one."""
+import numpy as np
 import pytest
-
-from common import World
 
 pytestmark = pytest.mark.gpu
 
 
-def test_gpu_index_over_contig_groups_equals_host_build(built, tmp_path, monkeypatch):
-    from rawhash_b200 import api
-    w = World(n_contigs=5, genome_len=1_200_000, n_reads=1, read_bp=1000, seed=51)
-    P = api.make_params("sensitive")
-    pore = api.load_pore(w.model, w.k)
-    names, seqs = w.genome_strings()
-    monkeypatch.delenv("RH_INDEX_GROUP_BASES", raising=False)
-    host = api.Index.build(P, pore, names, seqs, 8)
-    monkeypatch.setenv("RH_INDEX_GROUP_BASES", "500000")   # contigs of 240 kb: groups of two, two, one
-    dev = api.Index.build_gpu(P, pore, names, seqs, 0)
+@pytest.mark.parametrize("preset,r10", [("sensitive", False), ("fast", False), ("fast", True)])
+def test_device_index_equals_host_build(built, tmp_path, preset, r10):
+    import torch
+    from rawhash_b200 import api, synth
+    from common import model_for
+    kind, k = ("r10.4.1", 9) if r10 else ("r9.4", 6)
+    lens = [5_000_017, 3_000_001, 1_999_999, 777, 8, 4, 2_500_000]   # includes contigs shorter than k and than one window
+    G = synth.DeviceGenome([f"c{i}" for i in range(len(lens))], lens, device=torch.device("cuda", 0), seed=13)
+    P = api.make_params(preset, r10)
+    pore = api.load_pore(model_for(kind), k)
+    dev = api.Index.build_dev(P, pore, G.names, G.codes.data_ptr(), G.lens, 0)
+    assert dev.on_device == 0
+    lut = np.frombuffer(b"ACGT", dtype=np.uint8)
+    hc = G.host_contigs()
+    host = api.Index.build(P, pore, [n for n, _ in hc], [lut[c].tobytes() for _, c in hc], 16)
+    P2 = api.make_params(preset, r10)
+    assert dev.update_mapopt(P) == host.update_mapopt(P2)          # device radix select vs host nth_element
+    assert (dev.n_keys, dev.n_pos) == (host.n_keys, host.n_pos)
     a, b = str(tmp_path / "host.ind"), str(tmp_path / "dev.ind")
     host.dump(a, pore)
     dev.dump(b, pore)
