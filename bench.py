@@ -350,7 +350,7 @@ def main():
 
     # ---- timed: HBM-resident ----
     agg = {k: 0.0 for k in ("ms_event_kernel", "ms_seed", "ms_sort", "ms_sort_ties", "ms_chain", "ms_post", "ms_total")}
-    cnt = {k: 0 for k in ("raw_samples_consumed", "n_seeds", "event_kernel_launches", "kernel_launches", "n_chunks", "n_anchors", "n_rounds")}
+    cnt = {k: 0 for k in ("raw_samples_consumed", "n_seeds", "event_kernel_launches", "kernel_launches", "n_chunks", "n_anchors", "n_rounds", "event_stage_samples", "event_stage_seeds")}
     with ClockSampler(local_rank) as clk:
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -401,10 +401,12 @@ def main():
     if rank == 0:
         peak, peak_src = _peaks()
         ev_launches = max(iso["event_kernel_launches"], 1)
-        alg_bytes = 2.0 * iso["raw_samples_consumed"] + 16.0 * iso["n_seeds"]
+        # what the event-stage launches processed: 2 B per raw sample read + 16 B per seed emitted; the stage runs
+        # ahead of the stop decisions, so this includes chunks that were detected and sketched but never mapped
+        alg_bytes = 2.0 * iso["event_stage_samples"] + 16.0 * iso["event_stage_seeds"]
         ev_ms = iso["ms_event_kernel"]
         achieved = alg_bytes / (ev_ms * 1e-3) / 1e9 if ev_ms > 0 else 0.0
-        alg_bytes_timed = 2.0 * cnt["raw_samples_consumed"] + 16.0 * cnt["n_seeds"]
+        alg_bytes_timed = 2.0 * cnt["event_stage_samples"] + 16.0 * cnt["event_stage_seeds"]
         achieved_timed = alg_bytes_timed / (agg["ms_event_kernel"] * 1e-3) / 1e9 if agg["ms_event_kernel"] > 0 else 0.0
         ratio, ratio_src = _traffic_ratio()
         line = {
@@ -426,7 +428,9 @@ def main():
                          "traffic": (ratio * alg_bytes / ev_launches) if ratio else None, "traffic_source": ratio_src, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": alg_bytes / ev_launches, "avg_launch_ms": ev_ms / ev_launches,
                          "timing": "CUDA events on the launching stream around each event-stage launch group, in a one-worker pass of the same step right after the timed region (kernel timed alone)",
-                         "achieved_in_timed_region": achieved_timed},
+                         "achieved_in_timed_region": achieved_timed,
+                         "event_stage_chunks_per_mapped_chunk": (iso["event_stage_samples"] / max(iso["raw_samples_consumed"], 1)),
+                         "kernels": "k_evt_sums (warp/chunk) + k_evt_stream (lane/chunk: z, prefix sums, t-statistics, peak detectors) + k_evt_finish (CTA/chunk: segment sort, events, quantise, hash)"},
             "stage_ms_per_step": {k: v / args.steps for k, v in agg.items()},
             "stage_ms_note": "per-stage CUDA-event spans summed over the concurrent workers (they overlap in time; ms_total is the slowest worker)",
             "stage_ms_one_worker": {k: iso[k] for k in agg},

@@ -212,6 +212,8 @@ typedef struct rh_gpu_stats_s {
 	uint64_t event_kernel_launches;
 	uint64_t h2d_bytes, d2h_bytes;
 	double   ms_sort_ties;           /* part of ms_sort spent replaying klib's tie order */
+	uint64_t event_stage_samples;    /* raw samples / seeds the event-stage launches produced, including chunks computed */
+	uint64_t event_stage_seeds;      /* ahead of the read's stop decision and never mapped                              */
 } rh_gpu_stats_t;
 void rh_gpu_get_stats(const rh_gpu_ctx *ctx, rh_gpu_stats_t *st);
 

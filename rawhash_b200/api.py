@@ -91,6 +91,7 @@ class GpuStats(C.Structure):
         ("event_kernel_launches", C.c_uint64),
         ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64),
         ("ms_sort_ties", C.c_double),
+        ("event_stage_samples", C.c_uint64), ("event_stage_seeds", C.c_uint64),
     ]
 
     def as_dict(self):

@@ -983,14 +983,15 @@ __device__ void cta_klib_replay(tie_shared_t &T, uint8_t *bytes, klib_ws_t W, co
 }
 
 #define TIE_SIDE_WALKS 7           /* long sub-arrays of a tie chunk that walk side by side (warps - 1) */
-__host__ __device__ inline size_t tie_smem_bytes(uint32_t smem_cap) { return ((sizeof(tie_shared_t) + 15) & ~(size_t)15) + TIE_SIDE_WALKS * (sizeof(big_tab_t) + TIE_RING_BYTES) + smem_cap; }
-__global__ void __launch_bounds__(TIE_THREADS, 1) k_sort_ties(sort_args_t A, uint32_t smem_cap, uint32_t n_lo, uint32_t n_hi)
+#define TIE_LARGE_N 131072u        /* chunks from this size on get TIE_SIDE_WALKS table sets (one CTA per SM); smaller ones one set and full occupancy */
+__host__ __device__ inline size_t tie_smem_bytes(uint32_t smem_cap, uint32_t n_big) { return ((sizeof(tie_shared_t) + 15) & ~(size_t)15) + n_big * (sizeof(big_tab_t) + TIE_RING_BYTES) + smem_cap; }
+__global__ void __launch_bounds__(TIE_THREADS, 4) k_sort_ties(sort_args_t A, uint32_t smem_cap, uint32_t n_lo, uint32_t n_hi, uint32_t n_big)
 {
 	extern __shared__ __align__(16) uint8_t s_dyn[];
 	tie_shared_t &T = *(tie_shared_t *)s_dyn;
 	big_tab_t *s_big = (big_tab_t *)(s_dyn + ((sizeof(tie_shared_t) + 15) & ~(size_t)15));
-	uint8_t *s_ring = (uint8_t *)(s_big + TIE_SIDE_WALKS);
-	uint8_t *s_bytes = s_ring + TIE_SIDE_WALKS * TIE_RING_BYTES;
+	uint8_t *s_ring = (uint8_t *)(s_big + n_big);
+	uint8_t *s_bytes = s_ring + n_big * TIE_RING_BYTES;
 	const uint32_t tid = threadIdx.x;
 	if (blockIdx.x >= *A.tie_count) return;
 	slot_t *S = &A.slots[A.tie_list[blockIdx.x]];
@@ -1008,7 +1009,7 @@ __global__ void __launch_bounds__(TIE_THREADS, 1) k_sort_ties(sort_args_t A, uin
 	W.wl0 = (uint2 *)M.regs; W.wl1 = W.wl0 + (n / 64 + 2);
 	uint8_t *bytes = n <= smem_cap ? s_bytes : (uint8_t *)M.t + n;
 	W.qbytes = (uint8_t *)(((uintptr_t)((uint8_t *)M.t + 2 * (size_t)n) + 15) & ~(uintptr_t)15); /* M.t is 4n bytes: flags, digits, displaced digits */
-	W.big = s_big; W.ring = s_ring; W.n_big = TIE_SIDE_WALKS;
+	W.big = s_big; W.ring = s_ring; W.n_big = n_big;
 	for (uint32_t i = tid; i < n; i += TIE_THREADS) { W.xk[i] = in[i].x | (tied[i] ? TIE_FLAG : 0ULL); W.ord[i] = i; }
 	cta_klib_replay<false>(T, bytes, W, n, A.prof);
 	RH_PROF_BEGIN(A.prof);

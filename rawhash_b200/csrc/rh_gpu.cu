@@ -26,6 +26,7 @@
 #include "rh_host.h"
 #include "rh_kernels.cuh"
 #include "rh_signal.cuh"
+#include "rh_event_stream.cuh"
 #include "rh_anchor_sort.cuh"
 #include "rh_chain_finish.cuh"
 
@@ -82,6 +83,10 @@ struct rh_worker {
 	dbuf<read_state_t> d_rs;
 	dbuf<slot_t> d_slots;
 	dbuf<float> d_z, d_events, d_ps, d_pq, d_t1, d_t2;
+	dbuf<chunk_norm_t> d_norm;
+	dbuf<uint2> d_groups;
+	dbuf<slot_t> d_pre;            /* slots of the chunks whose event stage ran ahead of their round */
+	int fast_w1 = 0, fast_w2 = 0; /* exhaustive self-test at init: x / w by reciprocal + two FMAs is exact for this window length */
 	dbuf<uint32_t> d_peaks, d_seed_hash, d_seed_pos, d_seed_cnt, d_seed_dst;
 	dbuf<uint64_t> d_seed_src;
 	dbuf<uint8_t> d_arena;
@@ -185,35 +190,58 @@ struct round_io {
 	int tap = 0;
 	rh_tap_t *tap_out = nullptr; uint64_t *tap_off = nullptr; /* running offsets: ev, seed, anc, u, ca, reg */
 	uint32_t tap_chunk = 0;
+	bool events_done = false;          /* slots already carry the event stage's results (computed ahead, event_stage()) */
 };
 
-int run_round(rh_worker *c, round_io &io, int carry_in_idx)
+/* The event stage over `hs.size()` chunks whose slots live at d_slots: assigns the scratch offsets, uploads the slots,
+ * launches.  groups = runs of consecutive slots that are successive chunks of ONE read (their sums chain). */
+int event_stage(rh_worker *c, std::vector<slot_t> &hs, dbuf<slot_t> &d_slots, const std::vector<uint2> &groups)
 {
-	const uint32_t ns = (uint32_t)io.slots.size();
+	const uint32_t ns = (uint32_t)hs.size();
 	if (ns == 0) return RH_OK;
 	cudaStream_t s = c->stream;
-	/* scratch offsets */
 	uint64_t zt = 0, et = 0;
-	for (slot_t &sl : io.slots) {
+	uint32_t max_len = 0;
+	for (slot_t &sl : hs) {
 		sl.z_off = zt; zt += ((uint64_t)sl.chunk_len + 3) & ~3ULL; /* chunks start 16-byte aligned */
 		sl.e_cap = (uint32_t)((uint64_t)sl.chunk_len * 2 / 3 + 8);
 		sl.e_off = et; et += sl.e_cap;
+		max_len = std::max(max_len, sl.chunk_len);
 	}
 	int rc;
-	if ((rc = c->d_z.reserve(zt))) return rc;
+	const bool streaming = max_len <= EVS_MAXN && !getenv("RH_EVENT_OLD"); /* ordinary chunks: no intermediates in HBM (rh_event_stream.cuh) */
 	if ((rc = c->d_events.reserve(et)) || (rc = c->d_peaks.reserve(et)) || (rc = c->d_seed_hash.reserve(et)) || (rc = c->d_seed_pos.reserve(et)) ||
 	    (rc = c->d_seed_cnt.reserve(et)) || (rc = c->d_seed_dst.reserve(et)) || (rc = c->d_seed_src.reserve(et))) return rc;
-	if ((rc = upload(c->d_slots, io.slots, s))) return rc;
+	if ((rc = upload(d_slots, hs, s))) return rc;
 	c->st.h2d_bytes += ns * sizeof(slot_t);
-
-	if ((rc = c->d_ps.reserve(zt + 4 * (uint64_t)ns + 4)) || (rc = c->d_pq.reserve(zt + 4 * (uint64_t)ns + 4)) || (rc = c->d_t1.reserve(zt + 4 * (uint64_t)ns + 4)) || (rc = c->d_t2.reserve(zt + 4 * (uint64_t)ns + 4))) return rc;
-	sig_args_t a1;
-	a1.raw = c->raw_ptr; a1.rs = c->d_rs.p; a1.slots = c->d_slots.p; a1.n_slots = ns;
-	a1.z = c->d_z.p; a1.ps = c->d_ps.p; a1.pq = c->d_pq.p; a1.t1 = c->d_t1.p; a1.t2 = c->d_t2.p;
-	a1.peaks = c->d_peaks.p; a1.events = c->d_events.p; a1.seed_hash = c->d_seed_hash.p; a1.seed_pos = c->d_seed_pos.p;
-	a1.min_hash = c->d_seed_cnt.p; a1.min_pos = c->d_seed_dst.p; /* free until k_seed_count */
-	a1.prof = c->prof_on ? c->d_prof.p : nullptr;
-	{ /* the event stage: five launches back to back, timed as one span */
+	if (streaming) {
+		if ((rc = c->d_norm.reserve(ns)) || (rc = upload(c->d_groups, groups, s))) return rc;
+		c->st.h2d_bytes += groups.size() * sizeof(uint2);
+		evt_args_t e1;
+		e1.raw = c->raw_ptr; e1.rs = c->d_rs.p; e1.slots = d_slots.p; e1.n_slots = ns; e1.norm = c->d_norm.p;
+		e1.groups = c->d_groups.p; e1.n_groups = (uint32_t)groups.size();
+		e1.peaks = c->d_peaks.p; e1.events = c->d_events.p; e1.seed_hash = c->d_seed_hash.p; e1.seed_pos = c->d_seed_pos.p;
+		e1.min_hash = c->d_seed_cnt.p; e1.min_pos = c->d_seed_dst.p; /* free until k_seed_count */
+		e1.fast_w1 = c->fast_w1; e1.fast_w2 = c->fast_w2;
+		span_guard g(c, T_EVENT, 3);
+		k_evt_sums<<<(e1.n_groups * 32 + 127) / 128, 128, 0, s>>>(e1);
+		const uint32_t gb = (ns + EVS_THREADS - 1) / EVS_THREADS;
+		if (c->fast_w1 && c->fast_w2) k_evt_stream<true, true><<<gb, EVS_THREADS, 0, s>>>(e1, c->D);
+		else if (c->fast_w1) k_evt_stream<true, false><<<gb, EVS_THREADS, 0, s>>>(e1, c->D);
+		else if (c->fast_w2) k_evt_stream<false, true><<<gb, EVS_THREADS, 0, s>>>(e1, c->D);
+		else k_evt_stream<false, false><<<gb, EVS_THREADS, 0, s>>>(e1, c->D);
+		k_evt_finish<<<ns, EVF2_THREADS, 0, s>>>(e1, c->D);
+	} else {
+		for (const uint2 &g : groups) if (g.y != 1) { rh_set_error("internal: long chunks are detected one per read and launch"); return RH_ERR_ARG; }
+		if ((rc = c->d_z.reserve(zt))) return rc;
+		if ((rc = c->d_ps.reserve(zt + 4 * (uint64_t)ns + 4)) || (rc = c->d_pq.reserve(zt + 4 * (uint64_t)ns + 4)) || (rc = c->d_t1.reserve(zt + 4 * (uint64_t)ns + 4)) || (rc = c->d_t2.reserve(zt + 4 * (uint64_t)ns + 4))) return rc;
+		sig_args_t a1;
+		a1.raw = c->raw_ptr; a1.rs = c->d_rs.p; a1.slots = d_slots.p; a1.n_slots = ns;
+		a1.z = c->d_z.p; a1.ps = c->d_ps.p; a1.pq = c->d_pq.p; a1.t1 = c->d_t1.p; a1.t2 = c->d_t2.p;
+		a1.peaks = c->d_peaks.p; a1.events = c->d_events.p; a1.seed_hash = c->d_seed_hash.p; a1.seed_pos = c->d_seed_pos.p;
+		a1.min_hash = c->d_seed_cnt.p; a1.min_pos = c->d_seed_dst.p; /* free until k_seed_count */
+		a1.prof = c->prof_on ? c->d_prof.p : nullptr;
+		/* whole-read chunks (Rawsamble) and other long chunks: seven launches back to back, timed as one span */
 		span_guard g(c, T_EVENT, 7);
 		k_sig_norm<<<(ns * 32 + 127) / 128, 128, 0, s>>>(a1);
 		k_sig_prefix<<<(ns + 127) / 128, 128, 0, s>>>(a1);
@@ -222,6 +250,23 @@ int run_round(rh_worker *c, round_io &io, int carry_in_idx)
 		k_sig_events_fast<<<ns, EV_THREADS, 0, s>>>(a1);
 		k_sig_events<<<ns, EV_THREADS, 0, s>>>(a1);
 		k_sig_sketch<<<(ns + 127) / 128, 128, 0, s>>>(a1, c->D);
+	}
+	return RH_OK;
+}
+
+int run_round(rh_worker *c, round_io &io, int carry_in_idx)
+{
+	const uint32_t ns = (uint32_t)io.slots.size();
+	if (ns == 0) return RH_OK;
+	cudaStream_t s = c->stream;
+	int rc;
+	if (io.events_done) { /* computed ahead: the slots carry their counts and scratch offsets already */
+		if ((rc = upload(c->d_slots, io.slots, s))) return rc;
+		c->st.h2d_bytes += ns * sizeof(slot_t);
+	} else {
+		std::vector<uint2> groups(ns);
+		for (uint32_t i = 0; i < ns; ++i) groups[i] = make_uint2(i, 1u);
+		if ((rc = event_stage(c, io.slots, c->d_slots, groups))) return rc;
 	}
 	k2_args_t a2;
 	a2.slots = c->d_slots.p; a2.n_slots = ns; a2.rs = c->d_rs.p;
@@ -279,7 +324,10 @@ int run_round(rh_worker *c, round_io &io, int carry_in_idx)
 			 * than keeping the bytes in shared memory (149 vs 184 ms per 100 k reads) because twice as many chunks are
 			 * resident per SM and the walk is latency bound either way */
 			span_guard g(c, T_TIES, 1);
-			k_sort_ties<<<gn, TIE_THREADS, tie_smem_bytes(0), s>>>(as, 0u, 0u, 0xffffffffu);
+			uint32_t maxn = 0;
+			for (uint32_t q = g0; q < g1; ++q) if (!io.slots[q].gated) maxn = std::max(maxn, io.slots[q].n_anchors);
+			k_sort_ties<<<gn, TIE_THREADS, tie_smem_bytes(0, 1), s>>>(as, 0u, 0u, TIE_LARGE_N, 1u);
+			if (maxn >= TIE_LARGE_N) k_sort_ties<<<gn, TIE_THREADS, tie_smem_bytes(0, TIE_SIDE_WALKS), s>>>(as, 0u, TIE_LARGE_N, 0xffffffffu, (uint32_t)TIE_SIDE_WALKS);
 		}
 		if (io.tap) { /* sorted anchor list of the single tapped slot */
 			rh_tap_t *T = io.tap_out; const slot_t &sl = io.slots[0];
@@ -333,6 +381,7 @@ int run_round(rh_worker *c, round_io &io, int carry_in_idx)
 	for (const slot_t &sl : io.slots) {
 		c->st.raw_samples_consumed += sl.raw_used; c->st.n_chains += sl.n_u;
 		c->st.n_chunks++; c->st.n_events += sl.n_events; c->st.n_seeds += sl.n_seeds; c->st.n_anchors += sl.n_anchors;
+		if (!io.events_done) { c->st.event_stage_samples += sl.raw_used; c->st.event_stage_seeds += sl.n_seeds; }
 	}
 	return RH_OK;
 }
@@ -427,27 +476,79 @@ int map_resident(rh_worker *c, const batch_in &in, const std::vector<uint64_t> &
 	std::vector<uint32_t> active;
 	for (uint32_t i = 0; i < n; ++i) if (l_sig[i] > 0) active.push_back(i);
 	std::vector<uint32_t> rec_cnt(n);
+	auto chunk_of = [&](uint32_t r, uint32_t round, uint32_t *len) { /* chunk geometry of map_worker_for, rmap.cpp:402-421 */
+		const uint32_t qlen = l_sig[r];
+		const uint32_t l_chunk = (P.chunk_size > qlen || noadapt) ? qlen : P.chunk_size;
+		const uint64_t s_qs = (uint64_t)round * l_chunk;
+		if (s_qs >= qlen) return false;
+		*len = (uint32_t)std::min<uint64_t>(l_chunk, qlen - s_qs);
+		return true;
+	};
+	/* Event detection never looks at mapping results (only at the signal and the read's running sums), so the event stage
+	 * of the next `ahead` chunks of every active read runs in ONE launch set ("wave") ahead of their rounds: launches large
+	 * enough to fill the GPU instead of one small launch set per round, at the price of events for chunks a read may never
+	 * map.  Long chunks (whole-read Rawsamble) are detected one per read and launch. */
+	bool long_chunks = false;
+	for (uint32_t r : active) { uint32_t len0; if (chunk_of(r, 0, &len0) && len0 > EVS_MAXN) { long_chunks = true; break; } }
+	uint32_t ahead = 1;
+	if (!long_chunks && !noadapt && !getenv("RH_EVENT_OLD")) {
+		const char *e = getenv("RH_EVENT_AHEAD");
+		ahead = e ? (uint32_t)std::max(1, atoi(e)) : (uint32_t)std::max<size_t>(1, (size_t)131072 / std::max<size_t>(active.size(), 1));
+		ahead = std::min(ahead, max_chunk);
+	}
+	std::vector<slot_t> pre;            /* host copy of the wave's slots after their event stage */
+	std::vector<uint32_t> pre_first(n, 0xffffffffu);
+	uint32_t wave_base = 0, wave_end = 0;
 	uint32_t round = 0;
 	while (!active.empty() && round < max_chunk) {
-		/* split the active set into groups whose signal scratch fits the budget */
 		CUDA_TRY(cudaMemsetAsync(c->d_counters.p, 0, sizeof(unsigned long long), c->stream)); /* carry_top of the round's output arena */
-		size_t a0 = 0;
-		while (a0 < active.size()) {
-			round_io io;
-			uint64_t samples = 0; size_t a1 = a0;
-			while (a1 < active.size()) {
-				const uint32_t r = active[a1], qlen = l_sig[r];
-				const uint32_t l_chunk = (P.chunk_size > qlen || noadapt) ? qlen : P.chunk_size;
-				const uint64_t s_qs = (uint64_t)round * l_chunk;
-				const uint32_t len = (uint32_t)std::min<uint64_t>(l_chunk, qlen - s_qs);
-				if (samples + len > c->sig_budget && a1 > a0) break;
-				slot_t sl; memset(&sl, 0, sizeof(sl));
-				sl.read = r; sl.chunk_len = len; sl.c_count = round;
-				io.slots.push_back(sl);
-				samples += len; ++a1;
+		if (ahead > 1 && round == wave_end) { /* next wave: chunks [round, round + ahead) of every active read */
+			pre.clear();
+			std::vector<uint2> groups;
+			for (uint32_t r : active) {
+				const uint32_t first = (uint32_t)pre.size();
+				for (uint32_t cc = round; cc < round + ahead && cc < max_chunk; ++cc) {
+					uint32_t len2;
+					if (!chunk_of(r, cc, &len2)) break;
+					slot_t sl; memset(&sl, 0, sizeof(sl));
+					sl.read = r; sl.chunk_len = len2; sl.c_count = cc;
+					pre.push_back(sl);
+				}
+				pre_first[r] = first;
+				if (pre.size() > first) groups.push_back(make_uint2(first, (uint32_t)pre.size() - first));
 			}
+			if ((rc = event_stage(c, pre, c->d_pre, groups))) return rc;
+			CUDA_TRY(cudaMemcpyAsync(pre.data(), c->d_pre.p, pre.size() * sizeof(slot_t), cudaMemcpyDeviceToHost, c->stream));
+			CUDA_TRY(cudaStreamSynchronize(c->stream));
+			c->st.d2h_bytes += pre.size() * sizeof(slot_t);
+			for (const slot_t &sl : pre) { c->st.event_stage_samples += sl.raw_used; c->st.event_stage_seeds += sl.n_seeds; }
+			wave_base = round; wave_end = round + ahead;
+		}
+		if (ahead > 1) {
+			round_io io;
+			io.events_done = true;
+			io.slots.reserve(active.size());
+			for (uint32_t r : active) io.slots.push_back(pre[pre_first[r] + (round - wave_base)]);
 			if ((rc = run_round(c, io, round & 1))) return rc;
-			a0 = a1;
+		} else {
+			/* split the active set into groups whose signal scratch fits the budget */
+			size_t a0 = 0;
+			while (a0 < active.size()) {
+				round_io io;
+				uint64_t samples = 0; size_t a1 = a0;
+				while (a1 < active.size()) {
+					const uint32_t r = active[a1];
+					uint32_t len2 = 0;
+					chunk_of(r, round, &len2);
+					if (samples + len2 > c->sig_budget && a1 > a0) break;
+					slot_t sl; memset(&sl, 0, sizeof(sl));
+					sl.read = r; sl.chunk_len = len2; sl.c_count = round;
+					io.slots.push_back(sl);
+					samples += len2; ++a1;
+				}
+				if ((rc = run_round(c, io, round & 1))) return rc;
+				a0 = a1;
+			}
 		}
 		c->st.n_rounds++;
 		CUDA_TRY(cudaMemcpyAsync(rec_cnt.data(), c->d_rec_cnt.p, n * 4, cudaMemcpyDeviceToHost, c->stream));
@@ -504,7 +605,7 @@ namespace {
 void destroy_worker(rh_worker *w)
 {
 	if (!w) return;
-	w->d_ps.release(); w->d_pq.release(); w->d_t1.release(); w->d_t2.release();
+	w->d_ps.release(); w->d_pq.release(); w->d_t1.release(); w->d_t2.release(); w->d_norm.release(); w->d_groups.release(); w->d_pre.release();
 	w->d_rs.release(); w->d_slots.release(); w->d_z.release(); w->d_events.release(); w->d_peaks.release();
 	w->d_seed_hash.release(); w->d_seed_pos.release(); w->d_seed_cnt.release(); w->d_seed_dst.release(); w->d_seed_src.release();
 	w->d_arena.release(); w->d_carry[0].release(); w->d_carry[1].release(); w->d_counters.release(); w->d_err.release();
@@ -528,7 +629,7 @@ rh_worker *make_worker(rh_gpu_ctx *c, size_t arena_bytes)
 	cudaMemset(w->d_prof.p, 0, 64 * 8);
 	w->arena_bytes = arena_bytes;
 	const size_t carry_elems = arena_bytes / 8 / sizeof(anchor_t); /* initial size: grows on demand (run_round) */
-	w->sig_budget = std::max<size_t>(arena_bytes / 16 / 44, (size_t)1 << 20); /* ~44 B of scratch per sample */
+	w->sig_budget = std::max<size_t>(arena_bytes / 8 / 22, (size_t)1 << 20); /* ~85 KB of peak/event/seed scratch per 4000-sample chunk */
 	if (w->d_arena.reserve(arena_bytes) || w->d_carry[0].reserve(carry_elems) || w->d_carry[1].reserve(carry_elems)) { destroy_worker(w); return nullptr; }
 	w->arena_bytes = w->d_arena.cap;
 	return w;
@@ -542,6 +643,7 @@ void add_stats(rh_gpu_stats_t &a, const rh_gpu_stats_t &b)
 	a.ms_total = std::max(a.ms_total, b.ms_total);
 	a.ms_event_kernel += b.ms_event_kernel; a.ms_seed += b.ms_seed; a.ms_sort += b.ms_sort; a.ms_sort_ties += b.ms_sort_ties; a.ms_chain += b.ms_chain; a.ms_post += b.ms_post;
 	a.h2d_bytes += b.h2d_bytes; a.d2h_bytes += b.d2h_bytes;
+	a.event_stage_samples += b.event_stage_samples; a.event_stage_seeds += b.event_stage_seeds;
 }
 
 /* contiguous read ranges with (nearly) equal raw sample counts: b[0..k] */
@@ -714,7 +816,7 @@ extern "C" rh_gpu_ctx *rh_gpu_init(const rh_index_t *idx, const rh_params_t *p, 
 			if (cudaFuncSetAttribute(k_sort_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sort_smem_bytes(c->sort_smem_cap)) != cudaSuccess) return fail("cudaFuncSetAttribute(k_sort_smem) failed");
 		}
 	}
-	if (cudaFuncSetAttribute(k_sort_ties, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tie_smem_bytes(0)) != cudaSuccess) return fail("cudaFuncSetAttribute(k_sort_ties) failed");
+	if (cudaFuncSetAttribute(k_sort_ties, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tie_smem_bytes(0, TIE_SIDE_WALKS)) != cudaSuccess) return fail("cudaFuncSetAttribute(k_sort_ties) failed");
 	if (cudaDeviceSynchronize() != cudaSuccess) return fail("index upload failed");
 	/* ---- workers: the work arenas are split evenly ---- */
 	size_t free_b = 0, total_b = 0;
@@ -728,6 +830,19 @@ extern "C" rh_gpu_ctx *rh_gpu_init(const rh_index_t *idx, const rh_params_t *p, 
 		rh_worker *w = make_worker(c, (size_t)((double)arena_bytes / nw / 1.25) /* dbuf over-allocates by 25 % */);
 		if (!w) return fail(NULL);
 		c->workers.push_back(w);
+	}
+	{ /* exhaustive check of the reciprocal division for the two window lengths of this context */
+		unsigned long long *d_bad = nullptr, h_bad[2] = {0, 0};
+		if (cudaMalloc((void **)&d_bad, 16) != cudaSuccess) return fail("out of device memory");
+		cudaMemset(d_bad, 0, 16);
+		k_selftest_divw<<<1184, 256>>>((float)p->window_length1, d_bad);
+		k_selftest_divw<<<1184, 256>>>((float)p->window_length2, d_bad + 1);
+		if (cudaMemcpy(h_bad, d_bad, 16, cudaMemcpyDeviceToHost) != cudaSuccess) { cudaFree(d_bad); return fail("division self-test failed to run"); }
+		cudaFree(d_bad);
+		for (rh_worker *w : c->workers) { w->fast_w1 = h_bad[0] == 0; w->fast_w2 = h_bad[1] == 0; }
+		if (getenv("RH_CLI_VERBOSE") || getenv("RH_PROF"))
+			fprintf(stderr, "[rawhash_b200] x/w by reciprocal: w=%u mismatches %llu (in range %llu), w=%u mismatches %llu (in range %llu)\n", p->window_length1,
+			        h_bad[0] & 0xffffffffULL, h_bad[0] >> 32, p->window_length2, h_bad[1] & 0xffffffffULL, h_bad[1] >> 32);
 	}
 	c->n_active = nw;
 	return c;
