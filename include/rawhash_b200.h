@@ -96,6 +96,10 @@ typedef struct rh_map_rec_s {
 	uint32_t ci;             /* chunks consumed  (ci:i) */
 	uint32_t sl;             /* filtered signal length (sl:i) */
 	int32_t  cm, nc, s1;     /* cm:i nc:i s1:i */
+	float    mt_ms;          /* mt:f: the reference prints the wall time map_worker_for spent on the read (rmap.cpp:527).
+	                          * Reads of a batch are mapped together here, so a read is charged its share of the batch's
+	                          * stream time: batch_ms * (chunks this read consumed) / (chunks all reads consumed).  The shares
+	                          * add up to the batch time, and 1000 * bases / mt (test/scripts/pafstats.py:88) stays defined. */
 } rh_map_rec_t;
 
 /* ---- parameters / presets ---------------------------------------------- */
@@ -291,7 +295,7 @@ int  rh_slow5_write(const char *path, uint32_t n, const char *const *names,
                     int record_press, int signal_press);
 
 /* ---- PAF ------------------------------------------------------------------ */
-/* Formats records exactly like src/rmap.cpp:751-772 (mt:f: is printed as 0).
+/* Formats records exactly like src/rmap.cpp:751-772 (mt:f: carries rh_map_rec_t::mt_ms).
  * Returns a malloc'ed NUL-terminated string (free with rh_free). */
 char *rh_format_paf(const rh_index_t *idx, const rh_map_rec_t *recs, uint64_t n_recs,
                     const char *const *names);

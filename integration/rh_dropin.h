@@ -111,9 +111,9 @@ static void rh_dropin_map_step(step_mt *s)
 			o->mapq = r->mapq; o->rev = r->rev; o->mapped = r->mapped;
 			o->tags = (char *)malloc(1024);
 			if (r->mapped || r->nc >= 1) /* src/rmap.cpp:527-570 */
-				snprintf(o->tags, 1024, "mt:f:%.6f\tci:i:%u\tsl:i:%u\tcm:i:%d\tnc:i:%d\ts1:i:%d\tsm:f:%.2f", 0.0, r->ci, r->sl, r->cm, r->nc, r->s1, 0.0);
+				snprintf(o->tags, 1024, "mt:f:%.6f\tci:i:%u\tsl:i:%u\tcm:i:%d\tnc:i:%d\ts1:i:%d\tsm:f:%.2f", (double)r->mt_ms, r->ci, r->sl, r->cm, r->nc, r->s1, 0.0);
 			else
-				snprintf(o->tags, 1024, "mt:f:%.6f\tci:i:%u\tsl:i:%u\tcm:i:0\tnc:i:0\ts1:i:0\tsm:f:0", 0.0, r->ci, r->sl);
+				snprintf(o->tags, 1024, "mt:f:%.6f\tci:i:%u\tsl:i:%u\tcm:i:0\tnc:i:0\ts1:i:0\tsm:f:0", (double)r->mt_ms, r->ci, r->sl);
 		}
 		k = e;
 	}

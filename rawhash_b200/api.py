@@ -67,6 +67,7 @@ class MapRec(C.Structure):
         ("fragment_start_position", C.c_uint32), ("fragment_length", C.c_uint32),
         ("mapq", C.c_uint8), ("rev", C.c_uint8), ("mapped", C.c_uint8), ("_pad", C.c_uint8),
         ("ci", C.c_uint32), ("sl", C.c_uint32), ("cm", C.c_int32), ("nc", C.c_int32), ("s1", C.c_int32),
+        ("mt_ms", C.c_float),
     ]
 
 
@@ -75,7 +76,7 @@ MAPREC_DTYPE = np.dtype([
     ("read_start_position", "<u4"), ("read_end_position", "<u4"),
     ("fragment_start_position", "<u4"), ("fragment_length", "<u4"),
     ("mapq", "u1"), ("rev", "u1"), ("mapped", "u1"), ("_pad", "u1"),
-    ("ci", "<u4"), ("sl", "<u4"), ("cm", "<i4"), ("nc", "<i4"), ("s1", "<i4"),
+    ("ci", "<u4"), ("sl", "<u4"), ("cm", "<i4"), ("nc", "<i4"), ("s1", "<i4"), ("mt_ms", "<f4"),
 ])
 assert MAPREC_DTYPE.itemsize == C.sizeof(MapRec)
 

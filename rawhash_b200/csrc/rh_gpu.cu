@@ -86,6 +86,7 @@ struct rh_worker {
 	dbuf<chunk_norm_t> d_norm;
 	dbuf<uint2> d_groups;
 	dbuf<slot_t> d_pre;            /* slots of the chunks whose event stage ran ahead of their round */
+	uint32_t n_splits = 0;        /* times a read range had to be halved because it did not fit the device */
 	int fast_w1 = 0, fast_w2 = 0; /* exhaustive self-test at init: x / w by reciprocal + two FMAs is exact for this window length */
 	dbuf<uint32_t> d_peaks, d_seed_hash, d_seed_pos, d_seed_cnt, d_seed_dst;
 	dbuf<uint64_t> d_seed_src;
@@ -695,8 +696,37 @@ void run_job(job_t *j)
 		batch_in sub = *j->in;
 		sub.n = n; sub.offset += j->lo; sub.range += j->lo; sub.digitisation += j->lo;
 		if (sub.names) sub.names += j->lo;
-		const std::vector<uint64_t> b(j->beg->begin() + j->lo, j->beg->begin() + j->hi), l(j->len->begin() + j->lo, j->len->begin() + j->hi);
-		rc = map_resident(w, sub, b, l, &j->recs, &j->n_recs);
+		/* a range that does not fit the device (the chains carried between chunk rounds grow with the number of reads in
+		 * flight: ~3 MB per read against a human-size index) is mapped in halves, one after the other */
+		struct piece_t { uint32_t lo, hi; };
+		std::vector<piece_t> todo{{0u, n}};
+		std::vector<rh_map_rec_t> acc;
+		rh_gpu_stats_t st_sum; memset(&st_sum, 0, sizeof(st_sum));
+		while (!todo.empty() && rc == RH_OK) {
+			const piece_t pc = todo.back(); todo.pop_back();
+			batch_in part = sub;
+			part.n = pc.hi - pc.lo; part.offset += pc.lo; part.range += pc.lo; part.digitisation += pc.lo;
+			if (part.names) part.names += pc.lo;
+			const std::vector<uint64_t> b(j->beg->begin() + j->lo + pc.lo, j->beg->begin() + j->lo + pc.hi), l(j->len->begin() + j->lo + pc.lo, j->len->begin() + j->lo + pc.hi);
+			rh_map_rec_t *recs = nullptr; uint64_t n_recs = 0;
+			const rh_gpu_stats_t keep = w->st;
+			const int r1 = map_resident(w, part, b, l, &recs, &n_recs);
+			if (r1 == RH_ERR_NOMEM && part.n >= 128) { /* nothing of this piece was kept: retry as two */
+				w->st = keep;
+				cudaGetLastError();
+				const uint32_t mid = pc.lo + part.n / 2;
+				todo.push_back({mid, pc.hi}); todo.push_back({pc.lo, mid}); /* the lower half first: records stay in read order */
+				w->n_splits++;
+				continue;
+			}
+			rc = r1;
+			if (rc == RH_OK) { for (uint64_t q = 0; q < n_recs; ++q) { recs[q].read_idx += pc.lo; acc.push_back(recs[q]); } free(recs); }
+		}
+		if (rc == RH_OK) {
+			j->n_recs = acc.size();
+			j->recs = (rh_map_rec_t *)malloc((acc.size() ? acc.size() : 1) * sizeof(rh_map_rec_t));
+			memcpy(j->recs, acc.data(), acc.size() * sizeof(rh_map_rec_t));
+		}
 	}
 	cudaEventRecord(t1, w->stream);
 	cudaEventSynchronize(t1);
@@ -738,6 +768,12 @@ int map_batch(rh_gpu_ctx *c, const batch_in &in, const std::vector<uint64_t> &be
 		uint64_t o = 0;
 		for (job_t &j : jobs) {
 			for (uint64_t q = 0; q < j.n_recs; ++q) { out[o] = j.recs[q]; out[o].read_idx += j.lo; ++o; } /* rank order = input order */
+		}
+		{ /* mt:f: — every read is charged its share (by chunks consumed) of the batch's stream time */
+			unsigned long long chunks = 0; uint32_t prev = 0xffffffffu;
+			for (uint64_t q = 0; q < total; ++q) if (out[q].read_idx != prev) { prev = out[q].read_idx; chunks += out[q].ci; }
+			const double per_chunk = chunks ? c->st.ms_total / (double)chunks : 0.0;
+			for (uint64_t q = 0; q < total; ++q) out[q].mt_ms = (float)(per_chunk * out[q].ci);
 		}
 		*recs = out; *n_recs = total;
 	}

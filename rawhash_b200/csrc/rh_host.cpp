@@ -550,9 +550,9 @@ extern "C" char *rh_format_paf(const rh_index_t *idx, const rh_map_rec_t *recs, 
 	for (uint64_t i = 0; i < n_recs; ++i) {
 		const rh_map_rec_t &m = recs[i];
 		if (m.mapped || m.nc >= 1)
-			snprintf(tags, sizeof(tags), "mt:f:%.6f\tci:i:%d\tsl:i:%d\tcm:i:%d\tnc:i:%d\ts1:i:%d\tsm:f:%.2f", 0.0, (int)m.ci, (int)m.sl, m.cm, m.nc, m.s1, 0.0);
+			snprintf(tags, sizeof(tags), "mt:f:%.6f\tci:i:%d\tsl:i:%d\tcm:i:%d\tnc:i:%d\ts1:i:%d\tsm:f:%.2f", (double)m.mt_ms, (int)m.ci, (int)m.sl, m.cm, m.nc, m.s1, 0.0);
 		else
-			snprintf(tags, sizeof(tags), "mt:f:%.6f\tci:i:%d\tsl:i:%d\tcm:i:0\tnc:i:0\ts1:i:0\tsm:f:0", 0.0, (int)m.ci, (int)m.sl);
+			snprintf(tags, sizeof(tags), "mt:f:%.6f\tci:i:%d\tsl:i:%d\tcm:i:0\tnc:i:0\ts1:i:0\tsm:f:0", (double)m.mt_ms, (int)m.ci, (int)m.sl);
 		if (m.mapped) {
 			if (m.ref_id >= idx->names.size()) continue;
 			snprintf(line, sizeof(line), "%s\t%u\t%u\t%u\t%c\t%s\t%u\t%u\t%u\t%u\t%u\t%u\t%s\n", names[m.read_idx], m.read_length,

@@ -53,6 +53,7 @@ class MapRec(C.Structure):
         ("fragment_start_position", C.c_uint32), ("fragment_length", C.c_uint32),
         ("mapq", C.c_uint8), ("rev", C.c_uint8), ("mapped", C.c_uint8), ("_pad", C.c_uint8),
         ("ci", C.c_uint32), ("sl", C.c_uint32), ("cm", C.c_int32), ("nc", C.c_int32), ("s1", C.c_int32),
+        ("mt_ms", C.c_float),
     ]
 
 

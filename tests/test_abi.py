@@ -32,8 +32,8 @@ def test_every_declared_symbol_is_exported(built):
 def test_struct_layouts_match_header(built):
     from rawhash_b200 import api
     assert C.sizeof(api.Params) == C.sizeof(_bind.Params) == 192
-    assert C.sizeof(api.MapRec) == 56
-    assert api.MAPREC_DTYPE.itemsize == 56
+    assert C.sizeof(api.MapRec) == 60
+    assert api.MAPREC_DTYPE.itemsize == 60
 
 
 @pytest.mark.parametrize("case", CASES)
