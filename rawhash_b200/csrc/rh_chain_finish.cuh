@@ -283,7 +283,7 @@ __device__ void fin_radix_pass(tie_shared_t &T, const KeyT *__restrict__ kin, co
 /* Sort of m (key, payload = position) pairs in W.xk/W.ord whose keys are expected to be unique: every correct
  * sort then equals klib's, so a parallel LSD radix sort is used; if two equal keys do turn up, klib's exact
  * order is replayed instead.  W.sidx[pos] = payload at sorted position pos. */
-__device__ void fin_sort_unique(tie_shared_t &T, uint8_t *s_bytes, uint8_t *g_bytes, const klib_ws_t &W, uint32_t m, uint32_t *wsum)
+__device__ void fin_sort_unique(tie_shared_t &T, uint8_t *s_bytes, uint8_t *g_bytes, const klib_ws_t &W, uint32_t m, uint32_t *wsum, unsigned long long *prof = nullptr, int prof_slot = 0)
 {
 	if (m <= 64) { fin_sort(T, s_bytes, g_bytes, W, m, nullptr); return; }
 	const uint32_t tid = threadIdx.x, lane = tid & 31;
@@ -318,6 +318,7 @@ __device__ void fin_sort_unique(tie_shared_t &T, uint8_t *s_bytes, uint8_t *g_by
 	}
 	for (uint32_t i = tid; i < m; i += FIN_THREADS) { W.xk[i] = backup[i]; W.ord[i] = i; }
 	__syncthreads();
+	if (prof && tid == 0) atomicAdd(&prof[prof_slot], 1ULL);
 	fin_sort(T, s_bytes, g_bytes, W, m, nullptr);
 }
 
@@ -451,6 +452,7 @@ __global__ void __launch_bounds__(FIN_THREADS, 5) k_chain_finish(k3_args_t A, de
 				__syncthreads();
 			}
 			RH_PROF_MARK(A.prof, 32, tid == 0);
+			if (A.prof && tid == 0) { atomicAdd(&A.prof[48], (unsigned long long)n_z); atomicAdd(&A.prof[49], (unsigned long long)n_runs); atomicAdd(&A.prof[53], (unsigned long long)un); }
 			if (n_z > 0) {
 				/* ---- 2: z sorted by score exactly as klib leaves it ---- */
 				fin_sort(SH.T, SH.bytes, g_bytes, W, n_z, A.prof);
@@ -543,7 +545,7 @@ __global__ void __launch_bounds__(FIN_THREADS, 5) k_chain_finish(k3_args_t A, de
 				if (tid == 0 && carry_ok) { R->prev_off = co; R->prev_n = n_v; }
 				__syncthreads();
 				RH_PROF_MARK(A.prof, 35, tid == 0);
-				fin_sort_unique(SH.T, SH.bytes, g_bytes, W, n_u, SH.wsum);
+				fin_sort_unique(SH.T, SH.bytes, g_bytes, W, n_u, SH.wsum, A.prof, 50);
 				RH_PROF_MARK(A.prof, 36, tid == 0);
 				/* output offsets in target order, then copy chains and pre-compute the region keys (mm_gen_regs) */
 				uint32_t *kout = (uint32_t *)M.t;      /* chain_i0 is no longer needed */
@@ -574,7 +576,7 @@ __global__ void __launch_bounds__(FIN_THREADS, 5) k_chain_finish(k3_args_t A, de
 				__syncthreads();
 				RH_PROF_MARK(A.prof, 37, tid == 0);
 				/* ---- 5: mm_gen_regs ---- */
-				fin_sort_unique(SH.T, SH.bytes, g_bytes, W, n_u, SH.wsum);
+				fin_sort_unique(SH.T, SH.bytes, g_bytes, W, n_u, SH.wsum, A.prof, 51);
 				RH_PROF_MARK(A.prof, 38, tid == 0);
 				r = (dev_reg_t *)((uint8_t *)M.regs + fin_regs_off(un)); /* after the sort scratch */
 				for (uint32_t i = tid; i < n_u; i += FIN_THREADS) { /* descending key */
@@ -595,6 +597,7 @@ __global__ void __launch_bounds__(FIN_THREADS, 5) k_chain_finish(k3_args_t A, de
 			}
 		}
 	}
+	if (A.prof && tid == 0) { atomicAdd(&A.prof[52], (unsigned long long)n_u); atomicAdd(&A.prof[54], (unsigned long long)n_v); }
 	if (tid == 0) { S->n_u = n_u; S->n_v = n_v; S->n_regs = n_regs; }
 }
 

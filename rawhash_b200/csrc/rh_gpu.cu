@@ -558,7 +558,7 @@ int map_resident(rh_worker *c, const batch_in &in, const std::vector<uint64_t> &
 			unsigned long long h[64];
 			cudaMemcpy(h, c->d_prof.p, sizeof(h), cudaMemcpyDeviceToHost);
 			cudaMemset(c->d_prof.p, 0, sizeof(h));
-			fprintf(stderr, "[RH_PROF] round %u (%zu reads active) Mcycles:", round, active.size());
+			fprintf(stderr, "[RH_PROF] round %u (%zu reads active) units (cycles 1e6; [48] n_z [49] n_runs [50] start-ties [51] key-ties [52] n_u [53] n [54] n_v):", round, active.size());
 			for (int i = 0; i < 64; ++i) if (h[i]) fprintf(stderr, " [%d]=%.1f", i, h[i] / 1e6);
 			fprintf(stderr, "\n");
 		}
