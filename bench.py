@@ -320,7 +320,7 @@ def main():
     cal = (np.full(R, synth.OFFSET), np.full(R, synth.RANGE), np.full(R, synth.DIGITISATION))
 
     free_b, _ = torch.cuda.mem_get_info()
-    arena = int(float(os.environ["RH_ARENA_GB"]) * (1 << 30)) if "RH_ARENA_GB" in os.environ else int(free_b * 0.6)
+    arena = int(float(os.environ["RH_ARENA_GB"]) * (1 << 30)) if "RH_ARENA_GB" in os.environ else int(free_b * 0.55)
     mapper = api.Mapper(idx, P, local_rank, arena)
     n_workers = mapper.set_workers(int(os.environ.get("RH_WORKERS", "1")))   # concurrent read ranges (own CUDA stream each)
 

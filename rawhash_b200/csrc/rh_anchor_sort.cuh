@@ -33,6 +33,7 @@ struct sort_args_t {
 	uint32_t *tie_list;      /* slots (indices into `slots`) whose chunk has equal keys */
 	uint32_t *tie_count;
 	unsigned long long *prof;
+	uint32_t *err;
 	uint32_t posbits, ridbits; /* bits that hold any target position / target id of this index (fixed key packing) */
 };
 
@@ -392,7 +393,7 @@ struct big_tab_t {
 	                                   * .z = end of what the region's ring holds, .w = byte offset of the region's ring */
 	uint32_t ja[256];                 /* arrivals a region received before it became the one being closed  */
 	uint16_t cid[256];                /* ring slot of every occupied bin                                   */
-	uint32_t done, nact, M, RW;
+	uint32_t done, nact, M, RW, stuck;
 	uint32_t beg, len;
 	const uint8_t *Q;                 /* digits of the displaced elements (global)                         */
 	uint32_t *arr;                    /* out: where every displaced element arrives                        */
@@ -400,6 +401,7 @@ struct big_tab_t {
 };
 enum { TIE_IDENT = 0, TIE_WALK = 1, TIE_TWO = 2, TIE_BIG = 3 };
 #define BIG_ND_UNKNOWN 0xffffffffu
+#define BIG_SPIN_LIMIT (1u << 24)  /* polls of one ring (tens of milliseconds); a feeder pass takes microseconds */
 __device__ __forceinline__ uint4 lds_v4(uint32_t saddr) { uint4 v; asm volatile("ld.volatile.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(saddr)); return v; }
 __device__ __forceinline__ uint32_t lds_u32(uint32_t saddr) { uint32_t v; asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(v) : "r"(saddr)); return v; }
 __device__ __forceinline__ uint32_t lds_u8(uint32_t saddr) { uint32_t v; asm volatile("ld.volatile.shared.u8 %0, [%1];" : "=r"(v) : "r"(saddr)); return v; }
@@ -434,10 +436,11 @@ struct klib_ws_t {
 	uint32_t *zlist, *mlist; /* closed-form scratch, n words each                                       */
 	uint2 *term;             /* terminal bins of a level, <= n/2 entries (may alias zlist/mlist)         */
 	uint2 *wl0, *wl1;        /* pending sub-arrays (> 64 elements), n/64+2 entries each                 */
-	uint8_t *qbytes;         /* cta_big_level: digits of the displaced elements, n + 32 bytes, 16-byte aligned */
+	uint8_t *qbytes;         /* cta_big_level: digits of the displaced elements, n + 160 bytes, 16-byte aligned */
 	big_tab_t *big;          /* cta_big_*: n_big table sets in shared memory ...                                    */
 	uint8_t *ring;           /* ... and n_big x TIE_RING_BYTES of shared-memory rings (free while a long level runs)  */
 	uint32_t n_big;          /* long sub-arrays that can walk side by side (<= warps - 1)                          */
+	uint32_t *err;           /* device error word: 6 = a walk found its tables inconsistent                          */
 };
 
 
@@ -542,7 +545,7 @@ __device__ void cta_big_prepare(tie_shared_t &T, big_tab_t &B, const uint32_t w,
 		uint32_t nxt = M;
 		B.qb[256] = M;
 		for (int b = 255; b >= 0; --b) { if (B.qb[b] == 0xffffffffu) B.qb[b] = nxt; else nxt = B.qb[b]; }
-		B.done = 0; B.M = M; B.RW = RW; B.beg = beg; B.len = len; B.Q = Q; B.arr = arr; B.ring = ring;
+		B.done = 0; B.stuck = 0; B.M = M; B.RW = RW; B.beg = beg; B.len = len; B.Q = Q; B.arr = arr; B.ring = ring;
 	}
 	__syncthreads();
 	for (uint32_t b = tid; b < 256; b += TIE_THREADS) {
@@ -566,12 +569,13 @@ __device__ void big_walk(big_tab_t &B, unsigned long long *prof)
 		uint32_t k = 0;
 		while (k < 256 && B.qb[k + 1] == B.qb[k]) ++k;
 		B.ja[k] = 0;
+		uint32_t spins = 0; /* a ring that never fills means the tables are inconsistent: give up instead of hanging the device */
 		uint4 sk = lds_v4(st_s + k * 16);          /* region k's state lives in registers */
 		uint32_t ek = B.qb[k + 1];
 		for (;;) {
 			/* a cycle starts: take k's next displaced element */
 			uint32_t d = sk.y;
-			if (d == BIG_ND_UNKNOWN) { while (sk.z <= sk.x) sk.z = lds_u32(st_s + k * 16 + 8); d = lds_u8(ring_s + sk.w + (sk.x & rmask)); }
+			if (d == BIG_ND_UNKNOWN) { while (sk.z <= sk.x) { sk.z = lds_u32(st_s + k * 16 + 8); if (++spins > BIG_SPIN_LIMIT) goto stuck; } spins = 0; d = lds_u8(ring_s + sk.w + (sk.x & rmask)); }
 			uint32_t ab = sk.x;
 			uint4 sc = lds_v4(st_s + d * 16);      /* d != k: a displaced element never belongs to its own region */
 			sk.x = ab + 1;
@@ -582,7 +586,7 @@ __device__ void big_walk(big_tab_t &B, unsigned long long *prof)
 			uint32_t cur = d;
 			for (;;) { /* follow the cycle until an element of region k turns up */
 				d = sc.y;
-				if (d == BIG_ND_UNKNOWN) { while (sc.z <= sc.x) sc.z = lds_u32(st_s + cur * 16 + 8); d = lds_u8(ring_s + sc.w + (sc.x & rmask)); }
+				if (d == BIG_ND_UNKNOWN) { while (sc.z <= sc.x) { sc.z = lds_u32(st_s + cur * 16 + 8); if (++spins > BIG_SPIN_LIMIT) goto stuck; } spins = 0; d = lds_u8(ring_s + sc.w + (sc.x & rmask)); }
 				ab = sc.x;
 				const uint32_t nh = ab + 1;
 				if (d == k) {
@@ -607,14 +611,17 @@ __device__ void big_walk(big_tab_t &B, unsigned long long *prof)
 		}
 		if (prof) { atomicAdd(&prof[27], (unsigned long long)M); atomicAdd(&prof[29], 1ULL); }
 	}
+	if (false) { stuck: B.stuck = 1; }
 	__threadfence_block();
 	*(volatile uint32_t *)&B.done = 1;
 }
 
-/* ring feeder of up to m concurrent walks, by ONE warp: lane l serves regions l, l+32, ... of every walk.  Straight-line
- * and predicated, so the loads of all needy regions of a walk are in flight together; sleeps between polls so that its
+/* ring feeders of up to m concurrent walks: feeder warp `part` of `nparts` serves the region groups q = part, part + nparts, ...
+ * (group q = regions 32 q .. 32 q + 31, one per lane) of every walk.  Up to four 16-byte pieces per region and pass, all loads
+ * issued before the first store, so that a hot region (the one being closed gives up one element per cycle) is topped up at
+ * several times the rate of one piece per pass: the walk is bound by its slowest ring.  Sleeps between idle polls so that its
  * shared-memory traffic stays out of the walks' way. */
-__device__ void big_feed(big_tab_t *Bs, const uint32_t m, volatile uint32_t *left)
+__device__ void big_feed(big_tab_t *Bs, const uint32_t m, volatile uint32_t *left, const uint32_t part, const uint32_t nparts)
 {
 	const uint32_t lane = threadIdx.x & 31;
 	const uint32_t FULL = 0xffffffffu;
@@ -627,23 +634,30 @@ __device__ void big_feed(big_tab_t *Bs, const uint32_t m, volatile uint32_t *lef
 			const uint32_t st_s = (uint32_t)__cvta_generic_to_shared(B.st);
 			const uint8_t *__restrict__ Q = B.Q;
 			uint8_t *ring = B.ring;
-#pragma unroll
-			for (int q = 0; q < 8; ++q) {
+			for (uint32_t q = part; q < 8; q += nparts) {
 				const uint32_t b = lane + 32u * q;
 				const uint32_t qe = B.qb[b + 1];
-				bool need = false; uint32_t f = 0;
+				uint32_t f = 0, cnt = 0;
 				if (qe > B.qb[b]) {
 					f = lds_u32(st_s + b * 16 + 8);
-					need = f < qe && f + 16 <= lds_u32(st_s + b * 16) + RW;
+					const uint32_t lim = lds_u32(st_s + b * 16) + RW; /* entries below the head are free */
+					while (cnt < 4 && f + 16 * cnt < qe && f + 16 * cnt + 16 <= lim) ++cnt;
 				}
-				uint4 v = make_uint4(0, 0, 0, 0);
-				if (need) v = *(const uint4 *)(Q + f);
-				if (need) { *(uint4 *)(ring + (uint32_t)B.cid[b] * RW + (f & rmask)) = v; __threadfence_block(); sts_u32(st_s + b * 16 + 8, f + 16); }
-				any |= need;
+				uint4 v[4];
+#pragma unroll
+				for (uint32_t u = 0; u < 4; ++u) { v[u] = make_uint4(0, 0, 0, 0); if (u < cnt) v[u] = *(const uint4 *)(Q + f + 16 * u); }
+				if (cnt) {
+					uint8_t *rb = ring + (uint32_t)B.cid[b] * RW;
+#pragma unroll
+					for (uint32_t u = 0; u < 4; ++u) if (u < cnt) *(uint4 *)(rb + ((f + 16 * u) & rmask)) = v[u];
+					__threadfence_block();
+					sts_u32(st_s + b * 16 + 8, f + 16 * cnt);
+				}
+				any |= cnt != 0;
 			}
 		}
 		if (*left == 0) break;
-		if (!__any_sync(FULL, any)) __nanosleep(300);
+		if (!__any_sync(FULL, any)) __nanosleep(200);
 	}
 }
 
@@ -845,17 +859,23 @@ __device__ void cta_klib_replay(tie_shared_t &T, uint8_t *bytes, klib_ws_t W, co
 					RH_PROF_BEGIN(prof);
 					for (uint32_t j = 0; j < m; ++j) {
 						const uint32_t w = T.big_list[r0 + j], beg = T.seg_beg[w];
-						cta_big_prepare(T, W.big[j], w, bytes, beg, T.seg_len[w], dst, zlist + beg, mlist + beg, W.qbytes + ((beg + 15u) & ~15u), W.ring + j * TIE_RING_BYTES);
+						/* the displaced digits of a sub-array go to a 16-byte aligned slice; sub-arrays that walk side by side get
+						 * 16 more bytes per sub-array below them, or a nearly all-displaced one would run into its neighbour's slice */
+						uint32_t below = 0;
+						for (uint32_t j2 = 0; j2 < m; ++j2) below += T.seg_beg[T.big_list[r0 + j2]] < beg;
+						cta_big_prepare(T, W.big[j], w, bytes, beg, T.seg_len[w], dst, zlist + beg, mlist + beg, W.qbytes + ((beg + 15u) & ~15u) + 16u * below, W.ring + j * TIE_RING_BYTES);
 					}
 					if (tid == 0) T.big_left = m;
 					__syncthreads();
 					RH_PROF_MARK(prof, 24, tid == 0);
-					if (warp == 1) big_feed(W.big, m, (volatile uint32_t *)&T.big_left);
-					else if (lane == 0) {
+					{ /* walk j runs on lane 0 of warp 0 (j = 0) or warp j + 1; warp 1 and every warp without a walk feed the rings */
 						const uint32_t j = warp == 0 ? 0u : warp - 1u;
-						if (j < m) { big_walk(W.big[j], prof); __threadfence_block(); atomicSub(&T.big_left, 1u); }
+						const bool walks = warp != 1 && j < m;
+						if (!walks) big_feed(W.big, m, (volatile uint32_t *)&T.big_left, warp == 1 ? 0u : warp - m, (uint32_t)TIE_WARPS - m);
+						else if (lane == 0) { big_walk(W.big[j], prof); __threadfence_block(); atomicSub(&T.big_left, 1u); }
 					}
 					__syncthreads();
+					if (W.err && tid < m && W.big[tid].stuck) atomicExch(W.err, 6u);
 					RH_PROF_MARK(prof, 25, tid == 0);
 					for (uint32_t j = 0; j < m; ++j) cta_big_place(T, W.big[j], bytes, dst, zlist + W.big[j].beg);
 					RH_PROF_MARK(prof, 26, tid == 0);
@@ -1009,7 +1029,7 @@ __global__ void __launch_bounds__(TIE_THREADS, 4) k_sort_ties(sort_args_t A, uin
 	W.wl0 = (uint2 *)M.regs; W.wl1 = W.wl0 + (n / 64 + 2);
 	uint8_t *bytes = n <= smem_cap ? s_bytes : (uint8_t *)M.t + n;
 	W.qbytes = (uint8_t *)(((uintptr_t)((uint8_t *)M.t + 2 * (size_t)n) + 15) & ~(uintptr_t)15); /* M.t is 4n bytes: flags, digits, displaced digits */
-	W.big = s_big; W.ring = s_ring; W.n_big = n_big;
+	W.big = s_big; W.ring = s_ring; W.n_big = n_big; W.err = A.err;
 	for (uint32_t i = tid; i < n; i += TIE_THREADS) { W.xk[i] = in[i].x | (tied[i] ? TIE_FLAG : 0ULL); W.ord[i] = i; }
 	cta_klib_replay<false>(T, bytes, W, n, A.prof);
 	RH_PROF_BEGIN(A.prof);

@@ -405,7 +405,7 @@ __global__ void __launch_bounds__(FIN_THREADS, 5) k_chain_finish(k3_args_t A, de
 			W.wl0 = (uint2 *)M.regs; W.wl1 = W.wl0 + (un / 64 + 2);
 			uint8_t *g_bytes = (uint8_t *)(W.wl1 + (un / 64 + 2));
 			W.qbytes = (uint8_t *)(((uintptr_t)(g_bytes + un) + 15) & ~(uintptr_t)15); /* 2.25 n + 128 bytes of the 6 n + 256 byte sort scratch so far */
-			W.big = &SH.big; W.ring = SH.bytes; W.n_big = 1;
+			W.big = &SH.big; W.ring = SH.bytes; W.n_big = 1; W.err = A.err;
 			uint32_t *z_idx = (uint32_t *)M.v;
 			RH_PROF_BEGIN(A.prof);
 

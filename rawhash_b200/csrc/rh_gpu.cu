@@ -16,6 +16,7 @@
 #include <string.h>
 #include <math.h>
 #include <algorithm>
+#include <chrono>
 #include <numeric>
 #include <string>
 #include <thread>
@@ -52,6 +53,16 @@ template <class T> struct dbuf { /* grow-only device buffer */
 		cudaError_t e = cudaMalloc((void **)&p, want * sizeof(T));
 		if (e != cudaSuccess) { rh_set_error("cudaMalloc(%zu bytes): %s", want * sizeof(T), cudaGetErrorString(e)); return RH_ERR_NOMEM; }
 		cap = want;
+		return RH_OK;
+	}
+	int reserve_exact(size_t n) /* no head room: for buffers whose size the caller has already padded */
+	{
+		if (n <= cap) return RH_OK;
+		if (p) cudaFree(p);
+		p = nullptr; cap = 0;
+		cudaError_t e = cudaMalloc((void **)&p, n * sizeof(T));
+		if (e != cudaSuccess) { rh_set_error("cudaMalloc(%zu bytes): %s", n * sizeof(T), cudaGetErrorString(e)); return RH_ERR_NOMEM; }
+		cap = n;
 		return RH_OK;
 	}
 	void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
@@ -94,7 +105,7 @@ struct rh_worker {
 	dbuf<anchor_t> d_carry[2];
 	dbuf<unsigned long long> d_counters; /* [0] carry_top, [1] rec_top */
 	dbuf<uint32_t> d_err, d_rec_start, d_rec_cnt, d_tie_list, d_tie_count;
-	dbuf<unsigned long long> d_prof; bool prof_on = false;
+	dbuf<unsigned long long> d_prof; bool prof_on = false; bool trace = false;
 	dbuf<rh_map_rec_t> d_recs;
 	size_t arena_bytes = 0, sig_budget = 0;
 	uint32_t sort_posbits = 0, sort_ridbits = 0, sort_smem_cap = 0;
@@ -133,6 +144,7 @@ cudaEvent_t get_event(rh_worker *c)
 	if (c->ev_used == c->ev_pool.size()) { cudaEvent_t e; cudaEventCreate(&e); c->ev_pool.push_back(e); }
 	return c->ev_pool[c->ev_used++];
 }
+#define RH_TRACE(c, what) do { if ((c)->trace) { cudaError_t e_ = cudaStreamSynchronize((c)->stream); fprintf(stderr, "[trace] %s: %s\n", what, cudaGetErrorString(e_)); } } while (0)
 struct span_guard {
 	rh_worker *c; timed_span s; int n_launch;
 	span_guard(rh_worker *c_, int kind, int n_launch_ = 1) : c(c_), n_launch(n_launch_) { s.kind = kind; s.a = get_event(c); s.b = get_event(c); cudaEventRecord(s.a, c->stream); }
@@ -192,11 +204,15 @@ struct round_io {
 	rh_tap_t *tap_out = nullptr; uint64_t *tap_off = nullptr; /* running offsets: ev, seed, anc, u, ca, reg */
 	uint32_t tap_chunk = 0;
 	bool events_done = false;          /* slots already carry the event stage's results (computed ahead, event_stage()) */
+	/* streaming scheduler: slots [0, n_mandatory) must run in this round (their reads carry chain anchors in the round's
+	 * input arena); the slots after them are first chunks of reads waiting for admission and run only as far as they fill
+	 * the last anchor-arena group (at most max_optional of them).  n_run = slots that did run. */
+	uint32_t n_mandatory = 0xffffffffu, max_optional = 0, n_run = 0;
 };
 
 /* The event stage over `hs.size()` chunks whose slots live at d_slots: assigns the scratch offsets, uploads the slots,
  * launches.  groups = runs of consecutive slots that are successive chunks of ONE read (their sums chain). */
-int event_stage(rh_worker *c, std::vector<slot_t> &hs, dbuf<slot_t> &d_slots, const std::vector<uint2> &groups)
+int event_stage(rh_worker *c, std::vector<slot_t> &hs, dbuf<slot_t> &d_slots, const std::vector<uint2> &groups, bool preset_off = false)
 {
 	const uint32_t ns = (uint32_t)hs.size();
 	if (ns == 0) return RH_OK;
@@ -205,12 +221,16 @@ int event_stage(rh_worker *c, std::vector<slot_t> &hs, dbuf<slot_t> &d_slots, co
 	uint32_t max_len = 0;
 	for (slot_t &sl : hs) {
 		sl.z_off = zt; zt += ((uint64_t)sl.chunk_len + 3) & ~3ULL; /* chunks start 16-byte aligned */
-		sl.e_cap = (uint32_t)((uint64_t)sl.chunk_len * 2 / 3 + 8);
-		sl.e_off = et; et += sl.e_cap;
+		if (preset_off) et = std::max<uint64_t>(et, sl.e_off + sl.e_cap); /* the caller placed the chunk's scratch (a pool that outlives this call) */
+		else {
+			sl.e_cap = (uint32_t)((uint64_t)sl.chunk_len * 2 / 3 + 8);
+			sl.e_off = et; et += sl.e_cap;
+		}
 		max_len = std::max(max_len, sl.chunk_len);
 	}
 	int rc;
 	const bool streaming = max_len <= EVS_MAXN && !getenv("RH_EVENT_OLD"); /* ordinary chunks: no intermediates in HBM (rh_event_stream.cuh) */
+	if (preset_off && (!streaming || et > c->d_events.cap || et > c->d_seed_src.cap)) { rh_set_error("internal: event scratch pool too small"); return RH_ERR_ARG; }
 	if ((rc = c->d_events.reserve(et)) || (rc = c->d_peaks.reserve(et)) || (rc = c->d_seed_hash.reserve(et)) || (rc = c->d_seed_pos.reserve(et)) ||
 	    (rc = c->d_seed_cnt.reserve(et)) || (rc = c->d_seed_dst.reserve(et)) || (rc = c->d_seed_src.reserve(et))) return rc;
 	if ((rc = upload(d_slots, hs, s))) return rc;
@@ -278,6 +298,7 @@ int run_round(rh_worker *c, round_io &io, int carry_in_idx)
 		span_guard g(c, T_SEED);
 		k_seed_count<<<wblocks, 256, 0, s>>>(a2, c->I, c->D);
 	}
+	RH_TRACE(c, "k_seed_count");
 	CUDA_TRY(cudaMemcpyAsync(io.slots.data(), c->d_slots.p, ns * sizeof(slot_t), cudaMemcpyDeviceToHost, s));
 	CUDA_TRY(cudaMemcpyAsync(&c->carry_known, c->d_counters.p, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
 	CUDA_TRY(cudaStreamSynchronize(s));
@@ -292,14 +313,29 @@ int run_round(rh_worker *c, round_io &io, int carry_in_idx)
 	a3.recs = c->d_recs.p; a3.rec_top = c->d_counters.p + 1; a3.rec_cap = c->d_recs.cap;
 	a3.rec_start = c->d_rec_start.p; a3.rec_cnt = c->d_rec_cnt.p; a3.seq_len = c->d_seqlen.p; a3.tap = io.tap; a3.err = c->d_err.p; a3.prof = c->prof_on ? c->d_prof.p : nullptr;
 
+	/* Heaviest chunks first: CTAs are handed out in slot order and every kernel of a group lasts as long as its slowest
+	 * chunk, so the long ones must not start last.  (Results are filed per read: the slot order is free.) */
+	const uint32_t n_mand = std::min(io.n_mandatory, ns);
+	if (!io.tap) std::stable_sort(io.slots.begin(), io.slots.begin() + n_mand, [](const slot_t &a, const slot_t &b) { return a.n_anchors > b.n_anchors; });
+	uint32_t n_total = n_mand; /* slots that run in this round: grows while optional slots are admitted */
 	uint32_t g0 = 0;
-	while (g0 < ns) {
+	while (g0 < n_total || (g0 == 0 && n_mand == 0 && ns > 0)) {
 		uint64_t used = 0; uint32_t g1 = g0;
-		while (g1 < ns) {
+		while (g1 < n_total) {
 			const uint64_t need = slot_region_bytes(io.slots[g1].n_anchors);
 			if (need > c->arena_bytes) { rh_set_error("a single chunk needs %llu bytes of anchor arena (have %zu)", (unsigned long long)need, c->arena_bytes); return RH_ERR_NOMEM; }
 			if (used + need > c->arena_bytes) break;
 			io.slots[g1].a_off = used; used += need; ++g1;
+		}
+		if (g1 == n_mand && n_total == n_mand) { /* the last group of mandatory slots: reads waiting for admission fill what is left of the arena */
+			while (g1 < ns && g1 - n_mand < io.max_optional) {
+				const uint64_t need = slot_region_bytes(io.slots[g1].n_anchors);
+				if (need > c->arena_bytes) { rh_set_error("a single chunk needs %llu bytes of anchor arena (have %zu)", (unsigned long long)need, c->arena_bytes); return RH_ERR_NOMEM; }
+				if (used + need > c->arena_bytes) break;
+				io.slots[g1].a_off = used; used += need; ++g1;
+			}
+			n_total = g1;
+			if (g1 == g0) break; /* nothing to run */
 		}
 		const uint32_t gn = g1 - g0;
 		CUDA_TRY(cudaMemcpyAsync(c->d_slots.p + g0, io.slots.data() + g0, gn * sizeof(slot_t), cudaMemcpyHostToDevice, s));
@@ -307,10 +343,12 @@ int run_round(rh_worker *c, round_io &io, int carry_in_idx)
 		a2.slots = c->d_slots.p + g0; a2.n_slots = gn;
 		a3.slots = c->d_slots.p + g0; a3.n_slots = gn;
 		const uint32_t gw = (gn * RH_WARP + 255) / 256;
+		if (c->trace) fprintf(stderr, "[trace] group of %u slots at %u\n", gn, g0);
 		{ span_guard g(c, T_SEED); k_seed_expand<<<gw, 256, 0, s>>>(a2, c->I, c->D); }
+		RH_TRACE(c, "k_seed_expand");
 		if ((rc = c->d_tie_list.reserve(gn)) || (rc = c->d_tie_count.reserve(1))) return rc;
 		CUDA_TRY(cudaMemsetAsync(c->d_tie_count.p, 0, 4, s));
-		sort_args_t as; as.slots = a3.slots; as.n_slots = gn; as.arena = c->d_arena.p; as.tie_list = c->d_tie_list.p; as.tie_count = c->d_tie_count.p; as.prof = c->prof_on ? c->d_prof.p : nullptr;
+		sort_args_t as; as.slots = a3.slots; as.n_slots = gn; as.arena = c->d_arena.p; as.tie_list = c->d_tie_list.p; as.tie_count = c->d_tie_count.p; as.prof = c->prof_on ? c->d_prof.p : nullptr; as.err = c->d_err.p;
 		as.posbits = c->sort_posbits; as.ridbits = c->sort_ridbits;
 		{ /* chunks that fit shared memory (nearly all) sort there; the rest take the global-memory kernel */
 			uint32_t maxn = 0;
@@ -320,6 +358,7 @@ int run_round(rh_worker *c, round_io &io, int carry_in_idx)
 			if (cap) k_sort_smem<<<gn, SB_THREADS, sort_smem_bytes(cap), s>>>(as, cap);
 			if (maxn > cap) k_sort_block<<<gn, SORT_THREADS, 0, s>>>(as, cap);
 		}
+		RH_TRACE(c, "k_sort");
 		{
 			/* digit bytes live in the chunk's global scratch, shared memory holds only the walk tables: measured faster
 			 * than keeping the bytes in shared memory (149 vs 184 ms per 100 k reads) because twice as many chunks are
@@ -330,6 +369,7 @@ int run_round(rh_worker *c, round_io &io, int carry_in_idx)
 			k_sort_ties<<<gn, TIE_THREADS, tie_smem_bytes(0, 1), s>>>(as, 0u, 0u, TIE_LARGE_N, 1u);
 			if (maxn >= TIE_LARGE_N) k_sort_ties<<<gn, TIE_THREADS, tie_smem_bytes(0, TIE_SIDE_WALKS), s>>>(as, 0u, TIE_LARGE_N, 0xffffffffu, (uint32_t)TIE_SIDE_WALKS);
 		}
+		RH_TRACE(c, "k_sort_ties");
 		if (io.tap) { /* sorted anchor list of the single tapped slot */
 			rh_tap_t *T = io.tap_out; const slot_t &sl = io.slots[0];
 			if (!sl.gated) {
@@ -351,6 +391,7 @@ int run_round(rh_worker *c, round_io &io, int carry_in_idx)
 			        gn, na.size(), pc(na, .5), pc(na, .9), pc(na, .99), pc(na, 1.0), nt.size(), pc(nt, .5), pc(nt, .9), pc(nt, 1.0));
 		}
 		{ span_guard g(c, T_CHAIN); k_chain_dp<<<gn, DP_THREADS, 0, s>>>(a3, c->D); }
+		RH_TRACE(c, "k_chain_dp");
 		{ /* room for what this group's chains carry into the next round.  A chain of m anchors uses m-1 distinct anchors that
 		   * have a DP predecessor, so a chunk carries at most min(n_anchors, 2 n_link) anchors (a gated chunk: its prev_n) */
 			std::vector<slot_t> after(gn);
@@ -365,21 +406,24 @@ int run_round(rh_worker *c, round_io &io, int carry_in_idx)
 			}
 			if (c->carry_known + need > carry_out.cap) {
 				dbuf<anchor_t> bigger;
-				if ((rc = bigger.reserve((size_t)((c->carry_known + need) * 5 / 4)))) return rc;
+				if ((rc = bigger.reserve_exact((size_t)((c->carry_known + need) * 9 / 8 + 4096)))) return rc;
 				if (c->carry_known) CUDA_TRY(cudaMemcpy(bigger.p, carry_out.p, c->carry_known * sizeof(anchor_t), cudaMemcpyDeviceToDevice));
 				carry_out.release();
 				carry_out = bigger;
 				a2.carry_out = carry_out.p; a3.carry_out = carry_out.p; a3.carry_cap = carry_out.cap;
 			}
 		}
-		{ span_guard g(c, T_POST, 2); k_chain_finish<<<gn, FIN_THREADS, 0, s>>>(a3, c->D); k_chain_decide<<<(gn + DEC_WARPS - 1) / DEC_WARPS, DEC_WARPS * 32, 0, s>>>(a3, c->D); }
+		{ span_guard g(c, T_POST, 2); k_chain_finish<<<gn, FIN_THREADS, 0, s>>>(a3, c->D); RH_TRACE(c, "k_chain_finish"); k_chain_decide<<<(gn + DEC_WARPS - 1) / DEC_WARPS, DEC_WARPS * 32, 0, s>>>(a3, c->D); }
+		RH_TRACE(c, "k_chain_decide");
 		if (io.tap) {
 			CUDA_TRY(cudaMemcpyAsync(io.slots.data(), c->d_slots.p, sizeof(slot_t), cudaMemcpyDeviceToHost, s));
 			CUDA_TRY(cudaStreamSynchronize(s));
 		}
 		g0 = g1;
 	}
-	for (const slot_t &sl : io.slots) {
+	io.n_run = n_total;
+	for (uint32_t q = 0; q < n_total; ++q) {
+		const slot_t &sl = io.slots[q];
 		c->st.raw_samples_consumed += sl.raw_used; c->st.n_chains += sl.n_u;
 		c->st.n_chunks++; c->st.n_events += sl.n_events; c->st.n_seeds += sl.n_seeds; c->st.n_anchors += sl.n_anchors;
 		if (!io.events_done) { c->st.event_stage_samples += sl.raw_used; c->st.event_stage_seeds += sl.n_seeds; }
@@ -417,9 +461,9 @@ int check_dev_err(rh_worker *c)
 		rh_set_error("device reported: carry arena exhausted (top %llu, capacities %zu / %zu)", tops[0], c->d_carry[0].cap, c->d_carry[1].cap);
 		return RH_ERR_NOMEM;
 	}
-	const char *what = e == 2 ? "carry arena exhausted" : e == 3 ? "region scratch exhausted" : e == 4 ? "logf argument outside the exact table" : e == 5 ? "record arena exhausted" : "device error";
+	const char *what = e == 2 ? "carry arena exhausted" : e == 3 ? "region scratch exhausted" : e == 4 ? "logf argument outside the exact table" : e == 5 ? "record arena exhausted" : e == 6 ? "sort replay found inconsistent tables" : "device error";
 	rh_set_error("device reported: %s (code %u)", what, e);
-	return e == 4 ? RH_ERR_ARG : RH_ERR_NOMEM;
+	return e == 4 ? RH_ERR_ARG : e == 6 ? RH_ERR_CUDA : RH_ERR_NOMEM;
 }
 
 /* set up per-read state on the device; raw already resident in c->d_raw */
@@ -497,11 +541,123 @@ int map_resident(rh_worker *c, const batch_in &in, const std::vector<uint64_t> &
 		ahead = e ? (uint32_t)std::max(1, atoi(e)) : (uint32_t)std::max<size_t>(1, (size_t)131072 / std::max<size_t>(active.size(), 1));
 		ahead = std::min(ahead, max_chunk);
 	}
+	const bool stream_sched = ahead > 1 && !getenv("RH_SCHED_ROUNDS");
+	if (stream_sched) {
+		/* ---- streaming scheduler -------------------------------------------------------------------------------------
+		 * Reads are independent and a read's chunks are sequential (chunk c+1 chains onto the anchors chunk c carried over),
+		 * so a late chunk round holds few, large, slow chunks: run as rounds of the whole batch, most launches would be
+		 * nearly empty and still last as long as their slowest chunk.  Instead every iteration runs the next chunk of every
+		 * read in flight (mandatory: their carried anchors live in this iteration's input arena) and tops the last
+		 * anchor-arena group up with first chunks of reads that have not started yet.  The event stage of a cohort of
+		 * waiting reads (all their chunks: it never looks at mapping results) runs ahead in one launch set; its seeds live
+		 * in a pool block owned by the read until its final record is out. */
+		const uint32_t chunk_cap = max_chunk;
+		const uint32_t e_cap_max = (uint32_t)((uint64_t)P.chunk_size * 2 / 3 + 8);
+		uint32_t max_inflight = 4096, cohort = 2048;
+		if (const char *e = getenv("RH_MAX_INFLIGHT")) max_inflight = (uint32_t)std::max(1, atoi(e));
+		if (const char *e = getenv("RH_COHORT")) cohort = (uint32_t)std::max(1, atoi(e));
+		const uint32_t n_blocks = (uint32_t)std::min<size_t>(active.size(), (size_t)max_inflight + cohort + cohort / 2);
+		const uint64_t pool_entries = (uint64_t)n_blocks * chunk_cap * e_cap_max;
+		if ((rc = c->d_events.reserve(pool_entries)) || (rc = c->d_peaks.reserve(pool_entries)) || (rc = c->d_seed_hash.reserve(pool_entries)) || (rc = c->d_seed_pos.reserve(pool_entries)) ||
+		    (rc = c->d_seed_cnt.reserve(pool_entries)) || (rc = c->d_seed_dst.reserve(pool_entries)) || (rc = c->d_seed_src.reserve(pool_entries))) return rc;
+		std::vector<slot_t> table((size_t)n_blocks * chunk_cap);   /* host copy of every pool block's slots after their event stage */
+		std::vector<uint32_t> free_blocks(n_blocks);
+		for (uint32_t b = 0; b < n_blocks; ++b) free_blocks[b] = n_blocks - 1 - b;
+		std::vector<uint32_t> blk(n, 0xffffffffu), next_cc(n, 0), n_cc(n, 0);
+		std::vector<uint32_t> inflight, ready;  /* reads with a chunk behind them / reads whose events are staged */
+		size_t unseen = 0;                      /* next entry of `active` (reads with signal, input order) not yet staged */
+		const std::vector<uint32_t> order = active;
+		std::vector<uint32_t> rec_now(n);
+		uint32_t iter = 0;
+		const bool sched_verbose = getenv("RH_SCHED_VERBOSE") != NULL;
+		const auto t_sched0 = std::chrono::steady_clock::now();
+		while (!inflight.empty() || !ready.empty() || unseen < order.size()) {
+			/* stage the next cohort while few reads wait */
+			if (ready.size() < cohort / 2 && unseen < order.size() && !free_blocks.empty()) {
+				const size_t take = std::min<size_t>(std::min<size_t>(cohort, order.size() - unseen), free_blocks.size());
+				std::vector<slot_t> hs; std::vector<uint2> groups; std::vector<uint32_t> who;
+				hs.reserve(take * chunk_cap);
+				for (size_t q = 0; q < take; ++q) {
+					const uint32_t r = order[unseen + q];
+					const uint32_t b = free_blocks.back(); free_blocks.pop_back();
+					blk[r] = b; next_cc[r] = 0;
+					const uint32_t first = (uint32_t)hs.size();
+					for (uint32_t cc = 0; cc < chunk_cap; ++cc) {
+						uint32_t len2;
+						if (!chunk_of(r, cc, &len2)) break;
+						slot_t sl; memset(&sl, 0, sizeof(sl));
+						sl.read = r; sl.chunk_len = len2; sl.c_count = cc;
+						sl.e_cap = (uint32_t)((uint64_t)len2 * 2 / 3 + 8);
+						sl.e_off = ((uint64_t)b * chunk_cap + cc) * e_cap_max;
+						hs.push_back(sl);
+					}
+					groups.push_back(make_uint2(first, (uint32_t)hs.size() - first));
+					n_cc[r] = (uint32_t)hs.size() - first;
+					who.push_back(r);
+				}
+				if (c->trace) fprintf(stderr, "[trace] staging %zu reads, %zu chunks, %zu free blocks left\n", take, hs.size(), free_blocks.size());
+				if ((rc = event_stage(c, hs, c->d_pre, groups, true))) return rc;
+				RH_TRACE(c, "event stage");
+				CUDA_TRY(cudaMemcpyAsync(hs.data(), c->d_pre.p, hs.size() * sizeof(slot_t), cudaMemcpyDeviceToHost, c->stream));
+				CUDA_TRY(cudaStreamSynchronize(c->stream));
+				c->st.d2h_bytes += hs.size() * sizeof(slot_t);
+				for (size_t q = 0; q < who.size(); ++q) {
+					const uint2 g = groups[q];
+					for (uint32_t k = 0; k < g.y; ++k) table[(size_t)blk[who[q]] * chunk_cap + k] = hs[g.x + k];
+					ready.push_back(who[q]);
+				}
+				for (const slot_t &sl : hs) { c->st.event_stage_samples += sl.raw_used; c->st.event_stage_seeds += sl.n_seeds; }
+				unseen += take;
+			}
+			CUDA_TRY(cudaMemsetAsync(c->d_counters.p, 0, sizeof(unsigned long long), c->stream)); /* carry_top of the iteration's output arena */
+			round_io io;
+			io.events_done = true;
+			io.slots.reserve(inflight.size() + ready.size());
+			for (uint32_t r : inflight) io.slots.push_back(table[(size_t)blk[r] * chunk_cap + next_cc[r]]);
+			for (uint32_t r : ready) io.slots.push_back(table[(size_t)blk[r] * chunk_cap]);
+			io.n_mandatory = (uint32_t)inflight.size();
+			io.max_optional = inflight.size() >= max_inflight ? 0u : (uint32_t)std::min<size_t>(ready.size(), max_inflight - inflight.size());
+			if ((rc = run_round(c, io, (int)(iter & 1)))) return rc;
+			c->st.n_rounds++;
+			CUDA_TRY(cudaMemcpyAsync(rec_now.data(), c->d_rec_cnt.p, n * 4, cudaMemcpyDeviceToHost, c->stream));
+			CUDA_TRY(cudaStreamSynchronize(c->stream));
+			c->st.d2h_bytes += n * 4;
+			if (c->prof_on && getenv("RH_PROF_ROUNDS")) {
+				unsigned long long h[64];
+				cudaMemcpy(h, c->d_prof.p, sizeof(h), cudaMemcpyDeviceToHost);
+				cudaMemset(c->d_prof.p, 0, sizeof(h));
+				fprintf(stderr, "[RH_PROF] iteration %u (%zu in flight, %u admitted of %zu waiting) raw counters:", iter, inflight.size(), io.n_run - io.n_mandatory, ready.size());
+				for (int i = 0; i < 64; ++i) if (h[i]) fprintf(stderr, " [%d]=%llu", i, h[i]);
+				fprintf(stderr, "\n");
+			}
+			const uint32_t n_adm = io.n_run - io.n_mandatory;
+			if (sched_verbose) {
+				uint64_t na = 0; for (uint32_t q = 0; q < io.n_run; ++q) na += io.slots[q].n_anchors;
+				fprintf(stderr, "[rawhash_b200] iteration %u: %zu in flight + %u admitted (%zu waiting, %zu not staged), %.1f M anchors, carry arenas %zu/%zu MB, %.2f s since the call began\n", iter, inflight.size(), n_adm,
+				        ready.size() - n_adm, order.size() - unseen, na / 1e6, c->d_carry[0].cap * sizeof(anchor_t) >> 20, c->d_carry[1].cap * sizeof(anchor_t) >> 20,
+				        std::chrono::duration<double>(std::chrono::steady_clock::now() - t_sched0).count());
+			}
+			std::vector<uint32_t> next;
+			next.reserve(inflight.size() + n_adm);
+			auto settle = [&](uint32_t r) {
+				if (rec_now[r] == 0xffffffffu) { ++next_cc[r]; next.push_back(r); }
+				else { rec_cnt[r] = rec_now[r]; free_blocks.push_back(blk[r]); blk[r] = 0xffffffffu; }
+			};
+			for (uint32_t r : inflight) settle(r);
+			for (uint32_t q = 0; q < n_adm; ++q) settle(ready[q]);
+			ready.erase(ready.begin(), ready.begin() + n_adm);
+			if (inflight.empty() && n_adm == 0 && !ready.empty()) { rh_set_error("internal: the scheduler admitted no read"); return RH_ERR_CUDA; }
+			for (uint32_t r : next) if (next_cc[r] >= n_cc[r]) { rh_set_error("internal: read %u still active after its last chunk", r); return RH_ERR_CUDA; }
+			inflight.swap(next);
+			++iter;
+		}
+		active.clear();
+	}
 	std::vector<slot_t> pre;            /* host copy of the wave's slots after their event stage */
 	std::vector<uint32_t> pre_first(n, 0xffffffffu);
 	uint32_t wave_base = 0, wave_end = 0;
 	uint32_t round = 0;
-	while (!active.empty() && round < max_chunk) {
+	while (!stream_sched && !active.empty() && round < max_chunk) {
 		CUDA_TRY(cudaMemsetAsync(c->d_counters.p, 0, sizeof(unsigned long long), c->stream)); /* carry_top of the round's output arena */
 		if (ahead > 1 && round == wave_end) { /* next wave: chunks [round, round + ahead) of every active read */
 			pre.clear();
@@ -625,7 +781,7 @@ rh_worker *make_worker(rh_gpu_ctx *c, size_t arena_bytes)
 	w->err[0] = 0;
 	if (cudaStreamCreateWithFlags(&w->own_stream, cudaStreamNonBlocking) != cudaSuccess) { rh_set_error("cudaStreamCreate failed"); destroy_worker(w); return nullptr; }
 	w->stream = w->own_stream;
-	w->prof_on = getenv("RH_PROF") != NULL;
+	w->prof_on = getenv("RH_PROF") != NULL; w->trace = getenv("RH_TRACE") != NULL;
 	if (w->d_counters.reserve(2) || w->d_err.reserve(1) || w->d_prof.reserve(64)) { destroy_worker(w); return nullptr; }
 	cudaMemset(w->d_prof.p, 0, 64 * 8);
 	w->arena_bytes = arena_bytes;
@@ -717,6 +873,7 @@ void run_job(job_t *j)
 				const uint32_t mid = pc.lo + part.n / 2;
 				todo.push_back({mid, pc.hi}); todo.push_back({pc.lo, mid}); /* the lower half first: records stay in read order */
 				w->n_splits++;
+				fprintf(stderr, "[rawhash_b200] %u reads did not fit the device (%s): mapping them as two halves\n", part.n, rh_gpu_last_error());
 				continue;
 			}
 			rc = r1;
