@@ -473,6 +473,9 @@ __global__ void __launch_bounds__(FIN_THREADS, 5) k_chain_finish(k3_args_t A, de
 					const uint32_t lo = runs[rr], hi = rr + 1 < n_runs ? runs[rr + 1] : n_z;
 					const uint32_t L = hi - lo;
 					if (L > FIN_SHORT_RUN) { longs[atomicAdd(&SH.T.n_nxt, 1u)] = rr; continue; }
+					/* a lone candidate without a predecessor (most runs against a large index: a single random hit) is a chain of
+					 * one anchor, rejected by min_cnt >= 2, and nothing can reach its mark: skip the dependent loads of the attempt */
+					if (L == 1 && min_cnt > 1 && p[z_idx[lo]] < 0) continue;
 					uint32_t bound = 0xffffffffu;
 					for (uint32_t s2 = 0; s2 < L; ++s2) {
 						uint32_t best = 0, bj = lo; bool any = false;
