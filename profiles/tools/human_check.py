@@ -53,7 +53,7 @@ torch.cuda.synchronize()
 free_b, tot_b = torch.cuda.mem_get_info()
 out["free_gb_before_mapper"] = round(free_b / 2**30, 1)
 t0 = time.time()
-m = api.Mapper(idx, P, 0, int(free_b * 0.6))
+m = api.Mapper(idx, P, 0, int(float(os.environ['RH_ARENA_GB']) * 2**30) if 'RH_ARENA_GB' in os.environ else int(free_b * 0.6))
 out["mapper_init_s"] = round(time.time() - t0, 2)
 cal = lambda n: (np.full(n, synth.OFFSET), np.full(n, synth.RANGE), np.full(n, synth.DIGITISATION))
 names = [f"read_{i:07d}" for i in range(n_all)]

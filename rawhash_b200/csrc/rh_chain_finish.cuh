@@ -455,7 +455,7 @@ __global__ void __launch_bounds__(FIN_THREADS, 5) k_chain_finish(k3_args_t A, de
 			if (A.prof && tid == 0) { atomicAdd(&A.prof[48], (unsigned long long)n_z); atomicAdd(&A.prof[49], (unsigned long long)n_runs); atomicAdd(&A.prof[53], (unsigned long long)un); }
 			if (n_z > 0) {
 				/* ---- 2: z sorted by score exactly as klib leaves it ---- */
-				fin_sort(SH.T, SH.bytes, g_bytes, W, n_z, A.prof);
+				fin_sort(SH.T, SH.bytes, g_bytes, W, n_z, A.prof_replay ? A.prof : nullptr);
 				RH_PROF_MARK(A.prof, 33, tid == 0);
 				/* ---- 3: backtrack, best score first inside every run.  A run's candidates are contiguous in index order
 				 *      (a DP segment is a contiguous anchor range); what is needed is their order by position in the sorted z.

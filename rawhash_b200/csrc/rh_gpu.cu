@@ -84,7 +84,7 @@ struct rh_worker {
 	dev_params_t D;
 	const rh_index_s *idx = nullptr;
 	dev_index_t I;
-	cudaStream_t stream = nullptr, own_stream = nullptr;
+	cudaStream_t stream = nullptr, own_stream = nullptr, stream2 = nullptr; /* stream2: the heavy lane of run_round */
 	/* shared, owned by the context */
 	dbuf<float> d_logf; uint32_t logf_n = 0;
 	dbuf<uint32_t> d_seqlen;
@@ -104,7 +104,7 @@ struct rh_worker {
 	dbuf<uint8_t> d_arena;
 	dbuf<anchor_t> d_carry[2];
 	dbuf<unsigned long long> d_counters; /* [0] carry_top, [1] rec_top */
-	dbuf<uint32_t> d_err, d_rec_start, d_rec_cnt, d_tie_list, d_tie_count;
+	dbuf<uint32_t> d_err, d_rec_start, d_rec_cnt, d_tie_list, d_tie_count, d_tie_list2, d_tie_count2;
 	dbuf<unsigned long long> d_prof; bool prof_on = false; bool trace = false;
 	dbuf<rh_map_rec_t> d_recs;
 	size_t arena_bytes = 0, sig_budget = 0;
@@ -145,10 +145,12 @@ cudaEvent_t get_event(rh_worker *c)
 	return c->ev_pool[c->ev_used++];
 }
 #define RH_TRACE(c, what) do { if ((c)->trace) { cudaError_t e_ = cudaStreamSynchronize((c)->stream); fprintf(stderr, "[trace] %s: %s\n", what, cudaGetErrorString(e_)); } } while (0)
+#define RH_TRACE_ON(c, st, what) do { if ((c)->trace) { cudaError_t e_ = cudaStreamSynchronize(st); fprintf(stderr, "[trace] %s: %s\n", what, cudaGetErrorString(e_)); } } while (0)
 struct span_guard {
 	rh_worker *c; timed_span s; int n_launch;
-	span_guard(rh_worker *c_, int kind, int n_launch_ = 1) : c(c_), n_launch(n_launch_) { s.kind = kind; s.a = get_event(c); s.b = get_event(c); cudaEventRecord(s.a, c->stream); }
-	~span_guard() { cudaEventRecord(s.b, c->stream); c->spans.push_back(s); c->st.kernel_launches += n_launch; if (s.kind == T_EVENT) c->st.event_kernel_launches++; }
+	cudaStream_t st;
+	span_guard(rh_worker *c_, int kind, int n_launch_ = 1, cudaStream_t st_ = nullptr) : c(c_), n_launch(n_launch_), st(st_ ? st_ : c_->stream) { s.kind = kind; s.a = get_event(c); s.b = get_event(c); cudaEventRecord(s.a, st); }
+	~span_guard() { cudaEventRecord(s.b, st); c->spans.push_back(s); c->st.kernel_launches += n_launch; if (s.kind == T_EVENT) c->st.event_kernel_launches++; }
 };
 
 void fill_dev_params(const rh_params_t &P, dev_params_t &D)
@@ -311,78 +313,61 @@ int run_round(rh_worker *c, round_io &io, int carry_in_idx)
 	a3.carry_out = carry_out.p; a3.carry_top = c->d_counters.p; a3.carry_cap = carry_out.cap;
 	a3.logf_tab = c->d_logf.p; a3.logf_n = c->logf_n;
 	a3.recs = c->d_recs.p; a3.rec_top = c->d_counters.p + 1; a3.rec_cap = c->d_recs.cap;
-	a3.rec_start = c->d_rec_start.p; a3.rec_cnt = c->d_rec_cnt.p; a3.seq_len = c->d_seqlen.p; a3.tap = io.tap; a3.err = c->d_err.p; a3.prof = c->prof_on ? c->d_prof.p : nullptr;
+	a3.rec_start = c->d_rec_start.p; a3.rec_cnt = c->d_rec_cnt.p; a3.seq_len = c->d_seqlen.p; a3.tap = io.tap; a3.err = c->d_err.p; a3.prof = c->prof_on ? c->d_prof.p : nullptr; a3.prof_replay = getenv("RH_PROF_TIES_ONLY") ? 0 : 1;
 
 	/* Heaviest chunks first: CTAs are handed out in slot order and every kernel of a group lasts as long as its slowest
 	 * chunk, so the long ones must not start last.  (Results are filed per read: the slot order is free.) */
 	const uint32_t n_mand = std::min(io.n_mandatory, ns);
 	if (!io.tap) std::stable_sort(io.slots.begin(), io.slots.begin() + n_mand, [](const slot_t &a, const slot_t &b) { return a.n_anchors > b.n_anchors; });
-	uint32_t n_total = n_mand; /* slots that run in this round: grows while optional slots are admitted */
-	uint32_t g0 = 0;
-	while (g0 < n_total || (g0 == 0 && n_mand == 0 && ns > 0)) {
-		uint64_t used = 0; uint32_t g1 = g0;
-		while (g1 < n_total) {
-			const uint64_t need = slot_region_bytes(io.slots[g1].n_anchors);
-			if (need > c->arena_bytes) { rh_set_error("a single chunk needs %llu bytes of anchor arena (have %zu)", (unsigned long long)need, c->arena_bytes); return RH_ERR_NOMEM; }
-			if (used + need > c->arena_bytes) break;
-			io.slots[g1].a_off = used; used += need; ++g1;
-		}
-		if (g1 == n_mand && n_total == n_mand) { /* the last group of mandatory slots: reads waiting for admission fill what is left of the arena */
-			while (g1 < ns && g1 - n_mand < io.max_optional) {
-				const uint64_t need = slot_region_bytes(io.slots[g1].n_anchors);
-				if (need > c->arena_bytes) { rh_set_error("a single chunk needs %llu bytes of anchor arena (have %zu)", (unsigned long long)need, c->arena_bytes); return RH_ERR_NOMEM; }
-				if (used + need > c->arena_bytes) break;
-				io.slots[g1].a_off = used; used += need; ++g1;
-			}
-			n_total = g1;
-			if (g1 == g0) break; /* nothing to run */
-		}
+
+	unsigned long long committed = c->carry_known; /* upper bound of carry_top once everything launched so far has run */
+	/* front half of a group on stream `st`: slots up, anchors, sort (+ exact tie order), chaining DP */
+	auto front = [&](cudaStream_t st, uint32_t g0, uint32_t g1, dbuf<uint32_t> &tie_list, dbuf<uint32_t> &tie_count) -> int {
 		const uint32_t gn = g1 - g0;
-		CUDA_TRY(cudaMemcpyAsync(c->d_slots.p + g0, io.slots.data() + g0, gn * sizeof(slot_t), cudaMemcpyHostToDevice, s));
+		int rc2;
+		CUDA_TRY(cudaMemcpyAsync(c->d_slots.p + g0, io.slots.data() + g0, gn * sizeof(slot_t), cudaMemcpyHostToDevice, st));
 		c->st.h2d_bytes += gn * sizeof(slot_t);
-		a2.slots = c->d_slots.p + g0; a2.n_slots = gn;
-		a3.slots = c->d_slots.p + g0; a3.n_slots = gn;
+		k2_args_t b2 = a2; b2.slots = c->d_slots.p + g0; b2.n_slots = gn;
+		k3_args_t b3 = a3; b3.slots = c->d_slots.p + g0; b3.n_slots = gn;
 		const uint32_t gw = (gn * RH_WARP + 255) / 256;
-		if (c->trace) fprintf(stderr, "[trace] group of %u slots at %u\n", gn, g0);
-		{ span_guard g(c, T_SEED); k_seed_expand<<<gw, 256, 0, s>>>(a2, c->I, c->D); }
-		RH_TRACE(c, "k_seed_expand");
-		if ((rc = c->d_tie_list.reserve(gn)) || (rc = c->d_tie_count.reserve(1))) return rc;
-		CUDA_TRY(cudaMemsetAsync(c->d_tie_count.p, 0, 4, s));
-		sort_args_t as; as.slots = a3.slots; as.n_slots = gn; as.arena = c->d_arena.p; as.tie_list = c->d_tie_list.p; as.tie_count = c->d_tie_count.p; as.prof = c->prof_on ? c->d_prof.p : nullptr; as.err = c->d_err.p;
+		if (c->trace) fprintf(stderr, "[trace] group of %u slots at %u%s\n", gn, g0, st == s ? "" : " (heavy lane)");
+		{ span_guard g(c, T_SEED, 1, st); k_seed_expand<<<gw, 256, 0, st>>>(b2, c->I, c->D); }
+		RH_TRACE_ON(c, st, "k_seed_expand");
+		if ((rc2 = tie_list.reserve(gn)) || (rc2 = tie_count.reserve(1))) return rc2;
+		CUDA_TRY(cudaMemsetAsync(tie_count.p, 0, 4, st));
+		sort_args_t as; as.slots = b3.slots; as.n_slots = gn; as.arena = c->d_arena.p; as.tie_list = tie_list.p; as.tie_count = tie_count.p; as.prof = c->prof_on ? c->d_prof.p : nullptr; as.err = c->d_err.p;
 		as.posbits = c->sort_posbits; as.ridbits = c->sort_ridbits;
-		{ /* chunks that fit shared memory (nearly all) sort there; the rest take the global-memory kernel */
-			uint32_t maxn = 0;
-			for (uint32_t q = g0; q < g1; ++q) if (!io.slots[q].gated) maxn = std::max(maxn, io.slots[q].n_anchors);
+		uint32_t maxn = 0;
+		for (uint32_t q = g0; q < g1; ++q) if (!io.slots[q].gated) maxn = std::max(maxn, io.slots[q].n_anchors);
+		{ /* chunks that fit shared memory (nearly all against a small index) sort there; the rest take the global-memory kernel */
 			const uint32_t cap = std::min(c->sort_smem_cap, (maxn + 31) & ~31u); /* small groups: less shared memory, more CTAs per SM */
-			span_guard g(c, T_SORT, (cap ? 1 : 0) + (maxn > cap ? 1 : 0));
-			if (cap) k_sort_smem<<<gn, SB_THREADS, sort_smem_bytes(cap), s>>>(as, cap);
-			if (maxn > cap) k_sort_block<<<gn, SORT_THREADS, 0, s>>>(as, cap);
+			span_guard g(c, T_SORT, (cap ? 1 : 0) + (maxn > cap ? 1 : 0), st);
+			if (cap) k_sort_smem<<<gn, SB_THREADS, sort_smem_bytes(cap), st>>>(as, cap);
+			if (maxn > cap) k_sort_block<<<gn, SORT_THREADS, 0, st>>>(as, cap);
 		}
-		RH_TRACE(c, "k_sort");
+		RH_TRACE_ON(c, st, "k_sort");
 		{
 			/* digit bytes live in the chunk's global scratch, shared memory holds only the walk tables: measured faster
 			 * than keeping the bytes in shared memory (149 vs 184 ms per 100 k reads) because twice as many chunks are
 			 * resident per SM and the walk is latency bound either way */
-			span_guard g(c, T_TIES, 1);
-			uint32_t maxn = 0;
-			for (uint32_t q = g0; q < g1; ++q) if (!io.slots[q].gated) maxn = std::max(maxn, io.slots[q].n_anchors);
-			k_sort_ties<<<gn, TIE_THREADS, tie_smem_bytes(0, 1), s>>>(as, 0u, 0u, TIE_LARGE_N, 1u);
-			if (maxn >= TIE_LARGE_N) k_sort_ties<<<gn, TIE_THREADS, tie_smem_bytes(0, TIE_SIDE_WALKS), s>>>(as, 0u, TIE_LARGE_N, 0xffffffffu, (uint32_t)TIE_SIDE_WALKS);
+			span_guard g(c, T_TIES, 1, st);
+			k_sort_ties<<<gn, TIE_THREADS, tie_smem_bytes(0, 1), st>>>(as, 0u, 0u, TIE_LARGE_N, 1u);
+			if (maxn >= TIE_LARGE_N) k_sort_ties<<<gn, TIE_THREADS, tie_smem_bytes(0, TIE_SIDE_WALKS), st>>>(as, 0u, TIE_LARGE_N, 0xffffffffu, (uint32_t)TIE_SIDE_WALKS);
 		}
-		RH_TRACE(c, "k_sort_ties");
+		RH_TRACE_ON(c, st, "k_sort_ties");
 		if (io.tap) { /* sorted anchor list of the single tapped slot */
 			rh_tap_t *T = io.tap_out; const slot_t &sl = io.slots[0];
 			if (!sl.gated) {
 				if (io.tap_off[2] + sl.n_anchors > T->cap_anchors) return RH_ERR_NOMEM;
-				CUDA_TRY(cudaMemcpyAsync(T->anchors + 2 * io.tap_off[2], c->d_arena.p + sl.a_off, (size_t)sl.n_anchors * 16, cudaMemcpyDeviceToHost, s));
-				CUDA_TRY(cudaStreamSynchronize(s));
+				CUDA_TRY(cudaMemcpyAsync(T->anchors + 2 * io.tap_off[2], c->d_arena.p + sl.a_off, (size_t)sl.n_anchors * 16, cudaMemcpyDeviceToHost, st));
+				CUDA_TRY(cudaStreamSynchronize(st));
 				io.tap_off[2] += sl.n_anchors;
 			}
 		}
 		if (c->prof_on) { /* RH_PROF=1: distribution of chunk sizes and tie chunks in this group (debug aid, adds a sync) */
 			std::vector<slot_t> dbg(gn);
-			cudaMemcpyAsync(dbg.data(), c->d_slots.p + g0, gn * sizeof(slot_t), cudaMemcpyDeviceToHost, s);
-			cudaStreamSynchronize(s);
+			cudaMemcpyAsync(dbg.data(), c->d_slots.p + g0, gn * sizeof(slot_t), cudaMemcpyDeviceToHost, st);
+			cudaStreamSynchronize(st);
 			std::vector<uint32_t> na, nt;
 			for (const slot_t &q : dbg) { if (q.gated || q.n_anchors == 0) continue; na.push_back(q.n_anchors); if (q.n_ties) nt.push_back(q.n_anchors); }
 			std::sort(na.begin(), na.end()); std::sort(nt.begin(), nt.end());
@@ -390,36 +375,99 @@ int run_round(rh_worker *c, round_io &io, int carry_in_idx)
 			fprintf(stderr, "[RH_PROF] group: %u slots, %zu chained (n p50=%u p90=%u p99=%u max=%u), %zu with ties (n p50=%u p90=%u max=%u)\n",
 			        gn, na.size(), pc(na, .5), pc(na, .9), pc(na, .99), pc(na, 1.0), nt.size(), pc(nt, .5), pc(nt, .9), pc(nt, 1.0));
 		}
-		{ span_guard g(c, T_CHAIN); k_chain_dp<<<gn, DP_THREADS, 0, s>>>(a3, c->D); }
-		RH_TRACE(c, "k_chain_dp");
-		{ /* room for what this group's chains carry into the next round.  A chain of m anchors uses m-1 distinct anchors that
-		   * have a DP predecessor, so a chunk carries at most min(n_anchors, 2 n_link) anchors (a gated chunk: its prev_n) */
-			std::vector<slot_t> after(gn);
-			CUDA_TRY(cudaMemcpyAsync(after.data(), c->d_slots.p + g0, gn * sizeof(slot_t), cudaMemcpyDeviceToHost, s));
-			CUDA_TRY(cudaMemcpyAsync(&c->carry_known, c->d_counters.p, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
-			CUDA_TRY(cudaStreamSynchronize(s));
-			c->st.d2h_bytes += gn * sizeof(slot_t) + 8;
-			unsigned long long need = 0;
-			for (uint32_t q = 0; q < gn; ++q) {
-				const slot_t &sl = after[q];
-				need += (sl.gated || sl.n_anchors == 0) ? sl.n_anchors : std::min<unsigned long long>(sl.n_anchors, 2ULL * sl.n_link);
-			}
-			if (c->carry_known + need > carry_out.cap) {
-				dbuf<anchor_t> bigger;
-				if ((rc = bigger.reserve_exact((size_t)((c->carry_known + need) * 9 / 8 + 4096)))) return rc;
-				if (c->carry_known) CUDA_TRY(cudaMemcpy(bigger.p, carry_out.p, c->carry_known * sizeof(anchor_t), cudaMemcpyDeviceToDevice));
-				carry_out.release();
-				carry_out = bigger;
-				a2.carry_out = carry_out.p; a3.carry_out = carry_out.p; a3.carry_cap = carry_out.cap;
-			}
+		{ span_guard g(c, T_CHAIN, 1, st); k_chain_dp<<<gn, DP_THREADS, 0, st>>>(b3, c->D); }
+		RH_TRACE_ON(c, st, "k_chain_dp");
+		return RH_OK;
+	};
+	/* back half: room in the output carry arena for what the group's chains carry into the next round, then backtrack,
+	 * regions, decisions.  A chain of m anchors uses m-1 distinct anchors that have a DP predecessor, so a chunk carries at
+	 * most min(n_anchors, 2 n_link) anchors (a gated chunk: its prev_n). */
+	auto back = [&](cudaStream_t st, uint32_t g0, uint32_t g1) -> int {
+		const uint32_t gn = g1 - g0;
+		int rc2;
+		std::vector<slot_t> after(gn);
+		CUDA_TRY(cudaMemcpyAsync(after.data(), c->d_slots.p + g0, gn * sizeof(slot_t), cudaMemcpyDeviceToHost, st));
+		CUDA_TRY(cudaStreamSynchronize(st));
+		c->st.d2h_bytes += gn * sizeof(slot_t);
+		unsigned long long need = 0;
+		for (uint32_t q = 0; q < gn; ++q) {
+			const slot_t &sl = after[q];
+			need += (sl.gated || sl.n_anchors == 0) ? sl.n_anchors : std::min<unsigned long long>(sl.n_anchors, 2ULL * sl.n_link);
 		}
-		{ span_guard g(c, T_POST, 2); k_chain_finish<<<gn, FIN_THREADS, 0, s>>>(a3, c->D); RH_TRACE(c, "k_chain_finish"); k_chain_decide<<<(gn + DEC_WARPS - 1) / DEC_WARPS, DEC_WARPS * 32, 0, s>>>(a3, c->D); }
-		RH_TRACE(c, "k_chain_decide");
+		if (committed + need > carry_out.cap) { /* grow: nothing may be writing the arena while it moves */
+			CUDA_TRY(cudaDeviceSynchronize());
+			unsigned long long top = 0;
+			CUDA_TRY(cudaMemcpy(&top, c->d_counters.p, sizeof(top), cudaMemcpyDeviceToHost));
+			dbuf<anchor_t> bigger;
+			if ((rc2 = bigger.reserve_exact((size_t)((committed + need) * 9 / 8 + 4096)))) return rc2;
+			if (top) CUDA_TRY(cudaMemcpy(bigger.p, carry_out.p, top * sizeof(anchor_t), cudaMemcpyDeviceToDevice));
+			carry_out.release();
+			carry_out = bigger;
+			a2.carry_out = carry_out.p; a3.carry_out = carry_out.p; a3.carry_cap = carry_out.cap;
+		}
+		committed += need;
+		k3_args_t b3 = a3; b3.slots = c->d_slots.p + g0; b3.n_slots = gn;
+		{ span_guard g(c, T_POST, 2, st); k_chain_finish<<<gn, FIN_THREADS, 0, st>>>(b3, c->D); RH_TRACE_ON(c, st, "k_chain_finish"); k_chain_decide<<<(gn + DEC_WARPS - 1) / DEC_WARPS, DEC_WARPS * 32, 0, st>>>(b3, c->D); }
+		RH_TRACE_ON(c, st, "k_chain_decide");
 		if (io.tap) {
-			CUDA_TRY(cudaMemcpyAsync(io.slots.data(), c->d_slots.p, sizeof(slot_t), cudaMemcpyDeviceToHost, s));
-			CUDA_TRY(cudaStreamSynchronize(s));
+			CUDA_TRY(cudaMemcpyAsync(io.slots.data(), c->d_slots.p, sizeof(slot_t), cudaMemcpyDeviceToHost, st));
+			CUDA_TRY(cudaStreamSynchronize(st));
 		}
+		return RH_OK;
+	};
+
+	/* Heavy lane (streaming scheduler): the largest chunks of the iteration (late chunks of reads that do not map: each
+	 * drags all chain anchors of its predecessors along) take several times as long as an average chunk in every kernel,
+	 * and a kernel lasts as long as its slowest chunk.  They run as a group of their own on a second stream, in a slice at
+	 * the top of the arena, next to the ordinary groups. */
+	uint32_t nh = 0; uint64_t heavy_bytes = 0;
+	if (!io.tap && io.n_mandatory != 0xffffffffu && c->stream2 && n_mand >= 64 && !getenv("RH_NO_HEAVY_LANE")) {
+		unsigned long long sum = 0;
+		for (uint32_t q = 0; q < n_mand; ++q) sum += io.slots[q].n_anchors;
+		const double avg = (double)sum / n_mand;
+		const uint64_t cap = c->arena_bytes / 8;
+		while (nh < n_mand / 4 && io.slots[nh].n_anchors > 1.25 * avg && heavy_bytes + slot_region_bytes(io.slots[nh].n_anchors) <= cap) heavy_bytes += slot_region_bytes(io.slots[nh++].n_anchors);
+		if (nh < 2) { nh = 0; heavy_bytes = 0; }
+	}
+	const uint64_t main_bytes = (c->arena_bytes - heavy_bytes) & ~(uint64_t)255; /* slot regions start 256-byte aligned */
+	bool heavy_back_due = false;
+	cudaStream_t sh = c->stream2;
+	if (nh) {
+		uint64_t off = main_bytes;
+		for (uint32_t q = 0; q < nh; ++q) { io.slots[q].a_off = off; off += slot_region_bytes(io.slots[q].n_anchors); }
+		if ((rc = front(sh, 0, nh, c->d_tie_list2, c->d_tie_count2))) return rc;
+		heavy_back_due = true;
+	}
+	uint32_t n_total = n_mand; /* slots that run in this round: grows while optional slots are admitted */
+	uint32_t g0 = nh;
+	while (g0 < n_total || (g0 == nh && n_mand == nh && ns > nh)) {
+		uint64_t used = 0; uint32_t g1 = g0;
+		while (g1 < n_total) {
+			const uint64_t need = slot_region_bytes(io.slots[g1].n_anchors);
+			if (need > main_bytes) { rh_set_error("a single chunk needs %llu bytes of anchor arena (have %llu)", (unsigned long long)need, (unsigned long long)main_bytes); return RH_ERR_NOMEM; }
+			if (used + need > main_bytes) break;
+			io.slots[g1].a_off = used; used += need; ++g1;
+		}
+		if (g1 == n_mand && n_total == n_mand) { /* the last group of mandatory slots: reads waiting for admission fill what is left of the arena */
+			while (g1 < ns && g1 - n_mand < io.max_optional) {
+				const uint64_t need = slot_region_bytes(io.slots[g1].n_anchors);
+				if (need > main_bytes) { rh_set_error("a single chunk needs %llu bytes of anchor arena (have %llu)", (unsigned long long)need, (unsigned long long)main_bytes); return RH_ERR_NOMEM; }
+				if (used + need > main_bytes) break;
+				io.slots[g1].a_off = used; used += need; ++g1;
+			}
+			n_total = g1;
+			if (g1 == g0) break; /* nothing to run */
+		}
+		if ((rc = front(s, g0, g1, c->d_tie_list, c->d_tie_count))) return rc;
+		if ((rc = back(s, g0, g1))) return rc;
+		if (heavy_back_due) { heavy_back_due = false; if ((rc = back(sh, 0, nh))) return rc; } /* its front half ran beside this group's */
 		g0 = g1;
+	}
+	if (heavy_back_due) { if ((rc = back(sh, 0, nh))) return rc; }
+	if (nh) { /* the round ends when both lanes have */
+		cudaEvent_t ev = get_event(c);
+		CUDA_TRY(cudaEventRecord(ev, sh));
+		CUDA_TRY(cudaStreamWaitEvent(s, ev, 0));
 	}
 	io.n_run = n_total;
 	for (uint32_t q = 0; q < n_total; ++q) {
@@ -769,6 +817,8 @@ void destroy_worker(rh_worker *w)
 	w->d_rec_start.release(); w->d_rec_cnt.release(); w->d_recs.release(); w->d_tie_list.release(); w->d_tie_count.release(); w->d_prof.release();
 	for (cudaEvent_t e : w->ev_pool) cudaEventDestroy(e);
 	if (w->own_stream) cudaStreamDestroy(w->own_stream);
+	if (w->stream2) cudaStreamDestroy(w->stream2);
+	w->d_tie_list2.release(); w->d_tie_count2.release();
 	delete w;
 }
 
@@ -781,6 +831,7 @@ rh_worker *make_worker(rh_gpu_ctx *c, size_t arena_bytes)
 	w->err[0] = 0;
 	if (cudaStreamCreateWithFlags(&w->own_stream, cudaStreamNonBlocking) != cudaSuccess) { rh_set_error("cudaStreamCreate failed"); destroy_worker(w); return nullptr; }
 	w->stream = w->own_stream;
+	if (cudaStreamCreateWithFlags(&w->stream2, cudaStreamNonBlocking) != cudaSuccess) w->stream2 = nullptr;
 	w->prof_on = getenv("RH_PROF") != NULL; w->trace = getenv("RH_TRACE") != NULL;
 	if (w->d_counters.reserve(2) || w->d_err.reserve(1) || w->d_prof.reserve(64)) { destroy_worker(w); return nullptr; }
 	cudaMemset(w->d_prof.p, 0, 64 * 8);

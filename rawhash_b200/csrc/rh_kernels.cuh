@@ -274,6 +274,7 @@ struct k3_args_t {
 	int tap;                         /* tap mode: never stop early */
 	uint32_t *err;
 	unsigned long long *prof;
+	int prof_replay;                 /* RH_PROF: 0 keeps k_chain_finish's score sort out of the replay counters [16..29] (RH_PROF_TIES_ONLY) */
 };
 
 /* mg_lchain_dp main loop, reference src/lchain.c:439-505.

@@ -114,3 +114,25 @@ def test_human_size_200_reads(built):
     m.close()
     assert st["n_anchors"] / max(st["n_chunks"], 1) > 200_000
     _assert_same(got, _reference_paf(W, raw_dev, raw_off, n, names))
+
+
+def test_streaming_scheduler_limits(built, monkeypatch):
+    """The streaming scheduler under tight limits: 128-read cohorts, at most 300 reads in flight and a 96 MB arena, so that
+    waiting reads are deferred again and again, the in-flight cap binds, every iteration runs several arena groups and the
+    heavy lane has work; the same batch through the plain chunk-round loop (RH_SCHED_ROUNDS) and through the reference."""
+    W = _world([f"chr{i + 1}" for i in range(8)], [750_000] * 8, "fast", seed=13)
+    n = 3000
+    raw_dev, raw_off = _reads(W, n, 17)
+    names = [f"read_{i:07d}" for i in range(n)]
+    exp = _reference_paf(W, raw_dev, raw_off, n, names)
+    monkeypatch.setenv("RH_MAX_INFLIGHT", "300")
+    monkeypatch.setenv("RH_COHORT", "128")
+    m = W["api"].Mapper(W["idx"], W["P"], 0, 96 << 20)
+    got, st = _gpu_paf(W, m, raw_dev, raw_off, n, names)
+    assert st["n_rounds"] > 12   # iterations: far more than the chunk rounds of one read
+    _assert_same(got, exp)
+    monkeypatch.setenv("RH_SCHED_ROUNDS", "1")
+    got2, st2 = _gpu_paf(W, m, raw_dev, raw_off, n, names)
+    m.close()
+    assert st2["n_rounds"] <= W["P"].max_num_chunk
+    _assert_same(got2, exp)
