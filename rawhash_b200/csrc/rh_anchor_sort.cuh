@@ -425,6 +425,9 @@ __device__ __forceinline__ uint32_t tie_tile_rank(bool flag, uint32_t *wsum, uin
 	return base + __popc(m & lanemask_lt());
 }
 
+/* modes of cta_klib_replay: a full sort, or only along the sub-arrays that hold an element with an equal key — marked in
+ * bit 31 of the key (anchor.x: always 0 there) or in bit 31 of the payload (keys that use all 64 bits) */
+enum { KLIB_ALL = 0, KLIB_TIES_KEYFLAG = 1, KLIB_TIES_PAYFLAG = 2 };
 #define TIE_FLAG (1ULL << 31)      /* bit 31 of anchor.x is always 0 (31-bit target position): carries "has an equal key" */
 
 /* global work space of one replay, every array sized for the n elements being sorted */
@@ -701,16 +704,18 @@ __device__ void cta_big_place(tie_shared_t &T, big_tab_t &B, const uint8_t *__re
  * TIE_THREADS threads.  ALL = false: only bins that hold a TIE_FLAGged element are followed and only
  * their positions of W.sidx are written (the caller already knows every other position).  ALL = true:
  * a full sort, every position of W.sidx is written. */
-template <bool ALL>
+template <int MODE>
 __device__ void cta_klib_replay(tie_shared_t &T, uint8_t *bytes, klib_ws_t W, const uint32_t n, unsigned long long *prof)
 {
+	constexpr bool ALL = MODE == KLIB_ALL;
 	const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 	const uint32_t FULL = 0xffffffffu;
 	uint64_t *xk = W.xk, *xk2 = W.xk2;
 	uint32_t *ord = W.ord, *ord2 = W.ord2;
 	uint32_t *__restrict__ dst = W.dst, *__restrict__ sidx = W.sidx, *zlist = W.zlist, *mlist = W.mlist;
 	uint2 *wl_cur = W.wl0, *wl_nxt = W.wl1, *term = W.term;
-	const uint64_t keymask = ALL ? ~0ULL : ~TIE_FLAG;
+	const uint64_t keymask = MODE == KLIB_TIES_KEYFLAG ? ~TIE_FLAG : ~0ULL;
+	const uint32_t plmask = MODE == KLIB_TIES_PAYFLAG ? 0x7fffffffu : 0xffffffffu; /* payload without its flag bit */
 	RH_PROF_BEGIN(prof);
 	__syncthreads();
 	if (tid == 0) { T.diff = 0ULL; T.n_nxt = 0; T.n_term = 0; }
@@ -741,6 +746,7 @@ __device__ void cta_klib_replay(tie_shared_t &T, uint8_t *bytes, klib_ws_t W, co
 			for (uint32_t w = 0; w < nb; ++w) {
 				const uint32_t beg = T.seg_beg[w], len = T.seg_len[w];
 				const uint64_t *__restrict__ xs = xk + beg;
+				const uint32_t *__restrict__ os = ord + beg;
 				for (uint32_t t0 = 0; t0 < len; t0 += TIE_THREADS) {
 					const uint32_t i = t0 + tid;
 					const bool ok = i < len;
@@ -751,7 +757,7 @@ __device__ void cta_klib_replay(tie_shared_t &T, uint8_t *bytes, klib_ws_t W, co
 						bytes[beg + i] = (uint8_t)d;
 						const uint32_t peers = digit_peers(act, d);
 						if ((peers & lanemask_lt()) == 0) atomicAdd(&T.tab[w][d], (uint32_t)__popc(peers));
-						if (!ALL && (x & TIE_FLAG)) atomicOr(&T.tflag[w][d >> 5], 1u << (d & 31));
+						if (MODE == KLIB_TIES_KEYFLAG ? (x & TIE_FLAG) != 0 : (MODE == KLIB_TIES_PAYFLAG && (os[i] & 0x80000000u))) atomicOr(&T.tflag[w][d >> 5], 1u << (d & 31));
 					}
 				}
 			}
@@ -943,7 +949,7 @@ __device__ void cta_klib_replay(tie_shared_t &T, uint8_t *bytes, klib_ws_t W, co
 				const uint32_t beg = T.seg_beg[w], len = T.seg_len[w], kind = T.seg_kind[w];
 				if (kind == TIE_IDENT) {
 					if (shift > 0) { if (tid == 0) wl_nxt[atomicAdd(&T.n_nxt, 1u)] = make_uint2(beg, len); }
-					else for (uint32_t i = tid; i < len; i += TIE_THREADS) sidx[beg + i] = ord2[beg + i];
+					else for (uint32_t i = tid; i < len; i += TIE_THREADS) sidx[beg + i] = ord2[beg + i] & plmask;
 					continue;
 				}
 				for (uint32_t b = tid; b < 256; b += TIE_THREADS) {
@@ -973,10 +979,10 @@ __device__ void cta_klib_replay(tie_shared_t &T, uint8_t *bytes, klib_ws_t W, co
 						if (32 + lane < tc) { o1 = ord2[ts + 32 + lane]; k1 = xk2[ts + 32 + lane] & keymask; }
 						uint32_t r0, r1;
 						warp_rank64(k0, k1, tc, lane, &r0, &r1);
-						if (lane < tc) sidx[ts + r0] = o0;
-						if (32 + lane < tc) sidx[ts + r1] = o1;
+						if (lane < tc) sidx[ts + r0] = o0 & plmask;
+						if (32 + lane < tc) sidx[ts + r1] = o1 & plmask;
 					} else {
-						for (uint32_t i = lane; i < tc; i += 32) sidx[ts + i] = ord2[ts + i];
+						for (uint32_t i = lane; i < tc; i += 32) sidx[ts + i] = ord2[ts + i] & plmask;
 					}
 				}
 				__syncthreads();
@@ -997,7 +1003,7 @@ __device__ void cta_klib_replay(tie_shared_t &T, uint8_t *bytes, klib_ws_t W, co
 	/* sub-arrays that ran out of varying bytes: fully equal keys keep their current order */
 	for (uint32_t s = 0; s < n_cur; ++s) {
 		const uint2 seg = wl_cur[s];
-		for (uint32_t i = tid; i < seg.y; i += TIE_THREADS) sidx[seg.x + i] = ord[seg.x + i];
+		for (uint32_t i = tid; i < seg.y; i += TIE_THREADS) sidx[seg.x + i] = ord[seg.x + i] & plmask;
 	}
 	__syncthreads();
 }
@@ -1031,7 +1037,7 @@ __global__ void __launch_bounds__(TIE_THREADS, 4) k_sort_ties(sort_args_t A, uin
 	W.qbytes = (uint8_t *)(((uintptr_t)((uint8_t *)M.t + 2 * (size_t)n) + 15) & ~(uintptr_t)15); /* M.t is 4n bytes: flags, digits, displaced digits */
 	W.big = s_big; W.ring = s_ring; W.n_big = n_big; W.err = A.err;
 	for (uint32_t i = tid; i < n; i += TIE_THREADS) { W.xk[i] = in[i].x | (tied[i] ? TIE_FLAG : 0ULL); W.ord[i] = i; }
-	cta_klib_replay<false>(T, bytes, W, n, A.prof);
+	cta_klib_replay<KLIB_TIES_KEYFLAG>(T, bytes, W, n, A.prof);
 	RH_PROF_BEGIN(A.prof);
 	const uint32_t *__restrict__ sidx = W.sidx;
 	anchor_t *__restrict__ out = M.A;

@@ -205,7 +205,7 @@ __device__ __forceinline__ uint32_t fin_tile_scan(uint32_t v, uint32_t *wsum, ui
 /* exact klib sort of m (key, payload) pairs already placed in W.xk/W.ord; W.sidx[pos] = payload at sorted position pos */
 __device__ __forceinline__ void fin_sort(tie_shared_t &T, uint8_t *s_bytes, uint8_t *g_bytes, const klib_ws_t &W, uint32_t m, unsigned long long *prof)
 {
-	if (m > 64) { cta_klib_replay<true>(T, m < TIE_BIG_MIN ? s_bytes : g_bytes, W, m, prof); return; } /* from TIE_BIG_MIN on, s_bytes is cta_big_level's ring */
+	if (m > 64) { cta_klib_replay<KLIB_ALL>(T, m < TIE_BIG_MIN ? s_bytes : g_bytes, W, m, prof); return; } /* from TIE_BIG_MIN on, s_bytes is cta_big_level's ring */
 	__syncthreads();
 	if (threadIdx.x < 32 && m > 0) { /* klib: insertion sort (stable) */
 		const uint32_t lane = threadIdx.x;
@@ -316,10 +316,17 @@ __device__ void fin_sort_unique(tie_shared_t &T, uint8_t *s_bytes, uint8_t *g_by
 		__syncthreads();
 		return;
 	}
-	for (uint32_t i = tid; i < m; i += FIN_THREADS) { W.xk[i] = backup[i]; W.ord[i] = i; }
+	/* equal keys: every position outside a group of equal keys is final in the stable order; klib's order inside the groups is
+	 * replayed along the sub-arrays that hold them only (the flag rides in bit 31 of the payload = original position) */
+	uint32_t *flag = W.dst; /* free until the replay's first level */
+	for (uint32_t i = tid; i < m; i += FIN_THREADS) { W.sidx[i] = va[i]; flag[i] = 0; }
+	__syncthreads();
+	for (uint32_t i = tid; i + 1 < m; i += FIN_THREADS) if (ka[i] == ka[i + 1]) { flag[va[i]] = 1; flag[va[i + 1]] = 1; }
+	__syncthreads();
+	for (uint32_t i = tid; i < m; i += FIN_THREADS) { W.xk[i] = backup[i]; W.ord[i] = i | (flag[i] ? 0x80000000u : 0u); }
 	__syncthreads();
 	if (prof && tid == 0) atomicAdd(&prof[prof_slot], 1ULL);
-	fin_sort(T, s_bytes, g_bytes, W, m, nullptr);
+	cta_klib_replay<KLIB_TIES_PAYFLAG>(T, m < TIE_BIG_MIN ? s_bytes : g_bytes, W, m, nullptr);
 }
 
 /* one backtrack attempt from candidate anchor i0 (mg_chain_backtrack body, lchain.c:162-181 + mg_chain_bk_end);

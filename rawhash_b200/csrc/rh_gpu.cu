@@ -110,6 +110,7 @@ struct rh_worker {
 	size_t arena_bytes = 0, sig_budget = 0;
 	uint32_t sort_posbits = 0, sort_ridbits = 0, sort_smem_cap = 0;
 	unsigned long long carry_known = 0; /* carry_top of the round's output arena at the last sync */
+	uint64_t rec_hint = 0, rec_cap_now = 0; bool retry_same = false; /* record arena overflow (all-vs-all: one record per chain): size it from the count and map the range again */
 	std::vector<timed_span> spans;
 	std::vector<cudaEvent_t> ev_pool; size_t ev_used = 0;
 	rh_gpu_stats_t st;
@@ -312,7 +313,7 @@ int run_round(rh_worker *c, round_io &io, int carry_in_idx)
 	a3.slots = nullptr; a3.n_slots = 0; a3.rs = c->d_rs.p; a3.arena = c->d_arena.p;
 	a3.carry_out = carry_out.p; a3.carry_top = c->d_counters.p; a3.carry_cap = carry_out.cap;
 	a3.logf_tab = c->d_logf.p; a3.logf_n = c->logf_n;
-	a3.recs = c->d_recs.p; a3.rec_top = c->d_counters.p + 1; a3.rec_cap = c->d_recs.cap;
+	a3.recs = c->d_recs.p; a3.rec_top = c->d_counters.p + 1; a3.rec_cap = c->rec_cap_now;
 	a3.rec_start = c->d_rec_start.p; a3.rec_cnt = c->d_rec_cnt.p; a3.seq_len = c->d_seqlen.p; a3.tap = io.tap; a3.err = c->d_err.p; a3.prof = c->prof_on ? c->d_prof.p : nullptr; a3.prof_replay = getenv("RH_PROF_TIES_ONLY") ? 0 : 1;
 
 	/* Heaviest chunks first: CTAs are handed out in slot order and every kernel of a group lasts as long as its slowest
@@ -503,6 +504,13 @@ int check_dev_err(rh_worker *c)
 	CUDA_TRY(cudaMemcpyAsync(&e, c->d_err.p, 4, cudaMemcpyDeviceToHost, c->stream));
 	CUDA_TRY(cudaStreamSynchronize(c->stream));
 	if (e == 0) return RH_OK;
+	if (e == 5) { /* rec_top kept counting past the capacity: it is the number of records the range needs */
+		unsigned long long tops[2] = {0, 0};
+		cudaMemcpy(tops, c->d_counters.p, sizeof(tops), cudaMemcpyDeviceToHost);
+		if (tops[1] + tops[1] / 4 + 1024 > c->rec_hint) { c->rec_hint = tops[1] + tops[1] / 4 + 1024; c->retry_same = true; }
+		rh_set_error("device reported: record arena exhausted (%llu records)", tops[1]);
+		return RH_ERR_NOMEM;
+	}
 	if (e == 2) {
 		unsigned long long tops[2] = {0, 0};
 		cudaMemcpy(tops, c->d_counters.p, sizeof(tops), cudaMemcpyDeviceToHost);
@@ -563,8 +571,13 @@ int map_resident(rh_worker *c, const batch_in &in, const std::vector<uint64_t> &
 	const rh_params_t &P = c->P;
 	const bool noadapt = c->D.noadapt != 0;
 	const uint32_t max_chunk = noadapt ? 1u : P.max_num_chunk;
-	const uint64_t rec_cap = (uint64_t)n * (c->D.ava ? 64 : 1) + 1024;
+	/* first guess: one record per read, 64 in all-vs-all mode (every chain is a record); an overflow re-sizes the arena from
+	 * the device's count and the range is mapped again (RH_REC_CAP_TEST: a deliberately small first guess, for the test) */
+	uint64_t rec_cap = (uint64_t)n * (c->D.ava ? 64 : 1) + 1024;
+	if (const char *e = getenv("RH_REC_CAP_TEST")) rec_cap = (uint64_t)std::max(1, atoi(e));
+	rec_cap = std::max<uint64_t>(rec_cap, c->rec_hint);
 	if ((rc = c->d_recs.reserve(rec_cap))) return rc;
+	c->rec_cap_now = rec_cap; /* not the buffer's (padded) capacity: the test hook needs the overflow */
 
 	std::vector<uint32_t> active;
 	for (uint32_t i = 0; i < n; ++i) if (l_sig[i] > 0) active.push_back(i);
@@ -601,13 +614,13 @@ int map_resident(rh_worker *c, const batch_in &in, const std::vector<uint64_t> &
 		 * in a pool block owned by the read until its final record is out. */
 		const uint32_t chunk_cap = max_chunk;
 		const uint32_t e_cap_max = (uint32_t)((uint64_t)P.chunk_size * 2 / 3 + 8);
-		uint32_t max_inflight = 4096, cohort = 2048;
+		uint32_t max_inflight = 3072, cohort = 4096; /* cohort: event-stage launches of ~40 000 chunks */
 		if (const char *e = getenv("RH_MAX_INFLIGHT")) max_inflight = (uint32_t)std::max(1, atoi(e));
 		if (const char *e = getenv("RH_COHORT")) cohort = (uint32_t)std::max(1, atoi(e));
 		const uint32_t n_blocks = (uint32_t)std::min<size_t>(active.size(), (size_t)max_inflight + cohort + cohort / 2);
 		const uint64_t pool_entries = (uint64_t)n_blocks * chunk_cap * e_cap_max;
-		if ((rc = c->d_events.reserve(pool_entries)) || (rc = c->d_peaks.reserve(pool_entries)) || (rc = c->d_seed_hash.reserve(pool_entries)) || (rc = c->d_seed_pos.reserve(pool_entries)) ||
-		    (rc = c->d_seed_cnt.reserve(pool_entries)) || (rc = c->d_seed_dst.reserve(pool_entries)) || (rc = c->d_seed_src.reserve(pool_entries))) return rc;
+		if ((rc = c->d_events.reserve_exact(pool_entries)) || (rc = c->d_peaks.reserve_exact(pool_entries)) || (rc = c->d_seed_hash.reserve_exact(pool_entries)) || (rc = c->d_seed_pos.reserve_exact(pool_entries)) ||
+		    (rc = c->d_seed_cnt.reserve_exact(pool_entries)) || (rc = c->d_seed_dst.reserve_exact(pool_entries)) || (rc = c->d_seed_src.reserve_exact(pool_entries))) return rc;
 		std::vector<slot_t> table((size_t)n_blocks * chunk_cap);   /* host copy of every pool block's slots after their event stage */
 		std::vector<uint32_t> free_blocks(n_blocks);
 		for (uint32_t b = 0; b < n_blocks; ++b) free_blocks[b] = n_blocks - 1 - b;
@@ -918,6 +931,11 @@ void run_job(job_t *j)
 			rh_map_rec_t *recs = nullptr; uint64_t n_recs = 0;
 			const rh_gpu_stats_t keep = w->st;
 			const int r1 = map_resident(w, part, b, l, &recs, &n_recs);
+			if (r1 == RH_ERR_NOMEM && w->retry_same) { /* the record arena was too small and has been re-sized from the count */
+				w->retry_same = false; w->st = keep; cudaGetLastError();
+				todo.push_back(pc);
+				continue;
+			}
 			if (r1 == RH_ERR_NOMEM && part.n >= 128) { /* nothing of this piece was kept: retry as two */
 				w->st = keep;
 				cudaGetLastError();

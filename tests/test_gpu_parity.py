@@ -184,9 +184,11 @@ def test_faster_preset_minimizers(built):
     _check_paf(w, "faster")
 
 
-def test_rawsamble_all_vs_all(built):
+def test_rawsamble_all_vs_all(built, monkeypatch):
     """-x ava: index built from the reads' own signals (event detection on the GPU), all-vs-all overlap,
-    every chain reported (RI_M_ALL_CHAINS), hits filtered by read-name order (rmap.cpp:82-86)."""
+    every chain reported (RI_M_ALL_CHAINS), hits filtered by read-name order (rmap.cpp:82-86).  Mapped a second
+    time with a record arena far too small for one record per chain: the range is mapped again with the arena
+    sized from the device's count, and the PAF is the same."""
     from rawhash_b200 import api, synth
     from _bind import OracleLib, strip_mt
     w = World(n_contigs=1, genome_len=60_000, n_reads=60, read_bp=4000, seed=23)
@@ -207,6 +209,11 @@ def test_rawsamble_all_vs_all(built):
     exp = strip_mt(exp).splitlines()
     assert len(exp) > n, "expected overlaps between reads"
     assert got == exp
+    monkeypatch.setenv("RH_REC_CAP_TEST", "16")   # first guess: 16 records for 72
+    m = api.Mapper(idx, P, 0, 1 << 30)
+    recs = m.map_batch(w.reads["raw"], *cal, w.names)
+    m.close()
+    assert strip_mt(idx.format_paf(recs, w.names)).splitlines() == exp
 
 
 def test_workers_and_device_resident_input(built, monkeypatch):
