@@ -55,10 +55,10 @@ def _configs():
                 sample_rate=4000, bp_per_sec=450, reads=100_000, ref_reads=2000),
         2: dict(workload="human-size: GRCh38-shaped synthetic genome (24 contigs, 3.09 Gb), -x fast, synthetic R9.4 4 kHz 450 bp/s reads of 5 kb (BASELINE configs[2])",
                 preset="fast", r10=False, names=synth.GRCH38_NAMES, lens=synth.GRCH38_LENS, kind="r9.4", k=6,
-                sample_rate=4000, bp_per_sec=450, reads=int(os.environ.get("RH_BENCH_READS_HUMAN", "16000")), ref_reads=400),
+                sample_rate=4000, bp_per_sec=450, reads=int(os.environ.get("RH_BENCH_READS_HUMAN", "24000")), ref_reads=400),
         3: dict(workload="human-size: GRCh38-shaped synthetic genome (24 contigs, 3.09 Gb), -x fast --r10, R10.4.1 9-mer model, synthetic 5 kHz 400 bp/s reads of 5 kb (BASELINE configs[3])",
                 preset="fast", r10=True, names=synth.GRCH38_NAMES, lens=synth.GRCH38_LENS, kind="r10.4.1", k=9,
-                sample_rate=5000, bp_per_sec=400, reads=int(os.environ.get("RH_BENCH_READS_HUMAN", "16000")), ref_reads=400),
+                sample_rate=5000, bp_per_sec=400, reads=int(os.environ.get("RH_BENCH_READS_HUMAN", "24000")), ref_reads=400),
     }
 
 
