@@ -79,23 +79,37 @@ __device__ __forceinline__ void warp_rank64(uint64_t k0, uint64_t k1, uint32_t c
 }
 
 /* One stable counting-sort pass of (key, idx) arrays on digit (key >> shift) & 255.
- * s_base[] must hold the exclusive bucket starts on entry. */
+ * s_base[] must hold the exclusive bucket starts on entry.
+ * A round takes SORT_SUB x SORT_THREADS keys: warp w owns SORT_SUB consecutive 32-key sub-tiles of the round, ranks them one
+ * after the other against its private counters (keys and ranks stay in registers), then the CTA turns the counters into bases —
+ * four barriers per 1024 keys, and four independent loads in flight per thread. */
+#define SORT_SUB 4
 template <class KeyT>
 __device__ __forceinline__ void sort_scatter_pass(const KeyT *__restrict__ kin, const uint32_t *__restrict__ iin, KeyT *__restrict__ kout, uint32_t *__restrict__ iout,
                                                   uint32_t n, uint32_t shift, uint32_t *s_base, uint32_t (*s_wcnt)[256])
 {
 	const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-	for (uint32_t t0 = 0; t0 < n; t0 += SORT_THREADS) {
+	const uint32_t FULL = 0xffffffffu;
+	for (uint32_t t0 = 0; t0 < n; t0 += SORT_THREADS * SORT_SUB) {
 		for (uint32_t k = tid; k < SORT_WARPS * 256; k += SORT_THREADS) (&s_wcnt[0][0])[k] = 0;
 		__syncthreads();
-		const uint32_t i = t0 + tid;
-		const bool ok = i < n;
-		KeyT key = 0; uint32_t ix = 0, d = 0, peers = 0;
-		if (ok) { key = kin[i]; ix = iin[i]; d = (uint32_t)(key >> shift) & 255; }
-		const uint32_t act = __ballot_sync(0xffffffffu, ok);
-		if (ok) {
-			peers = digit_peers(act, d);
-			if ((peers & lanemask_lt()) == 0) s_wcnt[warp][d] = __popc(peers);
+		KeyT key[SORT_SUB]; uint32_t ix[SORT_SUB], dg[SORT_SUB], rk[SORT_SUB];
+		const uint32_t w0 = t0 + warp * (32 * SORT_SUB) + lane;
+#pragma unroll
+		for (int u = 0; u < SORT_SUB; ++u) { const uint32_t i = w0 + 32 * u; key[u] = 0; ix[u] = 0; if (i < n) { key[u] = kin[i]; ix[u] = iin[i]; } }
+#pragma unroll
+		for (int u = 0; u < SORT_SUB; ++u) {
+			const bool ok = w0 + 32 * u < n;
+			const uint32_t act = __ballot_sync(FULL, ok);
+			dg[u] = (uint32_t)(key[u] >> shift) & 255; rk[u] = 0;
+			if (ok) {
+				const uint32_t peers = digit_peers(act, dg[u]);
+				const uint32_t off = s_wcnt[warp][dg[u]];
+				rk[u] = off + __popc(peers & lanemask_lt());
+				__syncwarp(act);
+				if ((peers & lanemask_lt()) == 0) s_wcnt[warp][dg[u]] = off + __popc(peers);
+			}
+			__syncwarp();
 		}
 		__syncthreads();
 		{ /* thread d: prefix over warps for digit d, advance the bucket base */
@@ -105,7 +119,9 @@ __device__ __forceinline__ void sort_scatter_pass(const KeyT *__restrict__ kin, 
 			s_base[tid] = run;
 		}
 		__syncthreads();
-		if (ok) { const uint32_t dst = s_wcnt[warp][d] + __popc(peers & lanemask_lt()); kout[dst] = key; iout[dst] = ix; }
+#pragma unroll
+		for (int u = 0; u < SORT_SUB; ++u)
+			if (w0 + 32 * u < n) { const uint32_t dst = s_wcnt[warp][dg[u]] + rk[u]; kout[dst] = key[u]; iout[dst] = ix[u]; }
 		__syncthreads();
 	}
 }
