@@ -442,7 +442,7 @@ def main():
         }
         if not args.no_cpu_baseline and world_size == 1:
             try:
-                cb, par = cpu_baseline_and_parity(world, mapper, raw_dev, raw_off, args.ref_reads or cfg["ref_reads"], cal)
+                cb, par = cpu_baseline_and_parity(world, mapper, raw_dev, raw_off, args.ref_reads or cfg["ref_reads"], cal, recs)
                 line["cpu_baseline"] = cb
                 line["parity"] = par
             except Exception as e:  # the number above stands; say why the baseline is missing
@@ -453,7 +453,7 @@ def main():
         dist.destroy_process_group()
 
 
-def cpu_baseline_and_parity(world, mapper, raw_dev, raw_off, n_sample, cal):
+def cpu_baseline_and_parity(world, mapper, raw_dev, raw_off, n_sample, cal, timed_recs):
     """The compiled reference on this box's host cores over the first n_sample reads of the step's batch, and the
     GPU's records for the same reads compared with the reference's PAF text (mt:f: aside)."""
     ref, _bind, prep = reference_handle(world)
@@ -469,7 +469,12 @@ def cpu_baseline_and_parity(world, mapper, raw_dev, raw_off, n_sample, cal):
     n_eq = sum(1 for a, b in zip(g, e) if a == b)
     cb = {"value": n_sample / secs, "unit": "reads/s", "cores": cores, "kind": "reference",
           "sample": f"first {n_sample} reads of the step's batch, kt_for(map_worker_for) wall time with {cores} threads, index load and file parsing excluded", **prep}
+    # the sample is mapped in a call of its own (a small batch takes the plain chunk-round loop); the timed batch's records
+    # for the same reads (streaming scheduler, other reads in flight beside them) must be the same records
+    cmp_fields = [f for f in recs.dtype.names if f != "mt_ms"]
+    head = timed_recs[timed_recs["read_idx"] < n_sample]
     par = {"reads": n_sample, "paf_lines_reference": len(e), "paf_lines_gpu": len(g), "lines_equal": n_eq, "equal": g == e,
+           "timed_batch_records_equal": bool(len(head) == len(recs) and np.array_equal(head[cmp_fields], recs[cmp_fields])),
            "against": "oracle/_ref/libref_tap.so (unmodified reference), same reads, PAF text without mt:f:"}
     return cb, par
 

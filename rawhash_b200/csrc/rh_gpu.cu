@@ -109,6 +109,7 @@ struct rh_worker {
 	dbuf<rh_map_rec_t> d_recs;
 	size_t arena_bytes = 0, sig_budget = 0;
 	uint32_t sort_posbits = 0, sort_ridbits = 0, sort_smem_cap = 0;
+	double hits_per_key = 0.0;    /* index positions per distinct key: first estimate of a chunk's anchors (scheduler choice) */
 	unsigned long long carry_known = 0; /* carry_top of the round's output arena at the last sync */
 	uint64_t rec_hint = 0, rec_cap_now = 0; bool retry_same = false; /* record arena overflow (all-vs-all: one record per chain): size it from the count and map the range again */
 	std::vector<timed_span> spans;
@@ -132,6 +133,7 @@ struct rh_gpu_ctx_s {
 	std::vector<uint32_t> name_order; /* sorted target names (indices) for Rawsamble */
 	dbuf<int16_t> d_raw;              /* raw samples of the current host-buffer call, shared by the workers */
 	uint32_t sort_posbits = 0, sort_ridbits = 0, sort_smem_cap = 0;
+	double hits_per_key = 0.0;
 	std::vector<rh_worker *> workers;
 	uint32_t n_active = 1;            /* workers used per call */
 	void *user_stream = nullptr;
@@ -602,7 +604,18 @@ int map_resident(rh_worker *c, const batch_in &in, const std::vector<uint64_t> &
 		ahead = e ? (uint32_t)std::max(1, atoi(e)) : (uint32_t)std::max<size_t>(1, (size_t)131072 / std::max<size_t>(active.size(), 1));
 		ahead = std::min(ahead, max_chunk);
 	}
-	const bool stream_sched = ahead > 1 && !getenv("RH_SCHED_ROUNDS");
+	/* Which loop: the streaming scheduler pays when the anchor arena holds far fewer chunks than there are reads (large
+	 * indexes: 5·10⁵ anchors per chunk against 3 Gb), so that plain chunk rounds would end in many nearly empty launches.
+	 * When a round of the whole batch is a handful of arena groups (small indexes), rounds launch less and are faster.
+	 * First estimate of a chunk's anchors: seeds per chunk (one per ~15 samples) x index positions per key x 1.7 (measured:
+	 * 1.85 at 12 Mb, 1.7 at 3.09 Gb — frequent keys are hit more often).  RH_SCHED_ROUNDS / RH_SCHED_STREAM force either. */
+	bool stream_sched = ahead > 1;
+	if (stream_sched && !getenv("RH_SCHED_STREAM")) {
+		const double est_anchors = 1.7 * ((double)P.chunk_size / 15.0) * std::max(c->hits_per_key, 1.0);
+		const double capacity = (double)c->arena_bytes / (double)slot_region_bytes((uint64_t)est_anchors);
+		if ((double)active.size() <= 4.0 * capacity) stream_sched = false;
+	}
+	if (getenv("RH_SCHED_ROUNDS")) stream_sched = false;
 	if (stream_sched) {
 		/* ---- streaming scheduler -------------------------------------------------------------------------------------
 		 * Reads are independent and a read's chunks are sequential (chunk c+1 chains onto the anchors chunk c carried over),
@@ -839,7 +852,7 @@ rh_worker *make_worker(rh_gpu_ctx *c, size_t arena_bytes)
 {
 	rh_worker *w = new rh_worker();
 	w->device = c->device; w->P = c->P; w->D = c->D; w->idx = c->idx; w->I = c->I;
-	w->sort_posbits = c->sort_posbits; w->sort_ridbits = c->sort_ridbits; w->sort_smem_cap = c->sort_smem_cap;
+	w->sort_posbits = c->sort_posbits; w->sort_ridbits = c->sort_ridbits; w->sort_smem_cap = c->sort_smem_cap; w->hits_per_key = c->hits_per_key;
 	w->d_logf = c->d_logf; w->logf_n = c->logf_n; w->d_seqlen = c->d_seqlen; w->name_order = &c->name_order; /* aliases: the context owns them */
 	w->err[0] = 0;
 	if (cudaStreamCreateWithFlags(&w->own_stream, cudaStreamNonBlocking) != cudaSuccess) { rh_set_error("cudaStreamCreate failed"); destroy_worker(w); return nullptr; }
@@ -1049,6 +1062,7 @@ extern "C" rh_gpu_ctx *rh_gpu_init(const rh_index_t *idx, const rh_params_t *p, 
 		else if (rh_index_dev_make_buckets(midx) != RH_OK) return fail(NULL);
 	}
 	const size_t nk = (size_t)V->n_keys;
+	c->hits_per_key = nk ? (double)V->n_pos / (double)nk : 0.0;
 	const int bits = V->bucket_bits;
 	std::vector<uint32_t> rank(idx->names.size());
 	c->name_order.resize(idx->names.size());

@@ -81,9 +81,12 @@ def test_yeast_size_20k_reads(built):
 
 
 @pytest.mark.parametrize("preset,r10", [("sensitive", False), ("fast", False), ("fast", True)])
-def test_150mb_600_reads_small_arena(built, preset, r10):
+def test_150mb_600_reads_small_arena(built, preset, r10, monkeypatch):
     """150 Mb, chunks of 10^4..10^5 anchors in an arena that holds a few dozen of them: global-memory sort, tie replay and
-    score sort through the long-sub-array path, many arena groups per round, carry arenas that have to grow."""
+    score sort through the long-sub-array path, many arena groups per round, carry arenas that have to grow.  By its own
+    estimate the library would map a batch this small in plain chunk rounds; the `fast` runs force the streaming scheduler."""
+    if preset == "fast":
+        monkeypatch.setenv("RH_SCHED_STREAM", "1")
     lens = [40_000_000, 35_000_000, 30_000_000, 25_000_000, 15_000_000, 5_000_000]
     W = _world([f"c{i}" for i in range(len(lens))], lens, preset, r10, seed=7)
     n = 600
