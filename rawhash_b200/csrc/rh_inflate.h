@@ -196,7 +196,7 @@ static bool huffman_block(stream_t &s, const tables_t &t, std::vector<uint8_t> &
 {
 	const entry_t *const lit = t.lit.data(), *const dst_tab = t.dist.data();
 	uint64_t bitbuf = s.bitbuf; unsigned bitcnt = s.bitcnt;
-	const uint8_t *in = s.in; const uint8_t *const in_limit = s.in_end + RH_INFLATE_SLACK - 8;
+	const uint8_t *in = s.in; const uint8_t *const in_limit = s.in_end + RH_INFLATE_SLACK - 16; /* an iteration refills twice: 8-byte loads up to in + 15 */
 	uint8_t *base = out.data(), *o = base + n_out, *o_limit = base + out.size() - (3 + 258 + 16);
 	bool ok = false;
 #define RHZ_REFILL() do { bitbuf |= load64(in) << bitcnt; in += (63 - bitcnt) >> 3; bitcnt |= 56; } while (0)

@@ -492,6 +492,7 @@ bool parse_binary_record(rec_t &r, int rec_method, int sig_method)
 	memcpy(&r.sampling_rate, p + at, 8); at += 8;
 	uint64_t len; memcpy(&len, p + at, 8); at += 8;
 	r.sig_at = at;
+	if (len > n - at) return false; /* before any arithmetic on it: a crafted length must not wrap (2 bytes per sample, or the compressed byte count) */
 	if (sig_method == SIG_NONE) { r.sig_bytes = len * 2; r.n_samples = len; }
 	else { r.sig_bytes = len; r.n_samples = svbzd_count(p + at, std::min<size_t>(len, n - at)); } /* length field = compressed bytes */
 	if (r.sig_bytes > n - r.sig_at) return false; /* auxiliary fields after the signal are not needed */

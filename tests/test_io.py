@@ -362,3 +362,24 @@ def test_random_files_round_trip_and_match_slow5lib(built, tmp_path):
         assert same_records(s5.read(p), want), (t, ext, rec, sig)
         got, _ = read_mine(p, threads=int(rng.integers(1, 5)), max_samples=int(rng.choice([1, 1000, 10**9])), max_reads=int(rng.choice([0, 1, 3])))
         assert same_records(got, want), (t, ext, rec, sig)
+
+
+def test_reader_rejects_a_crafted_signal_length(built, tmp_path):
+    """An uncompressed record whose length field is 2^63 + 2: twice that wraps to 4, which would pass a bounds check made
+    after the multiplication and hand a batch with an 18-byte arena and 2^63 + 2 samples to the mapper."""
+    import struct
+    from rawhash_b200 import api
+    raws = [np.arange(64, dtype=np.int16)]
+    p = str(tmp_path / "one.blow5")
+    api.write_slow5(p, ["r0"], raws, [0.0], [1402.882], [8192.0], 4000.0, 0, 0)
+    blob = bytearray(open(p, "rb").read())
+    at = blob.find(struct.pack("<Q", 64) + raws[0].tobytes())
+    assert at > 0, "length field followed by the samples"
+    for crafted in ((1 << 63) + 2, (1 << 64) - 1, 1 << 40):
+        blob[at:at + 8] = struct.pack("<Q", crafted)
+        bad = str(tmp_path / "crafted.blow5")
+        open(bad, "wb").write(bytes(blob))
+        with pytest.raises(api.RawHashError):
+            f = api.SignalFile(bad, 1)
+            while f.next_batch() is not None:
+                pass
