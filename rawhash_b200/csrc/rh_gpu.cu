@@ -568,6 +568,7 @@ int map_resident(rh_worker *c, const batch_in &in, const std::vector<uint64_t> &
 {
 	const uint32_t n = in.n;
 	std::vector<uint32_t> l_sig;
+	if (c->stream2) cudaStreamSynchronize(c->stream2); /* a call that failed half way (and is being retried in halves) may have left its heavy lane running */
 	int rc = setup_reads(c, in, beg, len, l_sig);
 	if (rc) return rc;
 	const rh_params_t &P = c->P;
