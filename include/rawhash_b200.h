@@ -246,6 +246,15 @@ int rh_gpu_tap_read(rh_gpu_ctx *ctx, const int16_t *raw, uint64_t raw_len,
                     double offset, double range, double digitisation,
                     const char *name, rh_tap_t *tap);
 
+/* How the library lays one chunk round out in its anchor arena (no device needed; the streaming scheduler calls the same
+ * code): n_anchors[n_chunks] = anchors per chunk, the first n_mandatory of which must run, the rest being first chunks of
+ * waiting reads in admission order (at most max_optional admitted).  Out: order[q] = input chunk at slot q (mandatory
+ * chunks heaviest first), a_off[q] = byte offset of slot q's region, groups = (first slot, count, heavy lane?) triples —
+ * the heavy group (largest chunks, second stream, top of the arena) first if there is one —, n_run = slots that run,
+ * main_bytes = arena bytes of the ordinary groups.  RH_ERR_NOMEM if one chunk exceeds the arena. */
+int rh_plan_round(const uint32_t *n_anchors, uint32_t n_chunks, uint32_t n_mandatory, uint32_t max_optional, uint64_t arena_bytes, int heavy_lane,
+                  uint32_t *order, uint64_t *a_off, uint32_t *groups, uint32_t groups_cap, uint32_t *n_groups, uint32_t *n_run, uint64_t *main_bytes);
+
 /* ---- files either side of the path (SURVEY.md §8b "file surfaces kept", §8f rank 3) -------------- */
 /* Write the index in the reference's `.ind` layout (ri_idx_dump, src/rindex.c:545-648): header, pore table,
  * sequence names/lengths, 2^14 buckets of (position array, key/value pairs).  The reference's ri_idx_load

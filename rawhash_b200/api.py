@@ -175,6 +175,7 @@ def _load():
         "rh_zlib_inflate": (i32, [vp, C.c_size_t, C.POINTER(vp), C.POINTER(C.c_size_t)]),
         "rh_find_sigfiles": (i32, [cp, C.POINTER(C.POINTER(vp)), C.POINTER(u32)]),
         "rh_slow5_write": (i32, [cp, u32, vp, vp, vp, vp, vp, vp, dbl, i32, i32]),
+        "rh_plan_round": (i32, [vp, u32, u32, u32, u64, i32, vp, vp, vp, u32, C.POINTER(u32), C.POINTER(u32), C.POINTER(u64)]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)  # AttributeError if the library does not export a declared symbol
@@ -549,3 +550,21 @@ def write_slow5(path: str, names, raws, offset, rng, digitisation, sampling_rate
     rc = _lib.rh_slow5_write(path.encode(), n, nm, ptrs, lens.ctypes.data, off.ctypes.data, rg.ctypes.data, dg.ctypes.data, float(sampling_rate), record_press, signal_press)
     if rc != 0:
         raise _err("rh_slow5_write")
+
+
+def plan_round(n_anchors, n_mandatory: int, max_optional: int, arena_bytes: int, heavy_lane: bool = True):
+    """Layout of one chunk round in the anchor arena (rh_plan_round; pure host logic, the scheduler calls the same code).
+    Returns dict(order, a_off, groups=[(first, count, heavy)], n_run, main_bytes)."""
+    na = np.ascontiguousarray(n_anchors, dtype=np.uint32)
+    ns = len(na)
+    order = np.zeros(max(ns, 1), dtype=np.uint32)
+    a_off = np.zeros(max(ns, 1), dtype=np.uint64)
+    cap = ns + 2
+    groups = np.zeros(3 * cap, dtype=np.uint32)
+    ng, nr, mb = C.c_uint32(0), C.c_uint32(0), C.c_uint64(0)
+    rc = _lib.rh_plan_round(na.ctypes.data, ns, n_mandatory, max_optional, arena_bytes, 1 if heavy_lane else 0,
+                            order.ctypes.data, a_off.ctypes.data, groups.ctypes.data, cap, C.byref(ng), C.byref(nr), C.byref(mb))
+    if rc != 0:
+        raise _err(f"rh_plan_round (rc={rc})")
+    g = groups[: 3 * ng.value].reshape(-1, 3)
+    return dict(order=order[:ns], a_off=a_off[:ns], groups=[(int(a), int(b), int(c)) for a, b, c in g], n_run=int(nr.value), main_bytes=int(mb.value))

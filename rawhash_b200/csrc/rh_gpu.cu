@@ -318,10 +318,19 @@ int run_round(rh_worker *c, round_io &io, int carry_in_idx)
 	a3.recs = c->d_recs.p; a3.rec_top = c->d_counters.p + 1; a3.rec_cap = c->rec_cap_now;
 	a3.rec_start = c->d_rec_start.p; a3.rec_cnt = c->d_rec_cnt.p; a3.seq_len = c->d_seqlen.p; a3.tap = io.tap; a3.err = c->d_err.p; a3.prof = c->prof_on ? c->d_prof.p : nullptr; a3.prof_replay = getenv("RH_PROF_TIES_ONLY") ? 0 : 1;
 
-	/* Heaviest chunks first: CTAs are handed out in slot order and every kernel of a group lasts as long as its slowest
-	 * chunk, so the long ones must not start last.  (Results are filed per read: the slot order is free.) */
+	/* The layout of the round: order of the chunks (heaviest first), arena groups, heavy lane — rh_plan_round_impl (rh_host.cpp). */
 	const uint32_t n_mand = std::min(io.n_mandatory, ns);
-	if (!io.tap) std::stable_sort(io.slots.begin(), io.slots.begin() + n_mand, [](const slot_t &a, const slot_t &b) { return a.n_anchors > b.n_anchors; });
+	rh_round_plan_t plan;
+	{
+		std::vector<uint32_t> sizes(ns);
+		for (uint32_t q = 0; q < ns; ++q) sizes[q] = io.slots[q].n_anchors;
+		const bool heavy_ok = !io.tap && io.n_mandatory != 0xffffffffu && c->stream2 && !getenv("RH_NO_HEAVY_LANE");
+		if ((rc = rh_plan_round_impl(sizes.data(), ns, n_mand, io.max_optional, c->arena_bytes, !io.tap, heavy_ok, &plan))) return rc;
+		std::vector<slot_t> ordered(n_mand);
+		for (uint32_t q = 0; q < n_mand; ++q) ordered[q] = io.slots[plan.order[q]]; /* waiting reads keep their order */
+		std::copy(ordered.begin(), ordered.end(), io.slots.begin());
+		for (uint32_t q = 0; q < plan.n_run; ++q) io.slots[q].a_off = plan.a_off[q];
+	}
 
 	unsigned long long committed = c->carry_known; /* upper bound of carry_top once everything launched so far has run */
 	/* front half of a group on stream `st`: slots up, anchors, sort (+ exact tie order), chaining DP */
@@ -422,56 +431,28 @@ int run_round(rh_worker *c, round_io &io, int carry_in_idx)
 	/* Heavy lane (streaming scheduler): the largest chunks of the iteration (late chunks of reads that do not map: each
 	 * drags all chain anchors of its predecessors along) take several times as long as an average chunk in every kernel,
 	 * and a kernel lasts as long as its slowest chunk.  They run as a group of their own on a second stream, in a slice at
-	 * the top of the arena, next to the ordinary groups. */
-	uint32_t nh = 0; uint64_t heavy_bytes = 0;
-	if (!io.tap && io.n_mandatory != 0xffffffffu && c->stream2 && n_mand >= 64 && !getenv("RH_NO_HEAVY_LANE")) {
-		unsigned long long sum = 0;
-		for (uint32_t q = 0; q < n_mand; ++q) sum += io.slots[q].n_anchors;
-		const double avg = (double)sum / n_mand;
-		const uint64_t cap = c->arena_bytes / 8;
-		while (nh < n_mand / 4 && io.slots[nh].n_anchors > 1.25 * avg && heavy_bytes + slot_region_bytes(io.slots[nh].n_anchors) <= cap) heavy_bytes += slot_region_bytes(io.slots[nh++].n_anchors);
-		if (nh < 2) { nh = 0; heavy_bytes = 0; }
-	}
-	const uint64_t main_bytes = (c->arena_bytes - heavy_bytes) & ~(uint64_t)255; /* slot regions start 256-byte aligned */
-	bool heavy_back_due = false;
+	 * the top of the arena, next to the ordinary groups: front half first, back half once the first ordinary group's back
+	 * half has been launched. */
 	cudaStream_t sh = c->stream2;
-	if (nh) {
-		uint64_t off = main_bytes;
-		for (uint32_t q = 0; q < nh; ++q) { io.slots[q].a_off = off; off += slot_region_bytes(io.slots[q].n_anchors); }
-		if ((rc = front(sh, 0, nh, c->d_tie_list2, c->d_tie_count2))) return rc;
+	const rh_round_group_t *heavy = (!plan.groups.empty() && plan.groups[0].heavy) ? &plan.groups[0] : nullptr;
+	bool heavy_back_due = false;
+	if (heavy) {
+		if ((rc = front(sh, heavy->first, heavy->first + heavy->count, c->d_tie_list2, c->d_tie_count2))) return rc;
 		heavy_back_due = true;
 	}
-	uint32_t n_total = n_mand; /* slots that run in this round: grows while optional slots are admitted */
-	uint32_t g0 = nh;
-	while (g0 < n_total || (g0 == nh && n_mand == nh && ns > nh)) {
-		uint64_t used = 0; uint32_t g1 = g0;
-		while (g1 < n_total) {
-			const uint64_t need = slot_region_bytes(io.slots[g1].n_anchors);
-			if (need > main_bytes) { rh_set_error("a single chunk needs %llu bytes of anchor arena (have %llu)", (unsigned long long)need, (unsigned long long)main_bytes); return RH_ERR_NOMEM; }
-			if (used + need > main_bytes) break;
-			io.slots[g1].a_off = used; used += need; ++g1;
-		}
-		if (g1 == n_mand && n_total == n_mand) { /* the last group of mandatory slots: reads waiting for admission fill what is left of the arena */
-			while (g1 < ns && g1 - n_mand < io.max_optional) {
-				const uint64_t need = slot_region_bytes(io.slots[g1].n_anchors);
-				if (need > main_bytes) { rh_set_error("a single chunk needs %llu bytes of anchor arena (have %llu)", (unsigned long long)need, (unsigned long long)main_bytes); return RH_ERR_NOMEM; }
-				if (used + need > main_bytes) break;
-				io.slots[g1].a_off = used; used += need; ++g1;
-			}
-			n_total = g1;
-			if (g1 == g0) break; /* nothing to run */
-		}
-		if ((rc = front(s, g0, g1, c->d_tie_list, c->d_tie_count))) return rc;
-		if ((rc = back(s, g0, g1))) return rc;
-		if (heavy_back_due) { heavy_back_due = false; if ((rc = back(sh, 0, nh))) return rc; } /* its front half ran beside this group's */
-		g0 = g1;
+	for (const rh_round_group_t &g : plan.groups) {
+		if (g.heavy) continue;
+		if ((rc = front(s, g.first, g.first + g.count, c->d_tie_list, c->d_tie_count))) return rc;
+		if ((rc = back(s, g.first, g.first + g.count))) return rc;
+		if (heavy_back_due) { heavy_back_due = false; if ((rc = back(sh, heavy->first, heavy->first + heavy->count))) return rc; } /* its front half ran beside this group's */
 	}
-	if (heavy_back_due) { if ((rc = back(sh, 0, nh))) return rc; }
-	if (nh) { /* the round ends when both lanes have */
+	if (heavy_back_due) { if ((rc = back(sh, heavy->first, heavy->first + heavy->count))) return rc; }
+	if (heavy) { /* the round ends when both lanes have */
 		cudaEvent_t ev = get_event(c);
 		CUDA_TRY(cudaEventRecord(ev, sh));
 		CUDA_TRY(cudaStreamWaitEvent(s, ev, 0));
 	}
+	const uint32_t n_total = plan.n_run;
 	io.n_run = n_total;
 	for (uint32_t q = 0; q < n_total; ++q) {
 		const slot_t &sl = io.slots[q];

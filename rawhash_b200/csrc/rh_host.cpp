@@ -374,6 +374,81 @@ static rh_index_t *index_build_host_one(const rh_params_t *p, const float *pore_
 	return idx;
 }
 
+/* ---- layout of one chunk round --------------------------------------------------------------------------
+ * Input: the anchor counts of ns chunks, the first n_mandatory of which must run in this round (their reads carry chain
+ * anchors in the round's input arena); the rest are first chunks of waiting reads, in admission order, of which at most
+ * max_optional may be admitted.  Output: the order the chunks take (mandatory ones heaviest first: CTAs are handed out in
+ * slot order and a kernel lasts as long as its slowest chunk), the groups that fill the arena one after the other, each
+ * chunk's region, and — when asked for — a heavy group of the largest chunks (more than 1.25 x the mean, at most a quarter
+ * of the mandatory chunks and an eighth of the arena, at least two) that runs beside the ordinary groups in a slice at the
+ * top of the arena.  Waiting reads only fill what the last ordinary group of mandatory chunks leaves free (a whole arena
+ * when nothing is mandatory), in order, up to the first that does not fit. */
+int rh_plan_round_impl(const uint32_t *n_anchors, uint32_t ns, uint32_t n_mandatory, uint32_t max_optional, uint64_t arena_bytes,
+                       bool heaviest_first, bool heavy_lane, rh_round_plan_t *plan)
+{
+	const uint32_t n_mand = std::min(n_mandatory, ns);
+	plan->order.resize(ns);
+	for (uint32_t q = 0; q < ns; ++q) plan->order[q] = q;
+	if (heaviest_first) std::stable_sort(plan->order.begin(), plan->order.begin() + n_mand, [&](uint32_t a, uint32_t b) { return n_anchors[a] > n_anchors[b]; });
+	auto size_of = [&](uint32_t q) { return rh_slot_region_bytes(n_anchors[plan->order[q]]); };
+	plan->a_off.assign(ns, 0);
+	plan->groups.clear();
+	uint32_t nh = 0; uint64_t heavy_bytes = 0;
+	if (heavy_lane && heaviest_first && n_mand >= 64) {
+		unsigned long long sum = 0;
+		for (uint32_t q = 0; q < n_mand; ++q) sum += n_anchors[plan->order[q]];
+		const double avg = (double)sum / n_mand;
+		const uint64_t cap = arena_bytes / 8;
+		while (nh < n_mand / 4 && n_anchors[plan->order[nh]] > 1.25 * avg && heavy_bytes + size_of(nh) <= cap) heavy_bytes += size_of(nh++);
+		if (nh < 2) { nh = 0; heavy_bytes = 0; }
+	}
+	const uint64_t main_bytes = (arena_bytes - heavy_bytes) & ~(uint64_t)255; /* regions start 256-byte aligned */
+	plan->main_bytes = main_bytes;
+	if (nh) {
+		uint64_t off = main_bytes;
+		for (uint32_t q = 0; q < nh; ++q) { plan->a_off[q] = off; off += size_of(q); }
+		plan->groups.push_back({0u, nh, 1u});
+	}
+	uint32_t n_total = n_mand, g0 = nh;
+	while (g0 < n_total || (g0 == nh && n_mand == nh && ns > nh)) {
+		uint64_t used = 0; uint32_t g1 = g0;
+		while (g1 < n_total) {
+			const uint64_t need = size_of(g1);
+			if (need > main_bytes) { rh_set_error("a single chunk needs %llu bytes of anchor arena (have %llu)", (unsigned long long)need, (unsigned long long)main_bytes); return RH_ERR_NOMEM; }
+			if (used + need > main_bytes) break;
+			plan->a_off[g1] = used; used += need; ++g1;
+		}
+		if (g1 == n_mand && n_total == n_mand) {
+			while (g1 < ns && g1 - n_mand < max_optional) {
+				const uint64_t need = size_of(g1);
+				if (need > main_bytes) { rh_set_error("a single chunk needs %llu bytes of anchor arena (have %llu)", (unsigned long long)need, (unsigned long long)main_bytes); return RH_ERR_NOMEM; }
+				if (used + need > main_bytes) break;
+				plan->a_off[g1] = used; used += need; ++g1;
+			}
+			n_total = g1;
+			if (g1 == g0) break; /* nothing to run */
+		}
+		plan->groups.push_back({g0, g1 - g0, 0u});
+		g0 = g1;
+	}
+	plan->n_run = n_total;
+	return RH_OK;
+}
+
+extern "C" int rh_plan_round(const uint32_t *n_anchors, uint32_t n_chunks, uint32_t n_mandatory, uint32_t max_optional, uint64_t arena_bytes, int heavy_lane,
+                             uint32_t *order, uint64_t *a_off, uint32_t *groups, uint32_t groups_cap, uint32_t *n_groups, uint32_t *n_run, uint64_t *main_bytes)
+{
+	if ((n_chunks && (!n_anchors || !order || !a_off)) || !n_groups || !n_run || (groups_cap && !groups)) { rh_set_error("rh_plan_round: null argument"); return RH_ERR_ARG; }
+	rh_round_plan_t plan;
+	const int rc = rh_plan_round_impl(n_anchors, n_chunks, n_mandatory, max_optional, arena_bytes, true, heavy_lane != 0, &plan);
+	if (rc != RH_OK) return rc;
+	for (uint32_t q = 0; q < n_chunks; ++q) { order[q] = plan.order[q]; a_off[q] = plan.a_off[q]; }
+	*n_groups = (uint32_t)plan.groups.size(); *n_run = plan.n_run;
+	if (main_bytes) *main_bytes = plan.main_bytes;
+	for (uint32_t g = 0; g < plan.groups.size() && g < groups_cap; ++g) { groups[3 * g] = plan.groups[g].first; groups[3 * g + 1] = plan.groups[g].count; groups[3 * g + 2] = plan.groups[g].heavy; }
+	return RH_OK;
+}
+
 extern "C" rh_index_t *rh_index_load(const char *path, rh_params_t *pp)
 { /* reader for the reference's `.ind` layout, src/rindex.c:650-776 (writer 545-648) */
 	FILE *f = fopen(path, "rb");

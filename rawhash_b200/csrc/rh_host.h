@@ -35,6 +35,20 @@ struct rh_index_s {
 
 struct rh_seed_t { uint64_t x, y; };
 
+/* ---- layout of one chunk round in the anchor arena (pure host logic: rh_plan_round, CPU-tested) ---- */
+#define RH_SLOT_BYTES_PER_ANCHOR 144
+static inline uint64_t rh_slot_region_bytes(uint64_t n_anchors) { return ((n_anchors * RH_SLOT_BYTES_PER_ANCHOR + 1024 + 255) / 256) * 256; }
+struct rh_round_group_t { uint32_t first, count, heavy; };   /* plan slots [first, first + count); heavy: the second-stream lane */
+struct rh_round_plan_t {
+	std::vector<uint32_t> order;            /* plan slot q = input slot order[q] (all ns slots; only [0, n_run) run) */
+	std::vector<uint64_t> a_off;            /* byte offset of plan slot q's region in the arena, q < n_run            */
+	std::vector<rh_round_group_t> groups;   /* the heavy group first (if any), then the ordinary groups in launch order */
+	uint32_t n_run = 0;                     /* mandatory slots + admitted optional slots                              */
+	uint64_t main_bytes = 0;                /* arena bytes of the ordinary groups; the heavy group sits above          */
+};
+int rh_plan_round_impl(const uint32_t *n_anchors, uint32_t ns, uint32_t n_mandatory, uint32_t max_optional, uint64_t arena_bytes,
+                       bool heaviest_first, bool heavy_lane, rh_round_plan_t *plan);
+
 /* sketch of one event array on the host (index build side; the read side runs on the GPU) */
 void rh_host_sketch(const rh_params_t &P, const float *ev, uint32_t len, uint32_t id, int strand, std::vector<rh_seed_t> &out);
 void rh_index_from_seeds(rh_index_s *idx, std::vector<rh_seed_t> &seeds, int n_threads);

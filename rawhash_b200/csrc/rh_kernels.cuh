@@ -59,7 +59,9 @@ struct slot_t {
 };
 
 /* layout of a slot's region in the anchor arena (n = n_anchors) */
-#define RH_SLOT_BYTES_PER_ANCHOR 144
+#ifndef RH_SLOT_BYTES_PER_ANCHOR
+#define RH_SLOT_BYTES_PER_ANCHOR 144 /* also in rh_host.h (rh_slot_region_bytes: the host-side planner) */
+#endif
 __host__ __device__ inline uint64_t slot_region_bytes(uint64_t n) { return ((n * RH_SLOT_BYTES_PER_ANCHOR + 1024 + 255) / 256) * 256; }
 /* the region-record area (48n + 1024 bytes at offset 96n): sort scratch of k_chain_finish first, records after */
 __host__ __device__ inline uint64_t fin_regs_off(uint64_t n) { return (6 * n + 256 + 63) & ~63ULL; }
