@@ -9,7 +9,8 @@ One "step" = one pass of the hot path over one batch of R synthetic reads
 Workloads (--config, numbering of BASELINE.json `configs`):
   2 (default)  human-size: GRCh38-shaped synthetic genome (24 contigs, 3.09 Gb), `-x fast`, synthetic R9.4 4 kHz
                450 bp/s reads of 5 kb — the configuration the metric is quoted on
-               (test/evaluation/read_mapping/d5_human_na12878_r94/run_rawhash2.sh:14-15)
+               (test/evaluation/read_mapping/d5_human_na12878_r94/run_rawhash2.sh:14-15); 24 000 reads per step, fewer
+               when the steps asked for would not fit the run's time budget (_reads_per_step)
   3            the same genome with the R10.4.1 9-mer model, `-x fast --r10`, 5 kHz / 400 bp/s
   1            yeast-size: 12 Mb / 16 contigs, `-x sensitive` (the round-1 workload, a parity-test size)
 
@@ -55,11 +56,30 @@ def _configs():
                 sample_rate=4000, bp_per_sec=450, reads=100_000, ref_reads=2000),
         2: dict(workload="human-size: GRCh38-shaped synthetic genome (24 contigs, 3.09 Gb), -x fast, synthetic R9.4 4 kHz 450 bp/s reads of 5 kb (BASELINE configs[2])",
                 preset="fast", r10=False, names=synth.GRCH38_NAMES, lens=synth.GRCH38_LENS, kind="r9.4", k=6,
-                sample_rate=4000, bp_per_sec=450, reads=int(os.environ.get("RH_BENCH_READS_HUMAN", "24000")), ref_reads=400),
+                sample_rate=4000, bp_per_sec=450, reads=int(os.environ.get("RH_BENCH_READS_HUMAN", "24000")), ref_reads=400, rate_est=700.0),
         3: dict(workload="human-size: GRCh38-shaped synthetic genome (24 contigs, 3.09 Gb), -x fast --r10, R10.4.1 9-mer model, synthetic 5 kHz 400 bp/s reads of 5 kb (BASELINE configs[3])",
                 preset="fast", r10=True, names=synth.GRCH38_NAMES, lens=synth.GRCH38_LENS, kind="r10.4.1", k=9,
-                sample_rate=5000, bp_per_sec=400, reads=int(os.environ.get("RH_BENCH_READS_HUMAN", "24000")), ref_reads=400),
+                sample_rate=5000, bp_per_sec=400, reads=int(os.environ.get("RH_BENCH_READS_HUMAN", "24000")), ref_reads=400, rate_est=380.0),
     }
+
+
+E2E_STEPS_MAX = 4   # the end-to-end leg repeats the same step from host buffers: a few steps time it as well as K do
+
+
+def _reads_per_step(cfg, args):
+    """Reads per step per GPU.  A step of the human-size workload lasts tens of seconds, and a batch ends with a tail of
+    nearly empty iterations whatever its size, so large batches are the efficient ones (24 000 by default); but the whole
+    run — W warm-up, K timed, the end-to-end steps and two more — has to fit a time budget (RH_BENCH_BUDGET_S, 540 s), so
+    the batch shrinks when many steps are asked for.  `rate_est` = reads/s expected of this workload on one B200."""
+    if args.reads:
+        return args.reads
+    R = cfg["reads"]
+    rate = cfg.get("rate_est")
+    if rate and "RH_BENCH_READS_HUMAN" not in os.environ:
+        total_steps = args.warmup + args.steps + min(args.steps, E2E_STEPS_MAX) + 2
+        budget = float(os.environ.get("RH_BENCH_BUDGET_S", "540"))
+        R = min(R, max(4000, int(budget * rate / total_steps) // 1000 * 1000))
+    return R
 
 
 def _peaks():
@@ -311,7 +331,8 @@ def main():
 
     world = World(cfg, local_rank)   # genome + rh_index_build_dev: not part of the timed region
     P, idx = world.P, world.idx
-    R = args.reads or cfg["reads"]
+    R = _reads_per_step(cfg, args)
+    e2e_steps = max(1, min(args.steps, E2E_STEPS_MAX))
     t0 = time.time()
     raw_dev, raw_off, lens, truth = world.reads(R, 1000 + rank)
     torch.cuda.synchronize()
@@ -370,7 +391,7 @@ def main():
         f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         f0.record()
         h2d = d2h = 0
-        for _ in range(args.steps):
+        for _ in range(e2e_steps):
             recs_h = step_host()
             st = mapper.stats()
             h2d += st["h2d_bytes"]; d2h += st["d2h_bytes"]
@@ -420,8 +441,8 @@ def main():
                        "index_positions": int(idx.n_pos), "genome_bases": int(world.G.total), "genome_generation_s": round(world.t_genome, 2),
                        "index_build_s": round(world.t_index, 2), "index_built_on": "gpu (rh_index_build_dev, device-resident)", "read_synthesis_s": round(t_synth, 2),
                        "parallelism": f"index replicated, reads sharded x{world_size}", "workers_per_gpu": n_workers},
-            "e2e": {"value": tot_reads * args.steps / (ms_e2e * 1e-3), "unit": "reads/s",
-                    "h2d_bytes_per_step": h2d // args.steps, "d2h_bytes_per_step": d2h // args.steps, "records_equal_to_resident_run": same},
+            "e2e": {"value": tot_reads * e2e_steps / (ms_e2e * 1e-3), "unit": "reads/s", "steps": e2e_steps,
+                    "h2d_bytes_per_step": h2d // e2e_steps, "d2h_bytes_per_step": d2h // e2e_steps, "records_equal_to_resident_run": same},
             "gpu_launches": int(cnt["kernel_launches"]),
             "clocks": clocks,
             "roofline": {"kernel": "event stage (raw int16 -> events -> quantise -> hash), timed as one span per launch group", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",

@@ -48,3 +48,28 @@ def test_human_size_reference_arm_says_why_it_needs_the_gpu(built):
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1"],
                        capture_output=True, text=True, timeout=300, cwd=ROOT)
     assert r.returncode != 0 and r.stdout.strip() == "" and "index table from the GPU builder" in r.stderr
+
+
+def test_batch_size_follows_the_time_budget(monkeypatch):
+    """The human-size batch shrinks when the steps asked for would not fit the run's time budget (the driver runs
+    --steps 20 --warmup 5); explicit sizes win; the yeast-size config has no budget rule."""
+    import importlib.util
+    import types
+    monkeypatch.delenv("RH_BENCH_READS_HUMAN", raising=False)
+    monkeypatch.delenv("RH_BENCH_BUDGET_S", raising=False)
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
+    b = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(b)
+    cfgs = b._configs()
+    A = types.SimpleNamespace
+    assert b._reads_per_step(cfgs[2], A(reads=0, steps=2, warmup=3)) == 24000
+    r20 = b._reads_per_step(cfgs[2], A(reads=0, steps=20, warmup=5))
+    assert 8000 <= r20 <= 14000
+    total_steps = 5 + 20 + min(20, b.E2E_STEPS_MAX) + 2
+    assert total_steps * r20 / cfgs[2]["rate_est"] <= 540
+    assert b._reads_per_step(cfgs[3], A(reads=0, steps=20, warmup=5)) < r20          # the R10 workload is slower per read
+    assert b._reads_per_step(cfgs[2], A(reads=0, steps=500, warmup=5)) == 4000       # floor
+    assert b._reads_per_step(cfgs[2], A(reads=1234, steps=20, warmup=5)) == 1234
+    assert b._reads_per_step(cfgs[1], A(reads=0, steps=20, warmup=5)) == 100000
+    monkeypatch.setenv("RH_BENCH_BUDGET_S", "2000")
+    assert b._reads_per_step(cfgs[2], A(reads=0, steps=20, warmup=5)) == 24000
